@@ -1,0 +1,214 @@
+"""ctypes binding of libanerf_b200.so (the C ABI in include/anerf_b200.h).
+
+The library is the only compute path: if it is missing or a call fails, this module raises --
+there is no PyTorch or CPU fallback behind these functions."""
+import ctypes as C
+import os
+
+import torch
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libanerf_b200.so")
+_lib = None
+
+SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "anerf_pack_net",
+           "anerf_render_workspace_bytes", "anerf_render_fwd", "anerf_render_fwd_host", "anerf_density_points",
+           "anerf_selftest_gemm", "anerf_last_error", "anerf_version"]
+
+
+class NetConfig(C.Structure):
+    _fields_ = [("n_joints", C.c_int32), ("depth", C.c_int32), ("width", C.c_int32), ("skip", C.c_int32),
+                ("framecode_ch", C.c_int32), ("n_framecodes", C.c_int32), ("operand_format", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class NetParams(C.Structure):
+    _fields_ = [("pts_w", C.c_void_p * 8), ("pts_b", C.c_void_p * 8), ("alpha_w", C.c_void_p), ("alpha_b", C.c_void_p),
+                ("feature_w", C.c_void_p), ("feature_b", C.c_void_p), ("views_w", C.c_void_p), ("views_b", C.c_void_p),
+                ("rgb_w", C.c_void_p), ("rgb_b", C.c_void_p), ("framecodes", C.c_void_p)]
+
+
+class RenderOpts(C.Structure):
+    _fields_ = [("n_rays", C.c_int32), ("n_samples", C.c_int32), ("n_importance", C.c_int32), ("lindisp", C.c_int32),
+                ("softplus", C.c_int32), ("eval_mean_framecode", C.c_int32), ("density_scale", C.c_float),
+                ("softplus_shift", C.c_float), ("tau_pts", C.c_float), ("tau_views", C.c_float),
+                ("cutoff_pts", C.c_float * 24), ("cutoff_views", C.c_float * 24)]
+
+
+class RenderInputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("rays", "skts", "cyls", "cams", "t_rand", "u_rand", "noise0", "noise1")]
+
+
+class RenderOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0", "alpha0",
+                                          "z_all", "raw")]
+
+
+def lib_path():
+    return _LIB_PATH
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(f"{_LIB_PATH} is missing: build it with `python -m anerf_b200.build` "
+                           "(anerf_b200 has no fallback path)")
+    lib = C.CDLL(_LIB_PATH)
+    lib.anerf_last_error.restype = C.c_char_p
+    lib.anerf_packed_bytes.restype = C.c_size_t
+    lib.anerf_packed_bytes.argtypes = [C.c_void_p]
+    lib.anerf_render_workspace_bytes.restype = C.c_size_t
+    lib.anerf_render_workspace_bytes.argtypes = [C.c_int32]
+    lib.anerf_plan_create.argtypes = [C.POINTER(NetConfig), C.POINTER(C.c_void_p)]
+    lib.anerf_plan_destroy.argtypes = [C.c_void_p]
+    lib.anerf_plan_destroy.restype = None
+    lib.anerf_pack_net.argtypes = [C.c_void_p, C.POINTER(NetParams), C.c_void_p, C.c_void_p]
+    lib.anerf_render_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.POINTER(RenderInputs),
+                                     C.POINTER(RenderOutputs), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.anerf_render_fwd_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RenderOpts),
+                                          C.POINTER(RenderInputs), C.POINTER(RenderOutputs), C.c_void_p]
+    lib.anerf_density_points.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_void_p]
+    lib.anerf_selftest_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RuntimeError(f"anerf_b200: {load().anerf_last_error().decode()} (status {rc})")
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Plan:
+    """Owns an anerf_plan (layer program + K maps of one network configuration)."""
+
+    def __init__(self, n_joints, depth, width, skips=(4,), framecode_ch=0, n_framecodes=0, operand_format=1):
+        skip = -1
+        for s in skips:
+            if s < depth - 1:
+                if skip >= 0:
+                    raise NotImplementedError("only one skip connection is supported")
+                skip = int(s)
+        self.cfg = NetConfig(n_joints, depth, width, skip, framecode_ch, n_framecodes, operand_format, 0)
+        self.handle = C.c_void_p()
+        check(load().anerf_plan_create(C.byref(self.cfg), C.byref(self.handle)))
+        self.packed_bytes = load().anerf_packed_bytes(self.handle)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                load().anerf_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+    def pack(self, sd, out=None):
+        """sd: mapping of reference state_dict names -> fp32 CUDA tensors.  Returns the packed image (uint8)."""
+        dev = sd['pts_linears.0.weight'].device
+        if out is None:
+            out = torch.empty(self.packed_bytes, dtype=torch.uint8, device=dev)
+        keep = []
+
+        def p(name):
+            t = sd[name].detach()
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.float().contiguous()
+            keep.append(t)
+            return t.data_ptr()
+        prm = NetParams()
+        for i in range(self.cfg.depth):
+            prm.pts_w[i] = p(f'pts_linears.{i}.weight')
+            prm.pts_b[i] = p(f'pts_linears.{i}.bias')
+        prm.alpha_w, prm.alpha_b = p('alpha_linear.weight'), p('alpha_linear.bias')
+        prm.feature_w, prm.feature_b = p('feature_linear.weight'), p('feature_linear.bias')
+        prm.views_w, prm.views_b = p('views_linears.0.weight'), p('views_linears.0.bias')
+        prm.rgb_w, prm.rgb_b = p('rgb_linear.weight'), p('rgb_linear.bias')
+        if self.cfg.framecode_ch > 0:
+            prm.framecodes = p('framecodes.codes.weight')
+        check(load().anerf_pack_net(self.handle, C.byref(prm), _ptr(out), _stream()))
+        return out
+
+
+def make_opts(n_rays, n_samples, n_importance, tau_pts=20., tau_views=20., cutoff_pts=0.5, cutoff_views=0.5,
+              n_joints=24, lindisp=False, softplus=False, softplus_shift=0., density_scale=1.,
+              eval_mean_framecode=False):
+    o = RenderOpts()
+    o.n_rays, o.n_samples, o.n_importance = n_rays, n_samples, n_importance
+    o.lindisp, o.softplus, o.eval_mean_framecode = int(lindisp), int(softplus), int(eval_mean_framecode)
+    o.density_scale, o.softplus_shift, o.tau_pts, o.tau_views = density_scale, softplus_shift, tau_pts, tau_views
+    for name, v in (("cutoff_pts", cutoff_pts), ("cutoff_views", cutoff_views)):
+        arr = getattr(o, name)
+        vals = [float(v)] * 24 if not hasattr(v, '__len__') else [float(x) for x in v] + [0.] * (24 - len(v))
+        for j in range(24):
+            arr[j] = vals[j]
+    return o
+
+
+def render_fwd(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, cams=None, t_rand=None, u_rand=None,
+               noise0=None, noise1=None, want_taps=False):
+    """One chunk on the device.  All tensors fp32 contiguous CUDA.  Returns the reference's output dict
+    (core/raycasters.py:711-724) plus 'z_all'/'raw' taps when asked."""
+    N, Sc, Si = opts.n_rays, opts.n_samples, opts.n_importance
+    dev = rays.device
+    Sf = Sc + Si
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    out = dict(rgb_map=f(N, 3), disp_map=f(N), acc_map=f(N), alpha=f(N, Sf if Si > 0 else Sc))
+    if Si > 0:
+        out.update(rgb0=f(N, 3), disp0=f(N), acc0=f(N), alpha0=f(N, Sc))
+    if want_taps:
+        out['raw'] = f(N, Sf if Si > 0 else Sc, 4)
+        if Si > 0:
+            out['z_all'] = f(N, Sf)
+    ws_bytes = load().anerf_render_workspace_bytes(N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    for t in (rays, skts, cyls, cams, t_rand, u_rand, noise0, noise1):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+    rin = RenderInputs(_ptr(rays), _ptr(skts), _ptr(cyls), _ptr(cams), _ptr(t_rand), _ptr(u_rand), _ptr(noise0), _ptr(noise1))
+    rout = RenderOutputs(*[_ptr(out.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0",
+                                                      "alpha0", "z_all", "raw")])
+    check(load().anerf_render_fwd(plan.handle, _ptr(packed_coarse), _ptr(packed_fine), C.byref(opts), C.byref(rin),
+                                  C.byref(rout), _ptr(ws), ws_bytes, _stream()))
+    return out
+
+
+def render_fwd_host(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, cams=None, out=None):
+    """Same through host (CPU, ideally pinned) tensors: H2D + kernels + D2H inside the call."""
+    N, Sc, Si = opts.n_rays, opts.n_samples, opts.n_importance
+    Sf = Sc + Si
+    if out is None:
+        f = lambda *s: torch.empty(*s, dtype=torch.float32).pin_memory()
+        out = dict(rgb_map=f(N, 3), disp_map=f(N), acc_map=f(N), alpha=f(N, Sf if Si > 0 else Sc))
+        if Si > 0:
+            out.update(rgb0=f(N, 3), disp0=f(N), acc0=f(N), alpha0=f(N, Sc))
+    for t in (rays, skts, cyls, cams):
+        assert t is None or (not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+    rin = RenderInputs(_ptr(rays), _ptr(skts), _ptr(cyls), _ptr(cams), None, None, None, None)
+    rout = RenderOutputs(*[_ptr(out.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0",
+                                                      "alpha0", "z_all", "raw")])
+    check(load().anerf_render_fwd_host(plan.handle, _ptr(packed_coarse), _ptr(packed_fine), C.byref(opts), C.byref(rin),
+                                       C.byref(rout), _stream()))
+    return out
+
+
+def density_points(plan, packed, opts, pts, skts):
+    sigma = torch.empty(pts.shape[0], dtype=torch.float32, device=pts.device)
+    check(load().anerf_density_points(plan.handle, _ptr(packed), C.byref(opts), _ptr(pts), _ptr(skts), pts.shape[0],
+                                      _ptr(sigma), _stream()))
+    return sigma
+
+
+def selftest_gemm(A, B, fmt):
+    N, K = B.shape
+    D = torch.empty(2, 128, N, dtype=torch.float32, device=A.device)
+    check(load().anerf_selftest_gemm(_ptr(A), _ptr(B), _ptr(D), N, K, fmt, _stream()))
+    return D

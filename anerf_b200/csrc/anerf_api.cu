@@ -1,0 +1,355 @@
+// C ABI of libanerf_b200.so (see include/anerf_b200.h).  Host-side logic only: argument checks,
+// the layer program / K maps of a network configuration, launches.  No torch, no CPU compute path.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/anerf_b200.h"
+#include "render_kernels.cuh"
+
+using namespace anerf;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(ANERF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// pinned status word shared by all launches of the process
+DeviceStatus* g_status_host = nullptr;   // mapped pinned memory
+DeviceStatus* g_status_dev = nullptr;
+std::mutex g_status_mu;
+
+int ensure_status() {
+  std::lock_guard<std::mutex> lk(g_status_mu);
+  if (g_status_host) return 0;
+  CUDA_TRY(cudaHostAlloc((void**)&g_status_host, sizeof(DeviceStatus), cudaHostAllocMapped));
+  memset(g_status_host, 0, sizeof(DeviceStatus));
+  CUDA_TRY(cudaHostGetDevicePointer((void**)&g_status_dev, g_status_host, 0));
+  return 0;
+}
+
+int check_device_status() {
+  if (g_status_host && g_status_host->code != 0) {
+    return fail(ANERF_ERR_DEVICE, "device protocol error code=%u site=%u block=%u thread=%u", g_status_host->code,
+                g_status_host->where, g_status_host->block, g_status_host->thread);
+  }
+  return 0;
+}
+
+}  // namespace
+
+struct anerf_plan {
+  anerf_net_config cfg;
+  NetDims dims;
+  NetProgram prog;
+  int* d_kmap[kMaxLayers];   // device: packed K index -> reference column (-1 = zero)
+  int k_in[kMaxLayers];      // reference fan-in of each layer
+  int n_sm;
+  int max_smem;
+};
+
+extern "C" {
+
+const char* anerf_last_error(void) { return g_err.c_str(); }
+int anerf_version(void) { return 100; }
+
+int anerf_plan_create(const anerf_net_config* cfg, anerf_plan** out) {
+  if (!cfg || !out) return fail(ANERF_ERR_INVALID, "null argument");
+  if (cfg->n_joints < 1 || cfg->n_joints > kMaxJoints) return fail(ANERF_ERR_INVALID, "n_joints must be 1..24");
+  if (cfg->width != 64 && cfg->width != 128 && cfg->width != 256) return fail(ANERF_ERR_INVALID, "width must be 64, 128 or 256");
+  if (cfg->depth < 2 || cfg->depth > 8) return fail(ANERF_ERR_INVALID, "depth must be 2..8");
+  if (cfg->framecode_ch != 0 && cfg->framecode_ch != 16) return fail(ANERF_ERR_INVALID, "framecode_ch must be 0 or 16");
+  if (cfg->framecode_ch > 0 && cfg->n_framecodes < 1) return fail(ANERF_ERR_INVALID, "n_framecodes must be >= 1");
+  if (cfg->operand_format != 0 && cfg->operand_format != 1) return fail(ANERF_ERR_INVALID, "operand_format must be 0 (fp16) or 1 (bf16)");
+  if (cfg->skip >= cfg->depth - 1 && cfg->skip != -1)
+    return fail(ANERF_ERR_INVALID, "skip=%d: a skip connection after the last trunk layer is not supported (use -1 when skips >= depth-1)", cfg->skip);
+  anerf_plan* p = new anerf_plan();
+  p->cfg = *cfg;
+  p->dims.J = cfg->n_joints;
+  p->dims.D = cfg->depth;
+  p->dims.W = cfg->width;
+  p->dims.skip = cfg->skip < 0 ? -1 : cfg->skip;
+  p->dims.fc_ch = cfg->framecode_ch;
+  p->dims.n_fc = cfg->framecode_ch > 0 ? cfg->n_framecodes : 0;
+  p->prog = make_program(p->dims);
+  for (int l = 0; l < kMaxLayers; ++l) p->d_kmap[l] = nullptr;
+  const NetDims& d = p->dims;
+  for (int l = 0; l < p->prog.n_layers; ++l) {
+    int kp = p->prog.layer[l].chunks * kKC;
+    std::vector<int> km(kp);
+    for (int k = 0; k < kp; ++k) km[k] = layer_ref_col(d, l, k);
+    if (l == 0) p->k_in[l] = in_pts_ref(d);
+    else if (l < d.D) p->k_in[l] = d.W + ((l - 1) == d.skip ? in_pts_ref(d) : 0);
+    else if (l == d.D) p->k_in[l] = d.W;
+    else p->k_in[l] = d.W + in_views_ref(d) + d.fc_ch;
+    for (int k = 0; k < kp; ++k)
+      if (km[k] >= p->k_in[l]) { delete p; return fail(ANERF_ERR_INVALID, "internal: kmap out of range"); }
+    cudaError_t e = cudaMalloc((void**)&p->d_kmap[l], kp * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemcpy(p->d_kmap[l], km.data(), kp * sizeof(int), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { anerf_plan_destroy(p); return fail(ANERF_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e)); }
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&p->n_sm, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&p->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  *out = p;
+  return ANERF_OK;
+}
+
+void anerf_plan_destroy(anerf_plan* p) {
+  if (!p) return;
+  for (int l = 0; l < kMaxLayers; ++l)
+    if (p->d_kmap[l]) cudaFree(p->d_kmap[l]);
+  delete p;
+}
+
+size_t anerf_packed_bytes(const anerf_plan* plan) { return plan ? plan->prog.packed_bytes : 0; }
+
+int anerf_pack_net(const anerf_plan* plan, const anerf_net_params* prm, void* packed, void* stream_) {
+  if (!plan || !prm || !packed) return fail(ANERF_ERR_INVALID, "null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const NetProgram& pg = plan->prog;
+  const NetDims& d = plan->dims;
+  uint8_t* img = (uint8_t*)packed;
+  float* smalls = (float*)(img + pg.smalls_off);
+  const int fmt = plan->cfg.operand_format;
+  std::vector<float> header(kSmallsHeader, 1.0f);
+  for (int l = 0; l < pg.n_layers; ++l) {
+    const float* w = l < d.D ? prm->pts_w[l] : (l == d.D ? prm->feature_w : prm->views_w);
+    const float* b = l < d.D ? prm->pts_b[l] : (l == d.D ? prm->feature_b : prm->views_b);
+    if (!w || !b) return fail(ANERF_ERR_INVALID, "missing parameter pointer for layer %d", l);
+    int n = pg.layer[l].n, chunks = pg.layer[l].chunks;
+    long long total = (long long)chunks * n * 4;
+    int blocks = (int)((total + 255) / 256);
+    float scale = 1.0f;   // fp16 operands: weights are pre-scaled by 2^8 (exact) to keep the lo parts normal
+    if (fmt == 0) { scale = 256.0f; header[l] = 1.0f / 256.0f; }
+    if (fmt == 1)
+      anerf_pack_layer_kernel<1><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, scale, img + pg.layer[l].w_off);
+    else
+      anerf_pack_layer_kernel<0><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, scale, img + pg.layer[l].w_off);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.bias[l], b, n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  }
+  CUDA_TRY(cudaMemcpyAsync(smalls, header.data(), kSmallsHeader * sizeof(float), cudaMemcpyHostToDevice, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));   // header is a stack-owned host buffer
+  if (!prm->alpha_w || !prm->alpha_b || !prm->rgb_w || !prm->rgb_b) return fail(ANERF_ERR_INVALID, "missing alpha/rgb parameters");
+  CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.alpha_w, prm->alpha_w, d.W * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.alpha_b, prm->alpha_b, sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.rgb_w, prm->rgb_w, 3 * (d.W / 2) * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.rgb_b, prm->rgb_b, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  if (d.fc_ch > 0) {
+    if (!prm->framecodes) return fail(ANERF_ERR_INVALID, "framecodes pointer missing");
+    anerf_pack_framecodes_kernel<<<1, 32, 0, stream>>>(prm->framecodes, d.n_fc, d.fc_ch, smalls + pg.sm.framecodes);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return ANERF_OK;
+}
+
+size_t anerf_render_workspace_bytes(int32_t n_rays) { return (size_t)(n_rays > 0 ? n_rays : 1) * 2 * sizeof(float); }
+
+// rays per item: fill the 128-row tiles of both passes as well as possible
+static int choose_rays_per_item(int Sc, int Sf, int n_rays) {
+  int best = 1;
+  double best_u = -1.0;
+  for (int R = 1; R <= kMaxRaysPerItem; ++R) {
+    int rows = R * (Sf > Sc ? Sf : Sc);
+    if (rows > 768 && R > 1) break;
+    int tiles = ceil_div(R * Sc, kTileM) + (Sf > Sc ? ceil_div(R * Sf, kTileM) : 0);
+    double u = (double)(R * Sc + (Sf > Sc ? R * Sf : 0)) / (double)(tiles * kTileM);
+    if (u > best_u + 1e-9) { best_u = u; best = R; }
+  }
+  (void)n_rays;
+  return best;
+}
+
+static int launch_fused(const anerf_plan* plan, RenderKParams& P, bool density, cudaStream_t stream) {
+  int rc = ensure_status();
+  if (rc) return rc;
+  P.status = g_status_dev;
+  if (P.sl.total > plan->max_smem) return fail(ANERF_ERR_INVALID, "configuration needs %d B of shared memory (> %d)", P.sl.total, plan->max_smem);
+  int grid = P.n_items < plan->n_sm ? P.n_items : plan->n_sm;
+  if (grid < 1) return ANERF_OK;
+  const int fmt = plan->cfg.operand_format;
+#define ANERF_LAUNCH(FMT, DENS)                                                                              \
+  do {                                                                                                       \
+    CUDA_TRY(cudaFuncSetAttribute(anerf_fused_kernel<FMT, DENS>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.sl.total)); \
+    anerf_fused_kernel<FMT, DENS><<<grid, kThreads, P.sl.total, stream>>>(P);                              \
+  } while (0)
+  if (fmt == 1) { if (density) ANERF_LAUNCH(1, true); else ANERF_LAUNCH(1, false); }
+  else          { if (density) ANERF_LAUNCH(0, true); else ANERF_LAUNCH(0, false); }
+#undef ANERF_LAUNCH
+  CUDA_TRY(cudaGetLastError());
+  return ANERF_OK;
+}
+
+static void fill_common(const anerf_plan* plan, const anerf_render_opts* o, RenderKParams& P) {
+  P.prog = plan->prog;
+  P.lindisp = o->lindisp;
+  P.softplus = o->softplus;
+  P.eval_mean_fc = o->eval_mean_framecode;
+  P.B = o->density_scale;
+  P.shift = o->softplus_shift;
+  P.tau_p = o->tau_pts;
+  P.tau_v = o->tau_views;
+  for (int j = 0; j < kMaxJoints; ++j) { P.cut_p[j] = o->cutoff_pts[j]; P.cut_v[j] = o->cutoff_views[j]; }
+}
+
+int anerf_render_fwd(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
+                     const anerf_render_opts* o, const anerf_render_inputs* in, const anerf_render_outputs* out,
+                     void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!plan || !packed_coarse || !o || !in || !out) return fail(ANERF_ERR_INVALID, "null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance;
+  if (N == 0) return ANERF_OK;
+  if (N < 0 || Sc < 4 || Si < 0) return fail(ANERF_ERR_INVALID, "bad sizes n_rays=%d n_samples=%d n_importance=%d", N, Sc, Si);
+  if (Sc + Si > 512) return fail(ANERF_ERR_INVALID, "n_samples + n_importance must be <= 512");
+  if (Si > 0 && !packed_fine) return fail(ANERF_ERR_INVALID, "packed_fine missing");
+  if (!in->rays || !in->skts || !in->cyls) return fail(ANERF_ERR_INVALID, "rays/skts/cyls missing");
+  if (plan->dims.fc_ch > 0 && !in->cams && !o->eval_mean_framecode) return fail(ANERF_ERR_INVALID, "cams missing (framecodes enabled)");
+  if (!out->rgb_map || !out->disp_map || !out->acc_map) return fail(ANERF_ERR_INVALID, "rgb/disp/acc outputs missing");
+  if (!workspace || workspace_bytes < anerf_render_workspace_bytes(N)) return fail(ANERF_ERR_INVALID, "workspace too small");
+  if (!(o->density_scale != 0.f)) return fail(ANERF_ERR_INVALID, "density_scale must be non-zero");
+
+  anerf_nearfar_kernel<<<1, 1024, 0, stream>>>(in->rays, in->cyls, N, (float*)workspace);
+  CUDA_TRY(cudaGetLastError());
+
+  RenderKParams P{};
+  fill_common(plan, o, P);
+  P.packed[0] = (const uint8_t*)packed_coarse;
+  P.packed[1] = (const uint8_t*)(Si > 0 ? packed_fine : packed_coarse);
+  P.n_rays = N; P.Sc = Sc; P.Si = Si; P.Sf = Sc + Si;
+  int R = choose_rays_per_item(Sc, Si > 0 ? Sc + Si : Sc, N);
+  for (;; --R) {
+    P.sl = make_smem_layout(plan->dims, plan->prog.sm.fixed_floats, R, Sc, Sc + Si);
+    if (P.sl.total <= plan->max_smem || R == 1) break;
+  }
+  P.R = R;
+  P.tilesC = ceil_div(R * Sc, kTileM);
+  P.tilesF = Si > 0 ? ceil_div(R * (Sc + Si), kTileM) : 0;
+  P.n_items = ceil_div(N, R);
+  P.rays = in->rays; P.skts = in->skts; P.cams = in->cams;
+  P.t_rand = in->t_rand; P.u_rand = in->u_rand; P.noise0 = in->noise0; P.noise1 = in->noise1;
+  P.nearfar = (const float*)workspace;
+  P.rgb_map = out->rgb_map; P.disp_map = out->disp_map; P.acc_map = out->acc_map; P.alpha = out->alpha;
+  P.rgb0 = out->rgb0; P.disp0 = out->disp0; P.acc0 = out->acc0; P.alpha0 = out->alpha0;
+  P.z_all_out = out->z_all; P.raw_out = out->raw;
+  return launch_fused(plan, P, false, stream);
+}
+
+int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf_render_opts* o, const float* pts,
+                         const float* skts, int64_t n_points, float* sigma, void* stream_) {
+  if (!plan || !packed || !o || !pts || !skts || !sigma) return fail(ANERF_ERR_INVALID, "null argument");
+  if (n_points <= 0) return ANERF_OK;
+  if (n_points > (int64_t)1 << 37) return fail(ANERF_ERR_INVALID, "too many points");
+  RenderKParams P{};
+  fill_common(plan, o, P);
+  P.packed[0] = P.packed[1] = (const uint8_t*)packed;
+  P.sl = make_smem_layout(plan->dims, plan->prog.sm.fixed_floats, 1, 4, 4);
+  P.R = 1; P.Sc = 4; P.Sf = 4;
+  P.n_items = (int)((n_points + kTileM - 1) / kTileM);
+  P.pts = pts; P.skts = skts; P.sigma = sigma; P.n_points = n_points;
+  return launch_fused(plan, P, true, (cudaStream_t)stream_);
+}
+
+int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
+                          const anerf_render_opts* o, const anerf_render_inputs* hin,
+                          const anerf_render_outputs* hout, void* stream_) {
+  if (!plan || !o || !hin || !hout) return fail(ANERF_ERR_INVALID, "null argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance, Sf = Sc + Si, J = plan->dims.J;
+  if (N <= 0) return ANERF_OK;
+  // one device arena per call (cudaMallocAsync keeps it in the stream's pool, so repeated calls reuse memory)
+  struct Seg { const void* h; size_t bytes; size_t off; };
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  size_t off = 0;
+  auto seg = [&](const void* h, size_t bytes) { Seg s{h, bytes, off}; off += al(bytes); return s; };
+  Seg s_rays = seg(hin->rays, (size_t)N * 8 * 4), s_skts = seg(hin->skts, (size_t)N * J * 16 * 4),
+      s_cyls = seg(hin->cyls, (size_t)N * 5 * 4), s_cams = seg(hin->cams, hin->cams ? (size_t)N * 4 : 0),
+      s_tr = seg(hin->t_rand, hin->t_rand ? (size_t)N * Sc * 4 : 0), s_ur = seg(hin->u_rand, hin->u_rand ? (size_t)N * Si * 4 : 0),
+      s_n0 = seg(hin->noise0, hin->noise0 ? (size_t)N * Sc * 4 : 0), s_n1 = seg(hin->noise1, hin->noise1 ? (size_t)N * Sf * 4 : 0);
+  Seg o_rgb = seg(hout->rgb_map, (size_t)N * 3 * 4), o_disp = seg(hout->disp_map, (size_t)N * 4), o_acc = seg(hout->acc_map, (size_t)N * 4),
+      o_alpha = seg(hout->alpha, hout->alpha ? (size_t)N * (Si > 0 ? Sf : Sc) * 4 : 0), o_rgb0 = seg(hout->rgb0, hout->rgb0 ? (size_t)N * 3 * 4 : 0),
+      o_disp0 = seg(hout->disp0, hout->disp0 ? (size_t)N * 4 : 0), o_acc0 = seg(hout->acc0, hout->acc0 ? (size_t)N * 4 : 0),
+      o_alpha0 = seg(hout->alpha0, hout->alpha0 ? (size_t)N * Sc * 4 : 0), o_zall = seg(hout->z_all, hout->z_all ? (size_t)N * Sf * 4 : 0),
+      o_raw = seg(hout->raw, hout->raw ? (size_t)N * (Si > 0 ? Sf : Sc) * 16 : 0);
+  size_t ws_off = off;
+  off += al(anerf_render_workspace_bytes(N));
+  uint8_t* arena = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&arena, off, stream));
+  auto up = [&](const Seg& s) -> const float* {
+    if (!s.h || !s.bytes) return nullptr;
+    cudaMemcpyAsync(arena + s.off, s.h, s.bytes, cudaMemcpyHostToDevice, stream);
+    return (const float*)(arena + s.off);
+  };
+  auto dv = [&](const Seg& s) -> float* { return (s.h && s.bytes) ? (float*)(arena + s.off) : nullptr; };
+  anerf_render_inputs din{up(s_rays), up(s_skts), up(s_cyls), up(s_cams), up(s_tr), up(s_ur), up(s_n0), up(s_n1)};
+  anerf_render_outputs dout{dv(o_rgb), dv(o_disp), dv(o_acc), dv(o_alpha), dv(o_rgb0), dv(o_disp0), dv(o_acc0), dv(o_alpha0), dv(o_zall), dv(o_raw)};
+  int rc = anerf_render_fwd(plan, packed_coarse, packed_fine, o, &din, &dout, arena + ws_off, anerf_render_workspace_bytes(N), stream);
+  if (rc == ANERF_OK) {
+    const Seg* outs[] = {&o_rgb, &o_disp, &o_acc, &o_alpha, &o_rgb0, &o_disp0, &o_acc0, &o_alpha0, &o_zall, &o_raw};
+    for (const Seg* s : outs)
+      if (s->h && s->bytes) cudaMemcpyAsync((void*)s->h, arena + s->off, s->bytes, cudaMemcpyDeviceToHost, stream);
+  }
+  cudaFreeAsync(arena, stream);
+  cudaError_t e = cudaStreamSynchronize(stream);
+  if (rc != ANERF_OK) return rc;
+  if (e != cudaSuccess) { check_device_status(); return g_err.empty() ? fail(ANERF_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e)) : ANERF_ERR_DEVICE; }
+  return check_device_status();
+}
+
+int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t format, void* stream_) {
+  if (!A || !B || !D) return fail(ANERF_ERR_INVALID, "null argument");
+  if (K <= 0 || K % kKC != 0) return fail(ANERF_ERR_INVALID, "K must be a positive multiple of 32");
+  if (N != 32 && N != 64 && N != 128 && N != 256) return fail(ANERF_ERR_INVALID, "N must be 32, 64, 128 or 256");
+  if (format < 0 || format > 2) return fail(ANERF_ERR_INVALID, "format must be 0, 1 or 2");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = ensure_status();
+  if (rc) return rc;
+  const int chunks = K / kKC;
+  std::vector<int> km(K);
+  for (int k = 0; k < K; ++k) km[k] = k;
+  int* d_km = nullptr;
+  uint8_t* d_pack = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d_km, K * sizeof(int)));
+  CUDA_TRY(cudaMalloc((void**)&d_pack, (size_t)chunks * N * 128));
+  CUDA_TRY(cudaMemcpy(d_km, km.data(), K * sizeof(int), cudaMemcpyHostToDevice));
+  int blocks = (chunks * N * 4 + 255) / 256;
+  int smem = kAStages * kAStageBytes + kBStages * kBStageBytes + 8 * (2 * kAStages + 2 * kBStages + 2) + 16;
+#define ANERF_ST(FMT)                                                                                       \
+  do {                                                                                                      \
+    anerf_pack_layer_kernel<FMT><<<blocks, 256, 0, stream>>>(B, K, d_km, N, chunks, 1.0f, d_pack);          \
+    cudaFuncSetAttribute(anerf_selftest_gemm_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
+    anerf_selftest_gemm_kernel<FMT><<<1, kThreads, smem, stream>>>(A, d_pack, D, N, K, g_status_dev);       \
+  } while (0)
+  if (format == 0) ANERF_ST(0); else if (format == 1) ANERF_ST(1); else ANERF_ST(2);
+#undef ANERF_ST
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(d_km);
+  cudaFree(d_pack);
+  if (e != cudaSuccess) { check_device_status(); return fail(ANERF_ERR_CUDA, "selftest failed: %s [%s]", cudaGetErrorString(e), g_err.c_str()); }
+  return check_device_status();
+}
+
+}  // extern "C"

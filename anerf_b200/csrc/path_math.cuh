@@ -1,0 +1,222 @@
+// Scalar stages of the A-NeRF hot path as __host__ __device__ functions, shared by the CUDA kernels
+// and by the host-side layout tests (tests/test_host_layout.py compiles this header with g++ to check
+// the K-permutation of the packed weights against the encoders' emission order -- the kernels
+// themselves never run on the CPU).
+//
+// Reference lines each function follows are cited at the function.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ANERF_HD __host__ __device__ __forceinline__
+#else
+#define ANERF_HD inline
+#endif
+
+namespace anerf {
+
+// ------------------------------------------------------------------------------------------------
+// static shape of the encodings (all shipped configs: multires=7, multires_views=4;
+// reference configs/*/*.txt, run_nerf.py:273-283)
+// ------------------------------------------------------------------------------------------------
+constexpr int kF = 7;                        // distance frequencies
+constexpr int kFv = 4;                       // view-direction frequencies
+constexpr int kPtsPerJoint = 1 + 2 * kF + 3; // 18: [v, (sin,cos) x 7] * w  ++  r(3)
+constexpr int kViewPerJoint = 3 * (1 + 2 * kFv);  // 27: [d, (sin,cos) x 4] x 3 components, * w
+constexpr int kPtsGroupJoints = 4;           // 4 joints -> 72 values = 9 x 8
+constexpr int kViewGroupJoints = 8;          // 8 joints -> 216 values = 27 x 8
+constexpr int kPtsGroupK = kPtsGroupJoints * kPtsPerJoint;     // 72
+constexpr int kViewGroupK = kViewGroupJoints * kViewPerJoint;  // 216
+constexpr int kMaxJoints = 24;
+constexpr int kKC = 32;                      // K elements per operand chunk (two K=16 MMA slabs)
+constexpr int kTileM = 128;                  // rows (samples) per tile = UMMA M
+
+ANERF_HD int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+struct NetDims {
+  int J;       // joints
+  int D;       // trunk depth (pts_linears)
+  int W;       // trunk width
+  int skip;    // index i such that layer i+1 takes cat[enc, h] (reference skips=[4]); -1 = none
+  int fc_ch;   // per-frame appearance code channels appended to the view input (0 or 16)
+  int n_fc;    // rows of the framecode table
+};
+
+// K extents (in elements) of the three kinds of A-operand parts, each padded to whole chunks.
+ANERF_HD int pts_k(const NetDims& d) { return ceil_div(d.J, kPtsGroupJoints) * kPtsGroupK; }
+ANERF_HD int pts_chunks(const NetDims& d) { return ceil_div(pts_k(d), kKC); }
+ANERF_HD int view_k_enc(const NetDims& d) { return ceil_div(d.J, kViewGroupJoints) * kViewGroupK; }
+ANERF_HD int view_chunks(const NetDims& d) { return ceil_div(view_k_enc(d) + d.fc_ch, kKC); }
+ANERF_HD int hid_chunks(const NetDims& d) { return d.W / kKC; }
+ANERF_HD int in_pts_ref(const NetDims& d) { return d.J * (1 + 2 * kF) + d.J * 3; }
+ANERF_HD int in_views_ref(const NetDims& d) { return d.J * kViewPerJoint; }
+
+// Layer program: l in [0,D) trunk, l == D feature_linear, l == D+1 views_linears[0].
+ANERF_HD int layer_n(const NetDims& d, int l) { return l <= d.D ? d.W : d.W / 2; }
+ANERF_HD int layer_chunks(const NetDims& d, int l) {
+  if (l == 0) return pts_chunks(d);
+  if (l < d.D) return hid_chunks(d) + ((l - 1) == d.skip ? pts_chunks(d) : 0);
+  if (l == d.D) return hid_chunks(d);
+  return view_chunks(d) + hid_chunks(d);
+}
+
+// Map packed K index of layer l -> column of the reference weight matrix (or -1 for zero padding).
+// Reference column orders: pts input = [k*J + j (k = 0 raw, 1+2f sin, 2+2f cos) | 15J + 3j + c]
+// (cutoff_embedder.py:147-172, raycasters.py:560-569); skip layer input = cat[pts input, h]
+// (nerf.py:100-101); views layer input = cat[feature, k*3J + 3j + c, framecode] (nerf.py:121-125).
+ANERF_HD int pts_part_ref_col(const NetDims& d, int k) {
+  if (k >= pts_k(d)) return -1;
+  int g = k / kPtsGroupK, within = k % kPtsGroupK;
+  int j = g * kPtsGroupJoints + within / kPtsPerJoint, q = within % kPtsPerJoint;
+  if (j >= d.J) return -1;
+  return q < 1 + 2 * kF ? q * d.J + j : (1 + 2 * kF) * d.J + 3 * j + (q - (1 + 2 * kF));
+}
+ANERF_HD int view_part_ref_col(const NetDims& d, int k) {   // relative to the start of input_views
+  int ke = view_k_enc(d);
+  if (k >= ke) return (k - ke) < d.fc_ch ? in_views_ref(d) + (k - ke) : -1;
+  int g = k / kViewGroupK, within = k % kViewGroupK;
+  int j = g * kViewGroupJoints + within / kViewPerJoint, q = within % kViewPerJoint;
+  if (j >= d.J) return -1;
+  return (q / 3) * 3 * d.J + 3 * j + (q % 3);
+}
+ANERF_HD int layer_ref_col(const NetDims& d, int l, int k) {
+  int P = pts_chunks(d) * kKC, V = view_chunks(d) * kKC;
+  if (l == 0) return pts_part_ref_col(d, k);
+  if (l < d.D) {
+    if ((l - 1) == d.skip) return k < P ? pts_part_ref_col(d, k) : in_pts_ref(d) + (k - P);
+    return k;
+  }
+  if (l == d.D) return k;
+  if (k < V) { int c = view_part_ref_col(d, k); return c < 0 ? -1 : d.W + c; }
+  return k - V;   // feature part
+}
+
+// ------------------------------------------------------------------------------------------------
+// torch.linspace(0, 1, n)[i] in fp32: symmetric evaluation, as ATen's range factory computes it
+// (used by ray_utils.py:176,218 for t_vals and the deterministic importance draws u).
+// ------------------------------------------------------------------------------------------------
+ANERF_HD float linspace01(int i, int n) {
+  if (n == 1) return 0.f;
+  float step = 1.0f / (float)(n - 1);
+  return i < n / 2 ? step * (float)i : 1.0f - step * (float)(n - 1 - i);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a2: ray / bounding-cylinder intersection in the x-z plane (ray_utils.py:292-326).
+// Returns near', far' (NaN when the ray's projection misses the circle) .
+// ------------------------------------------------------------------------------------------------
+ANERF_HD void near_far_cylinder(const float o[3], const float d[3], const float cyl[3], float near, float far,
+                                float& nn, float& ff, bool& miss) {
+  float pnx = o[0] + d[0] * near, pnz = o[2] + d[2] * near;
+  float pfx = o[0] + d[0] * far, pfz = o[2] + d[2] * far;
+  float ncx = cyl[0] - pnx, ncz = cyl[1] - pnz;
+  float sx = pfx - pnx, sz = pfz - pnz;
+  float seg = sqrtf(sx * sx + sz * sz);
+  float scale = sqrtf(d[0] * d[0] + d[2] * d[2]);
+  float cross = ncx * sz - ncz * sx;
+  float dl = fabsf(cross) / seg;
+  float q2 = cyl[2] * cyl[2] - dl * dl;
+  float Q = sqrtf(q2);                       // NaN for q2 < 0, like tensor.pow(0.5)
+  float K = (ncx * sx + ncz * sz) / seg;
+  float outside = (Q < K) ? 1.f : 0.f;
+  nn = near + outside * (K - Q) / scale;
+  ff = near + (K + Q) / scale;
+  miss = Q != Q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// a4-a8: one joint of the distance/bone encoding of a world point (encoders.py:8-23,120,189;
+// cutoff_embedder.py:111-174 with dist_inputs=False, cutoff_inputs=True).
+// skt = rows 0..2 of the 4x4 world->bone transform, row-major (12 floats).
+// out[18] = [v w, sin(2^f v) w, cos(2^f v) w (f=0..6), r0, r1, r2];  also returns v.
+// sin/cos of 2^f v: two accurate evaluations (f=0 and f=3) + at most three exact-angle doublings
+// each, which stays within a few ulp of evaluating sinf(2^f v) directly (2^f v is exact in fp32).
+// ------------------------------------------------------------------------------------------------
+ANERF_HD float cutoff_w(float v, float tau, float cut) {
+  float a = tau * (v - cut);
+  return 1.0f - 1.0f / (1.0f + expf(-a));
+}
+
+ANERF_HD void bone_local(const float* skt, const float p[3], float x[3]) {
+  x[0] = skt[0] * p[0] + skt[1] * p[1] + skt[2] * p[2] + skt[3];
+  x[1] = skt[4] * p[0] + skt[5] * p[1] + skt[6] * p[2] + skt[7];
+  x[2] = skt[8] * p[0] + skt[9] * p[1] + skt[10] * p[2] + skt[11];
+}
+
+ANERF_HD float encode_joint_pts(const float* skt, const float p[3], float tau, float cut, float* out) {
+  float x[3];
+  bone_local(skt, p, x);
+  float v = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  float inv = 1.0f / fmaxf(v, 1e-12f);
+  float w = cutoff_w(v, tau, cut);
+  out[0] = v * w;
+  float s, c;
+#if defined(__CUDA_ARCH__)
+  sincosf(v, &s, &c);
+#else
+  s = sinf(v); c = cosf(v);
+#endif
+  float s3, c3;
+#if defined(__CUDA_ARCH__)
+  sincosf(v * 8.0f, &s3, &c3);
+#else
+  s3 = sinf(v * 8.0f); c3 = cosf(v * 8.0f);
+#endif
+#pragma unroll
+  for (int f = 0; f < kF; ++f) {
+    if (f == 3) { s = s3; c = c3; }
+    out[1 + 2 * f] = s * w;
+    out[2 + 2 * f] = c * w;
+    float s2 = 2.0f * s * c;
+    float c2 = 1.0f - 2.0f * s * s;
+    s = s2; c = c2;
+  }
+  out[15] = x[0] * inv;
+  out[16] = x[1] * inv;
+  out[17] = x[2] * inv;
+  return v;
+}
+
+// distance of a world point to one joint only (for the view-direction cutoff weight)
+ANERF_HD float joint_dist(const float* skt, const float p[3]) {
+  float x[3];
+  bone_local(skt, p, x);
+  return sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a5, a7, a10 (per-ray part): unit bone-local ray direction and its sin/cos features
+// (encoders.py:25-37,189; cutoff_embedder.py:116-124).  out[27] = [d_c, sin(2^f d_c), cos(2^f d_c)]
+// at index 3*kk + c, kk = 0 raw, 1+2f sin, 2+2f cos.  The per-sample factor w_j is applied later.
+// ------------------------------------------------------------------------------------------------
+ANERF_HD void encode_joint_viewdir(const float* skt, const float d[3], float* out) {
+  float x[3];
+  x[0] = skt[0] * d[0] + skt[1] * d[1] + skt[2] * d[2];
+  x[1] = skt[4] * d[0] + skt[5] * d[1] + skt[6] * d[2];
+  x[2] = skt[8] * d[0] + skt[9] * d[1] + skt[10] * d[2];
+  float n = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  float inv = 1.0f / fmaxf(n, 1e-12f);
+  for (int c = 0; c < 3; ++c) {
+    float u = x[c] * inv;
+    out[c] = u;
+    for (int f = 0; f < kFv; ++f) {
+      float a = u * (float)(1 << f);
+      out[3 * (1 + 2 * f) + c] = sinf(a);
+      out[3 * (2 + 2 * f) + c] = cosf(a);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a12: per-sample part of raw2outputs (nerf.py:150-190)
+// ------------------------------------------------------------------------------------------------
+ANERF_HD float density_act(float raw_sigma, float B, float noise, int softplus, float shift) {
+  float x = raw_sigma / B + noise;   // raw / B + noise (nerf.py:153)
+  if (!softplus) return fmaxf(x, 0.f);
+  x -= shift;
+  return x > 20.f ? x : log1pf(expf(x));
+}
+ANERF_HD float sigmoid_rgb(float x) { return (1.0f / (1.0f + expf(-x))) * 1.002f - 0.001f; }
+
+}  // namespace anerf

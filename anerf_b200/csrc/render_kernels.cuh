@@ -1,0 +1,946 @@
+// The fused A-NeRF ray-marching kernel for sm_100a and its helpers.
+//
+// One persistent CTA per SM processes "items" of R rays.  Per item:
+//   sample coarse depths -> [coarse net over R*Sc rows] -> composite -> inverse-CDF importance
+//   sampling + merge -> [fine net over R*(Sc+Si) rows] -> composite -> outputs.
+// A "net pass" over one tile of 128 rows (samples) runs the whole 8x256 MLP with activations never
+// leaving the SM:
+//   * 4 worker warps (thread == row == TMEM lane) produce the A operand in 32-wide K chunks, either
+//     by computing the encodings of their sample (bone-local transform, cutoff positional encoding)
+//     or by draining the previous layer's accumulators from TMEM (bias, ReLU), split every value into
+//     hi + lo 16-bit parts and store them in the UMMA K-major core-matrix layout (A ring);
+//   * 1 loader thread streams the pre-packed weights (same layout, hi + lo) from L2 with 1-D bulk
+//     TMA copies into the B ring;
+//   * 1 MMA thread issues, per chunk, 2 K-slabs x 3 tcgen05.mma (hi*hi + lo*hi + hi*lo) into a
+//     128 x N fp32 accumulator in TMEM; accumulators ping-pong between two 256-column regions so the
+//     drain of layer l overlaps the MMAs of layer l+1 chunk by chunk.
+// Layer program and K layout: path_math.cuh.  Protocol: mbarrier full/empty rings, bounded waits.
+#pragma once
+#include "tc_sm100.cuh"
+#include "path_math.cuh"
+
+namespace anerf {
+
+constexpr int kAStages = 4;
+constexpr int kBStages = 3;
+constexpr int kAHalfBytes = kTileM * kKC * 2;        // 8 KB: hi (or lo) part of one A chunk
+constexpr int kAStageBytes = 2 * kAHalfBytes;        // 16 KB
+constexpr int kBStageBytes = 256 * kKC * 2 * 2;      // 32 KB (N = 256)
+constexpr int kMaxLayers = 10;
+constexpr int kWorkerThreads = 128;
+constexpr int kMmaWarp = 4;
+constexpr int kLoadWarp = 5;
+constexpr int kThreads = 192;
+constexpr int kTmemCols = 512;
+constexpr int kSmallsHeader = 16;                    // floats: per-layer output scales
+constexpr int kMaxRaysPerItem = 8;
+
+struct LayerProg {
+  int n;            // output features (UMMA N)
+  int chunks;       // K chunks of 32
+  unsigned w_off;   // byte offset of the layer's first chunk in the packed image
+};
+
+// offsets (in floats) inside the fp32 "smalls" block of a packed image
+struct SmallsLayout {
+  int bias[kMaxLayers];
+  int alpha_w, alpha_b, rgb_w, rgb_b;
+  int fixed_floats;     // everything above (copied to shared memory)
+  int framecodes;       // [n_fc + 1][fc_ch] (last row = mean code); stays in global memory
+  int total_floats;
+};
+
+struct NetProgram {
+  NetDims dims;
+  int n_layers;         // D + 2
+  LayerProg layer[kMaxLayers];
+  unsigned smalls_off;  // byte offset of the smalls block in the packed image
+  SmallsLayout sm;
+  unsigned packed_bytes;
+};
+
+inline __host__ __device__ int align_up(int x, int a) { return (x + a - 1) / a * a; }
+
+inline __host__ NetProgram make_program(const NetDims& d) {
+  NetProgram p{};
+  p.dims = d;
+  p.n_layers = d.D + 2;
+  unsigned off = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    p.layer[l].n = layer_n(d, l);
+    p.layer[l].chunks = layer_chunks(d, l);
+    p.layer[l].w_off = off;
+    off += (unsigned)p.layer[l].chunks * (unsigned)p.layer[l].n * 128u;   // N * 32 * 2 B * (hi + lo)
+  }
+  p.smalls_off = off;
+  int f = kSmallsHeader;
+  for (int l = 0; l < p.n_layers; ++l) { p.sm.bias[l] = f; f += align_up(p.layer[l].n, 4); }
+  p.sm.alpha_w = f; f += d.W;
+  p.sm.alpha_b = f; f += 4;
+  p.sm.rgb_w = f; f += 3 * (d.W / 2);
+  p.sm.rgb_b = f; f += 4;
+  p.sm.fixed_floats = f;
+  p.sm.framecodes = f; f += (d.n_fc + 1) * d.fc_ch;
+  p.sm.total_floats = align_up(f, 4);
+  p.packed_bytes = off + (unsigned)p.sm.total_floats * 4u;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory carve-up of the fused kernel
+// ------------------------------------------------------------------------------------------------
+struct SmemLayout {
+  int a_ring, b_ring, smalls0, smalls1, ray, skt, view_tab, fcode, z_coarse, z_all, raw, wts, cdf, bars, tmem_ptr;
+  int total;
+};
+// ray_s: 12 floats per ray: o(3) d(3) near far |d| pad(3)
+inline __host__ __device__ SmemLayout make_smem_layout(const NetDims& d, int smalls_fixed_floats, int R, int Sc, int Sf) {
+  SmemLayout L{};
+  int off = 0;
+  L.a_ring = off; off += kAStages * kAStageBytes;
+  L.b_ring = off; off += kBStages * kBStageBytes;
+  L.smalls0 = off; off += align_up(smalls_fixed_floats * 4, 16);
+  L.smalls1 = off; off += align_up(smalls_fixed_floats * 4, 16);
+  L.ray = off; off += R * 12 * 4;
+  L.skt = off; off += align_up(R * d.J * 12 * 4, 16);
+  L.view_tab = off; off += R * view_k_enc(d) * 4;
+  L.fcode = off; off += 2 * R * 16 * 4;      // [net][ray][16]
+  int rows = R * (Sf > Sc ? Sf : Sc);
+  L.z_coarse = off; off += align_up(R * Sc * 4, 16);
+  L.z_all = off; off += align_up(rows * 4, 16);
+  L.raw = off; off += rows * 16;
+  L.wts = off; off += align_up(rows * 4, 16);
+  L.cdf = off; off += align_up(R * Sc * 4, 16);
+  L.bars = off; off += 8 * (2 * kAStages + 2 * kBStages + 2);
+  L.tmem_ptr = off; off += 16;
+  L.total = off;
+  return L;
+}
+
+struct RenderKParams {
+  NetProgram prog;
+  const uint8_t* packed[2];
+  // problem
+  int n_rays, Sc, Si, Sf, R, tilesC, tilesF, n_items;
+  int lindisp, softplus, eval_mean_fc;
+  float B, shift, tau_p, tau_v;
+  float cut_p[kMaxJoints], cut_v[kMaxJoints];
+  const float *rays, *skts, *cams, *t_rand, *u_rand, *noise0, *noise1;
+  const float* nearfar;     // [N,2] from the near/far pre-kernel
+  float *rgb_map, *disp_map, *acc_map, *alpha, *rgb0, *disp0, *acc0, *alpha0, *z_all_out, *raw_out;
+  // density-only mode (mesh grid): one pose, explicit points
+  const float* pts;
+  float* sigma;
+  long long n_points;
+  DeviceStatus* status;
+  SmemLayout sl;
+};
+
+#ifdef __CUDACC__
+
+// ------------------------------------------------------------------------------------------------
+// pipeline context shared by the three roles
+// ------------------------------------------------------------------------------------------------
+struct Pipe {
+  uint8_t* a_ring;
+  uint8_t* b_ring;
+  uint64_t* a_full;
+  uint64_t* a_empty;
+  uint64_t* b_full;
+  uint64_t* b_empty;
+  uint64_t* d_full;    // [2]
+  uint32_t tmem_base;
+  DeviceStatus* st;
+};
+
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// A-operand producer state of one worker thread (== one row of the tile)
+template <int FMT>
+struct AProducer {
+  const Pipe& pp;
+  uint32_t seq;       // chunk sequence number (monotonic over the kernel's lifetime)
+  uint32_t g;         // next 8-wide K group inside the current chunk (0..3)
+  uint32_t row_off;   // (row/8)*128 + (row%8)*16
+  uint8_t* stage;
+  __device__ AProducer(const Pipe& p, int row) : pp(p), seq(0), g(0), row_off((row >> 3) * 128 + (row & 7) * 16), stage(nullptr) {}
+
+  __device__ __forceinline__ void put8(const float (&x)[8]) {
+    if (g == 0) {
+      uint32_t s = seq % kAStages;
+      mbar_wait(&pp.a_empty[s], ((seq / kAStages) & 1) ^ 1, pp.st, 100 + s);
+      stage = pp.a_ring + s * kAStageBytes;
+    }
+    uint4 hi, lo;
+    Split<FMT>::pair(x[0], x[1], hi.x, lo.x);
+    Split<FMT>::pair(x[2], x[3], hi.y, lo.y);
+    Split<FMT>::pair(x[4], x[5], hi.z, lo.z);
+    Split<FMT>::pair(x[6], x[7], hi.w, lo.w);
+    uint32_t off = (g >> 1) * 4096 + (g & 1) * 2048 + row_off;
+    *reinterpret_cast<uint4*>(stage + off) = hi;
+    *reinterpret_cast<uint4*>(stage + kAHalfBytes + off) = lo;
+    if (++g == 4) {
+      fence_proxy_async_smem();
+      mbar_arrive(&pp.a_full[seq % kAStages]);
+      ++seq;
+      g = 0;
+    }
+  }
+  __device__ __forceinline__ void flush() {
+    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    while (g != 0) put8(z);
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// MMA issuer: one thread.  All chunks of one layer.
+// ------------------------------------------------------------------------------------------------
+template <int FMT>
+__device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint32_t& b_seq, int N, int chunks,
+                                          int region) {
+  const uint32_t id_hh = make_idesc_f16(fmt_hi(FMT), fmt_hi(FMT), kTileM, N);
+  const uint32_t id_lh = make_idesc_f16(fmt_lo(FMT), fmt_hi(FMT), kTileM, N);
+  const uint32_t id_hl = make_idesc_f16(fmt_hi(FMT), fmt_lo(FMT), kTileM, N);
+  const uint32_t dcol = pp.tmem_base + (uint32_t)region * 256u;
+  const uint32_t a_base = smem_u32(pp.a_ring), b_base = smem_u32(pp.b_ring);
+  for (int c = 0; c < chunks; ++c) {
+    uint32_t sa = a_seq % kAStages, sb = b_seq % kBStages;
+    mbar_wait(&pp.a_full[sa], (a_seq / kAStages) & 1, pp.st, 200 + sa);
+    mbar_wait(&pp.b_full[sb], (b_seq / kBStages) & 1, pp.st, 300 + sb);
+    tc_fence_after_sync();
+    uint32_t a_hi = a_base + sa * kAStageBytes, a_lo = a_hi + kAHalfBytes;
+    uint32_t b_hi = b_base + sb * kBStageBytes, b_lo = b_hi + (uint32_t)N * 64u;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      uint64_t da_hi = smem_desc(a_hi + s * 4096, 2048, 128);
+      uint64_t da_lo = smem_desc(a_lo + s * 4096, 2048, 128);
+      uint64_t db_hi = smem_desc(b_hi + s * (uint32_t)N * 32u, (uint32_t)N * 16u, 128);
+      uint64_t db_lo = smem_desc(b_lo + s * (uint32_t)N * 32u, (uint32_t)N * 16u, 128);
+      umma_f16(dcol, da_hi, db_hi, id_hh, (c > 0 || s > 0) ? 1u : 0u);
+      umma_f16(dcol, da_lo, db_hi, id_lh, 1u);
+      umma_f16(dcol, da_hi, db_lo, id_hl, 1u);
+    }
+    umma_commit(&pp.a_empty[sa]);
+    umma_commit(&pp.b_empty[sb]);
+    ++a_seq;
+    ++b_seq;
+  }
+  umma_commit(&pp.d_full[region]);
+}
+
+// weight loader: one thread.  All chunks of one layer.
+__device__ __forceinline__ void load_layer(const Pipe& pp, uint32_t& b_seq, const uint8_t* src, int N, int chunks) {
+  const uint32_t bytes = (uint32_t)N * 128u;
+  for (int c = 0; c < chunks; ++c) {
+    uint32_t sb = b_seq % kBStages;
+    mbar_wait(&pp.b_empty[sb], ((b_seq / kBStages) & 1) ^ 1, pp.st, 400 + sb);
+    mbar_arrive_expect_tx(&pp.b_full[sb], bytes);
+    bulk_g2s(pp.b_ring + sb * kBStageBytes, src + (size_t)c * bytes, bytes, &pp.b_full[sb]);
+    ++b_seq;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// worker-side building blocks
+// ------------------------------------------------------------------------------------------------
+struct RowCtx {
+  float p[3];          // world position of this row's sample
+  const float* skt;    // this row's ray: [J][12] in shared memory
+  const float* vtab;   // this row's ray: view table
+  const float* fcode;  // this row's ray: frame code (16)
+};
+
+// layer-0 / skip-layer part: distance + bone encodings of the row's sample, 4 joints at a time
+template <int FMT>
+__device__ __forceinline__ void produce_pts_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P) {
+  const int J = P.prog.dims.J;
+  const int groups = ceil_div(J, kPtsGroupJoints);
+  for (int grp = 0; grp < groups; ++grp) {
+    float vals[kPtsGroupK];
+#pragma unroll
+    for (int jj = 0; jj < kPtsGroupJoints; ++jj) {
+      int j = grp * kPtsGroupJoints + jj;
+      if (j < J) {
+        encode_joint_pts(rc.skt + j * 12, rc.p, P.tau_p, P.cut_p[j], &vals[jj * kPtsPerJoint]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < kPtsPerJoint; ++q) vals[jj * kPtsPerJoint + q] = 0.f;
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < kPtsGroupK / 8; ++t) {
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = vals[8 * t + i];
+      ap.put8(x);
+    }
+  }
+  ap.flush();
+}
+
+// views-layer part: per-ray direction features times the per-sample cutoff weight, 8 joints at a time
+template <int FMT>
+__device__ __forceinline__ void produce_view_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P) {
+  const int J = P.prog.dims.J;
+  const int groups = ceil_div(J, kViewGroupJoints);
+  for (int grp = 0; grp < groups; ++grp) {
+    float w[kViewGroupJoints];
+#pragma unroll
+    for (int jj = 0; jj < kViewGroupJoints; ++jj) {
+      int j = grp * kViewGroupJoints + jj;
+      w[jj] = j < J ? cutoff_w(joint_dist(rc.skt + j * 12, rc.p), P.tau_v, P.cut_v[j]) : 0.f;
+    }
+    const float4* tab = reinterpret_cast<const float4*>(rc.vtab + grp * kViewGroupK);
+#pragma unroll
+    for (int t = 0; t < kViewGroupK / 8; ++t) {
+      float4 t0 = tab[2 * t], t1 = tab[2 * t + 1];
+      float x[8];
+      x[0] = t0.x * w[(8 * t + 0) / kViewPerJoint];
+      x[1] = t0.y * w[(8 * t + 1) / kViewPerJoint];
+      x[2] = t0.z * w[(8 * t + 2) / kViewPerJoint];
+      x[3] = t0.w * w[(8 * t + 3) / kViewPerJoint];
+      x[4] = t1.x * w[(8 * t + 4) / kViewPerJoint];
+      x[5] = t1.y * w[(8 * t + 5) / kViewPerJoint];
+      x[6] = t1.z * w[(8 * t + 6) / kViewPerJoint];
+      x[7] = t1.w * w[(8 * t + 7) / kViewPerJoint];
+      ap.put8(x);
+    }
+  }
+  if (P.prog.dims.fc_ch > 0) {
+    for (int t = 0; t < P.prog.dims.fc_ch / 8; ++t) {
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = rc.fcode[8 * t + i];
+      ap.put8(x);
+    }
+  }
+  ap.flush();
+}
+
+// wait for the accumulators of the layer that used `region`, then walk them 32 columns at a time.
+// f(cb, x[32]) receives scale*acc + bias (ReLU applied when RELU).
+template <bool RELU, typename F>
+__device__ __forceinline__ void drain_region(const Pipe& pp, uint32_t (&d_cnt)[2], int region, int N,
+                                             const float* bias, float scale, int warp, F&& f) {
+  mbar_wait(&pp.d_full[region], d_cnt[region] & 1, pp.st, 500 + region);
+  ++d_cnt[region];
+  tc_fence_after_sync();
+  const uint32_t taddr = pp.tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)region * 256u;
+  for (int cb = 0; cb < N / 32; ++cb) {
+    uint32_t v[32];
+    tmem_ld32(taddr + cb * 32, v);
+    tmem_ld_wait();
+    float x[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float y = fmaf(__uint_as_float(v[i]), scale, bias[cb * 32 + i]);
+      x[i] = RELU ? fmaxf(y, 0.f) : y;
+    }
+    f(cb, x);
+  }
+  tc_fence_before_sync();
+}
+
+template <int FMT>
+__device__ __forceinline__ void emit32(AProducer<FMT>& ap, const float (&x)[32]) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = x[8 * t + i];
+    ap.put8(y);
+  }
+}
+
+// One tile (128 rows) through one network.  Returns (rgb logits, raw sigma) of this thread's row.
+// DENSITY: trunk + alpha only.
+template <int FMT, bool DENSITY>
+__device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe& pp, uint32_t (&d_cnt)[2],
+                                                  const RowCtx& rc, const RenderKParams& P, const float* sm,
+                                                  int warp) {
+  const NetProgram& pg = P.prog;
+  const int D = pg.dims.D, W = pg.dims.W;
+  produce_pts_chunks<FMT>(ap, rc, P);                                   // layer 0 operand
+  for (int l = 1; l < D; ++l) {                                          // operand of trunk layer l
+    if ((l - 1) == pg.dims.skip) produce_pts_chunks<FMT>(ap, rc, P);
+    drain_region<true>(pp, d_cnt, (l - 1) & 1, W, sm + pg.sm.bias[l - 1], sm[l - 1], warp,
+                       [&](int, const float (&x)[32]) { emit32<FMT>(ap, x); });
+  }
+  float sigma = 0.f;
+  const float* wa = sm + pg.sm.alpha_w;
+  if (DENSITY) {
+    drain_region<true>(pp, d_cnt, (D - 1) & 1, W, sm + pg.sm.bias[D - 1], sm[D - 1], warp,
+                       [&](int cb, const float (&x)[32]) {
+#pragma unroll
+                         for (int i = 0; i < 32; ++i) sigma = fmaf(x[i], wa[cb * 32 + i], sigma);
+                       });
+    return make_float4(0.f, 0.f, 0.f, sigma + sm[pg.sm.alpha_b]);
+  }
+  // operand of feature_linear (= h of the last trunk layer); alpha_linear in fp32 on the way
+  drain_region<true>(pp, d_cnt, (D - 1) & 1, W, sm + pg.sm.bias[D - 1], sm[D - 1], warp,
+                     [&](int cb, const float (&x)[32]) {
+#pragma unroll
+                       for (int i = 0; i < 32; ++i) sigma = fmaf(x[i], wa[cb * 32 + i], sigma);
+                       emit32<FMT>(ap, x);
+                     });
+  sigma += sm[pg.sm.alpha_b];
+  // operand of views_linears[0]: view encoding first (independent of feature), then feature (no ReLU)
+  produce_view_chunks<FMT>(ap, rc, P);
+  drain_region<false>(pp, d_cnt, D & 1, W, sm + pg.sm.bias[D], sm[D], warp,
+                      [&](int, const float (&x)[32]) { emit32<FMT>(ap, x); });
+  // views layer output -> rgb_linear in fp32
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+  const float* wr = sm + pg.sm.rgb_w;
+  const int H = W / 2;
+  drain_region<true>(pp, d_cnt, (D + 1) & 1, H, sm + pg.sm.bias[D + 1], sm[D + 1], warp,
+                     [&](int cb, const float (&x)[32]) {
+#pragma unroll
+                       for (int i = 0; i < 32; ++i) {
+                         r0 = fmaf(x[i], wr[cb * 32 + i], r0);
+                         r1 = fmaf(x[i], wr[H + cb * 32 + i], r1);
+                         r2 = fmaf(x[i], wr[2 * H + cb * 32 + i], r2);
+                       }
+                     });
+  const float* br = sm + pg.sm.rgb_b;
+  return make_float4(r0 + br[0], r1 + br[1], r2 + br[2], sigma);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-ray stages executed by one warp
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// a12 (nerf.py:150-205): alpha compositing of one ray.  z, raw: shared memory [S]; wts: shared [S] (out).
+__device__ __forceinline__ void composite_ray(int lane, int S, const float* z, const float4* raw, float dnorm,
+                                              const float* noise, const RenderKParams& P, float* wts,
+                                              float* alpha_out, float* rgb_out, float* disp_out, float* acc_out) {
+  const int per = (S + 31) / 32;
+  const int i0 = lane * per;
+  float prod = 1.f;
+  for (int k = 0; k < per; ++k) {
+    int i = i0 + k;
+    if (i < S) {
+      float dist = (i + 1 < S ? z[i + 1] - z[i] : 1e10f) * dnorm;
+      float sg = density_act(raw[i].w, P.B, noise ? noise[i] : 0.f, P.softplus, P.shift);
+      float a = 1.f - expf(-sg * dist);
+      wts[i] = a;
+      prod *= (1.f - a + 1e-10f);
+    }
+  }
+  float incl = prod;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl *= t;
+  }
+  float T = __shfl_up_sync(0xffffffffu, incl, 1);
+  if (lane == 0) T = 1.f;
+  float cr = 0.f, cg = 0.f, cb = 0.f, depth = 0.f, wsum = 0.f;
+  for (int k = 0; k < per; ++k) {
+    int i = i0 + k;
+    if (i < S) {
+      float a = wts[i];
+      float w = a * T;
+      T *= (1.f - a + 1e-10f);
+      if (alpha_out) alpha_out[i] = a;
+      wts[i] = w;
+      float4 r = raw[i];
+      cr = fmaf(w, sigmoid_rgb(r.x), cr);
+      cg = fmaf(w, sigmoid_rgb(r.y), cg);
+      cb = fmaf(w, sigmoid_rgb(r.z), cb);
+      depth = fmaf(w, z[i], depth);
+      wsum += w;
+    }
+  }
+  cr = warp_sum(cr); cg = warp_sum(cg); cb = warp_sum(cb); depth = warp_sum(depth); wsum = warp_sum(wsum);
+  if (lane == 0) {
+    if (rgb_out) { rgb_out[0] = cr; rgb_out[1] = cg; rgb_out[2] = cb; }
+    float disp = 1.f / fmaxf(1e-10f, depth / (wsum + 1e-10f));
+    if (fabsf(wsum) <= 1e-8f) disp = 0.f;             // torch.isclose(sum, 0): atol 1e-8
+    if (disp_out) *disp_out = disp;
+    if (acc_out) *acc_out = fminf(wsum, 1.f);
+  }
+  __syncwarp();
+}
+
+// a13 (ray_utils.py:157-201, 255-289): inverse-CDF sampling of Si new depths from the coarse weights and
+// merge with the Sc coarse depths into a sorted list.  zc, w: shared [Sc]; cdf: shared scratch [Sc];
+// tmp: shared scratch [Sc+Si]; z_all: shared out [Sc+Si].
+__device__ __forceinline__ void importance_ray(int lane, int Sc, int Si, const float* zc, const float* w,
+                                               const float* u_rand, float* cdf, float* tmp, float* z_all) {
+  const int nb = Sc - 1, nw = Sc - 2;
+  double part = 0.0;
+  for (int i = lane; i < nw; i += 32) part += (double)(w[1 + i] + 1e-5f);
+  const float total = (float)warp_sum(part);
+  const int per = (nw + 31) / 32;
+  const int i0 = lane * per;
+  double loc = 0.0;
+  for (int k = 0; k < per; ++k) {
+    int i = i0 + k;
+    if (i < nw) loc += (double)((w[1 + i] + 1e-5f) / total);
+  }
+  double incl = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    double t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  double run = incl - loc;
+  for (int k = 0; k < per; ++k) {
+    int i = i0 + k;
+    if (i < nw) {
+      run += (double)((w[1 + i] + 1e-5f) / total);
+      cdf[i + 1] = (float)run;
+    }
+  }
+  if (lane == 0) cdf[0] = 0.f;
+  __syncwarp();
+  for (int m = lane; m < Si; m += 32) {
+    float u = u_rand ? u_rand[m] : linspace01(m, Si);
+    int lo = 0, hi = nb;                      // searchsorted(cdf, u, right=True)
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (cdf[mid] > u) hi = mid; else lo = mid + 1;
+    }
+    int below = max(lo - 1, 0), above = min(lo, nb - 1);
+    float cb = cdf[below], ca = cdf[above];
+    float bb = 0.5f * (zc[below + 1] + zc[below]), ba = 0.5f * (zc[above + 1] + zc[above]);
+    float denom = ca - cb;
+    if (denom < 1e-5f) denom = 1.f;
+    float t = (u - cb) / denom;
+    tmp[Sc + m] = bb + t * (ba - bb);
+  }
+  for (int i = lane; i < Sc; i += 32) tmp[i] = zc[i];
+  __syncwarp();
+  const int Sf = Sc + Si;
+  for (int e = lane; e < Sf; e += 32) {       // rank sort (stable), identical result to torch.sort on values
+    float x = tmp[e];
+    int r = 0;
+    for (int q = 0; q < Sf; ++q) {
+      float y = tmp[q];
+      r += (y < x || (y == x && q < e)) ? 1 : 0;
+    }
+    z_all[r] = x;
+  }
+  __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// the fused kernel
+// ------------------------------------------------------------------------------------------------
+template <int FMT, bool DENSITY>
+__global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_constant__ RenderKParams P) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const SmemLayout& L = P.sl;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const NetProgram& pg = P.prog;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  Pipe pp;
+  pp.a_ring = smem + L.a_ring;
+  pp.b_ring = smem + L.b_ring;
+  pp.a_full = bars;
+  pp.a_empty = bars + kAStages;
+  pp.b_full = bars + 2 * kAStages;
+  pp.b_empty = bars + 2 * kAStages + kBStages;
+  pp.d_full = bars + 2 * kAStages + 2 * kBStages;
+  pp.st = P.status;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr);
+
+  if (tid == 0) {
+    for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], kWorkerThreads); mbar_init(&pp.a_empty[i], 1); }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); }
+    mbar_init(&pp.d_full[0], 1);
+    mbar_init(&pp.d_full[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+  // both networks' small fp32 parameters -> shared memory
+  {
+    const int nf = pg.sm.fixed_floats;
+    for (int net = 0; net < 2; ++net) {
+      const float* src = reinterpret_cast<const float*>(P.packed[net] + pg.smalls_off);
+      float* dst = reinterpret_cast<float*>(smem + (net ? L.smalls1 : L.smalls0));
+      for (int i = tid; i < nf; i += kThreads) dst[i] = src[i];
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  pp.tmem_base = *tmem_slot;
+
+  const int passes = DENSITY ? 1 : (P.tilesC + P.tilesF);
+
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      uint32_t a_seq = 0, b_seq = 0;
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x)
+        for (int ps = 0; ps < passes; ++ps) {
+          const int nl = DENSITY ? pg.dims.D : pg.n_layers;
+          for (int l = 0; l < nl; ++l) mma_layer<FMT>(pp, a_seq, b_seq, pg.layer[l].n, pg.layer[l].chunks, l & 1);
+        }
+    }
+    __syncwarp();
+  } else if (warp == kLoadWarp) {
+    if (lane == 0) {
+      uint32_t b_seq = 0;
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x)
+        for (int ps = 0; ps < passes; ++ps) {
+          const uint8_t* img = P.packed[(!DENSITY && ps >= P.tilesC) ? 1 : 0];
+          const int nl = DENSITY ? pg.dims.D : pg.n_layers;
+          for (int l = 0; l < nl; ++l) load_layer(pp, b_seq, img + pg.layer[l].w_off, pg.layer[l].n, pg.layer[l].chunks);
+        }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------- worker warps (rows) -------------------------------------
+    const int row = tid;
+    AProducer<FMT> ap(pp, row);
+    uint32_t d_cnt[2] = {0u, 0u};
+    float* ray_s = reinterpret_cast<float*>(smem + L.ray);
+    float* skt_s = reinterpret_cast<float*>(smem + L.skt);
+    float* vtab_s = reinterpret_cast<float*>(smem + L.view_tab);
+    float* fc_s = reinterpret_cast<float*>(smem + L.fcode);
+    float* zc_s = reinterpret_cast<float*>(smem + L.z_coarse);
+    float* za_s = reinterpret_cast<float*>(smem + L.z_all);
+    float4* raw_s = reinterpret_cast<float4*>(smem + L.raw);
+    float* w_s = reinterpret_cast<float*>(smem + L.wts);
+    float* cdf_s = reinterpret_cast<float*>(smem + L.cdf);
+    const float* sm0 = reinterpret_cast<const float*>(smem + L.smalls0);
+    const float* sm1 = reinterpret_cast<const float*>(smem + L.smalls1);
+    const int J = pg.dims.J;
+    const int VK = view_k_enc(pg.dims);
+
+    if (DENSITY) {
+      // one pose for the whole launch
+      for (int i = tid; i < J * 12; i += kWorkerThreads) skt_s[i] = P.skts[(i / 12) * 16 + (i % 12)];
+      worker_sync();
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        long long idx = (long long)item * kTileM + row;
+        bool valid = idx < P.n_points;
+        long long ci = valid ? idx : (P.n_points - 1);
+        RowCtx rc;
+        rc.p[0] = P.pts[ci * 3 + 0]; rc.p[1] = P.pts[ci * 3 + 1]; rc.p[2] = P.pts[ci * 3 + 2];
+        rc.skt = skt_s; rc.vtab = nullptr; rc.fcode = nullptr;
+        float4 r = worker_net_pass<FMT, true>(ap, pp, d_cnt, rc, P, sm0, warp);
+        if (valid) P.sigma[idx] = r.w;
+      }
+    } else {
+      const int R = P.R, Sc = P.Sc, Sf = P.Sf, Si = P.Si;
+      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const int ray0 = item * R;
+        // ---- (1) per-ray inputs -------------------------------------------------------------
+        if (tid < R) {
+          int gr = min(ray0 + tid, P.n_rays - 1);
+          const float* rp = P.rays + (size_t)gr * 8;
+          float* d = ray_s + tid * 12;
+          d[0] = rp[0]; d[1] = rp[1]; d[2] = rp[2]; d[3] = rp[3]; d[4] = rp[4]; d[5] = rp[5];
+          d[6] = P.nearfar[gr * 2]; d[7] = P.nearfar[gr * 2 + 1];
+          d[8] = sqrtf(rp[3] * rp[3] + rp[4] * rp[4] + rp[5] * rp[5]);
+        }
+        for (int i = tid; i < R * J * 12; i += kWorkerThreads) {
+          int r = i / (J * 12), e = i % (J * 12);
+          int gr = min(ray0 + r, P.n_rays - 1);
+          skt_s[i] = P.skts[(size_t)gr * J * 16 + (e / 12) * 16 + (e % 12)];
+        }
+        if (pg.dims.fc_ch > 0) {
+          for (int i = tid; i < 2 * R * 16; i += kWorkerThreads) {
+            int net = i / (R * 16), r = (i / 16) % R, q = i % 16;
+            int gr = min(ray0 + r, P.n_rays - 1);
+            int cam = P.eval_mean_fc ? pg.dims.n_fc : (int)P.cams[gr];
+            cam = min(max(cam, 0), pg.dims.n_fc);
+            const float* codes = reinterpret_cast<const float*>(P.packed[net] + pg.smalls_off) + pg.sm.framecodes;
+            fc_s[i] = q < pg.dims.fc_ch ? codes[cam * pg.dims.fc_ch + q] : 0.f;
+          }
+        }
+        worker_sync();
+        // ---- (2) per-ray view-direction table, coarse depths --------------------------------
+        {
+          const int JV = ceil_div(J, kViewGroupJoints) * kViewGroupJoints;
+          for (int u = tid; u < R * JV; u += kWorkerThreads) {
+            int r = u / JV, j = u % JV;
+            float* o = vtab_s + r * VK + j * kViewPerJoint;
+            if (j < J) {
+              encode_joint_viewdir(skt_s + (r * J + j) * 12, ray_s + r * 12 + 3, o);
+            } else {
+              for (int q = 0; q < kViewPerJoint; ++q) o[q] = 0.f;
+            }
+          }
+          for (int i = tid; i < R * Sc; i += kWorkerThreads) {
+            int r = i / Sc, s = i % Sc;
+            float near = ray_s[r * 12 + 6], far = ray_s[r * 12 + 7];
+            auto zat = [&](int k) {
+              float t = linspace01(k, Sc);
+              return P.lindisp ? 1.f / (1.f / near * (1.f - t) + 1.f / far * t) : near * (1.f - t) + far * t;
+            };
+            float z = zat(s);
+            if (P.t_rand) {
+              int gr = min(ray0 + r, P.n_rays - 1);
+              float lower = s == 0 ? z : 0.5f * (zat(s - 1) + z);
+              float upper = s == Sc - 1 ? z : 0.5f * (z + zat(s + 1));
+              z = lower + (upper - lower) * P.t_rand[(size_t)gr * Sc + s];
+            }
+            zc_s[i] = z;
+          }
+        }
+        worker_sync();
+        // ---- (3) coarse network ---------------------------------------------------------------
+        for (int t = 0; t < P.tilesC; ++t) {
+          int g = t * kTileM + row;
+          int r = g / Sc, s = g % Sc;
+          bool valid = r < R;
+          if (!valid) { r = R - 1; s = Sc - 1; }
+          float z = zc_s[r * Sc + s];
+          RowCtx rc;
+          const float* rr = ray_s + r * 12;
+          rc.p[0] = rr[0] + rr[3] * z; rc.p[1] = rr[1] + rr[4] * z; rc.p[2] = rr[2] + rr[5] * z;
+          rc.skt = skt_s + r * J * 12; rc.vtab = vtab_s + r * VK; rc.fcode = fc_s + r * 16;
+          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, sm0, warp);
+          if (valid) raw_s[g] = o;
+        }
+        worker_sync();
+        // ---- (4) composite coarse, (5) importance sampling -------------------------------------
+        const bool fine = Si > 0;
+        for (int r = warp; r < R; r += 4) {
+          int gr = ray0 + r;
+          bool live = gr < P.n_rays;
+          int grc = min(gr, P.n_rays - 1);
+          float* a_out = fine ? P.alpha0 : P.alpha;
+          float* rgb_o = fine ? P.rgb0 : P.rgb_map;
+          float* disp_o = fine ? P.disp0 : P.disp_map;
+          float* acc_o = fine ? P.acc0 : P.acc_map;
+          composite_ray(lane, Sc, zc_s + r * Sc, raw_s + r * Sc, ray_s[r * 12 + 8],
+                        P.noise0 ? P.noise0 + (size_t)grc * Sc : nullptr, P, w_s + r * Sc,
+                        (live && a_out) ? a_out + (size_t)gr * Sc : nullptr,
+                        (live && rgb_o) ? rgb_o + (size_t)gr * 3 : nullptr,
+                        (live && disp_o) ? disp_o + gr : nullptr, (live && acc_o) ? acc_o + gr : nullptr);
+          if (!fine && live && P.raw_out)
+            for (int i = lane; i < Sc; i += 32) reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sc + i] = raw_s[r * Sc + i];
+        }
+        if (!fine) { worker_sync(); continue; }
+        worker_sync();   // raw_s is free from here (used as scratch by importance_ray)
+        for (int r = warp; r < R; r += 4) {
+          int grc = min(ray0 + r, P.n_rays - 1);
+          importance_ray(lane, Sc, Si, zc_s + r * Sc, w_s + r * Sc,
+                         P.u_rand ? P.u_rand + (size_t)grc * Si : nullptr, cdf_s + r * Sc,
+                         reinterpret_cast<float*>(raw_s) + r * Sf, za_s + r * Sf);
+          if (P.z_all_out && ray0 + r < P.n_rays)
+            for (int i = lane; i < Sf; i += 32) P.z_all_out[(size_t)(ray0 + r) * Sf + i] = za_s[r * Sf + i];
+        }
+        worker_sync();
+        // ---- (6) fine network on all sorted samples --------------------------------------------
+        for (int t = 0; t < P.tilesF; ++t) {
+          int g = t * kTileM + row;
+          int r = g / Sf, s = g % Sf;
+          bool valid = r < R;
+          if (!valid) { r = R - 1; s = Sf - 1; }
+          float z = za_s[r * Sf + s];
+          RowCtx rc;
+          const float* rr = ray_s + r * 12;
+          rc.p[0] = rr[0] + rr[3] * z; rc.p[1] = rr[1] + rr[4] * z; rc.p[2] = rr[2] + rr[5] * z;
+          rc.skt = skt_s + r * J * 12; rc.vtab = vtab_s + r * VK; rc.fcode = fc_s + (R + r) * 16;
+          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, sm1, warp);
+          if (valid) raw_s[g] = o;
+        }
+        worker_sync();
+        // ---- (7) composite fine ------------------------------------------------------------------
+        for (int r = warp; r < R; r += 4) {
+          int gr = ray0 + r;
+          bool live = gr < P.n_rays;
+          int grc = min(gr, P.n_rays - 1);
+          composite_ray(lane, Sf, za_s + r * Sf, raw_s + r * Sf, ray_s[r * 12 + 8],
+                        P.noise1 ? P.noise1 + (size_t)grc * Sf : nullptr, P, w_s + r * Sf,
+                        (live && P.alpha) ? P.alpha + (size_t)gr * Sf : nullptr,
+                        (live && P.rgb_map) ? P.rgb_map + (size_t)gr * 3 : nullptr,
+                        (live && P.disp_map) ? P.disp_map + gr : nullptr,
+                        (live && P.acc_map) ? P.acc_map + gr : nullptr);
+          if (live && P.raw_out)
+            for (int i = lane; i < Sf; i += 32) reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sf + i] = raw_s[r * Sf + i];
+        }
+        worker_sync();
+      }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(pp.tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a2 pre-kernel: near/far of every ray of the chunk + the chunk-wide nanmean repair
+// (ray_utils.py:292-344).  One CTA; the reduction is what makes the result chunk-dependent.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024, 1) anerf_nearfar_kernel(const float* __restrict__ rays,
+                                                                const float* __restrict__ cyls, int n,
+                                                                float* __restrict__ nearfar) {
+  __shared__ double s_sum[2][32];
+  __shared__ int s_cnt[2][32];
+  __shared__ float s_mean[2];
+  __shared__ int s_any;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double sn = 0.0, sf = 0.0;
+  int cn = 0, cf = 0;
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float* r = rays + (size_t)i * 8;
+    float nn, ff;
+    bool miss;
+    near_far_cylinder(r, r + 3, cyls + (size_t)i * 5, r[6], r[7], nn, ff, miss);
+    nearfar[2 * i] = nn;
+    nearfar[2 * i + 1] = ff;
+    if (nn == nn) { sn += nn; ++cn; }
+    if (ff == ff) { sf += ff; ++cf; }
+  }
+  sn = warp_sum(sn); sf = warp_sum(sf);
+  cn = __reduce_add_sync(0xffffffffu, cn); cf = __reduce_add_sync(0xffffffffu, cf);
+  if (lane == 0) { s_sum[0][warp] = sn; s_sum[1][warp] = sf; s_cnt[0][warp] = cn; s_cnt[1][warp] = cf; }
+  __syncthreads();
+  if (warp == 0) {
+    int nwarps = blockDim.x >> 5;
+    double a = lane < nwarps ? s_sum[0][lane] : 0.0, b = lane < nwarps ? s_sum[1][lane] : 0.0;
+    int ca = lane < nwarps ? s_cnt[0][lane] : 0, cb = lane < nwarps ? s_cnt[1][lane] : 0;
+    a = warp_sum(a); b = warp_sum(b);
+    ca = __reduce_add_sync(0xffffffffu, ca); cb = __reduce_add_sync(0xffffffffu, cb);
+    if (lane == 0) {
+      s_mean[0] = ca > 0 ? (float)(a / ca) : nanf("");
+      s_mean[1] = cb > 0 ? (float)(b / cb) : nanf("");
+      s_any = (ca < n) ? 1 : 0;       // torch.isnan(new_near).any()
+    }
+  }
+  __syncthreads();
+  if (!s_any) return;
+  const float mn = s_mean[0], mf = s_mean[1];
+  for (int i = tid; i < n; i += blockDim.x) {
+    const float* r = rays + (size_t)i * 8;
+    float nn, ff;
+    bool miss;
+    near_far_cylinder(r, r + 3, cyls + (size_t)i * 5, r[6], r[7], nn, ff, miss);
+    if (miss) {     // rows where Q is NaN get the chunk mean (or the original bound if no ray hit)
+      nearfar[2 * i] = (mn == mn) ? mn : r[6];
+      nearfar[2 * i + 1] = (mf == mf) ? mf : r[7];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: fp32 [N_out, K_in] -> chunks of [hi: 4 x N/8 x (8 x 8)] [lo: same], K permuted by kmap
+// ------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void anerf_pack_layer_kernel(const float* __restrict__ w, int k_in, const int* __restrict__ kmap,
+                                        int n, int chunks, float scale, uint8_t* __restrict__ out) {
+  // one thread per (chunk, n, 8-wide k group): writes 16 B hi + 16 B lo
+  long long total = (long long)chunks * n * 4;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    int g = (int)(t & 3);
+    int nn = (int)((t >> 2) % n);
+    int c = (int)((t >> 2) / n);
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int src = kmap[c * kKC + g * 8 + i];
+      x[i] = src >= 0 ? w[(size_t)nn * k_in + src] * scale : 0.f;
+    }
+    uint4 hi, lo;
+    Split<FMT>::pair(x[0], x[1], hi.x, lo.x);
+    Split<FMT>::pair(x[2], x[3], hi.y, lo.y);
+    Split<FMT>::pair(x[4], x[5], hi.z, lo.z);
+    Split<FMT>::pair(x[6], x[7], hi.w, lo.w);
+    uint8_t* chunk = out + (size_t)c * n * 128;
+    size_t off = (size_t)g * n * 16 + (size_t)(nn >> 3) * 128 + (size_t)(nn & 7) * 16;
+    *reinterpret_cast<uint4*>(chunk + off) = hi;
+    *reinterpret_cast<uint4*>(chunk + (size_t)n * 64 + off) = lo;
+  }
+}
+
+// framecode mean row (embedding.py:22): codes [n, ch] -> dst[(n)*ch + q] = mean over rows; also copies rows
+__global__ void anerf_pack_framecodes_kernel(const float* __restrict__ codes, int n, int ch, float* __restrict__ dst) {
+  int q = threadIdx.x;
+  if (q >= ch) return;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) { float v = codes[i * ch + q]; dst[i * ch + q] = v; s += v; }
+  dst[n * ch + q] = s / (float)n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// self test: D[128,N] = A[128,K] * B[N,K]^T through exactly the producer / loader / MMA / drain code
+// ------------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const float* __restrict__ A,
+                                                                          const uint8_t* __restrict__ Bpacked,
+                                                                          float* __restrict__ Dout, int N, int K,
+                                                                          DeviceStatus* status) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAStages * kAStageBytes + kBStages * kBStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kAStages + 2 * kBStages + 2);
+  Pipe pp;
+  pp.a_ring = smem;
+  pp.b_ring = smem + kAStages * kAStageBytes;
+  pp.a_full = bars;
+  pp.a_empty = bars + kAStages;
+  pp.b_full = bars + 2 * kAStages;
+  pp.b_empty = bars + 2 * kAStages + kBStages;
+  pp.d_full = bars + 2 * kAStages + 2 * kBStages;
+  pp.st = status;
+  if (tid == 0) {
+    for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], kWorkerThreads); mbar_init(&pp.a_empty[i], 1); }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); }
+    mbar_init(&pp.d_full[0], 1);
+    mbar_init(&pp.d_full[1], 1);
+    fence_mbar_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  pp.tmem_base = *tmem_slot;
+  const int chunks = K / kKC;
+  // two back-to-back "layers" into regions 0 and 1 exercise ring wrap-around and both TMEM regions
+  if (warp == kMmaWarp) {
+    if (lane == 0) {
+      uint32_t a_seq = 0, b_seq = 0;
+      for (int rep = 0; rep < 2; ++rep) mma_layer<FMT>(pp, a_seq, b_seq, N, chunks, rep);
+    }
+    __syncwarp();
+  } else if (warp == kLoadWarp) {
+    if (lane == 0) {
+      uint32_t b_seq = 0;
+      for (int rep = 0; rep < 2; ++rep) load_layer(pp, b_seq, Bpacked, N, chunks);
+    }
+    __syncwarp();
+  } else {
+    AProducer<FMT> ap(pp, tid);
+    uint32_t d_cnt[2] = {0u, 0u};
+    for (int rep = 0; rep < 2; ++rep) {
+      for (int k8 = 0; k8 < K / 8; ++k8) {
+        float x[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = A[(size_t)tid * K + k8 * 8 + i];
+        ap.put8(x);
+      }
+    }
+    __shared__ float zero_bias[256];
+    for (int i = tid; i < 256; i += kWorkerThreads) zero_bias[i] = 0.f;
+    worker_sync();
+    for (int rep = 0; rep < 2; ++rep) {
+      drain_region<false>(pp, d_cnt, rep, N, zero_bias, 1.0f, warp, [&](int cb, const float (&x)[32]) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) Dout[(size_t)rep * kTileM * N + (size_t)tid * N + cb * 32 + i] = x[i];
+      });
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(pp.tmem_base, kTmemCols);
+}
+
+#endif  // __CUDACC__
+}  // namespace anerf

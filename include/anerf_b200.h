@@ -1,0 +1,157 @@
+/*
+ * anerf_b200 -- C ABI of the B200-native A-NeRF ray-marching hot path.
+ *
+ * Everything here takes plain pointers and sizes; device pointers are CUDA device addresses on the
+ * current device, `stream` is a cudaStream_t passed as void*.  No torch types cross this boundary.
+ * Every function returns 0 on success or a negative anerf_status; anerf_last_error() gives the
+ * message for the calling thread.  Nothing in this library has a CPU fallback.
+ *
+ * Reference interfaces each entry point stands in for (LemonATsu/A-NeRF, paths relative to the
+ * reference root):
+ *   anerf_plan_create / anerf_pack_net  <- NeRF.__init__ + RayCaster.load_state_dict
+ *                                          (core/networks/nerf.py:12-88, core/raycasters.py:768-788)
+ *   anerf_render_fwd                    <- RayCaster.render_rays  (core/raycasters.py:361-474) incl.
+ *                                          get_near_far_in_cylinder (core/utils/ray_utils.py:292-344),
+ *                                          sample_from_lineseg (:204-251), isample_from_lineseg (:255-289),
+ *                                          encode_inputs (core/raycasters.py:476-555), run_network (:557-577),
+ *                                          NeRF.forward + raw2outputs (core/networks/nerf.py:133-205)
+ *   anerf_render_fwd_host               <- the same call as core/trainer.py:64-79 batchify_rays makes it,
+ *                                          with host buffers (H2D/D2H inside)
+ *   anerf_density_points                <- RayCaster.render_pts_density / render_mesh_density
+ *                                          (core/raycasters.py:579-648)
+ */
+#ifndef ANERF_B200_H_
+#define ANERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  ANERF_OK = 0,
+  ANERF_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+  ANERF_ERR_CUDA = -2,         /* a CUDA runtime call failed */
+  ANERF_ERR_DEVICE = -3,       /* the kernel reported a protocol error (see anerf_last_error) */
+  ANERF_ERR_NOMEM = -4
+} anerf_status;
+
+/* Shape of one density/radiance MLP and of its encodings (create_raycaster flags,
+ * core/raycasters.py:17-104).  multires / multires_views are fixed at 7 / 4 (all shipped configs). */
+typedef struct {
+  int32_t n_joints;        /* 1..24 */
+  int32_t depth;           /* netdepth D (pts_linears), 2..8 */
+  int32_t width;           /* netwidth W: 64, 128 or 256 */
+  int32_t skip;            /* reference skips=[4]: layer skip+1 takes cat[encoding, h]; -1 if >= depth-1 */
+  int32_t framecode_ch;    /* 0, or 16 when opt_framecode */
+  int32_t n_framecodes;    /* rows of the framecode table */
+  int32_t operand_format;  /* 1 = bf16 hi/lo split (default), 0 = fp16 hi/lo split */
+  int32_t reserved;
+} anerf_net_config;
+
+/* Pointers to one network's fp32 parameters on the device, reference state_dict layout
+ * ([out, in] row-major weights). */
+typedef struct {
+  const float* pts_w[8];   /* pts_linears.i.weight */
+  const float* pts_b[8];
+  const float* alpha_w;    /* [1, W] */
+  const float* alpha_b;    /* [1] */
+  const float* feature_w;  /* [W, W] */
+  const float* feature_b;
+  const float* views_w;    /* [W/2, W + 27*J (+ framecode_ch)] */
+  const float* views_b;
+  const float* rgb_w;      /* [3, W/2] */
+  const float* rgb_b;
+  const float* framecodes; /* [n_framecodes, framecode_ch] or NULL */
+} anerf_net_params;
+
+typedef struct anerf_plan anerf_plan;   /* opaque: layer program + K maps for one anerf_net_config */
+
+int anerf_plan_create(const anerf_net_config* cfg, anerf_plan** out);
+void anerf_plan_destroy(anerf_plan* plan);
+/* Bytes of the packed (tensor-core operand layout) image of one network. */
+size_t anerf_packed_bytes(const anerf_plan* plan);
+/* fp32 parameters -> packed image (device to device, asynchronous on `stream`).  Call after every
+ * parameter update (load_state_dict, optimizer step). */
+int anerf_pack_net(const anerf_plan* plan, const anerf_net_params* params, void* packed, void* stream);
+
+/* Per-call options of render_rays (render_kwargs of core/raycasters.py:156-178). */
+typedef struct {
+  int32_t n_rays;
+  int32_t n_samples;         /* coarse samples per ray (N_samples) */
+  int32_t n_importance;      /* extra fine samples (N_importance), 0 = coarse pass only */
+  int32_t lindisp;
+  int32_t softplus;          /* density_type: 0 relu, 1 softplus */
+  int32_t eval_mean_framecode; /* eval with all cams < 0: use the mean code (embedding.py:21-22) */
+  float density_scale;       /* B */
+  float softplus_shift;
+  float tau_pts, tau_views;  /* CutoffEmbedder.tau of embed_fn / embeddirs_fn */
+  float cutoff_pts[24];      /* CutoffEmbedder.cutoff_dist per joint */
+  float cutoff_views[24];
+} anerf_render_opts;
+
+/* Device inputs.  rays: [N,8] = origin(3), direction(3), near, far (the first 8 columns of the
+ * reference's ray_batch; viewdirs are unused by the path, core/raycasters.py:413-417).
+ * skts: [N,J,4,4] world->bone transforms per ray.  cyls: [N,5].  cams: [N] float camera indices or NULL.
+ * Optional random draws (training): t_rand [N,Sc], u_rand [N,Si], noise0 [N,Sc], noise1 [N,Sc+Si]
+ * (already multiplied by raw_noise_std); NULL = deterministic sampling / no noise. */
+typedef struct {
+  const float* rays;
+  const float* skts;
+  const float* cyls;
+  const float* cams;
+  const float* t_rand;
+  const float* u_rand;
+  const float* noise0;
+  const float* noise1;
+} anerf_render_inputs;
+
+/* Device outputs ([N,...], fp32).  The *0 entries and z_all may be NULL; with n_importance == 0 the
+ * coarse results go to rgb_map/disp_map/acc_map/alpha. */
+typedef struct {
+  float* rgb_map;   /* [N,3] */
+  float* disp_map;  /* [N] */
+  float* acc_map;   /* [N] */
+  float* alpha;     /* [N, Sc+Si] */
+  float* rgb0;      /* [N,3] */
+  float* disp0;
+  float* acc0;
+  float* alpha0;    /* [N,Sc] */
+  float* z_all;     /* optional tap: sorted depths of the fine pass [N,Sc+Si] */
+  float* raw;       /* optional tap: network outputs of the last pass [N,S,4] */
+} anerf_render_outputs;
+
+size_t anerf_render_workspace_bytes(int32_t n_rays);
+
+/* One chunk of rays through the whole path on the device.  packed_fine may equal packed_coarse
+ * (single_net is not supported otherwise) and is ignored when n_importance == 0. */
+int anerf_render_fwd(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
+                     const anerf_render_opts* opts, const anerf_render_inputs* in,
+                     const anerf_render_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same, with HOST buffers for inputs and outputs (pinned or pageable); copies in and out on
+ * `stream` around the kernels and synchronises the stream before returning. */
+int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
+                          const anerf_render_opts* opts, const anerf_render_inputs* host_in,
+                          const anerf_render_outputs* host_out, void* stream);
+
+/* Raw (pre-activation) density of `n_points` world points under ONE pose: pts [P,3], skts [J,4,4],
+ * sigma [P].  Uses tau_pts / cutoff_pts of `opts` (other fields ignored). */
+int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf_render_opts* opts,
+                         const float* pts, const float* skts, int64_t n_points, float* sigma, void* stream);
+
+/* Build-time self test of the tensor-core building blocks: D[128,N] = A[128,K] * B[N,K]^T with the
+ * split-precision operand path (A, B, D fp32 on the device; K multiple of 32; N in {32,64,128,256}).
+ * format: 1 bf16, 0 fp16, 2 = bf16 hi parts with fp16 lo parts (probe of mixed-format MMA). */
+int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t format,
+                        void* stream);
+
+const char* anerf_last_error(void);
+int anerf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* ANERF_B200_H_ */

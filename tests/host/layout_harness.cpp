@@ -1,0 +1,58 @@
+// Host build of anerf_b200/csrc/path_math.cuh for tests/test_host_layout.py (TEST INFRASTRUCTURE).
+// Mirrors the order in which the kernel's producers emit A-operand values so that the K permutation
+// of the packed weights (layer_ref_col) can be checked against the oracle on the CPU.  Not a compute
+// path of the product.
+#include <cstring>
+#include "../../anerf_b200/csrc/path_math.cuh"
+
+using namespace anerf;
+
+extern "C" {
+
+int h_layer_chunks(int J, int D, int W, int skip, int fc, int l) {
+  NetDims d{J, D, W, skip, fc, fc ? 4 : 0};
+  return layer_chunks(d, l);
+}
+int h_layer_ref_col(int J, int D, int W, int skip, int fc, int l, int k) {
+  NetDims d{J, D, W, skip, fc, fc ? 4 : 0};
+  return layer_ref_col(d, l, k);
+}
+// emission order of produce_pts_chunks: groups of 4 joints x 18 values, zero padded to whole chunks
+void h_emit_pts(const float* skt /*[J][12]*/, const float* p, float tau, const float* cut, int J, float* out) {
+  NetDims d{J, 8, 256, 4, 0, 0};
+  int n = pts_chunks(d) * kKC;
+  memset(out, 0, n * sizeof(float));
+  int groups = ceil_div(J, kPtsGroupJoints);
+  int k = 0;
+  for (int g = 0; g < groups; ++g)
+    for (int jj = 0; jj < kPtsGroupJoints; ++jj, k += kPtsPerJoint) {
+      int j = g * kPtsGroupJoints + jj;
+      if (j < J) encode_joint_pts(skt + j * 12, p, tau, cut[j], out + k);
+    }
+}
+// emission order of produce_view_chunks
+void h_emit_view(const float* skt, const float* dir, const float* p, float tau, const float* cut, int J,
+                 const float* fcode, int fc, float* out) {
+  NetDims d{J, 8, 256, 4, fc, fc ? 4 : 0};
+  int n = view_chunks(d) * kKC;
+  memset(out, 0, n * sizeof(float));
+  int groups = ceil_div(J, kViewGroupJoints);
+  int k = 0;
+  for (int g = 0; g < groups; ++g)
+    for (int jj = 0; jj < kViewGroupJoints; ++jj, k += kViewPerJoint) {
+      int j = g * kViewGroupJoints + jj;
+      if (j >= J) continue;
+      float tab[kViewPerJoint];
+      encode_joint_viewdir(skt + j * 12, dir, tab);
+      float w = cutoff_w(joint_dist(skt + j * 12, p), tau, cut[j]);
+      for (int q = 0; q < kViewPerJoint; ++q) out[k + q] = tab[q] * w;
+    }
+  for (int q = 0; q < fc; ++q) out[k + q] = fcode[q];
+}
+float h_linspace01(int i, int n) { return linspace01(i, n); }
+void h_near_far(const float* o, const float* d, const float* cyl, float near, float far, float* out) {
+  bool miss;
+  near_far_cylinder(o, d, cyl, near, far, out[0], out[1], miss);
+  out[2] = miss ? 1.f : 0.f;
+}
+}

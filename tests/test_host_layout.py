@@ -1,0 +1,119 @@
+"""CPU checks of the host-side logic of the CUDA path: the K permutation that the weight packer
+applies must be the inverse of the order in which the kernel's producers emit encoding values.
+Compiles anerf_b200/csrc/path_math.cuh (the __host__ __device__ scalar stages) with g++."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from anerf_b200 import synthetic
+from oracle import anerf_oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("harness") / "layout_harness.so")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
+                           os.path.join(HERE, "host", "layout_harness.cpp"), "-o", so])
+    lib = C.CDLL(so)
+    lib.h_linspace01.restype = C.c_float
+    return lib
+
+
+def fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+@pytest.mark.parametrize("J,fc", [(24, 0), (24, 16), (1, 0), (5, 0)])
+def test_packed_k_order_inverts_producer_order(harness, J, fc):
+    rng = np.random.RandomState(J)
+    pose = synthetic.make_pose(3, J)
+    skt12 = np.ascontiguousarray(pose["skts"][:, :3, :].reshape(J, 12))
+    p = (pose["kps"][0] + rng.randn(3) * 0.3).astype(np.float32)
+    dirv = rng.randn(3).astype(np.float32)
+    cut = np.full(J, 0.5, np.float32)
+    tau = 20.0
+    cfg = orc.PathConfig(n_joints=J, framecode_ch=fc)
+    t = torch.as_tensor
+    xp, xv = orc.encode_samples(t(p)[None, None], t(dirv)[None], t(pose["skts"])[None], cfg)
+    xp, xv = xp[0, 0].numpy().astype(np.float64), xv[0, 0].numpy().astype(np.float64)
+    fcode = rng.randn(16).astype(np.float32)
+    D, W, skip = 8, 256, 4
+    nP = harness.h_layer_chunks(J, D, W, skip, fc, 0) * 32
+    nV = harness.h_layer_chunks(J, D, W, skip, fc, D + 1) * 32 - W
+    ep = np.zeros(nP, np.float32)
+    ev = np.zeros(nV, np.float32)
+    harness.h_emit_pts(fptr(skt12), fptr(p), C.c_float(tau), fptr(cut), J, fptr(ep))
+    harness.h_emit_view(fptr(skt12), fptr(dirv), fptr(p), C.c_float(tau), fptr(cut), J, fptr(fcode), fc, fptr(ev))
+    col = lambda l, k: harness.h_layer_ref_col(J, D, W, skip, fc, l, k)
+    # layer 0: emitted value k must be reference input column col(0,k)
+    for k in range(nP):
+        c = col(0, k)
+        assert (ep[k] == 0.0) if c < 0 else abs(ep[k] - xp[c]) < 2e-6, (k, c)
+    assert sorted(col(0, k) for k in range(nP) if col(0, k) >= 0) == list(range(cfg.in_pts))
+    # skip layer (l = skip + 1): [encoding | h]
+    l = skip + 1
+    cols = [col(l, k) for k in range(nP + W)]
+    assert cols[:nP] == [col(0, k) for k in range(nP)]
+    assert cols[nP:] == [cfg.in_pts + n for n in range(W)]
+    # plain trunk layer and feature layer: identity
+    assert [col(2, k) for k in range(W)] == list(range(W))
+    assert [col(D, k) for k in range(W)] == list(range(W))
+    # views layer: [view encoding (+ framecode) | feature]
+    ref_in = np.concatenate([np.zeros(W), xv, fcode[:fc].astype(np.float64)])
+    for k in range(nV):
+        c = col(D + 1, k)
+        assert (ev[k] == 0.0) if c < 0 else abs(ev[k] - ref_in[c]) < 2e-6, (k, c)
+    cols = [col(D + 1, k) for k in range(nV + W)]
+    assert cols[nV:] == list(range(W))
+    assert sorted(c for c in cols if c >= 0) == list(range(W + cfg.in_views + fc))
+
+
+def test_linspace_matches_torch(harness):
+    # ours is the scalar formula of ATen's CUDA linspace kernel (start + step*i below the middle,
+    # end - step*(n-1-i) above); the CPU kernel evaluates the same thing per SIMD vector and can
+    # differ in the last bit, hence 1 ulp.
+    for n in (2, 16, 63, 64, 128, 129):
+        ours = np.array([harness.h_linspace01(i, n) for i in range(n)], np.float32)
+        ref = torch.linspace(0., 1., n).numpy()
+        assert np.abs(ours - ref).max() <= 6e-8, n
+        assert ours[0] == 0. and ours[-1] == 1.
+
+
+def test_near_far_matches_oracle(harness):
+    scene = synthetic.make_scene(seed=5, n_rays=64)
+    scene["rays_d"][:4, 0] += 2.0
+    t = torch.as_tensor
+    N = 64
+    near, far = torch.zeros(N, 1), torch.ones(N, 1)
+    # oracle without the repair step = raw intersection
+    o, d, cyl = scene["rays_o"], scene["rays_d"], scene["cyls"]
+    out = np.zeros((N, 3), np.float32)
+    for i in range(N):
+        harness.h_near_far(fptr(np.ascontiguousarray(o[i])), fptr(np.ascontiguousarray(d[i])),
+                           fptr(np.ascontiguousarray(cyl[i])), C.c_float(0.), C.c_float(1.), fptr(out[i]))
+    nn, ff = orc.near_far_in_cylinder(t(o), t(d), t(cyl), near, far)
+    hit = out[:, 2] == 0
+    assert hit.sum() >= 50 and (~hit).sum() == 4
+    assert np.allclose(out[hit, 0], nn[:, 0].numpy()[hit], rtol=2e-6, atol=1e-6)
+    assert np.allclose(out[hit, 1], ff[:, 0].numpy()[hit], rtol=2e-6, atol=1e-6)
+    assert np.isnan(out[~hit, 0]).all()
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads on a CPU-only box and exports what include/anerf_b200.h declares."""
+    import re
+    from anerf_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    hdr = open(os.path.join(os.path.dirname(HERE), "include", "anerf_b200.h")).read()
+    declared = set(re.findall(r"\b(anerf_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.anerf_version() >= 100
