@@ -99,7 +99,7 @@ def test_near_far_matches_oracle(harness):
                            fptr(np.ascontiguousarray(cyl[i])), C.c_float(0.), C.c_float(1.), fptr(out[i]))
     nn, ff = orc.near_far_in_cylinder(t(o), t(d), t(cyl), near, far)
     hit = out[:, 2] == 0
-    assert hit.sum() >= 50 and (~hit).sum() == 4
+    assert hit.sum() >= 32 and (~hit).sum() >= 4 and not hit[:4].any()
     assert np.allclose(out[hit, 0], nn[:, 0].numpy()[hit], rtol=2e-6, atol=1e-6)
     assert np.allclose(out[hit, 1], ff[:, 0].numpy()[hit], rtol=2e-6, atol=1e-6)
     assert np.isnan(out[~hit, 0]).all()
