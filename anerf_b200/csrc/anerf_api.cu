@@ -134,7 +134,6 @@ int anerf_pack_net(const anerf_plan* plan, const anerf_net_params* prm, void* pa
   uint8_t* img = (uint8_t*)packed;
   float* smalls = (float*)(img + pg.smalls_off);
   const int fmt = plan->cfg.operand_format;
-  std::vector<float> header(kSmallsHeader, 1.0f);
   for (int l = 0; l < pg.n_layers; ++l) {
     const float* w = l < d.D ? prm->pts_w[l] : (l == d.D ? prm->feature_w : prm->views_w);
     const float* b = l < d.D ? prm->pts_b[l] : (l == d.D ? prm->feature_b : prm->views_b);
@@ -142,17 +141,14 @@ int anerf_pack_net(const anerf_plan* plan, const anerf_net_params* prm, void* pa
     int n = pg.layer[l].n, chunks = pg.layer[l].chunks;
     long long total = (long long)chunks * n * 4;
     int blocks = (int)((total + 255) / 256);
-    float scale = 1.0f;   // fp16 operands: weights are pre-scaled by 2^8 (exact) to keep the lo parts normal
-    if (fmt == 0) { scale = 256.0f; header[l] = 1.0f / 256.0f; }
+    anerf_layer_scale_kernel<<<1, 1024, 0, stream>>>(w, (long long)n * plan->k_in[l], fmt, smalls + l);
     if (fmt == 1)
-      anerf_pack_layer_kernel<1><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, scale, img + pg.layer[l].w_off);
+      anerf_pack_layer_kernel<1><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, smalls + l, img + pg.layer[l].w_off);
     else
-      anerf_pack_layer_kernel<0><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, scale, img + pg.layer[l].w_off);
+      anerf_pack_layer_kernel<0><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, smalls + l, img + pg.layer[l].w_off);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.bias[l], b, n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   }
-  CUDA_TRY(cudaMemcpyAsync(smalls, header.data(), kSmallsHeader * sizeof(float), cudaMemcpyHostToDevice, stream));
-  CUDA_TRY(cudaStreamSynchronize(stream));   // header is a stack-owned host buffer
   if (!prm->alpha_w || !prm->alpha_b || !prm->rgb_w || !prm->rgb_b) return fail(ANERF_ERR_INVALID, "missing alpha/rgb parameters");
   CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.alpha_w, prm->alpha_w, d.W * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.alpha_b, prm->alpha_b, sizeof(float), cudaMemcpyDeviceToDevice, stream));
@@ -322,7 +318,7 @@ int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int
   if (!A || !B || !D) return fail(ANERF_ERR_INVALID, "null argument");
   if (K <= 0 || K % kKC != 0) return fail(ANERF_ERR_INVALID, "K must be a positive multiple of 32");
   if (N != 32 && N != 64 && N != 128 && N != 256) return fail(ANERF_ERR_INVALID, "N must be 32, 64, 128 or 256");
-  if (format < 0 || format > 2) return fail(ANERF_ERR_INVALID, "format must be 0, 1 or 2");
+  if (format != 0 && format != 1) return fail(ANERF_ERR_INVALID, "format must be 0 (fp16) or 1 (bf16)");
   cudaStream_t stream = (cudaStream_t)stream_;
   int rc = ensure_status();
   if (rc) return rc;
@@ -331,6 +327,10 @@ int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int
   for (int k = 0; k < K; ++k) km[k] = k;
   int* d_km = nullptr;
   uint8_t* d_pack = nullptr;
+  float* d_one = nullptr;
+  const float one = 1.0f;
+  CUDA_TRY(cudaMalloc((void**)&d_one, sizeof(float)));
+  CUDA_TRY(cudaMemcpy(d_one, &one, sizeof(float), cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc((void**)&d_km, K * sizeof(int)));
   CUDA_TRY(cudaMalloc((void**)&d_pack, (size_t)chunks * N * 128));
   CUDA_TRY(cudaMemcpy(d_km, km.data(), K * sizeof(int), cudaMemcpyHostToDevice));
@@ -338,16 +338,17 @@ int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int
   int smem = kAStages * kAStageBytes + kBStages * kBStageBytes + 8 * (2 * kAStages + 2 * kBStages + 2) + 16;
 #define ANERF_ST(FMT)                                                                                       \
   do {                                                                                                      \
-    anerf_pack_layer_kernel<FMT><<<blocks, 256, 0, stream>>>(B, K, d_km, N, chunks, 1.0f, d_pack);          \
+    anerf_pack_layer_kernel<FMT><<<blocks, 256, 0, stream>>>(B, K, d_km, N, chunks, d_one, d_pack);          \
     cudaFuncSetAttribute(anerf_selftest_gemm_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
     anerf_selftest_gemm_kernel<FMT><<<1, kThreads, smem, stream>>>(A, d_pack, D, N, K, g_status_dev);       \
   } while (0)
-  if (format == 0) ANERF_ST(0); else if (format == 1) ANERF_ST(1); else ANERF_ST(2);
+  if (format == 0) ANERF_ST(0); else ANERF_ST(1);
 #undef ANERF_ST
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   cudaFree(d_km);
   cudaFree(d_pack);
+  cudaFree(d_one);
   if (e != cudaSuccess) { check_device_status(); return fail(ANERF_ERR_CUDA, "selftest failed: %s [%s]", cudaGetErrorString(e), g_err.c_str()); }
   return check_device_status();
 }

@@ -833,9 +833,36 @@ __global__ void __launch_bounds__(1024, 1) anerf_nearfar_kernel(const float* __r
 // ------------------------------------------------------------------------------------------------
 // weight packing: fp32 [N_out, K_in] -> chunks of [hi: 4 x N/8 x (8 x 8)] [lo: same], K permuted by kmap
 // ------------------------------------------------------------------------------------------------
+// Per-layer operand scale.  bf16 operands: 1.  fp16 operands: the power of two that brings max|W| into
+// [2^12, 2^13), so that the lo parts (|lo| <= 2^-11 |hi|) stay normal fp16 numbers; the fused kernel
+// multiplies the accumulators by the exact inverse (`inv_scale`, smalls header) before adding the bias.
+__global__ void anerf_layer_scale_kernel(const float* __restrict__ w, long long count, int fmt,
+                                         float* __restrict__ inv_scale) {
+  __shared__ float s_max[32];
+  float m = 0.f;
+  if (fmt == 0)
+    for (long long i = threadIdx.x; i < count; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, s_max[i]);
+    int k = 0;
+    if (fmt == 0 && m > 0.f && m < 3.0e38f) {
+      int e;
+      frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)
+      k = min(max(13 - e, -24), 24);
+    }
+    *inv_scale = ldexpf(1.0f, -k);
+  }
+}
+
 template <int FMT>
 __global__ void anerf_pack_layer_kernel(const float* __restrict__ w, int k_in, const int* __restrict__ kmap,
-                                        int n, int chunks, float scale, uint8_t* __restrict__ out) {
+                                        int n, int chunks, const float* __restrict__ inv_scale,
+                                        uint8_t* __restrict__ out) {
+  const float scale = 1.0f / *inv_scale;   // exact: power of two
   // one thread per (chunk, n, 8-wide k group): writes 16 B hi + 16 B lo
   long long total = (long long)chunks * n * 4;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {

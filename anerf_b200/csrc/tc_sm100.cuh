@@ -197,18 +197,10 @@ template <> struct Split<0> {  // fp16 (values must be within half range; used w
   }
 };
 
-template <> struct Split<2> {  // probe: bf16 hi part, fp16 lo part (mixed-format MMA, selftest only)
-  static __device__ __forceinline__ void pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    float2 hf = __bfloat1622float2(h);
-    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
-  }
-};
-// operand formats of the hi and lo parts for a Split<FMT>
+// tcgen05 operand format code of a Split<FMT> (A and B must use the same format: a probe with bf16 hi
+// parts and fp16 lo parts in one kind::f16 MMA raises 'illegal instruction' on sm_100a).
 __host__ __device__ constexpr uint32_t fmt_hi(int FMT) { return FMT == 0 ? 0u : 1u; }
-__host__ __device__ constexpr uint32_t fmt_lo(int FMT) { return FMT == 1 ? 1u : 0u; }
+__host__ __device__ constexpr uint32_t fmt_lo(int FMT) { return FMT == 0 ? 0u : 1u; }
 
 #endif  // __CUDACC__
 }  // namespace anerf

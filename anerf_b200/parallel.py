@@ -1,0 +1,95 @@
+"""One process per GPU: how the ray-marching path shards.
+
+Rays are independent given the weights and the pose, so nothing on the data path needs a collective:
+  * rendering  -- frames are dealt round-robin to ranks (`frames_for_rank`); inside a frame the unit of
+                  work stays the reference's 4096-ray chunk, because the near/far repair of rays that
+                  miss the bounding cylinder is a chunk-wide mean (core/utils/ray_utils.py:328-342);
+                  finished pixels [rays, 5] (rgb, disp, acc) are gathered on rank 0 (`gather_pixels`);
+  * mesh grids -- voxels are split into contiguous slabs per rank (`slab_for_rank`) and the densities
+                  gathered on rank 0 (`gather_slabs`).
+This replaces the reference's single-process nn.DataParallel (core/raycasters.py:157).  The backend is
+NCCL on GPUs; the same functions run on gloo/CPU tensors in the tests (the gather is plain data movement).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_distributed(backend=None):
+    """Initialise torch.distributed from the torchrun environment.  Returns (rank, world, local_rank)."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        if backend == "nccl":
+            torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29511")
+        dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                **({"device_id": torch.device("cuda", local)} if backend == "nccl" else {}))
+    return rank, world, local
+
+
+def frames_for_rank(n_frames, rank, world):
+    """Frame f is rendered by rank f mod world."""
+    return list(range(rank, n_frames, world))
+
+
+def slab_for_rank(n, rank, world):
+    """Contiguous [start, stop) slab of n voxels (or chunks) for this rank; sizes differ by at most one."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def gather_pixels(local_frames, n_frames, rank, world, dst=0):
+    """local_frames: {frame index: tensor [rays, C]} rendered by this rank.  Returns the list of all
+    n_frames tensors on rank `dst` (None elsewhere).  One gather per round of `world` frames."""
+    if world == 1:
+        return [local_frames[f] for f in range(n_frames)]
+    out = [None] * n_frames if rank == dst else None
+    some = next(iter(local_frames.values())) if local_frames else None
+    rounds = (n_frames + world - 1) // world
+    for r in range(rounds):
+        f = r * world + rank
+        mine = local_frames.get(f)
+        shape_src = some if some is not None else None
+        if mine is None:
+            # ranks without a frame in the last round still take part with an empty placeholder
+            mine = torch.zeros_like(shape_src) if shape_src is not None else torch.zeros(0)
+        bufs = [torch.empty_like(mine) for _ in range(world)] if rank == dst else None
+        dist.gather(mine.contiguous(), bufs, dst=dst)
+        if rank == dst:
+            for src in range(world):
+                g = r * world + src
+                if g < n_frames:
+                    out[g] = bufs[src]
+    return out
+
+
+def gather_slabs(local, n, rank, world, dst=0):
+    """local: this rank's slab [stop-start, ...] of a length-n array split by `slab_for_rank`.
+    Returns the full array on rank `dst` (None elsewhere)."""
+    if world == 1:
+        return local
+    sizes = [slab_for_rank(n, r, world) for r in range(world)]
+    longest = max(b - a for a, b in sizes)
+    pad = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+    dist.gather(pad, bufs, dst=dst)
+    if rank != dst:
+        return None
+    return torch.cat([bufs[r][:sizes[r][1] - sizes[r][0]] for r in range(world)], 0)
+
+
+def max_over_ranks(value, device):
+    """Device-timed milliseconds -> max over ranks (the job's time)."""
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

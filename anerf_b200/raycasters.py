@@ -1,0 +1,504 @@
+"""Host side of the drop-in boundary: `create_raycaster` / `RayCaster` with the reference's names,
+argument meaning and error behaviour (reference: core/raycasters.py:17-184, 326-794), so that the
+reference's run_nerf.py / run_render.py call it unchanged.
+
+The modules below only *hold* parameters and buffers under the reference's state_dict layout
+(core/networks/nerf.py:57-88, core/cutoff_embedder.py:91-95, core/networks/embedding.py:9);
+all arithmetic happens in libanerf_b200.so through the C ABI (`anerf_b200._lib`).  There is no
+PyTorch or CPU fallback: if the library is missing, or a tensor is not on a CUDA device, calls raise.
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+MULTIRES, MULTIRES_VIEWS = 7, 4     # the encodings compiled into the kernels (all shipped configs)
+
+
+# ------------------------------------------------------------------------------------------------
+# parameter containers
+# ------------------------------------------------------------------------------------------------
+class Embedder(nn.Module):
+    """Plain positional encoding descriptor (core/cutoff_embedder.py:9-58).  With num_freqs == 0 it is the
+    identity (`embedbones_fn` of every shipped config)."""
+
+    def __init__(self, input_dims, num_freqs):
+        super().__init__()
+        self.input_dims, self.num_freqs = input_dims, num_freqs
+        self.out_dim = input_dims * (1 + 2 * num_freqs)
+
+    def update_threshold(self, *args, **kwargs):
+        pass
+
+    def update_tau(self, *args, **kwargs):
+        pass
+
+    def update_alpha(self, *args, **kwargs):
+        pass
+
+    def get_tau(self):
+        return 0.0
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError("anerf_b200 embedders hold parameters only; encoding runs inside the fused CUDA kernel")
+
+
+class CutoffEmbedder(Embedder):
+    """Cutoff positional encoding parameters (core/cutoff_embedder.py:61-197): `cutoff_dist` per joint
+    (Parameter without grad) and the sigmoid sharpness `tau` (buffer), with the reference's schedule."""
+
+    def __init__(self, input_dims, num_freqs, cutoff_dist, cutoff_dim, dist_inputs):
+        super().__init__(input_dims, num_freqs)
+        self.dist_inputs = dist_inputs
+        self.cutoff_dim = cutoff_dim
+        self.cutoff_dist = nn.Parameter(torch.ones(cutoff_dim) * cutoff_dist, requires_grad=False)
+        self.init_tau = 20.
+        self.register_buffer('tau', torch.tensor(self.init_tau))
+
+    def get_tau(self):
+        return self.tau.item()
+
+    def get_cutoff_dist(self):
+        return self.cutoff_dist
+
+    def update_threshold(self, global_step, tau_step, tau_rate, alpha_step, alpha_target):
+        self.update_tau(global_step, tau_step, tau_rate)
+
+    def update_tau(self, global_step, step, rate):
+        # tau = min(2000, 20 * rate^(step / (cutoff_step * 1000)))   (cutoff_embedder.py:181-183)
+        self.tau = (self.init_tau * torch.ones_like(self.tau) * rate ** (global_step / float(step * 1000))).clamp(max=2000.)
+
+
+class Optcodes(nn.Module):
+    """Per-frame appearance codes (core/networks/embedding.py:4-44)."""
+
+    def __init__(self, n_codes, code_ch):
+        super().__init__()
+        self.n_codes, self.code_ch = n_codes, code_ch
+        self.codes = nn.Embedding(n_codes, code_ch)
+        nn.init.xavier_normal_(self.codes.weight)
+
+
+class NeRF(nn.Module):
+    """Parameters of the density/radiance MLP under the reference's names (core/networks/nerf.py:12-88)."""
+
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_bones=0, input_ch_views=3, output_ch=4, skips=(4,),
+                 use_viewdirs=True, use_framecode=False, framecode_ch=16, n_framecodes=0, skel_type=None,
+                 density_scale=1.0):
+        super().__init__()
+        self.D, self.W = D, W
+        self.input_ch, self.input_ch_bones, self.input_ch_views = input_ch, input_ch_bones, input_ch_views
+        self.skips = list(skips)
+        self.use_viewdirs, self.use_framecode = use_viewdirs, use_framecode
+        self.framecode_ch, self.n_framecodes = framecode_ch, n_framecodes
+        self.output_ch, self.skel_type, self.density_scale = output_ch, skel_type, density_scale
+        dnet = input_ch + input_ch_bones
+        layers = [nn.Linear(dnet, W)]
+        for i in range(D - 1):
+            layers.append(nn.Linear(W + dnet if i in self.skips else W, W))
+        self.pts_linears = nn.ModuleList(layers)
+        self.alpha_linear = nn.Linear(W, 1)
+        vnet = input_ch_views + (framecode_ch if use_framecode else 0) + W
+        self.views_linears = nn.ModuleList([nn.Linear(vnet, W // 2)])
+        self.feature_linear = nn.Linear(W, W)
+        self.rgb_linear = nn.Linear(W // 2, 3)
+        if use_framecode:
+            self.framecodes = Optcodes(n_framecodes, framecode_ch)
+
+    @property
+    def dnet_input(self):
+        return self.input_ch + self.input_ch_bones
+
+    @property
+    def vnet_input(self):
+        return self.input_ch_views + (self.framecode_ch if self.use_framecode else 0) + self.W
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError("anerf_b200.NeRF holds parameters only; evaluation runs inside the fused CUDA kernel")
+
+
+class _EncoderTag:
+    """Stand-in for the reference's encoder objects inside `preproc_kwargs` (core/encoders.py); only the
+    default trio is compiled into the kernels, so these carry the name and nothing else."""
+
+    def __init__(self, name, dims):
+        self.encoder_name, self.dims = name, dims
+
+
+# ------------------------------------------------------------------------------------------------
+# the ray caster
+# ------------------------------------------------------------------------------------------------
+class RayCaster(nn.Module):
+
+    def __init__(self, network, embed_fn, embedbones_fn, embeddirs_fn, network_fine=None, joint_coords=None,
+                 single_net=False, operand_format=None):
+        super().__init__()
+        self.network = network
+        self.network_fine = network_fine
+        self.embed_fn = embed_fn
+        self.embedbones_fn = embedbones_fn
+        self.embeddirs_fn = embeddirs_fn
+        if joint_coords is not None:
+            n_j = joint_coords.shape[-3]
+            self.register_buffer('joint_coords', joint_coords.reshape(-1, n_j, 3, 3))
+        self.single_net = single_net
+        if operand_format is None:
+            operand_format = int(os.environ.get("ANERF_OPERAND_FORMAT", "0"))
+        self._operand_format = operand_format
+        self._plan = None
+        self._packed = {}        # net name -> (packed image tensor, version signature)
+
+    # ---- engine plumbing ---------------------------------------------------------------------
+    def _n_joints(self):
+        return self.embed_fn.cutoff_dim
+
+    def _get_plan(self):
+        if self._plan is None:
+            net = self.network
+            self._plan = _lib.Plan(self._n_joints(), net.D, net.W, net.skips,
+                                   net.framecode_ch if net.use_framecode else 0,
+                                   net.n_framecodes if net.use_framecode else 0, self._operand_format)
+        return self._plan
+
+    def _packed_image(self, which):
+        """Packed tensor-core image of a network, re-packed whenever a parameter changed in place
+        (optimizer step, load_state_dict) -- tracked through the tensors' version counters."""
+        net = self.network if which == 'network' else self.network_fine
+        params = list(net.parameters())
+        sig = tuple((p.data_ptr(), p._version) for p in params)
+        cached = self._packed.get(which)
+        if cached is not None and cached[1] == sig:
+            return cached[0]
+        sd = {k: v for k, v in net.state_dict().items()}
+        dev = params[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError("anerf_b200.RayCaster: parameters must live on a CUDA device (no CPU path)")
+        out = cached[0] if cached is not None and cached[0].device == dev else None
+        img = self._get_plan().pack(sd, out)
+        self._packed[which] = (img, sig)
+        return img
+
+    def _opts(self, n_rays, n_samples, n_importance, lindisp, density_scale, density_fn, eval_mean=False):
+        softplus, shift = False, 0.
+        if density_fn is not None and getattr(density_fn, 'anerf_softplus', False):
+            softplus, shift = True, float(density_fn.anerf_shift)
+        # embedder scalars live on the device; read them back only when they change (no per-chunk sync)
+        e0, e1 = self.embed_fn, self.embeddirs_fn
+        sig = (id(e0.tau), e0.tau._version, id(e1.tau), e1.tau._version, e0.cutoff_dist._version,
+               e1.cutoff_dist._version, e0.cutoff_dist.data_ptr(), e1.cutoff_dist.data_ptr())
+        if getattr(self, '_embed_cache', (None,))[0] != sig:
+            self._embed_cache = (sig, float(e0.tau), float(e1.tau), e0.cutoff_dist.detach().float().cpu().tolist(),
+                                 e1.cutoff_dist.detach().float().cpu().tolist())
+        _, tau_p, tau_v, cp, cv = self._embed_cache
+        return _lib.make_opts(n_rays, n_samples, n_importance, tau_pts=tau_p,
+                              tau_views=tau_v, cutoff_pts=cp, cutoff_views=cv,
+                              lindisp=bool(lindisp), softplus=softplus, softplus_shift=shift,
+                              density_scale=float(density_scale), eval_mean_framecode=eval_mean)
+
+    # ---- reference API -------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward_eval(self, *args, **kwargs):
+        return self.render_rays(*args, **kwargs)
+
+    def forward(self, *args, fwd_type='', **kwargs):
+        if fwd_type == 'density':
+            return self.render_pts_density(*args, **kwargs)
+        elif fwd_type == 'density_color':
+            raise NotImplementedError("fwd_type='density_color' needs texture layers the reference never defines")
+        elif fwd_type == 'mesh':
+            return self.render_mesh_density(*args, **kwargs)
+        if not self.training:
+            return self.forward_eval(*args, **kwargs)
+        return self.render_rays(*args, **kwargs)
+
+    def render_rays(self, ray_batch, N_samples, kp_batch, skts=None, cyls=None, bones=None, cams=None,
+                    subject_idxs=None, retraw=False, lindisp=False, perturb=0., N_importance=0, network_fine=None,
+                    raw_noise_std=0., ray_noise_std=0., verbose=False, ext_scale=0.001, pytest=False,
+                    preproc_kwargs={}, nerf_type="nerf", use_viewdirs=True, **unused):
+        """One chunk of rays -> {'rgb_map','disp_map','acc_map','alpha'[, 'rgb0','disp0','acc0','alpha0']}
+        (reference: core/raycasters.py:361-474, 711-724)."""
+        if skts is None or cyls is None:
+            raise NotImplementedError("anerf_b200 needs skts and cyls (the reference's skts=None path is unused)")
+        if ray_noise_std > 0.:
+            raise NotImplementedError("ray_noise_std > 0 is not supported")
+        if self.single_net and N_importance > 0:
+            raise NotImplementedError("single_net is not supported")
+        if subject_idxs is not None:
+            raise NotImplementedError("subject_idxs is not supported by the default encoders")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("anerf_b200 round 1 implements the forward path only; call under "
+                                      "torch.no_grad() / .eval() (training backward: see DESIGN.md 'next')")
+        dev = ray_batch.device
+        if dev.type != 'cuda':
+            raise RuntimeError("anerf_b200.RayCaster: inputs must be CUDA tensors (no CPU path)")
+        N = ray_batch.shape[0]
+        J = self._n_joints()
+        rays = ray_batch[:, :8].float().contiguous()
+        skts_c = skts.float().expand(N, J, 4, 4).contiguous()
+        cyls_c = cyls.float().expand(N, cyls.shape[-1]).contiguous()
+        density_scale = preproc_kwargs.get('density_scale', 1.0)
+        density_fn = preproc_kwargs.get('density_fn', None)
+        use_fc = self.network.use_framecode
+        cams_c, eval_mean = None, False
+        if use_fc:
+            if cams is None:
+                raise RuntimeError("opt_framecode networks need `cams`")
+            cams_c = cams.float().reshape(-1).expand(N).contiguous()
+            eval_mean = (not self.training) and bool(cams_c.max() < 0)     # embedding.py:21
+        Sc, Si = int(N_samples), int(N_importance)
+        t_rand = u_rand = noise0 = noise1 = None
+        if perturb > 0.:
+            if pytest:
+                np.random.seed(0)
+                t_rand = torch.as_tensor(np.random.rand(N, Sc), dtype=torch.float32, device=dev)
+                np.random.seed(0)
+                u_rand = torch.as_tensor(np.random.rand(N, Si), dtype=torch.float32, device=dev) if Si > 0 else None
+            else:
+                t_rand = torch.rand(N, Sc, device=dev)
+                u_rand = torch.rand(N, Si, device=dev) if Si > 0 else None
+        if raw_noise_std > 0.:
+            if pytest:
+                np.random.seed(0)
+                noise0 = torch.as_tensor(np.random.rand(N, Sc) * raw_noise_std, dtype=torch.float32, device=dev)
+                np.random.seed(0)
+                noise1 = torch.as_tensor(np.random.rand(N, Sc + Si) * raw_noise_std, dtype=torch.float32, device=dev)
+            else:
+                noise0 = torch.randn(N, Sc, device=dev) * (raw_noise_std * density_scale)
+                noise1 = torch.randn(N, Sc + Si, device=dev) * (raw_noise_std * density_scale) if Si > 0 else None
+        opts = self._opts(N, Sc, Si, lindisp, density_scale, density_fn, eval_mean)
+        p0 = self._packed_image('network')
+        p1 = self._packed_image('network_fine') if Si > 0 else None
+        with torch.cuda.device(dev):
+            out = _lib.render_fwd(self._get_plan(), p0, p1, opts, rays, skts_c, cyls_c, cams_c, t_rand, u_rand,
+                                  noise0, noise1, want_taps=bool(retraw))
+        return out
+
+    @torch.no_grad()
+    def render_mesh_density(self, kps, skts, bones, subject_idxs=None, radius=1.0, res=64, render_kwargs=None,
+                            netchunk=1024 * 64, v=None):
+        """[res+1]^3 raw densities around kps[0,0] (reference: core/raycasters.py:579-595)."""
+        t = np.linspace(-radius, radius, res + 1)
+        grid = np.stack(np.meshgrid(t, t, t), axis=-1).astype(np.float32)
+        sh = grid.shape
+        pts = torch.tensor(grid.reshape(-1, 3), device=kps.device) + kps[0, 0]
+        raw = self.render_pts_density(pts.reshape(-1, 1, 3), kps, skts, bones, render_kwargs, subject_idxs, netchunk)
+        return raw[..., :1].reshape(*sh[:-1]).transpose(1, 0)
+
+    @torch.no_grad()
+    def render_pts_density(self, pts, kps, skts, bones, render_kwargs=None, subject_idxs=None, netchunk=1024 * 64,
+                           network=None, color=False, v=None):
+        """Raw (pre-activation) density of world points under one pose (core/raycasters.py:597-648).
+        pts [P,1,3] or [P,3]; returns [P,1,1] like the reference's batchified forward."""
+        if color or v is not None:
+            raise NotImplementedError("density_color / precomputed v are not supported")
+        if network is None:
+            which = 'network_fine' if self.network_fine is not None else 'network'
+        else:
+            which = 'network_fine' if network is self.network_fine else 'network'
+        dev = pts.device
+        if dev.type != 'cuda':
+            raise RuntimeError("anerf_b200.RayCaster: inputs must be CUDA tensors (no CPU path)")
+        if skts.shape[0] != 1:
+            raise NotImplementedError("density queries take one pose (skts [1,J,4,4])")
+        opts = self._opts(0, 64, 0, False, 1.0, None)
+        with torch.cuda.device(dev):
+            sig = _lib.density_points(self._get_plan(), self._packed_image(which), opts,
+                                      pts.reshape(-1, 3).float().contiguous(), skts[0].float().contiguous())
+        return sig.reshape(-1, 1, 1)
+
+    def get_subject_joint_coords(self, subject_idxs=None, device=None):
+        return self.joint_coords.to(device)[subject_idxs]
+
+    def update_embed_fns(self, global_step, args):
+        freq_target = args.multires - 1
+        for fn in (self.embed_fn, self.embeddirs_fn, self.embedbones_fn):
+            if fn is not None:
+                fn.update_threshold(global_step, args.cutoff_step, args.cutoff_rate, args.freq_schedule_step, freq_target)
+
+    # the reference's nested checkpoint layout (core/raycasters.py:752-788)
+    @staticmethod
+    def _ckpt_key(k):
+        if k.endswith("_fine"):
+            return f"{k}_state_dict"
+        if k.endswith("_fn"):
+            return f"{k.split('_fn')[0]}_state_dict"
+        if k == "network":
+            return "network_fn_state_dict"
+        return f"{k}_state_dict"
+
+    def state_dict(self, *args, **kwargs):
+        return {self._ckpt_key(k): m.state_dict() for k, m in self._modules.items() if m is not None}
+
+    def load_state_dict(self, ckpt, strict=True):
+        for k, m in self._modules.items():
+            if m is None:
+                continue
+            key = self._ckpt_key(k)
+            try:
+                m.load_state_dict(ckpt[key], strict=strict)
+            except (KeyError, RuntimeError):
+                if k.startswith('network'):
+                    print('Error occur when loading state dict for network. Try loading with strict=False now')
+                    own = m.state_dict()
+                    filtered = {n: t for n, t in ckpt[key].items() if n in own and own[n].shape == t.shape}
+                    m.load_state_dict(filtered, strict=False)
+                else:
+                    print(f'Error occurr when loading state dict for {key}. The entity is not in the state dict?')
+
+    def get_embed_fns(self):
+        return self.embed_fn, self.embedbones_fn, self.embeddirs_fn
+
+    def get_networks(self):
+        return self.network, self.network_fine
+
+
+class _ModuleHolder(nn.Module):
+    """What `render_kwargs_train['ray_caster']` is in place of the reference's nn.DataParallel
+    (core/raycasters.py:157): callers reach the caster through `.module` (core/trainer.py:265,270,504).
+    Multi-GPU runs are one process per GPU (anerf_b200.parallel), so there is nothing to scatter here."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+
+def _softplus_fn(shift):
+    fn = lambda x: torch.nn.functional.softplus(x - shift, beta=1)
+    fn.anerf_softplus, fn.anerf_shift = True, shift
+    return fn
+
+
+def _load_ckpt_from_path(ray_caster, optimizer, ckpt_path, finetune=False):
+    """core/utils/run_nerf_helpers.py:6-17"""
+    ckpt = torch.load(ckpt_path, map_location='cpu', weights_only=False)
+    global_step = ckpt["global_step"]
+    ray_caster.load_state_dict(ckpt)
+    if optimizer is not None and not finetune and "optimizer_state_dict" in ckpt:
+        print("load optimizer from ckpt")
+        optimizer.load_state_dict(ckpt["optimizer_state_dict"])
+    return global_step, ray_caster, optimizer, ckpt
+
+
+def create_raycaster(args, data_attrs, device=None):
+    """Same contract as the reference's factory (core/raycasters.py:17-184): returns
+    (render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer, loaded_ckpt).
+    Flag combinations outside the compiled path raise NotImplementedError here."""
+    skel_type = data_attrs["skel_type"]
+    n_joints = len(skel_type.joint_names)
+    n_framecodes = data_attrs["n_views"] if args.n_framecodes is None else args.n_framecodes
+    g = lambda name, default: getattr(args, name, default)
+
+    def unsupported(cond, what):
+        if cond:
+            raise NotImplementedError(f"anerf_b200: {what} is not implemented (only the default A-NeRF encoders are)")
+    unsupported(g('pts_tr_type', 'local') != 'local', f"pts_tr_type={g('pts_tr_type', None)}")
+    unsupported(g('kp_dist_type', 'reldist') != 'reldist', f"kp_dist_type={g('kp_dist_type', None)}")
+    unsupported(g('view_type', 'relray') != 'relray', f"view_type={g('view_type', None)}")
+    unsupported(g('bone_type', 'reldir') != 'reldir', f"bone_type={g('bone_type', None)}")
+    unsupported(not g('use_viewdirs', True), "use_viewdirs=False")
+    unsupported(not g('use_cutoff', True) or not g('cutoff_viewdir', True) or not g('cutoff_inputs', True),
+                "disabling the cutoff (use_cutoff / cutoff_viewdir / cutoff_inputs)")
+    unsupported(g('normalize_cutoff', False) or g('cut_to_dist', False) or g('cutoff_shift', False)
+                or g('cutoff_bones', False) or g('freq_schedule', False) or g('opt_cutoff', False),
+                "normalize_cutoff / cut_to_dist / cutoff_shift / cutoff_bones / freq_schedule / opt_cutoff")
+    unsupported(g('multires', 7) != MULTIRES or g('multires_views', 4) != MULTIRES_VIEWS or g('multires_bones', 0) != 0,
+                "multires/multires_views/multires_bones other than 7/4/0")
+    unsupported(g('i_embed', 0) != 0, "i_embed != 0")
+    unsupported(g('single_net', False), "single_net")
+    unsupported(g('nerf_type', 'nerf') != 'nerf', f"nerf_type={g('nerf_type', None)}")
+    if args.density_type not in ('relu', 'softplus'):
+        raise NotImplementedError(f'density activation {args.density_type} is undefined')
+    if args.netwidth not in (64, 128, 256) or not (2 <= args.netdepth <= 8) or not (1 <= n_joints <= 24):
+        raise NotImplementedError("anerf_b200 supports netwidth in {64,128,256}, netdepth 2..8, up to 24 joints")
+
+    if device is None:
+        device = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+    cutoff_dist = args.cutoff_mm * args.ext_scale
+    embed_fn = CutoffEmbedder(n_joints, MULTIRES, cutoff_dist, n_joints, dist_inputs=False)
+    embedbones_fn = Embedder(n_joints * 3, 0)
+    embeddirs_fn = CutoffEmbedder(n_joints * 3, MULTIRES_VIEWS, cutoff_dist, n_joints, dist_inputs=True)
+    print(f'KPE: RelDist, BPE: VecNorm, VPE: VecNorm')
+
+    output_ch = 5 if args.N_importance > 0 else 4
+    nerf_kwargs = dict(D=args.netdepth, W=args.netwidth, input_ch=embed_fn.out_dim, input_ch_bones=embedbones_fn.out_dim,
+                       input_ch_views=embeddirs_fn.out_dim, output_ch=output_ch, skips=[4], use_viewdirs=True,
+                       use_framecode=bool(args.opt_framecode), framecode_ch=args.framecode_size,
+                       n_framecodes=n_framecodes, skel_type=skel_type, density_scale=args.density_scale)
+    model = NeRF(**nerf_kwargs)
+    model_fine = NeRF(**nerf_kwargs) if args.N_importance > 0 else None
+    ray_caster = RayCaster(model, embed_fn, embedbones_fn, embeddirs_fn, network_fine=model_fine,
+                           joint_coords=torch.tensor(data_attrs['joint_coords']), single_net=False).to(device)
+
+    # trainable variables, with the reference's --fix_layer freezing (core/raycasters.py:186-228)
+    if g('finetune', False) and g('fix_layer', 0) > 0:
+        for net in (model, model_fine):
+            if net is not None:
+                for i, l in enumerate(net.pts_linears):
+                    if i < args.fix_layer:
+                        for p in l.parameters():
+                            p.requires_grad = False
+    grad_vars = []
+    if g('weight_decay', None) is None:
+        for m in (model, model_fine, embed_fn, embedbones_fn, embeddirs_fn):
+            if m is not None:
+                grad_vars += [p for p in m.parameters() if p.requires_grad]
+    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+
+    start = 0
+    if args.ft_path is not None and args.ft_path != 'None':
+        ckpts = [args.ft_path]
+    else:
+        d = os.path.join(args.basedir, args.expname)
+        ckpts = [os.path.join(d, f) for f in sorted(os.listdir(d)) if 'tar' in f and 'pose' not in f] if os.path.isdir(d) else []
+    print('Found ckpts', ckpts)
+    loaded_ckpt = None
+    if len(ckpts) > 0 and not args.no_reload:
+        print('Reloading from', ckpts[-1])
+        start, ray_caster, optimizer, loaded_ckpt = _load_ckpt_from_path(ray_caster, optimizer, ckpts[-1], args.finetune)
+        if args.finetune:
+            start = 0
+            print(f"set global step to {start}")
+
+    density_fn = torch.nn.functional.relu if args.density_type == 'relu' else _softplus_fn(args.softplus_shift)
+    preproc_kwargs = {
+        'pts_tr_fn': _EncoderTag('W2LEncoder', n_joints),
+        'kp_input_fn': _EncoderTag('RelDist', n_joints),
+        'view_input_fn': _EncoderTag('VecNorm', n_joints * 3),
+        'bone_input_fn': _EncoderTag('VecNorm', n_joints * 3),
+        'density_scale': args.density_scale,
+        'density_fn': density_fn,
+    }
+    render_kwargs_train = {
+        'ray_caster': _ModuleHolder(ray_caster),
+        'perturb': args.perturb, 'N_importance': args.N_importance, 'N_samples': args.N_samples,
+        'use_viewdirs': args.use_viewdirs, 'raw_noise_std': args.raw_noise_std, 'ray_noise_std': args.ray_noise_std,
+        'ext_scale': args.ext_scale, 'preproc_kwargs': preproc_kwargs, 'lindisp': args.lindisp,
+        'nerf_type': args.nerf_type,
+    }
+    render_kwargs_test = dict(render_kwargs_train)
+    render_kwargs_test['ray_caster'] = ray_caster
+    render_kwargs_test['preproc_kwargs'] = dict(preproc_kwargs)
+    render_kwargs_test['perturb'] = False
+    render_kwargs_test['raw_noise_std'] = 0.
+    render_kwargs_test['ray_noise_std'] = 0.
+    print(f"#parameters: {sum(p.numel() for p in model.parameters() if p.requires_grad)}")
+    optimizer.zero_grad()
+    return render_kwargs_train, render_kwargs_test, start, grad_vars, optimizer, loaded_ckpt
+
+
+def batchify_rays(rays_flat, chunk=1024 * 32, ray_caster=None, **kwargs):
+    """The caller of the boundary, restated (core/trainer.py:64-79): slices every tensor kwarg per chunk.
+    Provided so that bench / tests drive the caster exactly as the reference's `render` does."""
+    all_ret = {}
+    for i in range(0, rays_flat.shape[0], chunk):
+        kw = {k: (v[i:i + chunk] if torch.is_tensor(v) else v) for k, v in kwargs.items()}
+        ret = ray_caster(rays_flat[i:i + chunk], **kw)
+        for k, v in ret.items():
+            all_ret.setdefault(k, []).append(v)
+    return {k: torch.cat(v, 0) for k, v in all_ret.items()}

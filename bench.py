@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""Benchmark of the A-NeRF ray-marching hot path (BASELINE.json metric: rays/sec at 512^2,
+64 coarse + 128 fine samples, 24 joints, 8x256 coarse + fine nets, 4096-ray chunks).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3                # our CUDA path
+    python bench.py --impl reference --steps 1 --warmup 1        # the reference algorithm on the host CPU
+    torchrun --nproc-per-node N ... bench.py --gpus N            # frame-parallel, one rank per GPU
+
+One "step" = one full synthetic 512x512 frame per rank (262,144 rays = 64 chunks of 4096) driven the way
+the reference's render() -> batchify_rays() drives the boundary.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from anerf_b200 import synthetic  # noqa: E402
+
+H = W = 512
+FOCAL = 500.0
+CHUNK = 4096
+N_SAMPLES, N_IMPORTANCE, N_JOINTS = 64, 128, 24
+FLOP_PER_RAY = 256 * 1723648           # 441.25 MFLOP forward
+METRIC = "rays/sec at 512^2 (64c+128f samples, 24 joints)"
+WORKLOAD = "SURREAL-style bullet-time frame 512x512, 4096-ray chunks, 64+128 samples, 24 joints, 8x256 coarse+fine (BASELINE.json configs[1])"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    return 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([x.strip() for x in o.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r[0].replace('.', '', 1).isdigit()]
+        mx = [float(r[1]) for r in self.rows if r[1].replace('.', '', 1).isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 3 + i and r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_args(**over):
+    """The flags create_raycaster reads, SURREAL-style (reference: configs/surreal/surreal.txt + --N_importance 128)."""
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="anerf_bench_")
+    os.makedirs(os.path.join(tmp, "exp"), exist_ok=True)
+    d = dict(n_framecodes=None, use_cutoff=True, normalize_cutoff=False, cutoff_mm=500., ext_scale=0.001,
+             cutoff_inputs=True, opt_cutoff=False, freq_schedule=False, init_freq=0., cut_to_dist=False,
+             cutoff_shift=False, multires=7, i_embed=0, cutoff_bones=False, multires_bones=0, use_viewdirs=True,
+             cutoff_viewdir=True, multires_views=4, N_importance=N_IMPORTANCE, netdepth=8, netwidth=256,
+             opt_framecode=False, framecode_size=16, density_scale=1.0, single_net=False, lrate=5e-4, ft_path=None,
+             basedir=tmp, expname="exp", no_reload=True, finetune=False, fix_layer=0, weight_decay=None,
+             density_type="relu", softplus_shift=0., pts_tr_type="local", kp_dist_type="reldist", view_type="relray",
+             bone_type="reldir", debug=True, perturb=0., N_samples=N_SAMPLES, raw_noise_std=0., ray_noise_std=0.,
+             lindisp=False, nerf_type="nerf", cutoff_step=250, cutoff_rate=10., freq_schedule_step=50)
+    d.update(over)
+    return argparse.Namespace(**d)
+
+
+def frame_inputs(frame_idx, n_frames_total=8):
+    """Synthetic bullet-time frame: same pose, camera orbiting; all 262,144 pixels; per-ray replicated
+    pose tensors as run_nerf.render_path builds them (run_nerf.py:84-90)."""
+    ang = 2 * np.pi * frame_idx / n_frames_total
+    sc = synthetic.make_scene(seed=0, n_rays=None, H=H, W=W, focal=FOCAL, n_joints=N_JOINTS, cam_angle=ang)
+    N = sc["rays_o"].shape[0]
+    rays = np.concatenate([sc["rays_o"], sc["rays_d"], np.zeros((N, 1), np.float32), np.ones((N, 1), np.float32)], 1)
+    return dict(rays=rays, skts=sc["skts"], cyls=sc["cyls"], kps=sc["kps"], bones=sc["bones"])
+
+
+def run_reference_arm(opt):
+    """The reference's algorithm on the host CPU (the oracle port of its PyTorch path; the Python reference
+    itself cannot travel to the GPU box).  Each step = a bounded sample of the frame."""
+    from oracle import anerf_oracle as orc
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_sample = opt.ref_rays
+    torch.set_num_threads(os.cpu_count() or 1)
+    fr = frame_inputs(0)
+    rng = np.random.RandomState(0)
+    idx = np.sort(rng.choice(H * W, n_sample, replace=False))
+    t = lambda a: torch.as_tensor(a[idx])
+    sd0 = orc.to_torch(synthetic.make_net_weights(101))
+    sd1 = orc.to_torch(synthetic.make_net_weights(202))
+    cfg = orc.PathConfig()
+    rays = t(fr["rays"])
+
+    def step():
+        with torch.no_grad():
+            orc.render_rays(sd0, sd1, cfg, rays[:, 0:3], rays[:, 3:6], t(fr["skts"]), t(fr["cyls"]))
+    for _ in range(opt.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(opt.steps):
+        step()
+    dt = time.perf_counter() - t0
+    v = n_sample * opt.steps / dt
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "rays/s", "n_gpus": opt.gpus, "steps": opt.steps,
+            "warmup": opt.warmup, "ms_per_step": 1e3 * dt / opt.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": f"{n_sample} rays of the frame per step"},
+            "cpu_baseline": {"value": v, "unit": "rays/s", "cores": cores, "kind": "port",
+                             "sample": f"{n_sample} rays x {opt.steps} steps (oracle port of the reference's PyTorch path; "
+                                       "the Python reference cannot travel to the GPU box)"},
+            "e2e": {"value": v, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_sample(n_sample=1024):
+    from oracle import anerf_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    fr = frame_inputs(0)
+    idx = np.sort(np.random.RandomState(0).choice(H * W, n_sample, replace=False))
+    t = lambda a: torch.as_tensor(a[idx])
+    sd0 = orc.to_torch(synthetic.make_net_weights(101))
+    sd1 = orc.to_torch(synthetic.make_net_weights(202))
+    cfg = orc.PathConfig()
+    rays = t(fr["rays"])
+    args = (sd0, sd1, cfg, rays[:, 0:3], rays[:, 3:6], t(fr["skts"]), t(fr["cyls"]))
+    with torch.no_grad():
+        orc.render_rays(*args)                       # warm-up
+        t0 = time.perf_counter()
+        ref = orc.render_rays(*args)
+        dt = time.perf_counter() - t0
+    return {"value": n_sample / dt, "unit": "rays/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_sample} rays of frame 0, one timed pass after one warm-up"}, idx, ref
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the CPU reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--format", type=int, default=None, help="operand format override: 0 fp16x3, 1 bf16x3")
+    opt = ap.parse_args()
+    if opt.impl == "reference":
+        return run_reference_arm(opt)
+
+    from anerf_b200 import _lib, build, parallel
+    from anerf_b200.raycasters import create_raycaster, batchify_rays
+    build.build()
+    rank, world, local = parallel.init_distributed()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (anerf_b200 has no CPU path)")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if opt.format is not None:
+        os.environ["ANERF_OPERAND_FORMAT"] = str(opt.format)
+
+    import collections
+    Skel = collections.namedtuple("Skel", ["joint_names", "joint_trees", "root_id"])
+    skel = Skel(synthetic.SMPL_JOINT_NAMES, synthetic.SMPL_PARENTS, 0)
+    data_attrs = dict(skel_type=skel, near=0., far=1., n_views=1,
+                      joint_coords=np.tile(np.eye(3, dtype=np.float32), (1, N_JOINTS, 1, 1)))
+    args = make_args()
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        _, rk, _, _, _, _ = create_raycaster(args, data_attrs, device=dev)
+    rc = rk["ray_caster"]
+    sd0 = {k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(101).items()}
+    sd1 = {k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(202).items()}
+    rc.network.load_state_dict(sd0)
+    rc.network_fine.load_state_dict(sd1)
+    rc.eval()
+    kw = {k: v for k, v in rk.items() if k not in ("ray_caster", "use_viewdirs")}
+
+    # two frames per rank, alternated, resident in HBM (402 MB of per-ray skts each: larger than the 126 MB L2)
+    my_frames = [rank * 2, rank * 2 + 1]
+    host = [frame_inputs(f, n_frames_total=2 * world * 4) for f in my_frames]
+    devf = [{k: torch.as_tensor(v).to(dev) for k, v in fr.items()} for fr in host]
+    n_rays = H * W
+    n_chunks = (n_rays + CHUNK - 1) // CHUNK
+
+    def render_frame(fr):
+        return batchify_rays(fr["rays"], CHUNK, ray_caster=rc, kp_batch=fr["kps"], skts=fr["skts"], cyls=fr["cyls"],
+                             bones=fr["bones"], cams=None, subject_idxs=None, **kw)
+
+    def step(i):
+        out = render_frame(devf[i % 2])
+        pix = torch.cat([out["rgb_map"], out["disp_map"][:, None], out["acc_map"][:, None]], 1)
+        if world > 1:                      # pixels of every rank's frame to rank 0 (bullet-time video)
+            bufs = [torch.empty_like(pix) for _ in range(world)] if rank == 0 else None
+            torch.distributed.gather(pix, bufs, dst=0)
+        return out
+
+    for i in range(max(opt.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(opt.steps):
+        out = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        torch.distributed.barrier()
+    clocks = sampler.stop()
+    ms = parallel.max_over_ranks(ms, dev)
+    rays_total = n_rays * opt.steps * world
+    value = rays_total / (ms * 1e-3)
+
+    # ---- dominant kernel: the fused render kernel, timed per launch with CUDA events on its stream -----
+    fr = devf[0]
+    sl = slice(0, CHUNK)
+    call = lambda: rc(fr["rays"][sl], kp_batch=fr["kps"][sl], skts=fr["skts"][sl], cyls=fr["cyls"][sl], bones=fr["bones"][sl],
+                      cams=None, subject_idxs=None, **kw)
+    evs = []
+    for c in range(n_chunks):
+        sl = slice(c * CHUNK, (c + 1) * CHUNK)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        call()
+        b.record()
+        evs.append((a, b))
+    torch.cuda.synchronize()
+    launch_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    peak, peak_src = load_peaks()
+    achieved = FLOP_PER_RAY * CHUNK / (launch_ms * 1e-3) / 1e12
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "fused_kernel_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "anerf_fused_kernel",
+                "launch_ms": launch_ms, "algorithmic_flop_per_launch": FLOP_PER_RAY * CHUNK,
+                "note": "achieved = algorithmic fp32-equivalent FLOPs; each product is issued as 3 fp16 MMAs "
+                        "(hi*hi+lo*hi+hi*lo), so tensor-pipe work is ~3.1x this (incl. K padding): issued_frac below",
+                "issued_frac": 3.1 * achieved / peak}
+
+    # ---- e2e: the C-ABI call with HOST buffers, H2D and D2H inside the timed region ------------------------
+    e2e = None
+    if rank == 0 or world > 1:
+        plan = rc._get_plan()
+        p0, p1 = rc._packed_image('network'), rc._packed_image('network_fine')
+        hp = host[0]
+        pin = lambda a: torch.as_tensor(np.ascontiguousarray(a)).pin_memory()
+        h_rays, h_skts, h_cyls = pin(hp["rays"]), pin(hp["skts"]), pin(hp["cyls"])
+        opts_full = _lib.make_opts(CHUNK, N_SAMPLES, N_IMPORTANCE, tau_pts=20., tau_views=20., cutoff_pts=0.5, cutoff_views=0.5)
+        f = lambda *s: torch.empty(*s, dtype=torch.float32).pin_memory()
+        Sf = N_SAMPLES + N_IMPORTANCE
+        h_out = dict(rgb_map=f(n_rays, 3), disp_map=f(n_rays), acc_map=f(n_rays), alpha=f(n_rays, Sf), rgb0=f(n_rays, 3),
+                     disp0=f(n_rays), acc0=f(n_rays), alpha0=f(n_rays, N_SAMPLES))
+
+        def e2e_frame():
+            for c in range(n_chunks):
+                sl = slice(c * CHUNK, (c + 1) * CHUNK)
+                _lib.render_fwd_host(plan, p0, p1, opts_full, h_rays[sl], h_skts[sl], h_cyls[sl], None,
+                                     out={k: v[sl] for k, v in h_out.items()})
+        e2e_frame()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(opt.steps, 2))
+        for _ in range(n_e2e):
+            e2e_frame()
+        torch.cuda.synchronize()
+        dt_ms = parallel.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+        h2d = n_rays * (8 + N_JOINTS * 16 + 5) * 4
+        d2h = n_rays * (3 + 1 + 1 + Sf + 3 + 1 + 1 + N_SAMPLES) * 4
+        e2e = {"value": n_rays * n_e2e * world / (dt_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "api": "anerf_render_fwd_host (C ABI, pinned host buffers, one call per 4096-ray chunk)"}
+
+    if rank != 0:
+        return
+    cpu_base, parity = None, None
+    if not opt.no_cpu_baseline and world == 1:
+        cpu_base, idx, ref = cpu_baseline_sample(1024)
+        # parity of the benchmarked configuration on the sampled rays (coarse outputs: unconditioned)
+        sub = {k: v[torch.as_tensor(idx, device=dev)] for k, v in devf[0].items()}
+        o = rc(sub["rays"], kp_batch=sub["kps"], skts=sub["skts"], cyls=sub["cyls"], bones=sub["bones"], cams=None,
+               subject_idxs=None, **kw)
+        rel = lambda a, b: float((a.cpu().double() - b.double()).abs().max() / b.double().abs().max())
+        mse = float(((o["rgb_map"].cpu().double() - ref["rgb_map"].double()) ** 2).mean())
+        parity = {"rays": len(idx), "rgb0_rel": rel(o["rgb0"], ref["rgb0"]), "acc0_rel": rel(o["acc0"], ref["acc0"]),
+                  "rgb_map_rel": rel(o["rgb_map"], ref["rgb_map"]),
+                  "rgb_map_psnr_db": float(-10 * np.log10(max(mse, 1e-30)))}
+    line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": opt.steps, "warmup": max(opt.warmup, 3),
+            "ms_per_step": ms / opt.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 via fp16 hi/lo split on tcgen05 (3 MMAs per product, fp32 accumulate)" if rc._operand_format == 0
+            else "f32 via bf16 hi/lo split on tcgen05 (3 MMAs per product, fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_step_per_gpu": n_rays, "chunks_per_step": n_chunks,
+                       "parallelism": f"frame-parallel x{world}, gather of [rays,5] pixels to rank 0" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2: 402 MB of per-ray skts per frame, two frames alternated"},
+            "clocks": clocks, "gpu_launches": 2 * n_chunks * opt.steps, "e2e": e2e, "roofline": roofline,
+            "cpu_baseline": cpu_base, "parity": parity}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -144,7 +144,7 @@ int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf
 
 /* Build-time self test of the tensor-core building blocks: D[128,N] = A[128,K] * B[N,K]^T with the
  * split-precision operand path (A, B, D fp32 on the device; K multiple of 32; N in {32,64,128,256}).
- * format: 1 bf16, 0 fp16, 2 = bf16 hi parts with fp16 lo parts (probe of mixed-format MMA). */
+ * format: 1 bf16, 0 fp16. */
 int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t format,
                         void* stream);
 

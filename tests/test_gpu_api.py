@@ -1,0 +1,110 @@
+"""The reference-facing Python boundary (create_raycaster / RayCaster) on the GPU."""
+import argparse
+import collections
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from anerf_b200 import synthetic
+from anerf_b200.raycasters import batchify_rays, create_raycaster
+from tests.common import build_case, load_golden, rel_err, run_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def make_args(**over):
+    tmp = tempfile.mkdtemp(prefix="anerf_t_")
+    os.makedirs(os.path.join(tmp, "exp"), exist_ok=True)
+    d = dict(n_framecodes=None, use_cutoff=True, normalize_cutoff=False, cutoff_mm=500., ext_scale=0.001,
+             cutoff_inputs=True, opt_cutoff=False, freq_schedule=False, init_freq=0., cut_to_dist=False,
+             cutoff_shift=False, multires=7, i_embed=0, cutoff_bones=False, multires_bones=0, use_viewdirs=True,
+             cutoff_viewdir=True, multires_views=4, N_importance=16, netdepth=8, netwidth=256, opt_framecode=False,
+             framecode_size=16, density_scale=1.0, single_net=False, lrate=5e-4, ft_path=None, basedir=tmp,
+             expname="exp", no_reload=False, finetune=False, fix_layer=0, weight_decay=None, density_type="relu",
+             softplus_shift=0., pts_tr_type="local", kp_dist_type="reldist", view_type="relray", bone_type="reldir",
+             debug=True, perturb=0., N_samples=64, raw_noise_std=0., ray_noise_std=0., lindisp=False, nerf_type="nerf",
+             cutoff_step=250, cutoff_rate=10., freq_schedule_step=50)
+    d.update(over)
+    return argparse.Namespace(**d)
+
+
+def data_attrs(J=24, n_views=1):
+    Skel = collections.namedtuple("Skel", ["joint_names", "joint_trees", "root_id"])
+    return dict(skel_type=Skel([f"j{i}" for i in range(J)], synthetic.SMPL_PARENTS[:J], 0), near=0., far=1.,
+                n_views=n_views, joint_coords=np.tile(np.eye(3, dtype=np.float32), (1, J, 1, 1)))
+
+
+def test_create_raycaster_contract_and_render():
+    case, gold = load_golden("surreal_j24_s64_i16_tau200")
+    scene, sd0, sd1, cfg, _ = build_case(case)
+    args = make_args()
+    rk_train, rk_test, start, grad_vars, optimizer, loaded = create_raycaster(args, data_attrs())
+    assert start == 0 and loaded is None and len(grad_vars) == 2 * 24
+    assert set(rk_test) == {'ray_caster', 'perturb', 'N_importance', 'N_samples', 'use_viewdirs', 'raw_noise_std',
+                            'ray_noise_std', 'ext_scale', 'preproc_kwargs', 'lindisp', 'nerf_type'}
+    rc = rk_test['ray_caster']
+    assert rk_train['ray_caster'].module is rc
+    assert sum(p.numel() for p in rc.network.parameters()) == 864260          # reference prints this number
+    assert set(rc.state_dict()) == {'network_fn_state_dict', 'network_fine_state_dict', 'embed_state_dict',
+                                    'embedbones_state_dict', 'embeddirs_state_dict'}
+    rc.network.load_state_dict({k: torch.as_tensor(v) for k, v in sd0.items()})
+    rc.network_fine.load_state_dict({k: torch.as_tensor(v) for k, v in sd1.items()})
+    rc.embed_fn.tau.fill_(200.)
+    rc.embeddirs_fn.tau.fill_(200.)
+    rc.eval()
+    dev = torch.device("cuda")
+    t = lambda a: torch.as_tensor(a).to(dev)
+    N = scene["rays_o"].shape[0]
+    rays = torch.cat([t(scene["rays_o"]), t(scene["rays_d"]), torch.zeros(N, 1, device=dev), torch.ones(N, 1, device=dev),
+                      torch.nn.functional.normalize(t(scene["rays_d"]), dim=-1)], 1)        # [N,11] like trainer.render
+    kw = {k: v for k, v in rk_test.items() if k not in ('ray_caster', 'use_viewdirs')}
+    out = batchify_rays(rays, 24, ray_caster=rc, kp_batch=t(scene["kps"]), skts=t(scene["skts"]), cyls=t(scene["cyls"]),
+                        bones=t(scene["bones"]), cams=None, subject_idxs=None, **kw)
+    one = rc(rays, kp_batch=t(scene["kps"]), skts=t(scene["skts"]), cyls=t(scene["cyls"]), bones=t(scene["bones"]),
+             cams=None, subject_idxs=None, **kw)
+    for k in ("rgb0", "disp0", "acc0", "alpha0"):
+        assert rel_err(one[k].cpu().numpy(), gold["ref_" + k]) < 1e-4, k
+        assert out[k].shape == one[k].shape
+    # checkpoint round trip through the reference's nested layout
+    path = os.path.join(args.basedir, args.expname, "000100.tar")
+    torch.save({'global_step': 100, 'optimizer_state_dict': optimizer.state_dict(), **rc.state_dict()}, path)
+    _, rk2, start2, _, _, loaded2 = create_raycaster(make_args(basedir=args.basedir), data_attrs())
+    assert start2 == 100 and loaded2 is not None
+    rc2 = rk2['ray_caster'].eval()
+    assert float(rc2.embed_fn.tau) == 200.
+    two = rc2(rays, kp_batch=t(scene["kps"]), skts=t(scene["skts"]), cyls=t(scene["cyls"]), bones=t(scene["bones"]),
+              cams=None, subject_idxs=None, **kw)
+    assert torch.equal(two["rgb_map"], one["rgb_map"])
+    # in-place parameter updates are picked up (re-pack on version change)
+    with torch.no_grad():
+        rc2.network_fine.rgb_linear.bias.add_(0.5)
+    three = rc2(rays, kp_batch=t(scene["kps"]), skts=t(scene["skts"]), cyls=t(scene["cyls"]), bones=t(scene["bones"]),
+                cams=None, subject_idxs=None, **kw)
+    assert not torch.equal(three["rgb_map"], one["rgb_map"]) and torch.equal(three["rgb0"], one["rgb0"])
+
+
+def test_unsupported_flags_raise():
+    for bad in (dict(kp_dist_type='relpos'), dict(view_type='world'), dict(single_net=True), dict(use_viewdirs=False),
+                dict(multires=10), dict(cutoff_bones=True)):
+        with pytest.raises(NotImplementedError):
+            create_raycaster(make_args(**bad), data_attrs())
+    with pytest.raises(NotImplementedError):
+        create_raycaster(make_args(density_type='gelu'), data_attrs())
+
+
+def test_mesh_density_entry_point():
+    case, gold = load_golden("mesh_j24_res15")
+    J = case["n_joints"]
+    pose = synthetic.make_pose(11, J)
+    _, rk, _, _, _, _ = create_raycaster(make_args(N_importance=16, no_reload=True), data_attrs(J))
+    rc = rk['ray_caster'].eval()
+    rc.network_fine.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(202).items()})
+    dev = torch.device("cuda")
+    t = lambda a: torch.as_tensor(a).to(dev)
+    sig = rc(kps=t(pose["kps"])[None], skts=t(pose["skts"])[None], bones=t(pose["bones"])[None], radius=case["radius"],
+             render_kwargs=rk['preproc_kwargs'], res=case["res"], netchunk=4096, fwd_type='mesh')
+    assert tuple(sig.shape) == (16, 16, 16)
+    assert rel_err(sig.cpu().numpy(), gold["ref_sigma"]) < 1e-4

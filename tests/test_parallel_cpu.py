@@ -1,0 +1,52 @@
+"""Multi-process sharding logic on CPU (gloo, world_size 2): frame dealing, pixel gather, slab split."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from anerf_b200 import parallel
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    r, w, _ = parallel.init_distributed(backend="gloo")
+    n_frames = 5
+    mine = {f: torch.full((7, 5), float(f)) + torch.arange(5.) * 0.1 for f in parallel.frames_for_rank(n_frames, r, w)}
+    frames = parallel.gather_pixels(mine, n_frames, r, w)
+    n = 11
+    a, b = parallel.slab_for_rank(n, r, w)
+    full = parallel.gather_slabs(torch.arange(a, b, dtype=torch.float32)[:, None] * torch.ones(1, 3), n, r, w)
+    tmax = parallel.max_over_ranks(10.0 + r, torch.device("cpu"))
+    if r == 0:
+        ok = all(torch.equal(frames[f], torch.full((7, 5), float(f)) + torch.arange(5.) * 0.1) for f in range(n_frames))
+        ok = ok and torch.equal(full, torch.arange(n, dtype=torch.float32)[:, None] * torch.ones(1, 3))
+        q.put((ok, tmax))
+    else:
+        assert frames is None and full is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_frame_and_slab_sharding_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok, tmax = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok and tmax == 11.0
+
+
+def test_slabs_cover_everything():
+    for n in (1, 7, 256, 257):
+        for w in (1, 2, 3, 8):
+            s = [parallel.slab_for_rank(n, r, w) for r in range(w)]
+            assert s[0][0] == 0 and s[-1][1] == n and all(s[i][1] == s[i + 1][0] for i in range(w - 1))
+            assert sorted(f for r in range(w) for f in parallel.frames_for_rank(n, r, w)) == list(range(n))
