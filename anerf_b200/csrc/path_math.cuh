@@ -25,14 +25,13 @@ constexpr int kFv = 4;                       // view-direction frequencies
 constexpr int kPtsPerJoint = 1 + 2 * kF + 3; // 18: [v, (sin,cos) x 7] * w  ++  r(3)
 constexpr int kViewPerJoint = 3 * (1 + 2 * kFv);  // 27: [d, (sin,cos) x 4] x 3 components, * w
 constexpr int kPtsGroupJoints = 4;           // 4 joints -> 72 values = 9 x 8
-constexpr int kViewGroupJoints = 8;          // 8 joints -> 216 values = 27 x 8
 constexpr int kPtsGroupK = kPtsGroupJoints * kPtsPerJoint;     // 72
-constexpr int kViewGroupK = kViewGroupJoints * kViewPerJoint;  // 216
 constexpr int kMaxJoints = 24;
 constexpr int kKC = 32;                      // K elements per operand chunk (two K=16 MMA slabs)
 constexpr int kTileM = 128;                  // rows (samples) per tile = UMMA M
 
 ANERF_HD int ceil_div(int a, int b) { return (a + b - 1) / b; }
+ANERF_HD int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
 struct NetDims {
   int J;       // joints
@@ -43,11 +42,24 @@ struct NetDims {
   int n_fc;    // rows of the framecode table
 };
 
-// K extents (in elements) of the three kinds of A-operand parts, each padded to whole chunks.
-ANERF_HD int pts_k(const NetDims& d) { return ceil_div(d.J, kPtsGroupJoints) * kPtsGroupK; }
-ANERF_HD int pts_chunks(const NetDims& d) { return ceil_div(pts_k(d), kKC); }
-ANERF_HD int view_k_enc(const NetDims& d) { return ceil_div(d.J, kViewGroupJoints) * kViewGroupK; }
-ANERF_HD int view_chunks(const NetDims& d) { return ceil_div(view_k_enc(d) + d.fc_ch, kKC); }
+// ------------------------------------------------------------------------------------------------
+// K layout of the A operand.  Two worker groups produce the operand chunks of a layer concurrently:
+// group g owns the chunks of parity g.  Every part therefore has an even number of chunks and its
+// values are dealt to the two groups as follows:
+//   pts part : the joints are split into two halves of `pts_half_joints` (multiple of 4) joints;
+//              half h emits its joint groups (4 joints x 18 values = 72 = 9 x 8) as one stream,
+//              zero padded to `pts_half_chunks` chunks, which occupies the chunks of parity h;
+//   view part: one chunk per joint (27 values + 5 zeros), joint j in chunk j (so parity = j & 1),
+//              padded to an even joint count; framecodes, if any, add one chunk (16 values) + one
+//              zero chunk;
+//   hidden   : column block cb (32 accumulator columns) is chunk cb.
+// ------------------------------------------------------------------------------------------------
+ANERF_HD int pts_half_joints(const NetDims& d) { return round_up(ceil_div(d.J, 2), kPtsGroupJoints); }
+ANERF_HD int pts_half_k(const NetDims& d) { return pts_half_joints(d) / kPtsGroupJoints * kPtsGroupK; }
+ANERF_HD int pts_half_chunks(const NetDims& d) { return ceil_div(pts_half_k(d), kKC); }
+ANERF_HD int pts_chunks(const NetDims& d) { return 2 * pts_half_chunks(d); }
+ANERF_HD int view_joint_chunks(const NetDims& d) { return round_up(d.J, 2); }
+ANERF_HD int view_chunks(const NetDims& d) { return view_joint_chunks(d) + (d.fc_ch > 0 ? 2 : 0); }
 ANERF_HD int hid_chunks(const NetDims& d) { return d.W / kKC; }
 ANERF_HD int in_pts_ref(const NetDims& d) { return d.J * (1 + 2 * kF) + d.J * 3; }
 ANERF_HD int in_views_ref(const NetDims& d) { return d.J * kViewPerJoint; }
@@ -66,19 +78,19 @@ ANERF_HD int layer_chunks(const NetDims& d, int l) {
 // (cutoff_embedder.py:147-172, raycasters.py:560-569); skip layer input = cat[pts input, h]
 // (nerf.py:100-101); views layer input = cat[feature, k*3J + 3j + c, framecode] (nerf.py:121-125).
 ANERF_HD int pts_part_ref_col(const NetDims& d, int k) {
-  if (k >= pts_k(d)) return -1;
-  int g = k / kPtsGroupK, within = k % kPtsGroupK;
-  int j = g * kPtsGroupJoints + within / kPtsPerJoint, q = within % kPtsPerJoint;
+  int c = k / kKC, half = c & 1;
+  int hk = (c >> 1) * kKC + (k % kKC);          // index inside the half's value stream
+  if (hk >= pts_half_k(d)) return -1;
+  int j = half * pts_half_joints(d) + (hk / kPtsGroupK) * kPtsGroupJoints + (hk % kPtsGroupK) / kPtsPerJoint;
+  int q = hk % kPtsPerJoint;
   if (j >= d.J) return -1;
   return q < 1 + 2 * kF ? q * d.J + j : (1 + 2 * kF) * d.J + 3 * j + (q - (1 + 2 * kF));
 }
 ANERF_HD int view_part_ref_col(const NetDims& d, int k) {   // relative to the start of input_views
-  int ke = view_k_enc(d);
-  if (k >= ke) return (k - ke) < d.fc_ch ? in_views_ref(d) + (k - ke) : -1;
-  int g = k / kViewGroupK, within = k % kViewGroupK;
-  int j = g * kViewGroupJoints + within / kViewPerJoint, q = within % kViewPerJoint;
-  if (j >= d.J) return -1;
-  return (q / 3) * 3 * d.J + 3 * j + (q % 3);
+  int c = k / kKC, q = k % kKC;
+  if (c >= view_joint_chunks(d)) return (c == view_joint_chunks(d) && q < d.fc_ch) ? in_views_ref(d) + q : -1;
+  if (c >= d.J || q >= kViewPerJoint) return -1;
+  return (q / 3) * 3 * d.J + 3 * c + (q % 3);
 }
 ANERF_HD int layer_ref_col(const NetDims& d, int l, int k) {
   int P = pts_chunks(d) * kKC, V = view_chunks(d) * kKC;

@@ -5,7 +5,8 @@
 //   sampling + merge -> [fine net over R*(Sc+Si) rows] -> composite -> outputs.
 // A "net pass" over one tile of 128 rows (samples) runs the whole 8x256 MLP with activations never
 // leaving the SM:
-//   * 4 worker warps (thread == row == TMEM lane) produce the A operand in 32-wide K chunks, either
+//   * 8 worker warps in two groups of 4 (thread == row == TMEM lane; the two groups share the rows and
+//     own the operand chunks of even / odd index) produce the A operand in 32-wide K chunks, either
 //     by computing the encodings of their sample (bone-local transform, cutoff positional encoding)
 //     or by draining the previous layer's accumulators from TMEM (bias, ReLU), split every value into
 //     hi + lo 16-bit parts and store them in the UMMA K-major core-matrix layout (A ring);
@@ -27,10 +28,12 @@ constexpr int kAHalfBytes = kTileM * kKC * 2;        // 8 KB: hi (or lo) part of
 constexpr int kAStageBytes = 2 * kAHalfBytes;        // 16 KB
 constexpr int kBStageBytes = 256 * kKC * 2 * 2;      // 32 KB (N = 256)
 constexpr int kMaxLayers = 10;
-constexpr int kWorkerThreads = 128;
-constexpr int kMmaWarp = 4;
-constexpr int kLoadWarp = 5;
-constexpr int kThreads = 192;
+constexpr int kWorkerWarps = 8;                      // two groups of 4 warps; group g owns the A chunks of parity g
+constexpr int kWorkerThreads = kWorkerWarps * 32;
+constexpr int kGroupThreads = 128;
+constexpr int kMmaWarp = 8;
+constexpr int kLoadWarp = 9;
+constexpr int kThreads = 320;
 constexpr int kTmemCols = 512;
 constexpr int kSmallsHeader = 16;                    // floats: per-layer output scales
 constexpr int kMaxRaysPerItem = 8;
@@ -103,12 +106,12 @@ inline __host__ __device__ SmemLayout make_smem_layout(const NetDims& d, int sma
   L.smalls1 = off; off += align_up(smalls_fixed_floats * 4, 16);
   L.ray = off; off += R * 12 * 4;
   L.skt = off; off += align_up(R * d.J * 12 * 4, 16);
-  L.view_tab = off; off += R * view_k_enc(d) * 4;
+  L.view_tab = off; off += R * view_joint_chunks(d) * kKC * 4;   // [ray][joint][32]
   L.fcode = off; off += 2 * R * 16 * 4;      // [net][ray][16]
   int rows = R * (Sf > Sc ? Sf : Sc);
   L.z_coarse = off; off += align_up(R * Sc * 4, 16);
   L.z_all = off; off += align_up(rows * 4, 16);
-  L.raw = off; off += rows * 16;
+  L.raw = off; off += 2 * rows * 16;         // [group][row] partial (r,g,b,sigma)
   L.wts = off; off += align_up(rows * 4, 16);
   L.cdf = off; off += align_up(R * Sc * 4, 16);
   L.bars = off; off += 8 * (2 * kAStages + 2 * kBStages + 2);
@@ -153,22 +156,30 @@ struct Pipe {
   DeviceStatus* st;
 };
 
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// A-operand producer state of one worker thread (== one row of the tile)
+// whole-warp wait: one lane polls the barrier, the warp reconverges on it
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, DeviceStatus* st, unsigned site) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, st, site);
+  __syncwarp();
+}
+
+// A-operand producer state of one worker thread (== one row of the tile).  Group g writes the chunks
+// whose sequence number has parity g (every operand part has an even number of chunks).
 template <int FMT>
 struct AProducer {
   const Pipe& pp;
-  uint32_t seq;       // chunk sequence number (monotonic over the kernel's lifetime)
+  uint32_t seq;       // sequence number of the chunk being filled (monotonic over the kernel's lifetime)
   uint32_t g;         // next 8-wide K group inside the current chunk (0..3)
   uint32_t row_off;   // (row/8)*128 + (row%8)*16
   uint8_t* stage;
-  __device__ AProducer(const Pipe& p, int row) : pp(p), seq(0), g(0), row_off((row >> 3) * 128 + (row & 7) * 16), stage(nullptr) {}
+  __device__ AProducer(const Pipe& p, int row, int group)
+      : pp(p), seq(group), g(0), row_off((row >> 3) * 128 + (row & 7) * 16), stage(nullptr) {}
 
   __device__ __forceinline__ void put8(const float (&x)[8]) {
     if (g == 0) {
       uint32_t s = seq % kAStages;
-      mbar_wait(&pp.a_empty[s], ((seq / kAStages) & 1) ^ 1, pp.st, 100 + s);
+      mbar_wait_warp(&pp.a_empty[s], ((seq / kAStages) & 1) ^ 1, pp.st, 100 + s);
       stage = pp.a_ring + s * kAStageBytes;
     }
     uint4 hi, lo;
@@ -180,15 +191,41 @@ struct AProducer {
     *reinterpret_cast<uint4*>(stage + off) = hi;
     *reinterpret_cast<uint4*>(stage + kAHalfBytes + off) = lo;
     if (++g == 4) {
-      fence_proxy_async_smem();
-      mbar_arrive(&pp.a_full[seq % kAStages]);
-      ++seq;
+      fence_proxy_async_smem();            // this thread's stores -> visible to the tensor core's reads
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&pp.a_full[seq % kAStages]);   // 4 warp arrivals per chunk
+      seq += 2;
       g = 0;
     }
+  }
+  // a whole chunk at once (requires g == 0: hidden-layer operands are chunk aligned)
+  __device__ __forceinline__ void put32(const float (&x)[32]) {
+    uint32_t s = seq % kAStages;
+    mbar_wait_warp(&pp.a_empty[s], ((seq / kAStages) & 1) ^ 1, pp.st, 110 + s);
+    uint8_t* st = pp.a_ring + s * kAStageBytes + row_off;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      uint4 hi, lo;
+      Split<FMT>::pair(x[8 * t + 0], x[8 * t + 1], hi.x, lo.x);
+      Split<FMT>::pair(x[8 * t + 2], x[8 * t + 3], hi.y, lo.y);
+      Split<FMT>::pair(x[8 * t + 4], x[8 * t + 5], hi.z, lo.z);
+      Split<FMT>::pair(x[8 * t + 6], x[8 * t + 7], hi.w, lo.w);
+      *reinterpret_cast<uint4*>(st + (t >> 1) * 4096 + (t & 1) * 2048) = hi;
+      *reinterpret_cast<uint4*>(st + kAHalfBytes + (t >> 1) * 4096 + (t & 1) * 2048) = lo;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&pp.a_full[s]);
+    seq += 2;
   }
   __device__ __forceinline__ void flush() {
     const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     while (g != 0) put8(z);
+  }
+  __device__ __forceinline__ void zero_chunk() {
+    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+    for (int t = 0; t < 4; ++t) put8(z);
   }
 };
 
@@ -198,15 +235,14 @@ struct AProducer {
 template <int FMT>
 __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint32_t& b_seq, int N, int chunks,
                                           int region) {
-  const uint32_t id_hh = make_idesc_f16(fmt_hi(FMT), fmt_hi(FMT), kTileM, N);
-  const uint32_t id_lh = make_idesc_f16(fmt_lo(FMT), fmt_hi(FMT), kTileM, N);
-  const uint32_t id_hl = make_idesc_f16(fmt_hi(FMT), fmt_lo(FMT), kTileM, N);
+  const uint32_t id = make_idesc_f16(fmt_hi(FMT), fmt_hi(FMT), kTileM, N);
   const uint32_t dcol = pp.tmem_base + (uint32_t)region * 256u;
   const uint32_t a_base = smem_u32(pp.a_ring), b_base = smem_u32(pp.b_ring);
+#pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
     uint32_t sa = a_seq % kAStages, sb = b_seq % kBStages;
-    mbar_wait(&pp.a_full[sa], (a_seq / kAStages) & 1, pp.st, 200 + sa);
     mbar_wait(&pp.b_full[sb], (b_seq / kBStages) & 1, pp.st, 300 + sb);
+    mbar_wait(&pp.a_full[sa], (a_seq / kAStages) & 1, pp.st, 200 + sa);
     tc_fence_after_sync();
     uint32_t a_hi = a_base + sa * kAStageBytes, a_lo = a_hi + kAHalfBytes;
     uint32_t b_hi = b_base + sb * kBStageBytes, b_lo = b_hi + (uint32_t)N * 64u;
@@ -216,9 +252,10 @@ __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint3
       uint64_t da_lo = smem_desc(a_lo + s * 4096, 2048, 128);
       uint64_t db_hi = smem_desc(b_hi + s * (uint32_t)N * 32u, (uint32_t)N * 16u, 128);
       uint64_t db_lo = smem_desc(b_lo + s * (uint32_t)N * 32u, (uint32_t)N * 16u, 128);
-      umma_f16(dcol, da_hi, db_hi, id_hh, (c > 0 || s > 0) ? 1u : 0u);
-      umma_f16(dcol, da_lo, db_hi, id_lh, 1u);
-      umma_f16(dcol, da_hi, db_lo, id_hl, 1u);
+      // the two small cross terms first, then the dominant one
+      umma_f16(dcol, da_lo, db_hi, id, (c > 0 || s > 0) ? 1u : 0u);
+      umma_f16(dcol, da_hi, db_lo, id, 1u);
+      umma_f16(dcol, da_hi, db_hi, id, 1u);
     }
     umma_commit(&pp.a_empty[sa]);
     umma_commit(&pp.b_empty[sb]);
@@ -231,6 +268,7 @@ __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint3
 // weight loader: one thread.  All chunks of one layer.
 __device__ __forceinline__ void load_layer(const Pipe& pp, uint32_t& b_seq, const uint8_t* src, int N, int chunks) {
   const uint32_t bytes = (uint32_t)N * 128u;
+#pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
     uint32_t sb = b_seq % kBStages;
     mbar_wait(&pp.b_empty[sb], ((b_seq / kBStages) & 1) ^ 1, pp.st, 400 + sb);
@@ -246,20 +284,23 @@ __device__ __forceinline__ void load_layer(const Pipe& pp, uint32_t& b_seq, cons
 struct RowCtx {
   float p[3];          // world position of this row's sample
   const float* skt;    // this row's ray: [J][12] in shared memory
-  const float* vtab;   // this row's ray: view table
+  const float* vtab;   // this row's ray: view table [J_even][32]
   const float* fcode;  // this row's ray: frame code (16)
 };
 
-// layer-0 / skip-layer part: distance + bone encodings of the row's sample, 4 joints at a time
+// layer-0 / skip-layer part: distance + bone encodings of the row's sample for the joints of this
+// group's half, 4 joints at a time
 template <int FMT>
-__device__ __forceinline__ void produce_pts_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P) {
+__device__ __forceinline__ void produce_pts_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P, int grp) {
   const int J = P.prog.dims.J;
-  const int groups = ceil_div(J, kPtsGroupJoints);
-  for (int grp = 0; grp < groups; ++grp) {
+  const int hj = pts_half_joints(P.prog.dims);
+  const int j0 = grp * hj;
+#pragma unroll 1
+  for (int jg = 0; jg < hj / kPtsGroupJoints; ++jg) {
     float vals[kPtsGroupK];
 #pragma unroll
     for (int jj = 0; jj < kPtsGroupJoints; ++jj) {
-      int j = grp * kPtsGroupJoints + jj;
+      int j = j0 + jg * kPtsGroupJoints + jj;
       if (j < J) {
         encode_joint_pts(rc.skt + j * 12, rc.p, P.tau_p, P.cut_p[j], &vals[jj * kPtsPerJoint]);
       } else {
@@ -276,65 +317,66 @@ __device__ __forceinline__ void produce_pts_chunks(AProducer<FMT>& ap, const Row
     }
   }
   ap.flush();
+  // pad this half's stream to pts_half_chunks chunks
+  const int used = ceil_div(pts_half_k(P.prog.dims), kKC);
+  for (int c = used; c < pts_half_chunks(P.prog.dims); ++c) ap.zero_chunk();
 }
 
-// views-layer part: per-ray direction features times the per-sample cutoff weight, 8 joints at a time
+// views-layer part: one chunk per joint = the ray's 27 direction features of that joint (+5 zeros)
+// times the sample's cutoff weight; this group takes the joints of its parity
 template <int FMT>
-__device__ __forceinline__ void produce_view_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P) {
+__device__ __forceinline__ void produce_view_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P, int grp) {
   const int J = P.prog.dims.J;
-  const int groups = ceil_div(J, kViewGroupJoints);
-  for (int grp = 0; grp < groups; ++grp) {
-    float w[kViewGroupJoints];
+  const int JE = view_joint_chunks(P.prog.dims);
+#pragma unroll 1
+  for (int j = grp; j < JE; j += 2) {
+    float w = j < J ? cutoff_w(joint_dist(rc.skt + j * 12, rc.p), P.tau_v, P.cut_v[j]) : 0.f;
+    const float4* tab = reinterpret_cast<const float4*>(rc.vtab + j * kKC);
 #pragma unroll
-    for (int jj = 0; jj < kViewGroupJoints; ++jj) {
-      int j = grp * kViewGroupJoints + jj;
-      w[jj] = j < J ? cutoff_w(joint_dist(rc.skt + j * 12, rc.p), P.tau_v, P.cut_v[j]) : 0.f;
-    }
-    const float4* tab = reinterpret_cast<const float4*>(rc.vtab + grp * kViewGroupK);
-#pragma unroll
-    for (int t = 0; t < kViewGroupK / 8; ++t) {
+    for (int t = 0; t < 4; ++t) {
       float4 t0 = tab[2 * t], t1 = tab[2 * t + 1];
-      float x[8];
-      x[0] = t0.x * w[(8 * t + 0) / kViewPerJoint];
-      x[1] = t0.y * w[(8 * t + 1) / kViewPerJoint];
-      x[2] = t0.z * w[(8 * t + 2) / kViewPerJoint];
-      x[3] = t0.w * w[(8 * t + 3) / kViewPerJoint];
-      x[4] = t1.x * w[(8 * t + 4) / kViewPerJoint];
-      x[5] = t1.y * w[(8 * t + 5) / kViewPerJoint];
-      x[6] = t1.z * w[(8 * t + 6) / kViewPerJoint];
-      x[7] = t1.w * w[(8 * t + 7) / kViewPerJoint];
+      float x[8] = {t0.x * w, t0.y * w, t0.z * w, t0.w * w, t1.x * w, t1.y * w, t1.z * w, t1.w * w};
       ap.put8(x);
     }
   }
   if (P.prog.dims.fc_ch > 0) {
-    for (int t = 0; t < P.prog.dims.fc_ch / 8; ++t) {
-      float x[8];
+    if (grp == 0) {
+#pragma unroll 1
+      for (int t = 0; t < 4; ++t) {
+        float x[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = rc.fcode[8 * t + i];
-      ap.put8(x);
+        for (int i = 0; i < 8; ++i) x[i] = (8 * t + i) < P.prog.dims.fc_ch ? rc.fcode[(8 * t + i) & 15] : 0.f;
+        ap.put8(x);
+      }
+    } else {
+      ap.zero_chunk();
     }
   }
-  ap.flush();
 }
 
-// wait for the accumulators of the layer that used `region`, then walk them 32 columns at a time.
-// f(cb, x[32]) receives scale*acc + bias (ReLU applied when RELU).
-template <bool RELU, typename F>
+// Wait for the accumulators of the layer that used `region`, then walk this group's column blocks
+// (32 columns each, parity grp).  f(cb, x[32]) receives scale*acc + bias (ReLU applied when RELU).
+template <int FMT, bool RELU, typename F>
 __device__ __forceinline__ void drain_region(const Pipe& pp, uint32_t (&d_cnt)[2], int region, int N,
-                                             const float* bias, float scale, int warp, F&& f) {
-  mbar_wait(&pp.d_full[region], d_cnt[region] & 1, pp.st, 500 + region);
+                                             const float* bias, float scale, int quarter, int grp, F&& f) {
+  mbar_wait_warp(&pp.d_full[region], d_cnt[region] & 1, pp.st, 500 + region);
   ++d_cnt[region];
   tc_fence_after_sync();
-  const uint32_t taddr = pp.tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)region * 256u;
-  for (int cb = 0; cb < N / 32; ++cb) {
+  const uint32_t taddr = pp.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)region * 256u;
+#pragma unroll 1
+  for (int cb = grp; cb < N / 32; cb += 2) {
     uint32_t v[32];
     tmem_ld32(taddr + cb * 32, v);
     tmem_ld_wait();
     float x[32];
+    const float4* b4 = reinterpret_cast<const float4*>(bias + cb * 32);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      float y = fmaf(__uint_as_float(v[i]), scale, bias[cb * 32 + i]);
-      x[i] = RELU ? fmaxf(y, 0.f) : y;
+    for (int i = 0; i < 8; ++i) {
+      float4 b = b4[i];
+      float y0 = fmaf(__uint_as_float(v[4 * i + 0]), scale, b.x), y1 = fmaf(__uint_as_float(v[4 * i + 1]), scale, b.y);
+      float y2 = fmaf(__uint_as_float(v[4 * i + 2]), scale, b.z), y3 = fmaf(__uint_as_float(v[4 * i + 3]), scale, b.w);
+      if (RELU) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
+      x[4 * i + 0] = y0; x[4 * i + 1] = y1; x[4 * i + 2] = y2; x[4 * i + 3] = y3;
     }
     f(cb, x);
   }
@@ -342,67 +384,60 @@ __device__ __forceinline__ void drain_region(const Pipe& pp, uint32_t (&d_cnt)[2
 }
 
 template <int FMT>
-__device__ __forceinline__ void emit32(AProducer<FMT>& ap, const float (&x)[32]) {
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    float y[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = x[8 * t + i];
-    ap.put8(y);
-  }
-}
+__device__ __forceinline__ void emit32(AProducer<FMT>& ap, const float (&x)[32]) { ap.put32(x); }
 
-// One tile (128 rows) through one network.  Returns (rgb logits, raw sigma) of this thread's row.
-// DENSITY: trunk + alpha only.
+// One tile (128 rows) through one network, this group's share.  Returns this group's partial
+// (rgb logits, raw sigma) of the thread's row; the two groups' partials add up to the result
+// (biases are added by group 0).  DENSITY: trunk + alpha only.
 template <int FMT, bool DENSITY>
 __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe& pp, uint32_t (&d_cnt)[2],
                                                   const RowCtx& rc, const RenderKParams& P, const float* sm,
-                                                  int warp) {
+                                                  int quarter, int grp) {
   const NetProgram& pg = P.prog;
   const int D = pg.dims.D, W = pg.dims.W;
-  produce_pts_chunks<FMT>(ap, rc, P);                                   // layer 0 operand
-  for (int l = 1; l < D; ++l) {                                          // operand of trunk layer l
-    if ((l - 1) == pg.dims.skip) produce_pts_chunks<FMT>(ap, rc, P);
-    drain_region<true>(pp, d_cnt, (l - 1) & 1, W, sm + pg.sm.bias[l - 1], sm[l - 1], warp,
-                       [&](int, const float (&x)[32]) { emit32<FMT>(ap, x); });
-  }
   float sigma = 0.f;
   const float* wa = sm + pg.sm.alpha_w;
-  if (DENSITY) {
-    drain_region<true>(pp, d_cnt, (D - 1) & 1, W, sm + pg.sm.bias[D - 1], sm[D - 1], warp,
-                       [&](int cb, const float (&x)[32]) {
+  // operands of trunk layers 0..D-1 and of feature_linear (l == D): [encoding part] + drain of layer l-1
+#pragma unroll 1
+  for (int l = 0; l <= D; ++l) {
+    if (l == 0 || ((l - 1) == pg.dims.skip && l < D)) produce_pts_chunks<FMT>(ap, rc, P, grp);
+    if (l > 0) {
+      const bool last = (l == D);                 // h of the last trunk layer: alpha_linear in fp32 on the way
+      const bool emit = !(DENSITY && last);
+      drain_region<FMT, true>(pp, d_cnt, (l - 1) & 1, W, sm + pg.sm.bias[l - 1], sm[l - 1], quarter, grp,
+                              [&](int cb, const float (&x)[32]) {
+                                if (last) {
 #pragma unroll
-                         for (int i = 0; i < 32; ++i) sigma = fmaf(x[i], wa[cb * 32 + i], sigma);
-                       });
-    return make_float4(0.f, 0.f, 0.f, sigma + sm[pg.sm.alpha_b]);
+                                  for (int i = 0; i < 32; ++i) sigma = fmaf(x[i], wa[cb * 32 + i], sigma);
+                                }
+                                if (emit) emit32<FMT>(ap, x);
+                              });
+    }
   }
-  // operand of feature_linear (= h of the last trunk layer); alpha_linear in fp32 on the way
-  drain_region<true>(pp, d_cnt, (D - 1) & 1, W, sm + pg.sm.bias[D - 1], sm[D - 1], warp,
-                     [&](int cb, const float (&x)[32]) {
-#pragma unroll
-                       for (int i = 0; i < 32; ++i) sigma = fmaf(x[i], wa[cb * 32 + i], sigma);
-                       emit32<FMT>(ap, x);
-                     });
-  sigma += sm[pg.sm.alpha_b];
+  if (grp == 0) sigma += sm[pg.sm.alpha_b];
+  if (DENSITY) return make_float4(0.f, 0.f, 0.f, sigma);
   // operand of views_linears[0]: view encoding first (independent of feature), then feature (no ReLU)
-  produce_view_chunks<FMT>(ap, rc, P);
-  drain_region<false>(pp, d_cnt, D & 1, W, sm + pg.sm.bias[D], sm[D], warp,
-                      [&](int, const float (&x)[32]) { emit32<FMT>(ap, x); });
+  produce_view_chunks<FMT>(ap, rc, P, grp);
+  drain_region<FMT, false>(pp, d_cnt, D & 1, W, sm + pg.sm.bias[D], sm[D], quarter, grp,
+                           [&](int, const float (&x)[32]) { emit32<FMT>(ap, x); });
   // views layer output -> rgb_linear in fp32
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
   const float* wr = sm + pg.sm.rgb_w;
   const int H = W / 2;
-  drain_region<true>(pp, d_cnt, (D + 1) & 1, H, sm + pg.sm.bias[D + 1], sm[D + 1], warp,
-                     [&](int cb, const float (&x)[32]) {
+  drain_region<FMT, true>(pp, d_cnt, (D + 1) & 1, H, sm + pg.sm.bias[D + 1], sm[D + 1], quarter, grp,
+                          [&](int cb, const float (&x)[32]) {
 #pragma unroll
-                       for (int i = 0; i < 32; ++i) {
-                         r0 = fmaf(x[i], wr[cb * 32 + i], r0);
-                         r1 = fmaf(x[i], wr[H + cb * 32 + i], r1);
-                         r2 = fmaf(x[i], wr[2 * H + cb * 32 + i], r2);
-                       }
-                     });
-  const float* br = sm + pg.sm.rgb_b;
-  return make_float4(r0 + br[0], r1 + br[1], r2 + br[2], sigma);
+                            for (int i = 0; i < 32; ++i) {
+                              r0 = fmaf(x[i], wr[cb * 32 + i], r0);
+                              r1 = fmaf(x[i], wr[H + cb * 32 + i], r1);
+                              r2 = fmaf(x[i], wr[2 * H + cb * 32 + i], r2);
+                            }
+                          });
+  if (grp == 0) {
+    const float* br = sm + pg.sm.rgb_b;
+    r0 += br[0]; r1 += br[1]; r2 += br[2];
+  }
+  return make_float4(r0, r1, r2, sigma);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -418,10 +453,12 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-// a12 (nerf.py:150-205): alpha compositing of one ray.  z, raw: shared memory [S]; wts: shared [S] (out).
-__device__ __forceinline__ void composite_ray(int lane, int S, const float* z, const float4* raw, float dnorm,
-                                              const float* noise, const RenderKParams& P, float* wts,
+// a12 (nerf.py:150-205): alpha compositing of one ray.  z: shared [S]; raw0/raw1: the two worker groups'
+// partial network outputs (shared, [S] each); wts: shared [S] (out).
+__device__ __forceinline__ void composite_ray(int lane, int S, const float* z, const float4* raw0, const float4* raw1,
+                                              float dnorm, const float* noise, const RenderKParams& P, float* wts,
                                               float* alpha_out, float* rgb_out, float* disp_out, float* acc_out) {
   const int per = (S + 31) / 32;
   const int i0 = lane * per;
@@ -430,7 +467,7 @@ __device__ __forceinline__ void composite_ray(int lane, int S, const float* z, c
     int i = i0 + k;
     if (i < S) {
       float dist = (i + 1 < S ? z[i + 1] - z[i] : 1e10f) * dnorm;
-      float sg = density_act(raw[i].w, P.B, noise ? noise[i] : 0.f, P.softplus, P.shift);
+      float sg = density_act(raw0[i].w + raw1[i].w, P.B, noise ? noise[i] : 0.f, P.softplus, P.shift);
       float a = 1.f - expf(-sg * dist);
       wts[i] = a;
       prod *= (1.f - a + 1e-10f);
@@ -453,7 +490,7 @@ __device__ __forceinline__ void composite_ray(int lane, int S, const float* z, c
       T *= (1.f - a + 1e-10f);
       if (alpha_out) alpha_out[i] = a;
       wts[i] = w;
-      float4 r = raw[i];
+      float4 r = add4(raw0[i], raw1[i]);
       cr = fmaf(w, sigmoid_rgb(r.x), cr);
       cg = fmaf(w, sigmoid_rgb(r.y), cg);
       cb = fmaf(w, sigmoid_rgb(r.z), cb);
@@ -557,7 +594,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr);
 
   if (tid == 0) {
-    for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], kWorkerThreads); mbar_init(&pp.a_empty[i], 1); }
+    for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 4); mbar_init(&pp.a_empty[i], 1); }
     for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); }
     mbar_init(&pp.d_full[0], 1);
     mbar_init(&pp.d_full[1], 1);
@@ -579,15 +616,14 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
   pp.tmem_base = *tmem_slot;
 
   const int passes = DENSITY ? 1 : (P.tilesC + P.tilesF);
+  const int nl = DENSITY ? pg.dims.D : pg.n_layers;
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
       uint32_t a_seq = 0, b_seq = 0;
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x)
-        for (int ps = 0; ps < passes; ++ps) {
-          const int nl = DENSITY ? pg.dims.D : pg.n_layers;
+        for (int ps = 0; ps < passes; ++ps)
           for (int l = 0; l < nl; ++l) mma_layer<FMT>(pp, a_seq, b_seq, pg.layer[l].n, pg.layer[l].chunks, l & 1);
-        }
     }
     __syncwarp();
   } else if (warp == kLoadWarp) {
@@ -596,15 +632,15 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x)
         for (int ps = 0; ps < passes; ++ps) {
           const uint8_t* img = P.packed[(!DENSITY && ps >= P.tilesC) ? 1 : 0];
-          const int nl = DENSITY ? pg.dims.D : pg.n_layers;
           for (int l = 0; l < nl; ++l) load_layer(pp, b_seq, img + pg.layer[l].w_off, pg.layer[l].n, pg.layer[l].chunks);
         }
     }
     __syncwarp();
   } else {
     // ------------------------------- worker warps (rows) -------------------------------------
-    const int row = tid;
-    AProducer<FMT> ap(pp, row);
+    const int grp = warp >> 2, quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    AProducer<FMT> ap(pp, row, grp);
     uint32_t d_cnt[2] = {0u, 0u};
     float* ray_s = reinterpret_cast<float*>(smem + L.ray);
     float* skt_s = reinterpret_cast<float*>(smem + L.skt);
@@ -618,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
     const float* sm0 = reinterpret_cast<const float*>(smem + L.smalls0);
     const float* sm1 = reinterpret_cast<const float*>(smem + L.smalls1);
     const int J = pg.dims.J;
-    const int VK = view_k_enc(pg.dims);
+    const int VK = view_joint_chunks(pg.dims) * kKC;
 
     if (DENSITY) {
       // one pose for the whole launch
@@ -631,11 +667,16 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         RowCtx rc;
         rc.p[0] = P.pts[ci * 3 + 0]; rc.p[1] = P.pts[ci * 3 + 1]; rc.p[2] = P.pts[ci * 3 + 2];
         rc.skt = skt_s; rc.vtab = nullptr; rc.fcode = nullptr;
-        float4 r = worker_net_pass<FMT, true>(ap, pp, d_cnt, rc, P, sm0, warp);
-        if (valid) P.sigma[idx] = r.w;
+        float4 r = worker_net_pass<FMT, true>(ap, pp, d_cnt, rc, P, sm0, quarter, grp);
+        raw_s[grp * kTileM + row] = r;
+        worker_sync();
+        if (grp == 0 && valid) P.sigma[idx] = raw_s[row].w + raw_s[kTileM + row].w;
+        worker_sync();
       }
     } else {
       const int R = P.R, Sc = P.Sc, Sf = P.Sf, Si = P.Si;
+      const int cap = R * (Sf > Sc ? Sf : Sc);          // rows per group plane of raw_s
+      const bool fine = Si > 0;
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const int ray0 = item * R;
         // ---- (1) per-ray inputs -------------------------------------------------------------
@@ -665,15 +706,12 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         worker_sync();
         // ---- (2) per-ray view-direction table, coarse depths --------------------------------
         {
-          const int JV = ceil_div(J, kViewGroupJoints) * kViewGroupJoints;
-          for (int u = tid; u < R * JV; u += kWorkerThreads) {
-            int r = u / JV, j = u % JV;
-            float* o = vtab_s + r * VK + j * kViewPerJoint;
-            if (j < J) {
-              encode_joint_viewdir(skt_s + (r * J + j) * 12, ray_s + r * 12 + 3, o);
-            } else {
-              for (int q = 0; q < kViewPerJoint; ++q) o[q] = 0.f;
-            }
+          const int JE = view_joint_chunks(pg.dims);
+          for (int u = tid; u < R * JE; u += kWorkerThreads) {
+            int r = u / JE, j = u % JE;
+            float* o = vtab_s + r * VK + j * kKC;
+            if (j < J) encode_joint_viewdir(skt_s + (r * J + j) * 12, ray_s + r * 12 + 3, o);
+            for (int q = (j < J ? kViewPerJoint : 0); q < kKC; ++q) o[q] = 0.f;
           }
           for (int i = tid; i < R * Sc; i += kWorkerThreads) {
             int r = i / Sc, s = i % Sc;
@@ -693,80 +731,77 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
           }
         }
         worker_sync();
-        // ---- (3) coarse network ---------------------------------------------------------------
-        for (int t = 0; t < P.tilesC; ++t) {
-          int g = t * kTileM + row;
-          int r = g / Sc, s = g % Sc;
+        // ---- (3)/(6) network passes: tilesC coarse tiles, then tilesF fine tiles; (4)(5)(7) between ------
+#pragma unroll 1
+        for (int ps = 0; ps < passes; ++ps) {
+          const bool is_fine = ps >= P.tilesC;
+          const int S = is_fine ? Sf : Sc;
+          const float* zsrc = is_fine ? za_s : zc_s;
+          int g = (is_fine ? ps - P.tilesC : ps) * kTileM + row;
+          int r = g / S, s = g % S;
           bool valid = r < R;
-          if (!valid) { r = R - 1; s = Sc - 1; }
-          float z = zc_s[r * Sc + s];
+          if (!valid) { r = R - 1; s = S - 1; }
+          float z = zsrc[r * S + s];
           RowCtx rc;
           const float* rr = ray_s + r * 12;
           rc.p[0] = rr[0] + rr[3] * z; rc.p[1] = rr[1] + rr[4] * z; rc.p[2] = rr[2] + rr[5] * z;
-          rc.skt = skt_s + r * J * 12; rc.vtab = vtab_s + r * VK; rc.fcode = fc_s + r * 16;
-          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, sm0, warp);
-          if (valid) raw_s[g] = o;
+          rc.skt = skt_s + r * J * 12; rc.vtab = vtab_s + r * VK; rc.fcode = fc_s + ((is_fine ? R : 0) + r) * 16;
+          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, is_fine ? sm1 : sm0, quarter, grp);
+          if (valid) raw_s[grp * cap + g] = o;
+          if (ps == P.tilesC - 1) {
+            worker_sync();
+            // ---- (4) composite coarse ---------------------------------------------------------------
+            for (int q = warp; q < R; q += kWorkerWarps) {
+              int gr = ray0 + q;
+              bool live = gr < P.n_rays;
+              int grc = min(gr, P.n_rays - 1);
+              float* a_out = fine ? P.alpha0 : P.alpha;
+              float* rgb_o = fine ? P.rgb0 : P.rgb_map;
+              float* disp_o = fine ? P.disp0 : P.disp_map;
+              float* acc_o = fine ? P.acc0 : P.acc_map;
+              composite_ray(lane, Sc, zc_s + q * Sc, raw_s + q * Sc, raw_s + cap + q * Sc, ray_s[q * 12 + 8],
+                            P.noise0 ? P.noise0 + (size_t)grc * Sc : nullptr, P, w_s + q * Sc,
+                            (live && a_out) ? a_out + (size_t)gr * Sc : nullptr,
+                            (live && rgb_o) ? rgb_o + (size_t)gr * 3 : nullptr,
+                            (live && disp_o) ? disp_o + gr : nullptr, (live && acc_o) ? acc_o + gr : nullptr);
+              if (!fine && live && P.raw_out)
+                for (int i = lane; i < Sc; i += 32)
+                  reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sc + i] = add4(raw_s[q * Sc + i], raw_s[cap + q * Sc + i]);
+            }
+            worker_sync();   // raw_s is free from here (plane 0 is scratch for importance_ray)
+            if (fine) {
+              // ---- (5) importance sampling -------------------------------------------------------------
+              for (int q = warp; q < R; q += kWorkerWarps) {
+                int grc = min(ray0 + q, P.n_rays - 1);
+                importance_ray(lane, Sc, Si, zc_s + q * Sc, w_s + q * Sc,
+                               P.u_rand ? P.u_rand + (size_t)grc * Si : nullptr, cdf_s + q * Sc,
+                               reinterpret_cast<float*>(raw_s) + q * Sf, za_s + q * Sf);
+                if (P.z_all_out && ray0 + q < P.n_rays)
+                  for (int i = lane; i < Sf; i += 32) P.z_all_out[(size_t)(ray0 + q) * Sf + i] = za_s[q * Sf + i];
+              }
+              worker_sync();
+            }
+          }
         }
-        worker_sync();
-        // ---- (4) composite coarse, (5) importance sampling -------------------------------------
-        const bool fine = Si > 0;
-        for (int r = warp; r < R; r += 4) {
-          int gr = ray0 + r;
-          bool live = gr < P.n_rays;
-          int grc = min(gr, P.n_rays - 1);
-          float* a_out = fine ? P.alpha0 : P.alpha;
-          float* rgb_o = fine ? P.rgb0 : P.rgb_map;
-          float* disp_o = fine ? P.disp0 : P.disp_map;
-          float* acc_o = fine ? P.acc0 : P.acc_map;
-          composite_ray(lane, Sc, zc_s + r * Sc, raw_s + r * Sc, ray_s[r * 12 + 8],
-                        P.noise0 ? P.noise0 + (size_t)grc * Sc : nullptr, P, w_s + r * Sc,
-                        (live && a_out) ? a_out + (size_t)gr * Sc : nullptr,
-                        (live && rgb_o) ? rgb_o + (size_t)gr * 3 : nullptr,
-                        (live && disp_o) ? disp_o + gr : nullptr, (live && acc_o) ? acc_o + gr : nullptr);
-          if (!fine && live && P.raw_out)
-            for (int i = lane; i < Sc; i += 32) reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sc + i] = raw_s[r * Sc + i];
+        if (fine) {
+          worker_sync();
+          // ---- (7) composite fine ------------------------------------------------------------------
+          for (int q = warp; q < R; q += kWorkerWarps) {
+            int gr = ray0 + q;
+            bool live = gr < P.n_rays;
+            int grc = min(gr, P.n_rays - 1);
+            composite_ray(lane, Sf, za_s + q * Sf, raw_s + q * Sf, raw_s + cap + q * Sf, ray_s[q * 12 + 8],
+                          P.noise1 ? P.noise1 + (size_t)grc * Sf : nullptr, P, w_s + q * Sf,
+                          (live && P.alpha) ? P.alpha + (size_t)gr * Sf : nullptr,
+                          (live && P.rgb_map) ? P.rgb_map + (size_t)gr * 3 : nullptr,
+                          (live && P.disp_map) ? P.disp_map + gr : nullptr,
+                          (live && P.acc_map) ? P.acc_map + gr : nullptr);
+            if (live && P.raw_out)
+              for (int i = lane; i < Sf; i += 32)
+                reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sf + i] = add4(raw_s[q * Sf + i], raw_s[cap + q * Sf + i]);
+          }
+          worker_sync();
         }
-        if (!fine) { worker_sync(); continue; }
-        worker_sync();   // raw_s is free from here (used as scratch by importance_ray)
-        for (int r = warp; r < R; r += 4) {
-          int grc = min(ray0 + r, P.n_rays - 1);
-          importance_ray(lane, Sc, Si, zc_s + r * Sc, w_s + r * Sc,
-                         P.u_rand ? P.u_rand + (size_t)grc * Si : nullptr, cdf_s + r * Sc,
-                         reinterpret_cast<float*>(raw_s) + r * Sf, za_s + r * Sf);
-          if (P.z_all_out && ray0 + r < P.n_rays)
-            for (int i = lane; i < Sf; i += 32) P.z_all_out[(size_t)(ray0 + r) * Sf + i] = za_s[r * Sf + i];
-        }
-        worker_sync();
-        // ---- (6) fine network on all sorted samples --------------------------------------------
-        for (int t = 0; t < P.tilesF; ++t) {
-          int g = t * kTileM + row;
-          int r = g / Sf, s = g % Sf;
-          bool valid = r < R;
-          if (!valid) { r = R - 1; s = Sf - 1; }
-          float z = za_s[r * Sf + s];
-          RowCtx rc;
-          const float* rr = ray_s + r * 12;
-          rc.p[0] = rr[0] + rr[3] * z; rc.p[1] = rr[1] + rr[4] * z; rc.p[2] = rr[2] + rr[5] * z;
-          rc.skt = skt_s + r * J * 12; rc.vtab = vtab_s + r * VK; rc.fcode = fc_s + (R + r) * 16;
-          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, sm1, warp);
-          if (valid) raw_s[g] = o;
-        }
-        worker_sync();
-        // ---- (7) composite fine ------------------------------------------------------------------
-        for (int r = warp; r < R; r += 4) {
-          int gr = ray0 + r;
-          bool live = gr < P.n_rays;
-          int grc = min(gr, P.n_rays - 1);
-          composite_ray(lane, Sf, za_s + r * Sf, raw_s + r * Sf, ray_s[r * 12 + 8],
-                        P.noise1 ? P.noise1 + (size_t)grc * Sf : nullptr, P, w_s + r * Sf,
-                        (live && P.alpha) ? P.alpha + (size_t)gr * Sf : nullptr,
-                        (live && P.rgb_map) ? P.rgb_map + (size_t)gr * 3 : nullptr,
-                        (live && P.disp_map) ? P.disp_map + gr : nullptr,
-                        (live && P.acc_map) ? P.acc_map + gr : nullptr);
-          if (live && P.raw_out)
-            for (int i = lane; i < Sf; i += 32) reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sf + i] = raw_s[r * Sf + i];
-        }
-        worker_sync();
       }
     }
   }
@@ -898,6 +933,7 @@ __global__ void anerf_pack_framecodes_kernel(const float* __restrict__ codes, in
 
 // ------------------------------------------------------------------------------------------------
 // self test: D[128,N] = A[128,K] * B[N,K]^T through exactly the producer / loader / MMA / drain code
+// (K/32 must be even: chunks are dealt to the two worker groups by parity)
 // ------------------------------------------------------------------------------------------------
 template <int FMT>
 __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const float* __restrict__ A,
@@ -908,6 +944,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAStages * kAStageBytes + kBStages * kBStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kAStages + 2 * kBStages + 2);
+  float* zero_bias = reinterpret_cast<float*>(tmem_slot + 4);
   Pipe pp;
   pp.a_ring = smem;
   pp.b_ring = smem + kAStages * kAStageBytes;
@@ -918,13 +955,14 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const 
   pp.d_full = bars + 2 * kAStages + 2 * kBStages;
   pp.st = status;
   if (tid == 0) {
-    for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], kWorkerThreads); mbar_init(&pp.a_empty[i], 1); }
+    for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 4); mbar_init(&pp.a_empty[i], 1); }
     for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); }
     mbar_init(&pp.d_full[0], 1);
     mbar_init(&pp.d_full[1], 1);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
+  for (int i = tid; i < 256; i += kThreads) zero_bias[i] = 0.f;
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -944,23 +982,22 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const 
     }
     __syncwarp();
   } else {
-    AProducer<FMT> ap(pp, tid);
+    const int grp = warp >> 2, quarter = warp & 3, row = quarter * 32 + lane;
+    AProducer<FMT> ap(pp, row, grp);
     uint32_t d_cnt[2] = {0u, 0u};
     for (int rep = 0; rep < 2; ++rep) {
-      for (int k8 = 0; k8 < K / 8; ++k8) {
-        float x[8];
+      for (int c = grp; c < chunks; c += 2)
+        for (int k8 = 0; k8 < 4; ++k8) {
+          float x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = A[(size_t)tid * K + k8 * 8 + i];
-        ap.put8(x);
-      }
+          for (int i = 0; i < 8; ++i) x[i] = A[(size_t)row * K + c * kKC + k8 * 8 + i];
+          ap.put8(x);
+        }
     }
-    __shared__ float zero_bias[256];
-    for (int i = tid; i < 256; i += kWorkerThreads) zero_bias[i] = 0.f;
-    worker_sync();
     for (int rep = 0; rep < 2; ++rep) {
-      drain_region<false>(pp, d_cnt, rep, N, zero_bias, 1.0f, warp, [&](int cb, const float (&x)[32]) {
+      drain_region<1, false>(pp, d_cnt, rep, N, zero_bias, 1.0f, quarter, grp, [&](int cb, const float (&x)[32]) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) Dout[(size_t)rep * kTileM * N + (size_t)tid * N + cb * 32 + i] = x[i];
+        for (int i = 0; i < 32; ++i) Dout[(size_t)rep * kTileM * N + (size_t)row * N + cb * 32 + i] = x[i];
       });
     }
   }

@@ -45,22 +45,27 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
+// One probe of the barrier phase.  With the suspend-time hint the thread sleeps in hardware
+// (SASS: TRYWAIT + NANOSLEEP.SYNCS) until the phase completes or ~`kSuspendNs` elapse, so a waiting
+// thread does not burn issue slots of its SM sub-partition.
+constexpr uint32_t kSuspendNs = 100000u;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendNs)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: ~seconds at any clock, then record + trap (never spin forever on a protocol bug).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, DeviceStatus* st, unsigned int site) {
   if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
+    if (t0 == 0) { t0 = clock64(); continue; }
     if (clock64() - t0 > 6000000000LL) {
       if (st != nullptr && atomicCAS(&st->code, 0u, (unsigned)kErrWaitTimeout) == 0u) {
         st->where = site;
@@ -185,15 +190,16 @@ template <> struct Split<1> {  // bf16
     lo = *reinterpret_cast<uint32_t*>(&l);
   }
 };
-template <> struct Split<0> {  // fp16 (values must be within half range; used with pre-scaled weights)
+template <> struct Split<0> {  // fp16; conversions saturate at +-65504 so an out-of-range value never becomes inf/NaN
+  static __device__ __forceinline__ uint32_t cvt2(float lo_half, float hi_half) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_half), "f"(lo_half));
+    return r;
+  }
   static __device__ __forceinline__ void pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-    a = fminf(fmaxf(a, -65504.f), 65504.f);
-    b = fminf(fmaxf(b, -65504.f), 65504.f);
-    __half2 h = __floats2half2_rn(a, b);
-    float2 hf = __half22float2(h);
-    __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-    hi = *reinterpret_cast<uint32_t*>(&h);
-    lo = *reinterpret_cast<uint32_t*>(&l);
+    hi = cvt2(a, b);
+    float2 hf = __half22float2(*reinterpret_cast<__half2*>(&hi));
+    lo = cvt2(a - hf.x, b - hf.y);
   }
 };
 

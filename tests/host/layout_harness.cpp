@@ -17,37 +17,41 @@ int h_layer_ref_col(int J, int D, int W, int skip, int fc, int l, int k) {
   NetDims d{J, D, W, skip, fc, fc ? 4 : 0};
   return layer_ref_col(d, l, k);
 }
-// emission order of produce_pts_chunks: groups of 4 joints x 18 values, zero padded to whole chunks
+// emission order of produce_pts_chunks: group g (= half g of the joints) streams its joint groups
+// (4 joints x 18 values) into the chunks of parity g
 void h_emit_pts(const float* skt /*[J][12]*/, const float* p, float tau, const float* cut, int J, float* out) {
   NetDims d{J, 8, 256, 4, 0, 0};
   int n = pts_chunks(d) * kKC;
   memset(out, 0, n * sizeof(float));
-  int groups = ceil_div(J, kPtsGroupJoints);
-  int k = 0;
-  for (int g = 0; g < groups; ++g)
-    for (int jj = 0; jj < kPtsGroupJoints; ++jj, k += kPtsPerJoint) {
-      int j = g * kPtsGroupJoints + jj;
-      if (j < J) encode_joint_pts(skt + j * 12, p, tau, cut[j], out + k);
-    }
+  int hj = pts_half_joints(d);
+  for (int grp = 0; grp < 2; ++grp) {
+    int hk = 0;   // position in this half's stream
+    for (int jg = 0; jg < hj / kPtsGroupJoints; ++jg)
+      for (int jj = 0; jj < kPtsGroupJoints; ++jj) {
+        int j = grp * hj + jg * kPtsGroupJoints + jj;
+        float v[kPtsPerJoint];
+        memset(v, 0, sizeof(v));
+        if (j < J) encode_joint_pts(skt + j * 12, p, tau, cut[j], v);
+        for (int q = 0; q < kPtsPerJoint; ++q, ++hk) {
+          int chunk = 2 * (hk / kKC) + grp;
+          out[chunk * kKC + hk % kKC] = v[q];
+        }
+      }
+  }
 }
-// emission order of produce_view_chunks
+// emission order of produce_view_chunks: joint j in chunk j (27 values + 5 zeros); framecode chunk after
 void h_emit_view(const float* skt, const float* dir, const float* p, float tau, const float* cut, int J,
                  const float* fcode, int fc, float* out) {
   NetDims d{J, 8, 256, 4, fc, fc ? 4 : 0};
   int n = view_chunks(d) * kKC;
   memset(out, 0, n * sizeof(float));
-  int groups = ceil_div(J, kViewGroupJoints);
-  int k = 0;
-  for (int g = 0; g < groups; ++g)
-    for (int jj = 0; jj < kViewGroupJoints; ++jj, k += kViewPerJoint) {
-      int j = g * kViewGroupJoints + jj;
-      if (j >= J) continue;
-      float tab[kViewPerJoint];
-      encode_joint_viewdir(skt + j * 12, dir, tab);
-      float w = cutoff_w(joint_dist(skt + j * 12, p), tau, cut[j]);
-      for (int q = 0; q < kViewPerJoint; ++q) out[k + q] = tab[q] * w;
-    }
-  for (int q = 0; q < fc; ++q) out[k + q] = fcode[q];
+  for (int j = 0; j < J; ++j) {
+    float tab[kViewPerJoint];
+    encode_joint_viewdir(skt + j * 12, dir, tab);
+    float w = cutoff_w(joint_dist(skt + j * 12, p), tau, cut[j]);
+    for (int q = 0; q < kViewPerJoint; ++q) out[j * kKC + q] = tab[q] * w;
+  }
+  for (int q = 0; q < fc; ++q) out[view_joint_chunks(d) * kKC + q] = fcode[q];
 }
 float h_linspace01(int i, int n) { return linspace01(i, n); }
 void h_near_far(const float* o, const float* d, const float* cyl, float near, float far, float* out) {
