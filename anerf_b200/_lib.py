@@ -12,7 +12,7 @@ _lib = None
 
 SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "anerf_pack_net",
            "anerf_render_workspace_bytes", "anerf_render_fwd", "anerf_render_fwd_host", "anerf_density_points",
-           "anerf_selftest_gemm", "anerf_last_error", "anerf_version"]
+           "anerf_selftest_gemm", "anerf_last_error", "anerf_version", "anerf_debug_set_trace"]
 
 
 class NetConfig(C.Structure):
@@ -72,6 +72,8 @@ def load():
     lib.anerf_density_points.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p]
     lib.anerf_selftest_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.anerf_debug_set_trace.argtypes = [C.c_void_p]
+    lib.anerf_debug_set_trace.restype = None
     _lib = lib
     return lib
 
@@ -209,6 +211,6 @@ def density_points(plan, packed, opts, pts, skts):
 
 def selftest_gemm(A, B, fmt):
     N, K = B.shape
-    D = torch.empty(2, 128, N, dtype=torch.float32, device=A.device)
+    D = torch.empty(2, 256, N, dtype=torch.float32, device=A.device)
     check(load().anerf_selftest_gemm(_ptr(A), _ptr(B), _ptr(D), N, K, fmt, _stream()))
     return D

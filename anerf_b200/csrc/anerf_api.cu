@@ -49,6 +49,8 @@ int ensure_status() {
   return 0;
 }
 
+long long* g_trace = nullptr;
+
 int check_device_status() {
   if (g_status_host && g_status_host->code != 0) {
     return fail(ANERF_ERR_DEVICE, "device protocol error code=%u site=%u block=%u thread=%u", g_status_host->code,
@@ -73,6 +75,8 @@ extern "C" {
 
 const char* anerf_last_error(void) { return g_err.c_str(); }
 int anerf_version(void) { return 100; }
+/* debug: device buffer of 3 x 1024 int64 that the next launches fill with a clock64 timeline of CTA 0 (NULL = off) */
+void anerf_debug_set_trace(long long* device_buffer) { g_trace = device_buffer; }
 
 int anerf_plan_create(const anerf_net_config* cfg, anerf_plan** out) {
   if (!cfg || !out) return fail(ANERF_ERR_INVALID, "null argument");
@@ -183,14 +187,28 @@ static int launch_fused(const anerf_plan* plan, RenderKParams& P, bool density, 
   int rc = ensure_status();
   if (rc) return rc;
   P.status = g_status_dev;
+  P.trace = g_trace;
   if (P.sl.total > plan->max_smem) return fail(ANERF_ERR_INVALID, "configuration needs %d B of shared memory (> %d)", P.sl.total, plan->max_smem);
+  // CTAs run as pairs (cluster of 2, cta_group::2 MMAs): an even grid, at most one CTA per SM
   int grid = P.n_items < plan->n_sm ? P.n_items : plan->n_sm;
   if (grid < 1) return ANERF_OK;
+  grid = (grid + 1) & ~1;
+  if (grid > (plan->n_sm & ~1)) grid = plan->n_sm & ~1;
   const int fmt = plan->cfg.operand_format;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = P.sl.total;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
 #define ANERF_LAUNCH(FMT, DENS)                                                                              \
   do {                                                                                                       \
     CUDA_TRY(cudaFuncSetAttribute(anerf_fused_kernel<FMT, DENS>, cudaFuncAttributeMaxDynamicSharedMemorySize, P.sl.total)); \
-    anerf_fused_kernel<FMT, DENS><<<grid, kThreads, P.sl.total, stream>>>(P);                              \
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, anerf_fused_kernel<FMT, DENS>, P));                                    \
   } while (0)
   if (fmt == 1) { if (density) ANERF_LAUNCH(1, true); else ANERF_LAUNCH(1, false); }
   else          { if (density) ANERF_LAUNCH(0, true); else ANERF_LAUNCH(0, false); }
@@ -335,12 +353,22 @@ int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int
   CUDA_TRY(cudaMalloc((void**)&d_pack, (size_t)chunks * N * 128));
   CUDA_TRY(cudaMemcpy(d_km, km.data(), K * sizeof(int), cudaMemcpyHostToDevice));
   int blocks = (chunks * N * 4 + 255) / 256;
-  int smem = kAStages * kAStageBytes + kBStages * kBStageBytes + 8 * (2 * kAStages + 2 * kBStages + 2) + 16 + 1024;
+  int smem = kAStages * kAStageBytes + kBStages * kBStageBytes + 8 * kNumBars + 16 + 1024;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
 #define ANERF_ST(FMT)                                                                                       \
   do {                                                                                                      \
     anerf_pack_layer_kernel<FMT><<<blocks, 256, 0, stream>>>(B, K, d_km, N, chunks, d_one, d_pack);          \
     cudaFuncSetAttribute(anerf_selftest_gemm_kernel<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); \
-    anerf_selftest_gemm_kernel<FMT><<<1, kThreads, smem, stream>>>(A, d_pack, D, N, K, g_status_dev);       \
+    cudaLaunchKernelEx(&cfg, anerf_selftest_gemm_kernel<FMT>, A, (const uint8_t*)d_pack, D, (int)N, (int)K, g_status_dev); \
   } while (0)
   if (format == 0) ANERF_ST(0); else ANERF_ST(1);
 #undef ANERF_ST

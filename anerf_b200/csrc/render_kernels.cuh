@@ -10,11 +10,14 @@
 //     by computing the encodings of their sample (bone-local transform, cutoff positional encoding)
 //     or by draining the previous layer's accumulators from TMEM (bias, ReLU), split every value into
 //     hi + lo 16-bit parts and store them in the UMMA K-major core-matrix layout (A ring);
-//   * 1 loader thread streams the pre-packed weights (same layout, hi + lo) from L2 with 1-D bulk
-//     TMA copies into the B ring;
-//   * 1 MMA thread issues, per chunk, 2 K-slabs x 3 tcgen05.mma (hi*hi + lo*hi + hi*lo) into a
-//     128 x N fp32 accumulator in TMEM; accumulators ping-pong between two 256-column regions so the
-//     drain of layer l overlaps the MMAs of layer l+1 chunk by chunk.
+//   * 1 loader thread per CTA streams this CTA's half (N/2 rows) of the pre-packed weight chunks
+//     (same layout, hi + lo) from L2 with 1-D bulk TMA copies into the B ring;
+//   * CTAs run as pairs (cluster of 2, cta_group::2): 1 MMA thread in the leader CTA issues, per chunk,
+//     2 K-slabs x 3 tcgen05.mma (lo*hi + hi*lo + hi*hi) of shape M=256 (both CTAs' 128 rows) x N into
+//     128 x N fp32 accumulators in each CTA's TMEM; every SM reads its own A rows and only half of B
+//     from its shared memory.  Accumulators ping-pong between two 256-column regions so the drain of
+//     layer l overlaps the MMAs of layer l+1 chunk by chunk.  The peer CTA's spare warp relays
+//     "my weight half has landed" to the leader.
 // Layer program and K layout: path_math.cuh.  Protocol: mbarrier full/empty rings, bounded waits.
 #pragma once
 #include "tc_sm100.cuh"
@@ -23,10 +26,11 @@
 namespace anerf {
 
 constexpr int kAStages = 4;
-constexpr int kBStages = 3;
+constexpr int kBStages = 6;
 constexpr int kAHalfBytes = kTileM * kKC * 2;        // 8 KB: hi (or lo) part of one A chunk
 constexpr int kAStageBytes = 2 * kAHalfBytes;        // 16 KB
-constexpr int kBStageBytes = 256 * kKC * 2 * 2;      // 32 KB (N = 256)
+constexpr int kBStageBytes = 128 * kKC * 2 * 2;      // 16 KB: this CTA's half (N/2 <= 128 rows) of a weight chunk, hi + lo
+constexpr int kNumBars = 2 * kAStages + 3 * kBStages + 2;
 constexpr int kMaxLayers = 10;
 constexpr int kWorkerWarps = 8;                      // two groups of 4 warps; group g owns the A chunks of parity g
 constexpr int kWorkerThreads = kWorkerWarps * 32;
@@ -114,7 +118,7 @@ inline __host__ __device__ SmemLayout make_smem_layout(const NetDims& d, int sma
   L.raw = off; off += 2 * rows * 16;         // [group][row] partial (r,g,b,sigma)
   L.wts = off; off += align_up(rows * 4, 16);
   L.cdf = off; off += align_up(R * Sc * 4, 16);
-  L.bars = off; off += 8 * (2 * kAStages + 2 * kBStages + 2);
+  L.bars = off; off += 8 * kNumBars;
   L.tmem_ptr = off; off += 16;
   L.total = off;
   return L;
@@ -136,6 +140,7 @@ struct RenderKParams {
   float* sigma;
   long long n_points;
   DeviceStatus* status;
+  long long* trace;         // optional debug timeline (anerf_debug_set_trace): [3 streams][1024] clock64 stamps of CTA 0
   SmemLayout sl;
 };
 
@@ -151,10 +156,37 @@ struct Pipe {
   uint64_t* a_empty;
   uint64_t* b_full;
   uint64_t* b_empty;
+  uint64_t* peer_b;    // leader only: the peer CTA's weight half of stage s has landed
   uint64_t* d_full;    // [2]
   uint32_t tmem_base;
+  uint32_t rank;       // CTA rank in the pair (0 = leader)
   DeviceStatus* st;
 };
+
+__device__ __forceinline__ void pipe_init(Pipe& pp, uint8_t* a_ring, uint8_t* b_ring, uint64_t* bars, DeviceStatus* st) {
+  pp.a_ring = a_ring;
+  pp.b_ring = b_ring;
+  pp.a_full = bars;
+  pp.a_empty = bars + kAStages;
+  pp.b_full = bars + 2 * kAStages;
+  pp.b_empty = bars + 2 * kAStages + kBStages;
+  pp.peer_b = bars + 2 * kAStages + 2 * kBStages;
+  pp.d_full = bars + 2 * kAStages + 3 * kBStages;
+  pp.rank = cluster_ctarank();
+  pp.st = st;
+}
+// thread 0 of each CTA; followed by a cluster-wide sync
+__device__ __forceinline__ void pipe_init_barriers(const Pipe& pp) {
+  for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 8); mbar_init(&pp.a_empty[i], 1); }   // 4 warps x 2 CTAs
+  for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); mbar_init(&pp.peer_b[i], 1); }
+  mbar_init(&pp.d_full[0], 1);
+  mbar_init(&pp.d_full[1], 1);
+  fence_mbar_init();
+}
+// a chunk of this CTA's A rows is complete: tell the leader's MMA thread
+__device__ __forceinline__ void a_chunk_ready(const Pipe& pp, uint32_t stage) {
+  if (pp.rank == 0) mbar_arrive(&pp.a_full[stage]); else mbar_arrive_remote(&pp.a_full[stage], 0);
+}
 
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -193,7 +225,7 @@ struct AProducer {
     if (++g == 4) {
       fence_proxy_async_smem();            // this thread's stores -> visible to the tensor core's reads
       __syncwarp();
-      if ((threadIdx.x & 31) == 0) mbar_arrive(&pp.a_full[seq % kAStages]);   // 4 warp arrivals per chunk
+      if ((threadIdx.x & 31) == 0) a_chunk_ready(pp, seq % kAStages);   // 4 warp arrivals per CTA per chunk
       seq += 2;
       g = 0;
     }
@@ -215,7 +247,7 @@ struct AProducer {
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(&pp.a_full[s]);
+    if ((threadIdx.x & 31) == 0) a_chunk_ready(pp, s);
     seq += 2;
   }
   __device__ __forceinline__ void flush() {
@@ -229,29 +261,42 @@ struct AProducer {
   }
 };
 
+// debug timeline: stream 0 = MMA thread, 1 = worker group 0 (warp 0), 2 = worker group 1 (warp 4); CTA 0 only
+struct Trace {
+  long long* p;
+  int n;
+  __device__ __forceinline__ void init(long long* base, int stream) { p = (base && blockIdx.x == 0) ? base + stream * 1024 : nullptr; n = 0; }
+  __device__ __forceinline__ void mark(int tag) {
+    if (p && n < 1022) { p[n++] = ((long long)tag << 48) | (clock64() & 0xFFFFFFFFFFFFLL); p[1023] = n; }
+  }
+};
+
 // ------------------------------------------------------------------------------------------------
-// MMA issuer: one thread.  All chunks of one layer.
+// MMA issuer: one thread of the leader CTA.  All chunks of one layer, for both CTAs of the pair.
 // ------------------------------------------------------------------------------------------------
 template <int FMT>
 __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint32_t& b_seq, int N, int chunks,
-                                          int region) {
-  const uint32_t id = make_idesc_f16(fmt_hi(FMT), fmt_hi(FMT), kTileM, N);
+                                          int region, Trace* tr = nullptr) {
+  const uint32_t id = make_idesc_f16(fmt_hi(FMT), fmt_hi(FMT), 2 * kTileM, N);
   const uint32_t dcol = pp.tmem_base + (uint32_t)region * 256u;
   const uint32_t a_base = smem_u32(pp.a_ring), b_base = smem_u32(pp.b_ring);
+  const uint32_t NH = (uint32_t)N / 2;           // B rows held by each CTA
 #pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
     uint32_t sa = a_seq % kAStages, sb = b_seq % kBStages;
     mbar_wait(&pp.b_full[sb], (b_seq / kBStages) & 1, pp.st, 300 + sb);
-    mbar_wait(&pp.a_full[sa], (a_seq / kAStages) & 1, pp.st, 200 + sa);
+    mbar_wait_cluster(&pp.peer_b[sb], (b_seq / kBStages) & 1, pp.st, 320 + sb);
+    mbar_wait_cluster(&pp.a_full[sa], (a_seq / kAStages) & 1, pp.st, 200 + sa);
     tc_fence_after_sync();
+    if (tr) tr->mark(c == 0 ? 1 : 2);        // 1: first chunk of a layer ready, 2: later chunk ready
     uint32_t a_hi = a_base + sa * kAStageBytes, a_lo = a_hi + kAHalfBytes;
-    uint32_t b_hi = b_base + sb * kBStageBytes, b_lo = b_hi + (uint32_t)N * 64u;
+    uint32_t b_hi = b_base + sb * kBStageBytes, b_lo = b_hi + NH * 64u;
 #pragma unroll
     for (int s = 0; s < 2; ++s) {
       uint64_t da_hi = smem_desc(a_hi + s * 4096, 2048, 128);
       uint64_t da_lo = smem_desc(a_lo + s * 4096, 2048, 128);
-      uint64_t db_hi = smem_desc(b_hi + s * (uint32_t)N * 32u, (uint32_t)N * 16u, 128);
-      uint64_t db_lo = smem_desc(b_lo + s * (uint32_t)N * 32u, (uint32_t)N * 16u, 128);
+      uint64_t db_hi = smem_desc(b_hi + s * NH * 32u, NH * 16u, 128);
+      uint64_t db_lo = smem_desc(b_lo + s * NH * 32u, NH * 16u, 128);
       // the two small cross terms first, then the dominant one
       umma_f16(dcol, da_lo, db_hi, id, (c > 0 || s > 0) ? 1u : 0u);
       umma_f16(dcol, da_hi, db_lo, id, 1u);
@@ -263,17 +308,31 @@ __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint3
     ++b_seq;
   }
   umma_commit(&pp.d_full[region]);
+  if (tr) tr->mark(3);                       // 3: layer fully issued
 }
 
-// weight loader: one thread.  All chunks of one layer.
+// weight loader: one thread per CTA.  This CTA's half of every chunk of one layer.
+// packed chunk = [half 0: hi, lo][half 1: hi, lo], each half N*64 bytes.
 __device__ __forceinline__ void load_layer(const Pipe& pp, uint32_t& b_seq, const uint8_t* src, int N, int chunks) {
-  const uint32_t bytes = (uint32_t)N * 128u;
+  const uint32_t bytes = (uint32_t)N * 64u;
+  src += (size_t)pp.rank * bytes;
 #pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
     uint32_t sb = b_seq % kBStages;
     mbar_wait(&pp.b_empty[sb], ((b_seq / kBStages) & 1) ^ 1, pp.st, 400 + sb);
     mbar_arrive_expect_tx(&pp.b_full[sb], bytes);
-    bulk_g2s(pp.b_ring + sb * kBStageBytes, src + (size_t)c * bytes, bytes, &pp.b_full[sb]);
+    bulk_g2s(pp.b_ring + sb * kBStageBytes, src + (size_t)c * 2 * bytes, bytes, &pp.b_full[sb]);
+    ++b_seq;
+  }
+}
+
+// peer CTA only, one thread: forward "my half of stage s has landed" to the leader's MMA thread
+__device__ __forceinline__ void relay_layer(const Pipe& pp, uint32_t& b_seq, int chunks) {
+#pragma unroll 1
+  for (int c = 0; c < chunks; ++c) {
+    uint32_t sb = b_seq % kBStages;
+    mbar_wait(&pp.b_full[sb], (b_seq / kBStages) & 1, pp.st, 600 + sb);
+    mbar_arrive_remote(&pp.peer_b[sb], 0);
     ++b_seq;
   }
 }
@@ -358,10 +417,13 @@ __device__ __forceinline__ void produce_view_chunks(AProducer<FMT>& ap, const Ro
 // (32 columns each, parity grp).  f(cb, x[32]) receives scale*acc + bias (ReLU applied when RELU).
 template <int FMT, bool RELU, typename F>
 __device__ __forceinline__ void drain_region(const Pipe& pp, uint32_t (&d_cnt)[2], int region, int N,
-                                             const float* bias, float scale, int quarter, int grp, F&& f) {
+                                             const float* bias, float scale, int quarter, int grp, F&& f,
+                                             Trace* tr = nullptr) {
+  if (tr) tr->mark(10);                      // 10: start waiting for the layer's accumulators
   mbar_wait_warp(&pp.d_full[region], d_cnt[region] & 1, pp.st, 500 + region);
   ++d_cnt[region];
   tc_fence_after_sync();
+  if (tr) tr->mark(11);                      // 11: accumulators ready
   const uint32_t taddr = pp.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)region * 256u;
 #pragma unroll 1
   for (int cb = grp; cb < N / 32; cb += 2) {
@@ -379,6 +441,7 @@ __device__ __forceinline__ void drain_region(const Pipe& pp, uint32_t (&d_cnt)[2
       x[4 * i + 0] = y0; x[4 * i + 1] = y1; x[4 * i + 2] = y2; x[4 * i + 3] = y3;
     }
     f(cb, x);
+    if (tr) tr->mark(12);                    // 12: one column block drained (and its chunk published)
   }
   tc_fence_before_sync();
 }
@@ -392,7 +455,7 @@ __device__ __forceinline__ void emit32(AProducer<FMT>& ap, const float (&x)[32])
 template <int FMT, bool DENSITY>
 __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe& pp, uint32_t (&d_cnt)[2],
                                                   const RowCtx& rc, const RenderKParams& P, const float* sm,
-                                                  int quarter, int grp) {
+                                                  int quarter, int grp, Trace* tr = nullptr) {
   const NetProgram& pg = P.prog;
   const int D = pg.dims.D, W = pg.dims.W;
   float sigma = 0.f;
@@ -400,7 +463,11 @@ __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe
   // operands of trunk layers 0..D-1 and of feature_linear (l == D): [encoding part] + drain of layer l-1
 #pragma unroll 1
   for (int l = 0; l <= D; ++l) {
-    if (l == 0 || ((l - 1) == pg.dims.skip && l < D)) produce_pts_chunks<FMT>(ap, rc, P, grp);
+    if (l == 0 || ((l - 1) == pg.dims.skip && l < D)) {
+      if (tr) tr->mark(20);                  // 20/21: encoding part begin/end
+      produce_pts_chunks<FMT>(ap, rc, P, grp);
+      if (tr) tr->mark(21);
+    }
     if (l > 0) {
       const bool last = (l == D);                 // h of the last trunk layer: alpha_linear in fp32 on the way
       const bool emit = !(DENSITY && last);
@@ -411,15 +478,17 @@ __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe
                                   for (int i = 0; i < 32; ++i) sigma = fmaf(x[i], wa[cb * 32 + i], sigma);
                                 }
                                 if (emit) emit32<FMT>(ap, x);
-                              });
+                              }, tr);
     }
   }
   if (grp == 0) sigma += sm[pg.sm.alpha_b];
   if (DENSITY) return make_float4(0.f, 0.f, 0.f, sigma);
   // operand of views_linears[0]: view encoding first (independent of feature), then feature (no ReLU)
+  if (tr) tr->mark(22);
   produce_view_chunks<FMT>(ap, rc, P, grp);
+  if (tr) tr->mark(23);
   drain_region<FMT, false>(pp, d_cnt, D & 1, W, sm + pg.sm.bias[D], sm[D], quarter, grp,
-                           [&](int, const float (&x)[32]) { emit32<FMT>(ap, x); });
+                           [&](int, const float (&x)[32]) { emit32<FMT>(ap, x); }, tr);
   // views layer output -> rgb_linear in fp32
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
   const float* wr = sm + pg.sm.rgb_w;
@@ -432,7 +501,7 @@ __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe
                               r1 = fmaf(x[i], wr[H + cb * 32 + i], r1);
                               r2 = fmaf(x[i], wr[2 * H + cb * 32 + i], r2);
                             }
-                          });
+                          }, tr);
   if (grp == 0) {
     const float* br = sm + pg.sm.rgb_b;
     r0 += br[0]; r1 += br[1]; r2 += br[2];
@@ -583,23 +652,10 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   Pipe pp;
-  pp.a_ring = smem + L.a_ring;
-  pp.b_ring = smem + L.b_ring;
-  pp.a_full = bars;
-  pp.a_empty = bars + kAStages;
-  pp.b_full = bars + 2 * kAStages;
-  pp.b_empty = bars + 2 * kAStages + kBStages;
-  pp.d_full = bars + 2 * kAStages + 2 * kBStages;
-  pp.st = P.status;
+  pipe_init(pp, smem + L.a_ring, smem + L.b_ring, bars, P.status);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_ptr);
 
-  if (tid == 0) {
-    for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 4); mbar_init(&pp.a_empty[i], 1); }
-    for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); }
-    mbar_init(&pp.d_full[0], 1);
-    mbar_init(&pp.d_full[1], 1);
-    fence_mbar_init();
-  }
+  if (tid == 0) pipe_init_barriers(pp);
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   // both networks' small fp32 parameters -> shared memory
   {
@@ -612,24 +668,32 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
   }
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();            // barrier inits of both CTAs are visible before any remote arrive
   tc_fence_after_sync();
   pp.tmem_base = *tmem_slot;
 
+  // both CTAs of a pair run the same number of items in lockstep (the MMAs span the pair); an item index
+  // past the end is processed as a dummy (clamped inputs, no outputs)
+  const int n_iter = (P.n_items + (int)gridDim.x - 1) / (int)gridDim.x;
   const int passes = DENSITY ? 1 : (P.tilesC + P.tilesF);
   const int nl = DENSITY ? pg.dims.D : pg.n_layers;
 
   if (warp == kMmaWarp) {
     if (lane == 0) {
       uint32_t a_seq = 0, b_seq = 0;
-      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x)
+      Trace trc; trc.init(P.trace, 0);
+      for (int it = 0; it < n_iter; ++it)
         for (int ps = 0; ps < passes; ++ps)
-          for (int l = 0; l < nl; ++l) mma_layer<FMT>(pp, a_seq, b_seq, pg.layer[l].n, pg.layer[l].chunks, l & 1);
+          for (int l = 0; l < nl; ++l) {
+            if (pp.rank == 0) mma_layer<FMT>(pp, a_seq, b_seq, pg.layer[l].n, pg.layer[l].chunks, l & 1, P.trace ? &trc : nullptr);
+            else relay_layer(pp, b_seq, pg.layer[l].chunks);
+          }
     }
     __syncwarp();
   } else if (warp == kLoadWarp) {
     if (lane == 0) {
       uint32_t b_seq = 0;
-      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x)
+      for (int it = 0; it < n_iter; ++it)
         for (int ps = 0; ps < passes; ++ps) {
           const uint8_t* img = P.packed[(!DENSITY && ps >= P.tilesC) ? 1 : 0];
           for (int l = 0; l < nl; ++l) load_layer(pp, b_seq, img + pg.layer[l].w_off, pg.layer[l].n, pg.layer[l].chunks);
@@ -642,6 +706,8 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
     const int row = quarter * 32 + lane;
     AProducer<FMT> ap(pp, row, grp);
     uint32_t d_cnt[2] = {0u, 0u};
+    Trace trc; trc.init((quarter == 0 && lane == 0) ? P.trace : nullptr, 1 + grp);
+    Trace* tr = trc.p ? &trc : nullptr;
     float* ray_s = reinterpret_cast<float*>(smem + L.ray);
     float* skt_s = reinterpret_cast<float*>(smem + L.skt);
     float* vtab_s = reinterpret_cast<float*>(smem + L.view_tab);
@@ -660,7 +726,8 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
       // one pose for the whole launch
       for (int i = tid; i < J * 12; i += kWorkerThreads) skt_s[i] = P.skts[(i / 12) * 16 + (i % 12)];
       worker_sync();
-      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      for (int it = 0; it < n_iter; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
         long long idx = (long long)item * kTileM + row;
         bool valid = idx < P.n_points;
         long long ci = valid ? idx : (P.n_points - 1);
@@ -677,8 +744,9 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
       const int R = P.R, Sc = P.Sc, Sf = P.Sf, Si = P.Si;
       const int cap = R * (Sf > Sc ? Sf : Sc);          // rows per group plane of raw_s
       const bool fine = Si > 0;
-      for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-        const int ray0 = item * R;
+      for (int it = 0; it < n_iter; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int ray0 = item * R;       // >= n_rays for a dummy item: every load clamps, every store is guarded
         // ---- (1) per-ray inputs -------------------------------------------------------------
         if (tid < R) {
           int gr = min(ray0 + tid, P.n_rays - 1);
@@ -746,7 +814,9 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
           const float* rr = ray_s + r * 12;
           rc.p[0] = rr[0] + rr[3] * z; rc.p[1] = rr[1] + rr[4] * z; rc.p[2] = rr[2] + rr[5] * z;
           rc.skt = skt_s + r * J * 12; rc.vtab = vtab_s + r * VK; rc.fcode = fc_s + ((is_fine ? R : 0) + r) * 16;
-          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, is_fine ? sm1 : sm0, quarter, grp);
+          if (tr) tr->mark(30 + ps);
+          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, is_fine ? sm1 : sm0, quarter, grp, tr);
+          if (tr) tr->mark(40 + ps);
           if (valid) raw_s[grp * cap + g] = o;
           if (ps == P.tilesC - 1) {
             worker_sync();
@@ -807,6 +877,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
   }
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();            // the peer may still be reading this CTA's barriers / TMEM pair state
   if (warp == kMmaWarp) tmem_dealloc(pp.tmem_base, kTmemCols);
 }
 
@@ -866,7 +937,7 @@ __global__ void __launch_bounds__(1024, 1) anerf_nearfar_kernel(const float* __r
 }
 
 // ------------------------------------------------------------------------------------------------
-// weight packing: fp32 [N_out, K_in] -> chunks of [hi: 4 x N/8 x (8 x 8)] [lo: same], K permuted by kmap
+// weight packing: fp32 [N_out, K_in] -> chunks of 2 halves x [hi: 4 x (N/2)/8 x (8 x 8)] [lo: same], K permuted by kmap
 // ------------------------------------------------------------------------------------------------
 // Per-layer operand scale.  bf16 operands: 1.  fp16 operands: the power of two that brings max|W| into
 // [2^12, 2^13), so that the lo parts (|lo| <= 2^-11 |hi|) stay normal fp16 numbers; the fused kernel
@@ -915,10 +986,13 @@ __global__ void anerf_pack_layer_kernel(const float* __restrict__ w, int k_in, c
     Split<FMT>::pair(x[2], x[3], hi.y, lo.y);
     Split<FMT>::pair(x[4], x[5], hi.z, lo.z);
     Split<FMT>::pair(x[6], x[7], hi.w, lo.w);
-    uint8_t* chunk = out + (size_t)c * n * 128;
-    size_t off = (size_t)g * n * 16 + (size_t)(nn >> 3) * 128 + (size_t)(nn & 7) * 16;
-    *reinterpret_cast<uint4*>(chunk + off) = hi;
-    *reinterpret_cast<uint4*>(chunk + (size_t)n * 64 + off) = lo;
+    // chunk = [half 0: hi, lo][half 1: hi, lo]; a half holds n/2 rows (the B rows one CTA of the pair feeds)
+    const int nh = n >> 1;
+    uint8_t* half = out + (size_t)c * n * 128 + (size_t)(nn / nh) * n * 64;
+    const int r = nn % nh;
+    size_t off = (size_t)g * nh * 16 + (size_t)(r >> 3) * 128 + (size_t)(r & 7) * 16;
+    *reinterpret_cast<uint4*>(half + off) = hi;
+    *reinterpret_cast<uint4*>(half + (size_t)nh * 64 + off) = lo;
   }
 }
 
@@ -932,8 +1006,8 @@ __global__ void anerf_pack_framecodes_kernel(const float* __restrict__ codes, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// self test: D[128,N] = A[128,K] * B[N,K]^T through exactly the producer / loader / MMA / drain code
-// (K/32 must be even: chunks are dealt to the two worker groups by parity)
+// self test: D[256,N] = A[256,K] * B[N,K]^T on one CTA pair through exactly the producer / loader / relay /
+// MMA / drain code (K/32 must be even: chunks are dealt to the two worker groups by parity)
 // ------------------------------------------------------------------------------------------------
 template <int FMT>
 __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const float* __restrict__ A,
@@ -943,28 +1017,16 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const 
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAStages * kAStageBytes + kBStages * kBStageBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kAStages + 2 * kBStages + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
   float* zero_bias = reinterpret_cast<float*>(tmem_slot + 4);
   Pipe pp;
-  pp.a_ring = smem;
-  pp.b_ring = smem + kAStages * kAStageBytes;
-  pp.a_full = bars;
-  pp.a_empty = bars + kAStages;
-  pp.b_full = bars + 2 * kAStages;
-  pp.b_empty = bars + 2 * kAStages + kBStages;
-  pp.d_full = bars + 2 * kAStages + 2 * kBStages;
-  pp.st = status;
-  if (tid == 0) {
-    for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 4); mbar_init(&pp.a_empty[i], 1); }
-    for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); }
-    mbar_init(&pp.d_full[0], 1);
-    mbar_init(&pp.d_full[1], 1);
-    fence_mbar_init();
-  }
+  pipe_init(pp, smem, smem + kAStages * kAStageBytes, bars, status);
+  if (tid == 0) pipe_init_barriers(pp);
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   for (int i = tid; i < 256; i += kThreads) zero_bias[i] = 0.f;
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();
   tc_fence_after_sync();
   pp.tmem_base = *tmem_slot;
   const int chunks = K / kKC;
@@ -972,7 +1034,10 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const 
   if (warp == kMmaWarp) {
     if (lane == 0) {
       uint32_t a_seq = 0, b_seq = 0;
-      for (int rep = 0; rep < 2; ++rep) mma_layer<FMT>(pp, a_seq, b_seq, N, chunks, rep);
+      for (int rep = 0; rep < 2; ++rep) {
+        if (pp.rank == 0) mma_layer<FMT>(pp, a_seq, b_seq, N, chunks, rep);
+        else relay_layer(pp, b_seq, chunks);
+      }
     }
     __syncwarp();
   } else if (warp == kLoadWarp) {
@@ -983,6 +1048,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const 
     __syncwarp();
   } else {
     const int grp = warp >> 2, quarter = warp & 3, row = quarter * 32 + lane;
+    const size_t grow = (size_t)pp.rank * kTileM + row;          // row of the 256-row problem
     AProducer<FMT> ap(pp, row, grp);
     uint32_t d_cnt[2] = {0u, 0u};
     for (int rep = 0; rep < 2; ++rep) {
@@ -990,19 +1056,20 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const 
         for (int k8 = 0; k8 < 4; ++k8) {
           float x[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = A[(size_t)row * K + c * kKC + k8 * 8 + i];
+          for (int i = 0; i < 8; ++i) x[i] = A[grow * K + c * kKC + k8 * 8 + i];
           ap.put8(x);
         }
     }
     for (int rep = 0; rep < 2; ++rep) {
       drain_region<1, false>(pp, d_cnt, rep, N, zero_bias, 1.0f, quarter, grp, [&](int cb, const float (&x)[32]) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) Dout[(size_t)rep * kTileM * N + (size_t)row * N + cb * 32 + i] = x[i];
+        for (int i = 0; i < 32; ++i) Dout[(size_t)rep * 2 * kTileM * N + grow * N + cb * 32 + i] = x[i];
       });
     }
   }
   tc_fence_before_sync();
   __syncthreads();
+  cluster_sync_all();
   if (warp == kMmaWarp) tmem_dealloc(pp.tmem_base, kTmemCols);
 }
 

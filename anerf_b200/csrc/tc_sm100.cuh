@@ -78,6 +78,57 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, Device
   }
 }
 
+// ---- CTA pair (cluster of 2) ------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// all threads of both CTAs
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster.
+// Default (cta-scope release) semantics, as CUTLASS's ClusterBarrier::arrive(cta_id): what the arrival
+// publishes is consumed by this CTA's own tensor core / async proxy (made visible by fence.proxy.async
+// before the arrive); a cluster-scope release here costs a MEMBAR per chunk (measured: -15 % throughput).
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+// wait with cluster-scope acquire (for barriers that a peer CTA arrives on)
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(kSuspendNs)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity, DeviceStatus* st, unsigned int site) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  long long t0 = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (t0 == 0) { t0 = clock64(); continue; }
+    if (clock64() - t0 > 6000000000LL) {
+      if (st != nullptr && atomicCAS(&st->code, 0u, (unsigned)kErrWaitTimeout) == 0u) {
+        st->where = site;
+        st->block = blockIdx.x;
+        st->thread = threadIdx.x;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+
 // ---- fences -------------------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads, bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {
@@ -100,14 +151,15 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
 
 // ---- tensor memory ------------------------------------------------------------------------------
 // Executed by one full warp.  Writes the TMEM base address to *smem_out.
+// (cta_group::2: executed by one warp in EACH CTA of the pair)
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_out, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)),
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)),
                "r"(ncols)
                : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread t of the warp owns lane
@@ -150,20 +202,23 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t fmt_a, uint32_t f
   return (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
-// D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread.
+// D[tmem] (+)= A[smem] * B[smem]^T over a CTA pair (M = 256: rows 0..127 in the leader's TMEM, 128..255
+// in the peer's; each CTA supplies its own A rows and N/2 rows of B at the same shared-memory offsets).
+// Issued by ONE thread of the leader CTA.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// Arrive on an mbarrier when all previously issued MMAs of this thread have completed
-// (implies tcgen05.fence::before_thread_sync).
+// Arrive on the mbarrier at this offset in BOTH CTAs of the pair when all previously issued MMAs of this
+// thread have completed (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
                : "memory");
 }
 

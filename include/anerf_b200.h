@@ -142,12 +142,16 @@ int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, con
 int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf_render_opts* opts,
                          const float* pts, const float* skts, int64_t n_points, float* sigma, void* stream);
 
-/* Build-time self test of the tensor-core building blocks: D[128,N] = A[128,K] * B[N,K]^T with the
- * split-precision operand path (A, B fp32 on the device, D [2,128,N] fp32: two passes; K multiple of 64;
+/* Build-time self test of the tensor-core building blocks on one CTA pair: D[256,N] = A[256,K] * B[N,K]^T with
+ * the split-precision operand path (A, B fp32 on the device, D [2,256,N] fp32: two passes; K multiple of 64;
  * N in {64,128,256}).
  * format: 1 bf16, 0 fp16. */
 int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t format,
                         void* stream);
+
+/* Debug aid: device buffer of 3 x 1024 int64; while set, launches record a clock64 timeline of CTA 0
+ * (stream 0 MMA thread, 1/2 worker groups; entries = tag << 48 | clock).  NULL switches it off. */
+void anerf_debug_set_trace(long long* device_buffer);
 
 const char* anerf_last_error(void);
 int anerf_version(void);

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("N,K", [(256, 64), (256, 256), (256, 448), (128, 960), (64, 64), (64, 192)])
 def test_split_gemm_matches_fp64(fmt, N, K):
     g = torch.Generator(device="cpu").manual_seed(N * 1000 + K)
-    A = torch.randn(128, K, generator=g).cuda()
+    A = torch.randn(256, K, generator=g).cuda()
     B = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
     D = _lib.selftest_gemm(A, B, fmt)
     torch.cuda.synchronize()

@@ -32,7 +32,7 @@ def gemm():
     for fmt in (1, 0):
         for N, K in [(256, 64), (256, 256), (128, 960), (64, 64), (64, 192)]:
             g = torch.Generator().manual_seed(1)
-            A = torch.randn(128, K, generator=g).cuda()
+            A = torch.randn(256, K, generator=g).cuda()
             B = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
             try:
                 D = _lib.selftest_gemm(A, B, fmt)
@@ -51,7 +51,7 @@ def accum_probe():
     out = {}
     for K in (64, 256, 1024, 4096):
         g = torch.Generator().manual_seed(K)
-        A = torch.rand(128, K, generator=g).bfloat16().float().cuda()          # positive: no cancellation
+        A = torch.rand(256, K, generator=g).bfloat16().float().cuda()          # positive: no cancellation
         B = torch.rand(256, K, generator=g).bfloat16().float().cuda()
         D = _lib.selftest_gemm(A, B, 1)[0].double()
         ref = A.double() @ B.double().t()
