@@ -279,8 +279,8 @@ int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf
   RenderKParams P{};
   fill_common(plan, o, P);
   P.packed[0] = P.packed[1] = (const uint8_t*)packed;
-  P.sl = make_smem_layout(plan->dims, plan->prog.sm.fixed_floats, 1, kTileM, kTileM);   // raw_s: 2 x 128 partials
-  P.R = 1; P.Sc = kTileM; P.Sf = kTileM;
+  P.sl = make_smem_layout(plan->dims, plan->prog.sm.fixed_floats, 1, 4, 4);
+  P.R = 1; P.Sc = 4; P.Sf = 4;
   P.n_items = (int)((n_points + kTileM - 1) / kTileM);
   P.pts = pts; P.skts = skts; P.sigma = sigma; P.n_points = n_points;
   return launch_fused(plan, P, true, (cudaStream_t)stream_);
@@ -334,7 +334,7 @@ int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, con
 
 int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t format, void* stream_) {
   if (!A || !B || !D) return fail(ANERF_ERR_INVALID, "null argument");
-  if (K <= 0 || K % (2 * kKC) != 0) return fail(ANERF_ERR_INVALID, "K must be a positive multiple of 64");
+  if (K <= 0 || K % kKC != 0) return fail(ANERF_ERR_INVALID, "K must be a positive multiple of 32");
   if (N != 64 && N != 128 && N != 256) return fail(ANERF_ERR_INVALID, "N must be 64, 128 or 256");
   if (format != 0 && format != 1) return fail(ANERF_ERR_INVALID, "format must be 0 (fp16) or 1 (bf16)");
   cudaStream_t stream = (cudaStream_t)stream_;

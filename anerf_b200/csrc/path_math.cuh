@@ -24,11 +24,11 @@ constexpr int kF = 7;                        // distance frequencies
 constexpr int kFv = 4;                       // view-direction frequencies
 constexpr int kPtsPerJoint = 1 + 2 * kF + 3; // 18: [v, (sin,cos) x 7] * w  ++  r(3)
 constexpr int kViewPerJoint = 3 * (1 + 2 * kFv);  // 27: [d, (sin,cos) x 4] x 3 components, * w
-constexpr int kPtsGroupJoints = 4;           // 4 joints -> 72 values = 9 x 8
-constexpr int kPtsGroupK = kPtsGroupJoints * kPtsPerJoint;     // 72
+constexpr int kGroups = 4;                   // worker groups; group g owns K elements [8g, 8g+8) of every 32-wide chunk
+constexpr int kPtsPairK = 40;                // 2 joints x 18 values + 4 zeros = 5 x 8
 constexpr int kMaxJoints = 24;
 constexpr int kKC = 32;                      // K elements per operand chunk (two K=16 MMA slabs)
-constexpr int kTileM = 128;                  // rows (samples) per tile = UMMA M
+constexpr int kTileM = 128;                  // rows (samples) per tile = UMMA M per CTA
 
 ANERF_HD int ceil_div(int a, int b) { return (a + b - 1) / b; }
 ANERF_HD int round_up(int a, int b) { return ceil_div(a, b) * b; }
@@ -43,23 +43,19 @@ struct NetDims {
 };
 
 // ------------------------------------------------------------------------------------------------
-// K layout of the A operand.  Two worker groups produce the operand chunks of a layer concurrently:
-// group g owns the chunks of parity g.  Every part therefore has an even number of chunks and its
-// values are dealt to the two groups as follows:
-//   pts part : the joints are split into two halves of `pts_half_joints` (multiple of 4) joints;
-//              half h emits its joint groups (4 joints x 18 values = 72 = 9 x 8) as one stream,
-//              zero padded to `pts_half_chunks` chunks, which occupies the chunks of parity h;
-//   view part: one chunk per joint (27 values + 5 zeros), joint j in chunk j (so parity = j & 1),
-//              padded to an even joint count; framecodes, if any, add one chunk (16 values) + one
-//              zero chunk;
-//   hidden   : column block cb (32 accumulator columns) is chunk cb.
+// K layout of the A operand.  Four worker groups produce every operand chunk together: group g
+// writes K elements [8g, 8g+8) of each 32-wide chunk.
+//   pts part : group g encodes joints g, g+4, g+8, ... two at a time (2 x 18 values + 4 zeros = 40
+//              = 5 x 8) and its value stream fills its 8-wide slot chunk after chunk;
+//   view part: one chunk per joint: the joint's 27 per-ray direction features (+5 zeros) times the
+//              sample's cutoff weight, group g takes features [8g, 8g+8); framecodes, if any, add
+//              one chunk (16 values + 16 zeros);
+//   hidden   : chunk cb = accumulator columns [32cb, 32cb+32), group g drains columns 32cb+8g..+8.
 // ------------------------------------------------------------------------------------------------
-ANERF_HD int pts_half_joints(const NetDims& d) { return round_up(ceil_div(d.J, 2), kPtsGroupJoints); }
-ANERF_HD int pts_half_k(const NetDims& d) { return pts_half_joints(d) / kPtsGroupJoints * kPtsGroupK; }
-ANERF_HD int pts_half_chunks(const NetDims& d) { return ceil_div(pts_half_k(d), kKC); }
-ANERF_HD int pts_chunks(const NetDims& d) { return 2 * pts_half_chunks(d); }
-ANERF_HD int view_joint_chunks(const NetDims& d) { return round_up(d.J, 2); }
-ANERF_HD int view_chunks(const NetDims& d) { return view_joint_chunks(d) + (d.fc_ch > 0 ? 2 : 0); }
+ANERF_HD int pts_group_joints(const NetDims& d) { return ceil_div(d.J, kGroups); }
+ANERF_HD int pts_pairs(const NetDims& d) { return ceil_div(pts_group_joints(d), 2); }
+ANERF_HD int pts_chunks(const NetDims& d) { return pts_pairs(d) * (kPtsPairK / 8); }
+ANERF_HD int view_chunks(const NetDims& d) { return d.J + (d.fc_ch > 0 ? 1 : 0); }
 ANERF_HD int hid_chunks(const NetDims& d) { return d.W / kKC; }
 ANERF_HD int in_pts_ref(const NetDims& d) { return d.J * (1 + 2 * kF) + d.J * 3; }
 ANERF_HD int in_views_ref(const NetDims& d) { return d.J * kViewPerJoint; }
@@ -78,18 +74,19 @@ ANERF_HD int layer_chunks(const NetDims& d, int l) {
 // (cutoff_embedder.py:147-172, raycasters.py:560-569); skip layer input = cat[pts input, h]
 // (nerf.py:100-101); views layer input = cat[feature, k*3J + 3j + c, framecode] (nerf.py:121-125).
 ANERF_HD int pts_part_ref_col(const NetDims& d, int k) {
-  int c = k / kKC, half = c & 1;
-  int hk = (c >> 1) * kKC + (k % kKC);          // index inside the half's value stream
-  if (hk >= pts_half_k(d)) return -1;
-  int j = half * pts_half_joints(d) + (hk / kPtsGroupK) * kPtsGroupJoints + (hk % kPtsGroupK) / kPtsPerJoint;
-  int q = hk % kPtsPerJoint;
+  int c = k / kKC, g = (k % kKC) / 8, e = k % 8;
+  int p = c * 8 + e;                             // position in group g's value stream
+  int pair = p / kPtsPairK, within = p % kPtsPairK;
+  if (within >= 2 * kPtsPerJoint) return -1;
+  int j = g + kGroups * (2 * pair + within / kPtsPerJoint);
+  int q = within % kPtsPerJoint;
   if (j >= d.J) return -1;
   return q < 1 + 2 * kF ? q * d.J + j : (1 + 2 * kF) * d.J + 3 * j + (q - (1 + 2 * kF));
 }
 ANERF_HD int view_part_ref_col(const NetDims& d, int k) {   // relative to the start of input_views
   int c = k / kKC, q = k % kKC;
-  if (c >= view_joint_chunks(d)) return (c == view_joint_chunks(d) && q < d.fc_ch) ? in_views_ref(d) + q : -1;
-  if (c >= d.J || q >= kViewPerJoint) return -1;
+  if (c >= d.J) return (c == d.J && q < d.fc_ch) ? in_views_ref(d) + q : -1;
+  if (q >= kViewPerJoint) return -1;
   return (q / 3) * 3 * d.J + 3 * c + (q % 3);
 }
 ANERF_HD int layer_ref_col(const NetDims& d, int l, int k) {

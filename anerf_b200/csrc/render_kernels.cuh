@@ -26,18 +26,17 @@
 namespace anerf {
 
 constexpr int kAStages = 4;
-constexpr int kBStages = 6;
+constexpr int kBStages = 5;
 constexpr int kAHalfBytes = kTileM * kKC * 2;        // 8 KB: hi (or lo) part of one A chunk
 constexpr int kAStageBytes = 2 * kAHalfBytes;        // 16 KB
 constexpr int kBStageBytes = 128 * kKC * 2 * 2;      // 16 KB: this CTA's half (N/2 <= 128 rows) of a weight chunk, hi + lo
 constexpr int kNumBars = 2 * kAStages + 3 * kBStages + 2;
 constexpr int kMaxLayers = 10;
-constexpr int kWorkerWarps = 8;                      // two groups of 4 warps; group g owns the A chunks of parity g
+constexpr int kWorkerWarps = 4 * kGroups;            // group g = warp / 4 owns K elements [8g, 8g+8) of every chunk
 constexpr int kWorkerThreads = kWorkerWarps * 32;
-constexpr int kGroupThreads = 128;
-constexpr int kMmaWarp = 8;
-constexpr int kLoadWarp = 9;
-constexpr int kThreads = 320;
+constexpr int kMmaWarp = kWorkerWarps;
+constexpr int kLoadWarp = kWorkerWarps + 1;
+constexpr int kThreads = (kWorkerWarps + 2) * 32;
 constexpr int kTmemCols = 512;
 constexpr int kSmallsHeader = 16;                    // floats: per-layer output scales
 constexpr int kMaxRaysPerItem = 8;
@@ -97,7 +96,7 @@ inline __host__ NetProgram make_program(const NetDims& d) {
 // shared-memory carve-up of the fused kernel
 // ------------------------------------------------------------------------------------------------
 struct SmemLayout {
-  int a_ring, b_ring, smalls0, smalls1, ray, skt, view_tab, fcode, z_coarse, z_all, raw, wts, cdf, bars, tmem_ptr;
+  int a_ring, b_ring, smalls0, smalls1, ray, skt, view_tab, fcode, z_coarse, z_all, raw, part, wj, wts, cdf, bars, tmem_ptr;
   int total;
 };
 // ray_s: 12 floats per ray: o(3) d(3) near far |d| pad(3)
@@ -110,12 +109,14 @@ inline __host__ __device__ SmemLayout make_smem_layout(const NetDims& d, int sma
   L.smalls1 = off; off += align_up(smalls_fixed_floats * 4, 16);
   L.ray = off; off += R * 12 * 4;
   L.skt = off; off += align_up(R * d.J * 12 * 4, 16);
-  L.view_tab = off; off += R * view_joint_chunks(d) * kKC * 4;   // [ray][joint][32]
+  L.view_tab = off; off += R * d.J * kKC * 4;          // [ray][joint][32]
   L.fcode = off; off += 2 * R * 16 * 4;      // [net][ray][16]
   int rows = R * (Sf > Sc ? Sf : Sc);
   L.z_coarse = off; off += align_up(R * Sc * 4, 16);
   L.z_all = off; off += align_up(rows * 4, 16);
-  L.raw = off; off += 2 * rows * 16;         // [group][row] partial (r,g,b,sigma)
+  L.raw = off; off += rows * 16;             // network outputs (r,g,b,sigma) of the item's samples
+  L.part = off; off += kGroups * kTileM * 16; // per-group partial outputs of the current tile
+  L.wj = off; off += d.J * kTileM * 4;        // view cutoff weights of the current tile [joint][row]
   L.wts = off; off += align_up(rows * 4, 16);
   L.cdf = off; off += align_up(R * Sc * 4, 16);
   L.bars = off; off += 8 * kNumBars;
@@ -177,7 +178,7 @@ __device__ __forceinline__ void pipe_init(Pipe& pp, uint8_t* a_ring, uint8_t* b_
 }
 // thread 0 of each CTA; followed by a cluster-wide sync
 __device__ __forceinline__ void pipe_init_barriers(const Pipe& pp) {
-  for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 8); mbar_init(&pp.a_empty[i], 1); }   // 4 warps x 2 CTAs
+  for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 2 * kWorkerWarps); mbar_init(&pp.a_empty[i], 1); }   // every worker warp of both CTAs
   for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); mbar_init(&pp.peer_b[i], 1); }
   mbar_init(&pp.d_full[0], 1);
   mbar_init(&pp.d_full[1], 1);
@@ -188,7 +189,7 @@ __device__ __forceinline__ void a_chunk_ready(const Pipe& pp, uint32_t stage) {
   if (pp.rank == 0) mbar_arrive(&pp.a_full[stage]); else mbar_arrive_remote(&pp.a_full[stage], 0);
 }
 
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // whole-warp wait: one lane polls the barrier, the warp reconverges on it
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, DeviceStatus* st, unsigned site) {
@@ -196,72 +197,39 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, D
   __syncwarp();
 }
 
-// A-operand producer state of one worker thread (== one row of the tile).  Group g writes the chunks
-// whose sequence number has parity g (every operand part has an even number of chunks).
+// A-operand producer state of one worker thread (= one row of the tile, one 8-wide K slot of every chunk).
+// All 16 worker warps of both CTAs of the pair contribute to every chunk, in chunk order.
 template <int FMT>
 struct AProducer {
   const Pipe& pp;
-  uint32_t seq;       // sequence number of the chunk being filled (monotonic over the kernel's lifetime)
-  uint32_t g;         // next 8-wide K group inside the current chunk (0..3)
-  uint32_t row_off;   // (row/8)*128 + (row%8)*16
-  uint8_t* stage;
+  uint32_t seq;        // sequence number of the next chunk (monotonic over the kernel's lifetime)
+  uint32_t slot_off;   // byte offset of this thread's 16 B inside the hi (or lo) half of a stage
   __device__ AProducer(const Pipe& p, int row, int group)
-      : pp(p), seq(group), g(0), row_off((row >> 3) * 128 + (row & 7) * 16), stage(nullptr) {}
+      : pp(p), seq(0), slot_off((group >> 1) * 4096 + (group & 1) * 2048 + (row >> 3) * 128 + (row & 7) * 16) {}
 
   __device__ __forceinline__ void put8(const float (&x)[8]) {
-    if (g == 0) {
-      uint32_t s = seq % kAStages;
-      mbar_wait_warp(&pp.a_empty[s], ((seq / kAStages) & 1) ^ 1, pp.st, 100 + s);
-      stage = pp.a_ring + s * kAStageBytes;
-    }
+    const uint32_t s = seq % kAStages;
+    mbar_wait_warp(&pp.a_empty[s], ((seq / kAStages) & 1) ^ 1, pp.st, 100 + s);
+    uint8_t* st = pp.a_ring + s * kAStageBytes + slot_off;
     uint4 hi, lo;
     Split<FMT>::pair(x[0], x[1], hi.x, lo.x);
     Split<FMT>::pair(x[2], x[3], hi.y, lo.y);
     Split<FMT>::pair(x[4], x[5], hi.z, lo.z);
     Split<FMT>::pair(x[6], x[7], hi.w, lo.w);
-    uint32_t off = (g >> 1) * 4096 + (g & 1) * 2048 + row_off;
-    *reinterpret_cast<uint4*>(stage + off) = hi;
-    *reinterpret_cast<uint4*>(stage + kAHalfBytes + off) = lo;
-    if (++g == 4) {
-      fence_proxy_async_smem();            // this thread's stores -> visible to the tensor core's reads
-      __syncwarp();
-      if ((threadIdx.x & 31) == 0) a_chunk_ready(pp, seq % kAStages);   // 4 warp arrivals per CTA per chunk
-      seq += 2;
-      g = 0;
-    }
-  }
-  // a whole chunk at once (requires g == 0: hidden-layer operands are chunk aligned)
-  __device__ __forceinline__ void put32(const float (&x)[32]) {
-    uint32_t s = seq % kAStages;
-    mbar_wait_warp(&pp.a_empty[s], ((seq / kAStages) & 1) ^ 1, pp.st, 110 + s);
-    uint8_t* st = pp.a_ring + s * kAStageBytes + row_off;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      uint4 hi, lo;
-      Split<FMT>::pair(x[8 * t + 0], x[8 * t + 1], hi.x, lo.x);
-      Split<FMT>::pair(x[8 * t + 2], x[8 * t + 3], hi.y, lo.y);
-      Split<FMT>::pair(x[8 * t + 4], x[8 * t + 5], hi.z, lo.z);
-      Split<FMT>::pair(x[8 * t + 6], x[8 * t + 7], hi.w, lo.w);
-      *reinterpret_cast<uint4*>(st + (t >> 1) * 4096 + (t & 1) * 2048) = hi;
-      *reinterpret_cast<uint4*>(st + kAHalfBytes + (t >> 1) * 4096 + (t & 1) * 2048) = lo;
-    }
-    fence_proxy_async_smem();
+    *reinterpret_cast<uint4*>(st) = hi;
+    *reinterpret_cast<uint4*>(st + kAHalfBytes) = lo;
+    fence_proxy_async_smem();            // this thread's stores -> visible to the tensor core's reads
     __syncwarp();
-    if ((threadIdx.x & 31) == 0) a_chunk_ready(pp, s);
-    seq += 2;
+    if ((threadIdx.x & 31) == 0) a_chunk_ready(pp, s);   // 16 warp arrivals per CTA per chunk
+    ++seq;
   }
-  __device__ __forceinline__ void flush() {
+  __device__ __forceinline__ void zero8() {
     const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    while (g != 0) put8(z);
-  }
-  __device__ __forceinline__ void zero_chunk() {
-    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-#pragma unroll 1
-    for (int t = 0; t < 4; ++t) put8(z);
+    put8(z);
   }
 };
 
-// debug timeline: stream 0 = MMA thread, 1 = worker group 0 (warp 0), 2 = worker group 1 (warp 4); CTA 0 only
+// debug timeline: stream 0 = MMA thread, 1 = worker warp 0 (group 0), 2 = worker warp 4 (group 1); CTA 0 only
 struct Trace {
   long long* p;
   int n;
@@ -343,23 +311,22 @@ __device__ __forceinline__ void relay_layer(const Pipe& pp, uint32_t& b_seq, int
 struct RowCtx {
   float p[3];          // world position of this row's sample
   const float* skt;    // this row's ray: [J][12] in shared memory
-  const float* vtab;   // this row's ray: view table [J_even][32]
+  const float* vtab;   // this row's ray: view table [J][32]
   const float* fcode;  // this row's ray: frame code (16)
 };
 
-// layer-0 / skip-layer part: distance + bone encodings of the row's sample for the joints of this
-// group's half, 4 joints at a time
+// layer-0 / skip-layer part: distance + bone encodings of the row's sample for this group's joints
+// (g, g+4, g+8, ...), two joints at a time: 36 values + 4 zeros = 5 slots
 template <int FMT>
 __device__ __forceinline__ void produce_pts_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P, int grp) {
   const int J = P.prog.dims.J;
-  const int hj = pts_half_joints(P.prog.dims);
-  const int j0 = grp * hj;
+  const int pairs = pts_pairs(P.prog.dims);
 #pragma unroll 1
-  for (int jg = 0; jg < hj / kPtsGroupJoints; ++jg) {
-    float vals[kPtsGroupK];
+  for (int pr = 0; pr < pairs; ++pr) {
+    float vals[kPtsPairK];
 #pragma unroll
-    for (int jj = 0; jj < kPtsGroupJoints; ++jj) {
-      int j = j0 + jg * kPtsGroupJoints + jj;
+    for (int jj = 0; jj < 2; ++jj) {
+      int j = grp + kGroups * (2 * pr + jj);
       if (j < J) {
         encode_joint_pts(rc.skt + j * 12, rc.p, P.tau_p, P.cut_p[j], &vals[jj * kPtsPerJoint]);
       } else {
@@ -368,53 +335,51 @@ __device__ __forceinline__ void produce_pts_chunks(AProducer<FMT>& ap, const Row
       }
     }
 #pragma unroll
-    for (int t = 0; t < kPtsGroupK / 8; ++t) {
+    for (int q = 2 * kPtsPerJoint; q < kPtsPairK; ++q) vals[q] = 0.f;
+#pragma unroll
+    for (int t = 0; t < kPtsPairK / 8; ++t) {
       float x[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] = vals[8 * t + i];
       ap.put8(x);
     }
   }
-  ap.flush();
-  // pad this half's stream to pts_half_chunks chunks
-  const int used = ceil_div(pts_half_k(P.prog.dims), kKC);
-  for (int c = used; c < pts_half_chunks(P.prog.dims); ++c) ap.zero_chunk();
+}
+
+// cutoff weights of the view encoding for this tile: group g computes joints g, g+4, ... of its row and
+// shares them through shared memory (wj[joint][row]); callers sync before produce_view_chunks
+__device__ __forceinline__ void compute_view_weights(const RowCtx& rc, const RenderKParams& P, int grp, int row, float* wj) {
+  const int J = P.prog.dims.J;
+#pragma unroll 1
+  for (int j = grp; j < J; j += kGroups)
+    wj[j * kTileM + row] = cutoff_w(joint_dist(rc.skt + j * 12, rc.p), P.tau_v, P.cut_v[j]);
 }
 
 // views-layer part: one chunk per joint = the ray's 27 direction features of that joint (+5 zeros)
-// times the sample's cutoff weight; this group takes the joints of its parity
+// times the sample's cutoff weight; this group contributes features [8g, 8g+8)
 template <int FMT>
-__device__ __forceinline__ void produce_view_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P, int grp) {
+__device__ __forceinline__ void produce_view_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P, int grp,
+                                                    int row, const float* wj) {
   const int J = P.prog.dims.J;
-  const int JE = view_joint_chunks(P.prog.dims);
 #pragma unroll 1
-  for (int j = grp; j < JE; j += 2) {
-    float w = j < J ? cutoff_w(joint_dist(rc.skt + j * 12, rc.p), P.tau_v, P.cut_v[j]) : 0.f;
-    const float4* tab = reinterpret_cast<const float4*>(rc.vtab + j * kKC);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float4 t0 = tab[2 * t], t1 = tab[2 * t + 1];
-      float x[8] = {t0.x * w, t0.y * w, t0.z * w, t0.w * w, t1.x * w, t1.y * w, t1.z * w, t1.w * w};
-      ap.put8(x);
-    }
+  for (int j = 0; j < J; ++j) {
+    const float w = wj[j * kTileM + row];
+    const float4* tab = reinterpret_cast<const float4*>(rc.vtab + j * kKC + grp * 8);
+    float4 t0 = tab[0], t1 = tab[1];
+    float x[8] = {t0.x * w, t0.y * w, t0.z * w, t0.w * w, t1.x * w, t1.y * w, t1.z * w, t1.w * w};
+    ap.put8(x);
   }
   if (P.prog.dims.fc_ch > 0) {
-    if (grp == 0) {
-#pragma unroll 1
-      for (int t = 0; t < 4; ++t) {
-        float x[8];
+    float x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = (8 * t + i) < P.prog.dims.fc_ch ? rc.fcode[(8 * t + i) & 15] : 0.f;
-        ap.put8(x);
-      }
-    } else {
-      ap.zero_chunk();
-    }
+    for (int i = 0; i < 8; ++i) x[i] = (grp * 8 + i) < P.prog.dims.fc_ch ? rc.fcode[(grp * 8 + i) & 15] : 0.f;
+    ap.put8(x);
   }
 }
 
-// Wait for the accumulators of the layer that used `region`, then walk this group's column blocks
-// (32 columns each, parity grp).  f(cb, x[32]) receives scale*acc + bias (ReLU applied when RELU).
+// Wait for the accumulators of the layer that used `region`, then walk its column blocks; this group
+// takes columns [32cb + 8g, 32cb + 8g + 8) of every block.  f(col0, x[8]) receives scale*acc + bias
+// (ReLU applied when RELU).
 template <int FMT, bool RELU, typename F>
 __device__ __forceinline__ void drain_region(const Pipe& pp, uint32_t (&d_cnt)[2], int region, int N,
                                              const float* bias, float scale, int quarter, int grp, F&& f,
@@ -424,38 +389,39 @@ __device__ __forceinline__ void drain_region(const Pipe& pp, uint32_t (&d_cnt)[2
   ++d_cnt[region];
   tc_fence_after_sync();
   if (tr) tr->mark(11);                      // 11: accumulators ready
-  const uint32_t taddr = pp.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)region * 256u;
+  const uint32_t taddr = pp.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)region * 256u + (uint32_t)grp * 8u;
+  uint32_t v[8];
+  tmem_ld8(taddr, v);
 #pragma unroll 1
-  for (int cb = grp; cb < N / 32; cb += 2) {
-    uint32_t v[32];
-    tmem_ld32(taddr + cb * 32, v);
+  for (int cb = 0; cb < N / 32; ++cb) {
     tmem_ld_wait();
-    float x[32];
-    const float4* b4 = reinterpret_cast<const float4*>(bias + cb * 32);
+    float a[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 b = b4[i];
-      float y0 = fmaf(__uint_as_float(v[4 * i + 0]), scale, b.x), y1 = fmaf(__uint_as_float(v[4 * i + 1]), scale, b.y);
-      float y2 = fmaf(__uint_as_float(v[4 * i + 2]), scale, b.z), y3 = fmaf(__uint_as_float(v[4 * i + 3]), scale, b.w);
-      if (RELU) { y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f); }
-      x[4 * i + 0] = y0; x[4 * i + 1] = y1; x[4 * i + 2] = y2; x[4 * i + 3] = y3;
+    for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(v[i]);
+    if (cb + 1 < N / 32) tmem_ld8(taddr + (cb + 1) * 32, v);        // next block in flight while this one is processed
+    const int col0 = cb * 32 + grp * 8;
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + col0), b1 = *reinterpret_cast<const float4*>(bias + col0 + 4);
+    float x[8];
+    x[0] = fmaf(a[0], scale, b0.x); x[1] = fmaf(a[1], scale, b0.y); x[2] = fmaf(a[2], scale, b0.z); x[3] = fmaf(a[3], scale, b0.w);
+    x[4] = fmaf(a[4], scale, b1.x); x[5] = fmaf(a[5], scale, b1.y); x[6] = fmaf(a[6], scale, b1.z); x[7] = fmaf(a[7], scale, b1.w);
+    if (RELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
     }
-    f(cb, x);
-    if (tr) tr->mark(12);                    // 12: one column block drained (and its chunk published)
+    f(col0, x);
+    if (tr) tr->mark(12);                    // 12: one column block drained (and its slot published)
   }
   tc_fence_before_sync();
 }
 
-template <int FMT>
-__device__ __forceinline__ void emit32(AProducer<FMT>& ap, const float (&x)[32]) { ap.put32(x); }
-
 // One tile (128 rows) through one network, this group's share.  Returns this group's partial
-// (rgb logits, raw sigma) of the thread's row; the two groups' partials add up to the result
-// (biases are added by group 0).  DENSITY: trunk + alpha only.
+// (rgb logits, raw sigma) of the thread's row; the four groups' partials add up to the result
+// (biases are added by group 0).  DENSITY: trunk + alpha only.  Contains ONE worker_sync (all 16 worker
+// warps call it) between the view-weight computation and the view chunks.
 template <int FMT, bool DENSITY>
 __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe& pp, uint32_t (&d_cnt)[2],
                                                   const RowCtx& rc, const RenderKParams& P, const float* sm,
-                                                  int quarter, int grp, Trace* tr = nullptr) {
+                                                  int quarter, int grp, int row, float* wj, Trace* tr = nullptr) {
   const NetProgram& pg = P.prog;
   const int D = pg.dims.D, W = pg.dims.W;
   float sigma = 0.f;
@@ -472,12 +438,12 @@ __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe
       const bool last = (l == D);                 // h of the last trunk layer: alpha_linear in fp32 on the way
       const bool emit = !(DENSITY && last);
       drain_region<FMT, true>(pp, d_cnt, (l - 1) & 1, W, sm + pg.sm.bias[l - 1], sm[l - 1], quarter, grp,
-                              [&](int cb, const float (&x)[32]) {
+                              [&](int col0, const float (&x)[8]) {
                                 if (last) {
 #pragma unroll
-                                  for (int i = 0; i < 32; ++i) sigma = fmaf(x[i], wa[cb * 32 + i], sigma);
+                                  for (int i = 0; i < 8; ++i) sigma = fmaf(x[i], wa[col0 + i], sigma);
                                 }
-                                if (emit) emit32<FMT>(ap, x);
+                                if (emit) ap.put8(x);
                               }, tr);
     }
   }
@@ -485,21 +451,23 @@ __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe
   if (DENSITY) return make_float4(0.f, 0.f, 0.f, sigma);
   // operand of views_linears[0]: view encoding first (independent of feature), then feature (no ReLU)
   if (tr) tr->mark(22);
-  produce_view_chunks<FMT>(ap, rc, P, grp);
+  compute_view_weights(rc, P, grp, row, wj);
+  worker_sync();
+  produce_view_chunks<FMT>(ap, rc, P, grp, row, wj);
   if (tr) tr->mark(23);
   drain_region<FMT, false>(pp, d_cnt, D & 1, W, sm + pg.sm.bias[D], sm[D], quarter, grp,
-                           [&](int, const float (&x)[32]) { emit32<FMT>(ap, x); }, tr);
+                           [&](int, const float (&x)[8]) { ap.put8(x); }, tr);
   // views layer output -> rgb_linear in fp32
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
   const float* wr = sm + pg.sm.rgb_w;
   const int H = W / 2;
   drain_region<FMT, true>(pp, d_cnt, (D + 1) & 1, H, sm + pg.sm.bias[D + 1], sm[D + 1], quarter, grp,
-                          [&](int cb, const float (&x)[32]) {
+                          [&](int col0, const float (&x)[8]) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                              r0 = fmaf(x[i], wr[cb * 32 + i], r0);
-                              r1 = fmaf(x[i], wr[H + cb * 32 + i], r1);
-                              r2 = fmaf(x[i], wr[2 * H + cb * 32 + i], r2);
+                            for (int i = 0; i < 8; ++i) {
+                              r0 = fmaf(x[i], wr[col0 + i], r0);
+                              r1 = fmaf(x[i], wr[H + col0 + i], r1);
+                              r2 = fmaf(x[i], wr[2 * H + col0 + i], r2);
                             }
                           }, tr);
   if (grp == 0) {
@@ -510,7 +478,7 @@ __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-ray stages executed by one warp
+// per-ray stages
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -524,9 +492,8 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-// a12 (nerf.py:150-205): alpha compositing of one ray.  z: shared [S]; raw0/raw1: the two worker groups'
-// partial network outputs (shared, [S] each); wts: shared [S] (out).
-__device__ __forceinline__ void composite_ray(int lane, int S, const float* z, const float4* raw0, const float4* raw1,
+// a12 (nerf.py:150-205): alpha compositing of one ray by one warp.  z, raw: shared [S]; wts: shared [S] (out).
+__device__ __forceinline__ void composite_ray(int lane, int S, const float* z, const float4* raw,
                                               float dnorm, const float* noise, const RenderKParams& P, float* wts,
                                               float* alpha_out, float* rgb_out, float* disp_out, float* acc_out) {
   const int per = (S + 31) / 32;
@@ -536,7 +503,7 @@ __device__ __forceinline__ void composite_ray(int lane, int S, const float* z, c
     int i = i0 + k;
     if (i < S) {
       float dist = (i + 1 < S ? z[i + 1] - z[i] : 1e10f) * dnorm;
-      float sg = density_act(raw0[i].w + raw1[i].w, P.B, noise ? noise[i] : 0.f, P.softplus, P.shift);
+      float sg = density_act(raw[i].w, P.B, noise ? noise[i] : 0.f, P.softplus, P.shift);
       float a = 1.f - expf(-sg * dist);
       wts[i] = a;
       prod *= (1.f - a + 1e-10f);
@@ -559,7 +526,7 @@ __device__ __forceinline__ void composite_ray(int lane, int S, const float* z, c
       T *= (1.f - a + 1e-10f);
       if (alpha_out) alpha_out[i] = a;
       wts[i] = w;
-      float4 r = add4(raw0[i], raw1[i]);
+      float4 r = raw[i];
       cr = fmaf(w, sigmoid_rgb(r.x), cr);
       cg = fmaf(w, sigmoid_rgb(r.y), cg);
       cb = fmaf(w, sigmoid_rgb(r.z), cb);
@@ -578,12 +545,10 @@ __device__ __forceinline__ void composite_ray(int lane, int S, const float* z, c
   __syncwarp();
 }
 
-// a13 (ray_utils.py:157-201, 255-289): inverse-CDF sampling of Si new depths from the coarse weights and
-// merge with the Sc coarse depths into a sorted list.  zc, w: shared [Sc]; cdf: shared scratch [Sc];
-// tmp: shared scratch [Sc+Si]; z_all: shared out [Sc+Si].
-__device__ __forceinline__ void importance_ray(int lane, int Sc, int Si, const float* zc, const float* w,
-                                               const float* u_rand, float* cdf, float* tmp, float* z_all) {
-  const int nb = Sc - 1, nw = Sc - 2;
+// a13, first part (ray_utils.py:157-166): cdf of the coarse weights of one ray, by one warp.
+// w: shared [Sc]; cdf: shared [Sc] (Sc-1 entries used).  fp64 running sum like torch's CPU cumsum.
+__device__ __forceinline__ void importance_cdf(int lane, int Sc, const float* w, float* cdf) {
+  const int nw = Sc - 2;
   double part = 0.0;
   for (int i = lane; i < nw; i += 32) part += (double)(w[1 + i] + 1e-5f);
   const float total = (float)warp_sum(part);
@@ -609,35 +574,21 @@ __device__ __forceinline__ void importance_ray(int lane, int Sc, int Si, const f
     }
   }
   if (lane == 0) cdf[0] = 0.f;
-  __syncwarp();
-  for (int m = lane; m < Si; m += 32) {
-    float u = u_rand ? u_rand[m] : linspace01(m, Si);
-    int lo = 0, hi = nb;                      // searchsorted(cdf, u, right=True)
-    while (lo < hi) {
-      int mid = (lo + hi) >> 1;
-      if (cdf[mid] > u) hi = mid; else lo = mid + 1;
-    }
-    int below = max(lo - 1, 0), above = min(lo, nb - 1);
-    float cb = cdf[below], ca = cdf[above];
-    float bb = 0.5f * (zc[below + 1] + zc[below]), ba = 0.5f * (zc[above + 1] + zc[above]);
-    float denom = ca - cb;
-    if (denom < 1e-5f) denom = 1.f;
-    float t = (u - cb) / denom;
-    tmp[Sc + m] = bb + t * (ba - bb);
+}
+// a13, second part (ray_utils.py:168-201): one inverse-CDF sample.  searchsorted(cdf, u, right=True).
+__device__ __forceinline__ float importance_sample(float u, int Sc, const float* zc, const float* cdf) {
+  const int nb = Sc - 1;
+  int lo = 0, hi = nb;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (cdf[mid] > u) hi = mid; else lo = mid + 1;
   }
-  for (int i = lane; i < Sc; i += 32) tmp[i] = zc[i];
-  __syncwarp();
-  const int Sf = Sc + Si;
-  for (int e = lane; e < Sf; e += 32) {       // rank sort (stable), identical result to torch.sort on values
-    float x = tmp[e];
-    int r = 0;
-    for (int q = 0; q < Sf; ++q) {
-      float y = tmp[q];
-      r += (y < x || (y == x && q < e)) ? 1 : 0;
-    }
-    z_all[r] = x;
-  }
-  __syncwarp();
+  int below = max(lo - 1, 0), above = min(lo, nb - 1);
+  float cb = cdf[below], ca = cdf[above];
+  float bb = 0.5f * (zc[below + 1] + zc[below]), ba = 0.5f * (zc[above + 1] + zc[above]);
+  float denom = ca - cb;
+  if (denom < 1e-5f) denom = 1.f;
+  return bb + (u - cb) / denom * (ba - bb);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -706,7 +657,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
     const int row = quarter * 32 + lane;
     AProducer<FMT> ap(pp, row, grp);
     uint32_t d_cnt[2] = {0u, 0u};
-    Trace trc; trc.init((quarter == 0 && lane == 0) ? P.trace : nullptr, 1 + grp);
+    Trace trc; trc.init((quarter == 0 && lane == 0 && grp < 2) ? P.trace : nullptr, 1 + grp);
     Trace* tr = trc.p ? &trc : nullptr;
     float* ray_s = reinterpret_cast<float*>(smem + L.ray);
     float* skt_s = reinterpret_cast<float*>(smem + L.skt);
@@ -715,12 +666,14 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
     float* zc_s = reinterpret_cast<float*>(smem + L.z_coarse);
     float* za_s = reinterpret_cast<float*>(smem + L.z_all);
     float4* raw_s = reinterpret_cast<float4*>(smem + L.raw);
+    float4* part_s = reinterpret_cast<float4*>(smem + L.part);
+    float* wj_s = reinterpret_cast<float*>(smem + L.wj);
     float* w_s = reinterpret_cast<float*>(smem + L.wts);
     float* cdf_s = reinterpret_cast<float*>(smem + L.cdf);
     const float* sm0 = reinterpret_cast<const float*>(smem + L.smalls0);
     const float* sm1 = reinterpret_cast<const float*>(smem + L.smalls1);
     const int J = pg.dims.J;
-    const int VK = view_joint_chunks(pg.dims) * kKC;
+    const int VK = J * kKC;
 
     if (DENSITY) {
       // one pose for the whole launch
@@ -734,15 +687,15 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         RowCtx rc;
         rc.p[0] = P.pts[ci * 3 + 0]; rc.p[1] = P.pts[ci * 3 + 1]; rc.p[2] = P.pts[ci * 3 + 2];
         rc.skt = skt_s; rc.vtab = nullptr; rc.fcode = nullptr;
-        float4 r = worker_net_pass<FMT, true>(ap, pp, d_cnt, rc, P, sm0, quarter, grp);
-        raw_s[grp * kTileM + row] = r;
+        float4 r = worker_net_pass<FMT, true>(ap, pp, d_cnt, rc, P, sm0, quarter, grp, row, wj_s);
+        part_s[grp * kTileM + row] = r;
         worker_sync();
-        if (grp == 0 && valid) P.sigma[idx] = raw_s[row].w + raw_s[kTileM + row].w;
+        if (grp == 0 && valid)
+          P.sigma[idx] = part_s[row].w + part_s[kTileM + row].w + part_s[2 * kTileM + row].w + part_s[3 * kTileM + row].w;
         worker_sync();
       }
     } else {
       const int R = P.R, Sc = P.Sc, Sf = P.Sf, Si = P.Si;
-      const int cap = R * (Sf > Sc ? Sf : Sc);          // rows per group plane of raw_s
       const bool fine = Si > 0;
       for (int it = 0; it < n_iter; ++it) {
         const int item = blockIdx.x + it * gridDim.x;
@@ -774,12 +727,11 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         worker_sync();
         // ---- (2) per-ray view-direction table, coarse depths --------------------------------
         {
-          const int JE = view_joint_chunks(pg.dims);
-          for (int u = tid; u < R * JE; u += kWorkerThreads) {
-            int r = u / JE, j = u % JE;
+          for (int u = tid; u < R * J; u += kWorkerThreads) {
+            int r = u / J, j = u % J;
             float* o = vtab_s + r * VK + j * kKC;
-            if (j < J) encode_joint_viewdir(skt_s + (r * J + j) * 12, ray_s + r * 12 + 3, o);
-            for (int q = (j < J ? kViewPerJoint : 0); q < kKC; ++q) o[q] = 0.f;
+            encode_joint_viewdir(skt_s + (r * J + j) * 12, ray_s + r * 12 + 3, o);
+            for (int q = kViewPerJoint; q < kKC; ++q) o[q] = 0.f;
           }
           for (int i = tid; i < R * Sc; i += kWorkerThreads) {
             int r = i / Sc, s = i % Sc;
@@ -815,12 +767,15 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
           rc.p[0] = rr[0] + rr[3] * z; rc.p[1] = rr[1] + rr[4] * z; rc.p[2] = rr[2] + rr[5] * z;
           rc.skt = skt_s + r * J * 12; rc.vtab = vtab_s + r * VK; rc.fcode = fc_s + ((is_fine ? R : 0) + r) * 16;
           if (tr) tr->mark(30 + ps);
-          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, is_fine ? sm1 : sm0, quarter, grp, tr);
+          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, is_fine ? sm1 : sm0, quarter, grp, row, wj_s, tr);
           if (tr) tr->mark(40 + ps);
-          if (valid) raw_s[grp * cap + g] = o;
+          part_s[grp * kTileM + row] = o;
+          worker_sync();
+          if (grp == 0 && valid)
+            raw_s[g] = add4(add4(part_s[row], part_s[kTileM + row]), add4(part_s[2 * kTileM + row], part_s[3 * kTileM + row]));
           if (ps == P.tilesC - 1) {
             worker_sync();
-            // ---- (4) composite coarse ---------------------------------------------------------------
+            // ---- (4) composite coarse: one warp per ray ----------------------------------------------
             for (int q = warp; q < R; q += kWorkerWarps) {
               int gr = ray0 + q;
               bool live = gr < P.n_rays;
@@ -829,27 +784,48 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
               float* rgb_o = fine ? P.rgb0 : P.rgb_map;
               float* disp_o = fine ? P.disp0 : P.disp_map;
               float* acc_o = fine ? P.acc0 : P.acc_map;
-              composite_ray(lane, Sc, zc_s + q * Sc, raw_s + q * Sc, raw_s + cap + q * Sc, ray_s[q * 12 + 8],
+              composite_ray(lane, Sc, zc_s + q * Sc, raw_s + q * Sc, ray_s[q * 12 + 8],
                             P.noise0 ? P.noise0 + (size_t)grc * Sc : nullptr, P, w_s + q * Sc,
                             (live && a_out) ? a_out + (size_t)gr * Sc : nullptr,
                             (live && rgb_o) ? rgb_o + (size_t)gr * 3 : nullptr,
                             (live && disp_o) ? disp_o + gr : nullptr, (live && acc_o) ? acc_o + gr : nullptr);
               if (!fine && live && P.raw_out)
-                for (int i = lane; i < Sc; i += 32)
-                  reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sc + i] = add4(raw_s[q * Sc + i], raw_s[cap + q * Sc + i]);
+                for (int i = lane; i < Sc; i += 32) reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sc + i] = raw_s[q * Sc + i];
+              if (fine) importance_cdf(lane, Sc, w_s + q * Sc, cdf_s + q * Sc);
             }
-            worker_sync();   // raw_s is free from here (plane 0 is scratch for importance_ray)
+            worker_sync();   // raw_s is free from here (scratch for the merge below)
             if (fine) {
-              // ---- (5) importance sampling -------------------------------------------------------------
-              for (int q = warp; q < R; q += kWorkerWarps) {
-                int grc = min(ray0 + q, P.n_rays - 1);
-                importance_ray(lane, Sc, Si, zc_s + q * Sc, w_s + q * Sc,
-                               P.u_rand ? P.u_rand + (size_t)grc * Si : nullptr, cdf_s + q * Sc,
-                               reinterpret_cast<float*>(raw_s) + q * Sf, za_s + q * Sf);
-                if (P.z_all_out && ray0 + q < P.n_rays)
-                  for (int i = lane; i < Sf; i += 32) P.z_all_out[(size_t)(ray0 + q) * Sf + i] = za_s[q * Sf + i];
+              // ---- (5) importance sampling: every worker thread takes samples, then ranks -------------
+              float* tmp = reinterpret_cast<float*>(raw_s);
+              for (int i = tid; i < R * Sf; i += kWorkerThreads) {
+                int q = i / Sf, e = i % Sf;
+                float v;
+                if (e < Sc) {
+                  v = zc_s[q * Sc + e];
+                } else {
+                  int m = e - Sc;
+                  int grc = min(ray0 + q, P.n_rays - 1);
+                  float u = P.u_rand ? P.u_rand[(size_t)grc * Si + m] : linspace01(m, Si);
+                  v = importance_sample(u, Sc, zc_s + q * Sc, cdf_s + q * Sc);
+                }
+                tmp[i] = v;
               }
               worker_sync();
+              for (int i = tid; i < R * Sf; i += kWorkerThreads) {   // rank sort (stable) == torch.sort on values
+                int q = i / Sf, e = i % Sf;
+                const float* t = tmp + q * Sf;
+                float x = t[e];
+                int rk = 0;
+                for (int k = 0; k < Sf; ++k) {
+                  float y = t[k];
+                  rk += (y < x || (y == x && k < e)) ? 1 : 0;
+                }
+                za_s[q * Sf + rk] = x;
+              }
+              worker_sync();
+              if (P.z_all_out)
+                for (int i = tid; i < R * Sf; i += kWorkerThreads)
+                  if (ray0 + i / Sf < P.n_rays) P.z_all_out[(size_t)ray0 * Sf + i] = za_s[i];
             }
           }
         }
@@ -860,15 +836,14 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
             int gr = ray0 + q;
             bool live = gr < P.n_rays;
             int grc = min(gr, P.n_rays - 1);
-            composite_ray(lane, Sf, za_s + q * Sf, raw_s + q * Sf, raw_s + cap + q * Sf, ray_s[q * 12 + 8],
+            composite_ray(lane, Sf, za_s + q * Sf, raw_s + q * Sf, ray_s[q * 12 + 8],
                           P.noise1 ? P.noise1 + (size_t)grc * Sf : nullptr, P, w_s + q * Sf,
                           (live && P.alpha) ? P.alpha + (size_t)gr * Sf : nullptr,
                           (live && P.rgb_map) ? P.rgb_map + (size_t)gr * 3 : nullptr,
                           (live && P.disp_map) ? P.disp_map + gr : nullptr,
                           (live && P.acc_map) ? P.acc_map + gr : nullptr);
             if (live && P.raw_out)
-              for (int i = lane; i < Sf; i += 32)
-                reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sf + i] = add4(raw_s[q * Sf + i], raw_s[cap + q * Sf + i]);
+              for (int i = lane; i < Sf; i += 32) reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sf + i] = raw_s[q * Sf + i];
           }
           worker_sync();
         }
@@ -1007,7 +982,7 @@ __global__ void anerf_pack_framecodes_kernel(const float* __restrict__ codes, in
 
 // ------------------------------------------------------------------------------------------------
 // self test: D[256,N] = A[256,K] * B[N,K]^T on one CTA pair through exactly the producer / loader / relay /
-// MMA / drain code (K/32 must be even: chunks are dealt to the two worker groups by parity)
+// MMA / drain code
 // ------------------------------------------------------------------------------------------------
 template <int FMT>
 __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const float* __restrict__ A,
@@ -1052,18 +1027,17 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const 
     AProducer<FMT> ap(pp, row, grp);
     uint32_t d_cnt[2] = {0u, 0u};
     for (int rep = 0; rep < 2; ++rep) {
-      for (int c = grp; c < chunks; c += 2)
-        for (int k8 = 0; k8 < 4; ++k8) {
-          float x[8];
+      for (int c = 0; c < chunks; ++c) {
+        float x[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = A[grow * K + c * kKC + k8 * 8 + i];
-          ap.put8(x);
-        }
+        for (int i = 0; i < 8; ++i) x[i] = A[grow * K + c * kKC + grp * 8 + i];
+        ap.put8(x);
+      }
     }
     for (int rep = 0; rep < 2; ++rep) {
-      drain_region<1, false>(pp, d_cnt, rep, N, zero_bias, 1.0f, quarter, grp, [&](int cb, const float (&x)[32]) {
+      drain_region<1, false>(pp, d_cnt, rep, N, zero_bias, 1.0f, quarter, grp, [&](int col0, const float (&x)[8]) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) Dout[(size_t)rep * 2 * kTileM * N + grow * N + cb * 32 + i] = x[i];
+        for (int i = 0; i < 8; ++i) Dout[(size_t)rep * 2 * kTileM * N + grow * N + col0 + i] = x[i];
       });
     }
   }

@@ -17,26 +17,23 @@ int h_layer_ref_col(int J, int D, int W, int skip, int fc, int l, int k) {
   NetDims d{J, D, W, skip, fc, fc ? 4 : 0};
   return layer_ref_col(d, l, k);
 }
-// emission order of produce_pts_chunks: group g (= half g of the joints) streams its joint groups
-// (4 joints x 18 values) into the chunks of parity g
+// emission order of produce_pts_chunks: group g encodes joints g, g+4, ... two at a time (36 values + 4 zeros)
+// and its stream fills K elements [8g, 8g+8) of chunk after chunk
 void h_emit_pts(const float* skt /*[J][12]*/, const float* p, float tau, const float* cut, int J, float* out) {
   NetDims d{J, 8, 256, 4, 0, 0};
   int n = pts_chunks(d) * kKC;
   memset(out, 0, n * sizeof(float));
-  int hj = pts_half_joints(d);
-  for (int grp = 0; grp < 2; ++grp) {
-    int hk = 0;   // position in this half's stream
-    for (int jg = 0; jg < hj / kPtsGroupJoints; ++jg)
-      for (int jj = 0; jj < kPtsGroupJoints; ++jj) {
-        int j = grp * hj + jg * kPtsGroupJoints + jj;
-        float v[kPtsPerJoint];
-        memset(v, 0, sizeof(v));
-        if (j < J) encode_joint_pts(skt + j * 12, p, tau, cut[j], v);
-        for (int q = 0; q < kPtsPerJoint; ++q, ++hk) {
-          int chunk = 2 * (hk / kKC) + grp;
-          out[chunk * kKC + hk % kKC] = v[q];
-        }
+  for (int g = 0; g < kGroups; ++g) {
+    int pos = 0;
+    for (int pair = 0; pair < pts_pairs(d); ++pair) {
+      float v[kPtsPairK];
+      memset(v, 0, sizeof(v));
+      for (int jj = 0; jj < 2; ++jj) {
+        int j = g + kGroups * (2 * pair + jj);
+        if (j < J) encode_joint_pts(skt + j * 12, p, tau, cut[j], v + jj * kPtsPerJoint);
       }
+      for (int q = 0; q < kPtsPairK; ++q, ++pos) out[(pos / 8) * kKC + g * 8 + pos % 8] = v[q];
+    }
   }
 }
 // emission order of produce_view_chunks: joint j in chunk j (27 values + 5 zeros); framecode chunk after
@@ -51,7 +48,7 @@ void h_emit_view(const float* skt, const float* dir, const float* p, float tau, 
     float w = cutoff_w(joint_dist(skt + j * 12, p), tau, cut[j]);
     for (int q = 0; q < kViewPerJoint; ++q) out[j * kKC + q] = tab[q] * w;
   }
-  for (int q = 0; q < fc; ++q) out[view_joint_chunks(d) * kKC + q] = fcode[q];
+  for (int q = 0; q < fc; ++q) out[J * kKC + q] = fcode[q];
 }
 float h_linspace01(int i, int n) { return linspace01(i, n); }
 void h_near_far(const float* o, const float* d, const float* cyl, float near, float far, float* out) {
