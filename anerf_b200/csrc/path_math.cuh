@@ -24,7 +24,7 @@ constexpr int kF = 7;                        // distance frequencies
 constexpr int kFv = 4;                       // view-direction frequencies
 constexpr int kPtsPerJoint = 1 + 2 * kF + 3; // 18: [v, (sin,cos) x 7] * w  ++  r(3)
 constexpr int kViewPerJoint = 3 * (1 + 2 * kFv);  // 27: [d, (sin,cos) x 4] x 3 components, * w
-constexpr int kGroups = 4;                   // worker groups; group g owns K elements [8g, 8g+8) of every 32-wide chunk
+constexpr int kGroups = 4;                   // worker groups; group g owns the chunks c with c % 4 == g of every operand part
 constexpr int kPtsPairK = 40;                // 2 joints x 18 values + 4 zeros = 5 x 8
 constexpr int kMaxJoints = 24;
 constexpr int kKC = 32;                      // K elements per operand chunk (two K=16 MMA slabs)
@@ -43,18 +43,20 @@ struct NetDims {
 };
 
 // ------------------------------------------------------------------------------------------------
-// K layout of the A operand.  Four worker groups produce every operand chunk together: group g
-// writes K elements [8g, 8g+8) of each 32-wide chunk.
+// K layout of the A operand.  Four worker groups produce the chunks of an operand part concurrently:
+// group g owns the chunks whose index inside the part is congruent to g mod 4 (whole 32-wide chunks, so
+// that one publish per chunk amortises the barrier / proxy-fence latency).
 //   pts part : group g encodes joints g, g+4, g+8, ... two at a time (2 x 18 values + 4 zeros = 40
-//              = 5 x 8) and its value stream fills its 8-wide slot chunk after chunk;
-//   view part: one chunk per joint: the joint's 27 per-ray direction features (+5 zeros) times the
-//              sample's cutoff weight, group g takes features [8g, 8g+8); framecodes, if any, add
-//              one chunk (16 values + 16 zeros);
-//   hidden   : chunk cb = accumulator columns [32cb, 32cb+32), group g drains columns 32cb+8g..+8.
+//              = 5 x 8) into its own value stream, zero padded to `pts_group_chunks` chunks; the
+//              part has 4 x pts_group_chunks chunks;
+//   view part: one chunk per joint (27 per-ray direction features + 5 zeros, times the sample's cutoff
+//              weight), joint j in chunk j; framecodes, if any, add one chunk (16 values + 16 zeros);
+//   hidden   : chunk cb = accumulator columns [32cb, 32cb+32).
 // ------------------------------------------------------------------------------------------------
 ANERF_HD int pts_group_joints(const NetDims& d) { return ceil_div(d.J, kGroups); }
 ANERF_HD int pts_pairs(const NetDims& d) { return ceil_div(pts_group_joints(d), 2); }
-ANERF_HD int pts_chunks(const NetDims& d) { return pts_pairs(d) * (kPtsPairK / 8); }
+ANERF_HD int pts_group_chunks(const NetDims& d) { return ceil_div(pts_pairs(d) * kPtsPairK, kKC); }
+ANERF_HD int pts_chunks(const NetDims& d) { return kGroups * pts_group_chunks(d); }
 ANERF_HD int view_chunks(const NetDims& d) { return d.J + (d.fc_ch > 0 ? 1 : 0); }
 ANERF_HD int hid_chunks(const NetDims& d) { return d.W / kKC; }
 ANERF_HD int in_pts_ref(const NetDims& d) { return d.J * (1 + 2 * kF) + d.J * 3; }
@@ -74,8 +76,9 @@ ANERF_HD int layer_chunks(const NetDims& d, int l) {
 // (cutoff_embedder.py:147-172, raycasters.py:560-569); skip layer input = cat[pts input, h]
 // (nerf.py:100-101); views layer input = cat[feature, k*3J + 3j + c, framecode] (nerf.py:121-125).
 ANERF_HD int pts_part_ref_col(const NetDims& d, int k) {
-  int c = k / kKC, g = (k % kKC) / 8, e = k % 8;
-  int p = c * 8 + e;                             // position in group g's value stream
+  int c = k / kKC, g = c % kGroups;
+  int p = (c / kGroups) * kKC + (k % kKC);       // position in group g's value stream
+  if (p >= pts_pairs(d) * kPtsPairK) return -1;
   int pair = p / kPtsPairK, within = p % kPtsPairK;
   if (within >= 2 * kPtsPerJoint) return -1;
   int j = g + kGroups * (2 * pair + within / kPtsPerJoint);

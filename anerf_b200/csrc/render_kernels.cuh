@@ -26,7 +26,7 @@
 namespace anerf {
 
 constexpr int kAStages = 4;
-constexpr int kBStages = 5;
+constexpr int kBStages = 6;
 constexpr int kAHalfBytes = kTileM * kKC * 2;        // 8 KB: hi (or lo) part of one A chunk
 constexpr int kAStageBytes = 2 * kAHalfBytes;        // 16 KB
 constexpr int kBStageBytes = 128 * kKC * 2 * 2;      // 16 KB: this CTA's half (N/2 <= 128 rows) of a weight chunk, hi + lo
@@ -96,7 +96,7 @@ inline __host__ NetProgram make_program(const NetDims& d) {
 // shared-memory carve-up of the fused kernel
 // ------------------------------------------------------------------------------------------------
 struct SmemLayout {
-  int a_ring, b_ring, smalls0, smalls1, ray, skt, view_tab, fcode, z_coarse, z_all, raw, part, wj, wts, cdf, bars, tmem_ptr;
+  int a_ring, b_ring, smalls0, smalls1, ray, skt, view_tab, fcode, z_coarse, z_all, raw, part, wts, cdf, bars, tmem_ptr;
   int total;
 };
 // ray_s: 12 floats per ray: o(3) d(3) near far |d| pad(3)
@@ -116,7 +116,6 @@ inline __host__ __device__ SmemLayout make_smem_layout(const NetDims& d, int sma
   L.z_all = off; off += align_up(rows * 4, 16);
   L.raw = off; off += rows * 16;             // network outputs (r,g,b,sigma) of the item's samples
   L.part = off; off += kGroups * kTileM * 16; // per-group partial outputs of the current tile
-  L.wj = off; off += d.J * kTileM * 4;        // view cutoff weights of the current tile [joint][row]
   L.wts = off; off += align_up(rows * 4, 16);
   L.cdf = off; off += align_up(R * Sc * 4, 16);
   L.bars = off; off += 8 * kNumBars;
@@ -178,7 +177,7 @@ __device__ __forceinline__ void pipe_init(Pipe& pp, uint8_t* a_ring, uint8_t* b_
 }
 // thread 0 of each CTA; followed by a cluster-wide sync
 __device__ __forceinline__ void pipe_init_barriers(const Pipe& pp) {
-  for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 2 * kWorkerWarps); mbar_init(&pp.a_empty[i], 1); }   // every worker warp of both CTAs
+  for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 8); mbar_init(&pp.a_empty[i], 1); }   // the 4 warps of the owning group, in both CTAs
   for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); mbar_init(&pp.peer_b[i], 1); }
   mbar_init(&pp.d_full[0], 1);
   mbar_init(&pp.d_full[1], 1);
@@ -191,41 +190,54 @@ __device__ __forceinline__ void a_chunk_ready(const Pipe& pp, uint32_t stage) {
 
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
-// whole-warp wait: one lane polls the barrier, the warp reconverges on it
+// whole-warp wait: every lane probes (warp-uniform control flow; a single-lane region would make the
+// compiler wrap the barrier instructions in ELECT loops)
 __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity, DeviceStatus* st, unsigned site) {
-  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, st, site);
+  mbar_wait(bar, parity, st, site);
   __syncwarp();
 }
 
-// A-operand producer state of one worker thread (= one row of the tile, one 8-wide K slot of every chunk).
-// All 16 worker warps of both CTAs of the pair contribute to every chunk, in chunk order.
+// A-operand producer state of one worker thread (= one row of the tile).  Group g fills the chunks of an
+// operand part whose index inside the part is congruent to g mod 4; `base` is the sequence number of the
+// part's first chunk (every worker advances it identically, part by part).
 template <int FMT>
 struct AProducer {
   const Pipe& pp;
-  uint32_t seq;        // sequence number of the next chunk (monotonic over the kernel's lifetime)
-  uint32_t slot_off;   // byte offset of this thread's 16 B inside the hi (or lo) half of a stage
-  __device__ AProducer(const Pipe& p, int row, int group)
-      : pp(p), seq(0), slot_off((group >> 1) * 4096 + (group & 1) * 2048 + (row >> 3) * 128 + (row & 7) * 16) {}
+  uint32_t base;       // sequence number (monotonic over the kernel's lifetime) of the current part's chunk 0
+  uint32_t row_off;    // (row/8)*128 + (row%8)*16
+  uint32_t cur;        // stage of the open chunk
+  uint8_t* stage;
+  __device__ AProducer(const Pipe& p, int row) : pp(p), base(0), row_off((row >> 3) * 128 + (row & 7) * 16), cur(0), stage(nullptr) {}
 
-  __device__ __forceinline__ void put8(const float (&x)[8]) {
-    const uint32_t s = seq % kAStages;
-    mbar_wait_warp(&pp.a_empty[s], ((seq / kAStages) & 1) ^ 1, pp.st, 100 + s);
-    uint8_t* st = pp.a_ring + s * kAStageBytes + slot_off;
+  // open chunk `c` of the current part: wait until the tensor core has released its ring stage
+  __device__ __forceinline__ void begin(uint32_t c) {
+    const uint32_t seq = base + c;
+    cur = seq % kAStages;
+    mbar_wait_warp(&pp.a_empty[cur], ((seq / kAStages) & 1) ^ 1, pp.st, 100 + cur);
+    stage = pp.a_ring + cur * kAStageBytes + row_off;
+  }
+  // K elements [8t, 8t+8) of the open chunk
+  __device__ __forceinline__ void store8(int t, const float (&x)[8]) {
     uint4 hi, lo;
     Split<FMT>::pair(x[0], x[1], hi.x, lo.x);
     Split<FMT>::pair(x[2], x[3], hi.y, lo.y);
     Split<FMT>::pair(x[4], x[5], hi.z, lo.z);
     Split<FMT>::pair(x[6], x[7], hi.w, lo.w);
-    *reinterpret_cast<uint4*>(st) = hi;
-    *reinterpret_cast<uint4*>(st + kAHalfBytes) = lo;
-    fence_proxy_async_smem();            // this thread's stores -> visible to the tensor core's reads
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) a_chunk_ready(pp, s);   // 16 warp arrivals per CTA per chunk
-    ++seq;
+    uint8_t* p = stage + (t >> 1) * 4096 + (t & 1) * 2048;
+    *reinterpret_cast<uint4*>(p) = hi;
+    *reinterpret_cast<uint4*>(p + kAHalfBytes) = lo;
   }
-  __device__ __forceinline__ void zero8() {
-    const float z[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    put8(z);
+  __device__ __forceinline__ void zero8(int t) {
+    uint8_t* p = stage + (t >> 1) * 4096 + (t & 1) * 2048;
+    *reinterpret_cast<uint4*>(p) = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(p + kAHalfBytes) = make_uint4(0u, 0u, 0u, 0u);
+  }
+  // publish the open chunk: one proxy fence per thread, one barrier arrival per warp
+  __device__ __forceinline__ void end() {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one()) a_chunk_ready(pp, cur);
+    __syncwarp();
   }
 };
 
@@ -242,6 +254,9 @@ struct Trace {
 // ------------------------------------------------------------------------------------------------
 // MMA issuer: one thread of the leader CTA.  All chunks of one layer, for both CTAs of the pair.
 // ------------------------------------------------------------------------------------------------
+// Executed by the WHOLE MMA warp of the leader CTA (warp-uniform control flow keeps addresses and loop
+// state in uniform registers; a divergent single-lane region makes the compiler wrap every UTCHMMA in an
+// ELECT/BRA.U.ANY loop, ~100 cycles per instruction); one elected lane issues.
 template <int FMT>
 __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint32_t& b_seq, int N, int chunks,
                                           int region, Trace* tr = nullptr) {
@@ -251,31 +266,39 @@ __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint3
   const uint32_t NH = (uint32_t)N / 2;           // B rows held by each CTA
 #pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
-    uint32_t sa = a_seq % kAStages, sb = b_seq % kBStages;
-    mbar_wait(&pp.b_full[sb], (b_seq / kBStages) & 1, pp.st, 300 + sb);
-    mbar_wait_cluster(&pp.peer_b[sb], (b_seq / kBStages) & 1, pp.st, 320 + sb);
-    mbar_wait_cluster(&pp.a_full[sa], (a_seq / kAStages) & 1, pp.st, 200 + sa);
+    const uint32_t sa = a_seq % kAStages, sb = b_seq % kBStages;
+    {
+      // the three "operand ready" barriers of this chunk are probed concurrently by different lanes
+      const int which = (threadIdx.x & 31) % 3;
+      uint64_t* bar = which == 0 ? &pp.a_full[sa] : (which == 1 ? &pp.b_full[sb] : &pp.peer_b[sb]);
+      const uint32_t par = which == 0 ? ((a_seq / kAStages) & 1) : ((b_seq / kBStages) & 1);
+      mbar_wait(bar, par, pp.st, 200 + 100 * which);
+      __syncwarp();
+    }
     tc_fence_after_sync();
     if (tr) tr->mark(c == 0 ? 1 : 2);        // 1: first chunk of a layer ready, 2: later chunk ready
-    uint32_t a_hi = a_base + sa * kAStageBytes, a_lo = a_hi + kAHalfBytes;
-    uint32_t b_hi = b_base + sb * kBStageBytes, b_lo = b_hi + NH * 64u;
+    const uint32_t a_hi = a_base + sa * kAStageBytes, a_lo = a_hi + kAHalfBytes;
+    const uint32_t b_hi = b_base + sb * kBStageBytes, b_lo = b_hi + NH * 64u;
+    if (elect_one()) {
 #pragma unroll
-    for (int s = 0; s < 2; ++s) {
-      uint64_t da_hi = smem_desc(a_hi + s * 4096, 2048, 128);
-      uint64_t da_lo = smem_desc(a_lo + s * 4096, 2048, 128);
-      uint64_t db_hi = smem_desc(b_hi + s * NH * 32u, NH * 16u, 128);
-      uint64_t db_lo = smem_desc(b_lo + s * NH * 32u, NH * 16u, 128);
-      // the two small cross terms first, then the dominant one
-      umma_f16(dcol, da_lo, db_hi, id, (c > 0 || s > 0) ? 1u : 0u);
-      umma_f16(dcol, da_hi, db_lo, id, 1u);
-      umma_f16(dcol, da_hi, db_hi, id, 1u);
+      for (int s = 0; s < 2; ++s) {
+        uint64_t da_hi = smem_desc(a_hi + s * 4096, 2048, 128);
+        uint64_t da_lo = smem_desc(a_lo + s * 4096, 2048, 128);
+        uint64_t db_hi = smem_desc(b_hi + s * NH * 32u, NH * 16u, 128);
+        uint64_t db_lo = smem_desc(b_lo + s * NH * 32u, NH * 16u, 128);
+        // the two small cross terms first, then the dominant one
+        umma_f16(dcol, da_lo, db_hi, id, (c > 0 || s > 0) ? 1u : 0u);
+        umma_f16(dcol, da_hi, db_lo, id, 1u);
+        umma_f16(dcol, da_hi, db_hi, id, 1u);
+      }
+      umma_commit(&pp.a_empty[sa]);
+      umma_commit(&pp.b_empty[sb]);
+      if (c == chunks - 1) umma_commit(&pp.d_full[region]);
     }
-    umma_commit(&pp.a_empty[sa]);
-    umma_commit(&pp.b_empty[sb]);
+    __syncwarp();
     ++a_seq;
     ++b_seq;
   }
-  umma_commit(&pp.d_full[region]);
   if (tr) tr->mark(3);                       // 3: layer fully issued
 }
 
@@ -316,11 +339,13 @@ struct RowCtx {
 };
 
 // layer-0 / skip-layer part: distance + bone encodings of the row's sample for this group's joints
-// (g, g+4, g+8, ...), two joints at a time: 36 values + 4 zeros = 5 slots
+// (g, g+4, g+8, ...), two joints at a time (36 values + 4 zeros = 5 slots of 8), streamed into the
+// group's chunks g, g+4, ... of the part
 template <int FMT>
 __device__ __forceinline__ void produce_pts_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P, int grp) {
   const int J = P.prog.dims.J;
   const int pairs = pts_pairs(P.prog.dims);
+  int slot = 0;
 #pragma unroll 1
   for (int pr = 0; pr < pairs; ++pr) {
     float vals[kPtsPairK];
@@ -341,135 +366,154 @@ __device__ __forceinline__ void produce_pts_chunks(AProducer<FMT>& ap, const Row
       float x[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) x[i] = vals[8 * t + i];
-      ap.put8(x);
+      if ((slot & 3) == 0) ap.begin((slot >> 2) * kGroups + grp);
+      ap.store8(slot & 3, x);
+      if ((slot & 3) == 3) ap.end();
+      ++slot;
     }
   }
-}
-
-// cutoff weights of the view encoding for this tile: group g computes joints g, g+4, ... of its row and
-// shares them through shared memory (wj[joint][row]); callers sync before produce_view_chunks
-__device__ __forceinline__ void compute_view_weights(const RowCtx& rc, const RenderKParams& P, int grp, int row, float* wj) {
-  const int J = P.prog.dims.J;
-#pragma unroll 1
-  for (int j = grp; j < J; j += kGroups)
-    wj[j * kTileM + row] = cutoff_w(joint_dist(rc.skt + j * 12, rc.p), P.tau_v, P.cut_v[j]);
+  const int total = pts_group_chunks(P.prog.dims) * 4;       // zero padding up to whole chunks
+  for (; slot < total; ++slot) {
+    if ((slot & 3) == 0) ap.begin((slot >> 2) * kGroups + grp);
+    ap.zero8(slot & 3);
+    if ((slot & 3) == 3) ap.end();
+  }
+  ap.base += pts_chunks(P.prog.dims);
 }
 
 // views-layer part: one chunk per joint = the ray's 27 direction features of that joint (+5 zeros)
-// times the sample's cutoff weight; this group contributes features [8g, 8g+8)
+// times the sample's cutoff weight; this group takes joints g, g+4, ...
 template <int FMT>
-__device__ __forceinline__ void produce_view_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P, int grp,
-                                                    int row, const float* wj) {
+__device__ __forceinline__ void produce_view_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P, int grp) {
   const int J = P.prog.dims.J;
 #pragma unroll 1
-  for (int j = 0; j < J; ++j) {
-    const float w = wj[j * kTileM + row];
-    const float4* tab = reinterpret_cast<const float4*>(rc.vtab + j * kKC + grp * 8);
-    float4 t0 = tab[0], t1 = tab[1];
-    float x[8] = {t0.x * w, t0.y * w, t0.z * w, t0.w * w, t1.x * w, t1.y * w, t1.z * w, t1.w * w};
-    ap.put8(x);
-  }
-  if (P.prog.dims.fc_ch > 0) {
-    float x[8];
+  for (int j = grp; j < J; j += kGroups) {
+    const float w = cutoff_w(joint_dist(rc.skt + j * 12, rc.p), P.tau_v, P.cut_v[j]);
+    const float4* tab = reinterpret_cast<const float4*>(rc.vtab + j * kKC);
+    ap.begin(j);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) x[i] = (grp * 8 + i) < P.prog.dims.fc_ch ? rc.fcode[(grp * 8 + i) & 15] : 0.f;
-    ap.put8(x);
+    for (int t = 0; t < 4; ++t) {
+      float4 t0 = tab[2 * t], t1 = tab[2 * t + 1];
+      float x[8] = {t0.x * w, t0.y * w, t0.z * w, t0.w * w, t1.x * w, t1.y * w, t1.z * w, t1.w * w};
+      ap.store8(t, x);
+    }
+    ap.end();
   }
+  if (P.prog.dims.fc_ch > 0 && grp == (J % kGroups)) {
+    ap.begin(J);
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      float x[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = (8 * t + i) < P.prog.dims.fc_ch ? rc.fcode[(8 * t + i) & 15] : 0.f;
+      ap.store8(t, x);
+    }
+    ap.end();
+  }
+  ap.base += view_chunks(P.prog.dims);
 }
 
-// Wait for the accumulators of the layer that used `region`, then walk its column blocks; this group
-// takes columns [32cb + 8g, 32cb + 8g + 8) of every block.  f(col0, x[8]) receives scale*acc + bias
-// (ReLU applied when RELU).
-template <int FMT, bool RELU, typename F>
-__device__ __forceinline__ void drain_region(const Pipe& pp, uint32_t (&d_cnt)[2], int region, int N,
-                                             const float* bias, float scale, int quarter, int grp, F&& f,
+// Wait for the accumulators of the layer that used `region`, then walk this group's column blocks
+// (cb = g, g+4, ...; 32 columns each, 8 at a time).  acc(col0, x[8]) sees scale*acc + bias (ReLU applied
+// when RELU); with EMIT the block also becomes chunk cb of the next layer's operand.
+template <int FMT, bool RELU, bool EMIT, typename F>
+__device__ __forceinline__ void drain_region(AProducer<FMT>& ap, const Pipe& pp, uint32_t (&d_cnt)[2], int region, int N,
+                                             const float* bias, float scale, int quarter, int grp, F&& acc,
                                              Trace* tr = nullptr) {
   if (tr) tr->mark(10);                      // 10: start waiting for the layer's accumulators
   mbar_wait_warp(&pp.d_full[region], d_cnt[region] & 1, pp.st, 500 + region);
   ++d_cnt[region];
   tc_fence_after_sync();
   if (tr) tr->mark(11);                      // 11: accumulators ready
-  const uint32_t taddr = pp.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)region * 256u + (uint32_t)grp * 8u;
+  const uint32_t taddr = pp.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)region * 256u;
+  const int nblk = N / 32;
   uint32_t v[8];
-  tmem_ld8(taddr, v);
+  if (grp < nblk) tmem_ld8(taddr + grp * 32, v);
 #pragma unroll 1
-  for (int cb = 0; cb < N / 32; ++cb) {
-    tmem_ld_wait();
-    float a[8];
+  for (int cb = grp; cb < nblk; cb += kGroups) {
+    if (EMIT) ap.begin(cb);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(v[i]);
-    if (cb + 1 < N / 32) tmem_ld8(taddr + (cb + 1) * 32, v);        // next block in flight while this one is processed
-    const int col0 = cb * 32 + grp * 8;
-    const float4 b0 = *reinterpret_cast<const float4*>(bias + col0), b1 = *reinterpret_cast<const float4*>(bias + col0 + 4);
-    float x[8];
-    x[0] = fmaf(a[0], scale, b0.x); x[1] = fmaf(a[1], scale, b0.y); x[2] = fmaf(a[2], scale, b0.z); x[3] = fmaf(a[3], scale, b0.w);
-    x[4] = fmaf(a[4], scale, b1.x); x[5] = fmaf(a[5], scale, b1.y); x[6] = fmaf(a[6], scale, b1.z); x[7] = fmaf(a[7], scale, b1.w);
-    if (RELU) {
+    for (int t = 0; t < 4; ++t) {
+      tmem_ld_wait();
+      float a[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+      for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(v[i]);
+      // next 8 columns in flight while these are processed
+      if (t < 3) tmem_ld8(taddr + cb * 32 + (t + 1) * 8, v);
+      else if (cb + kGroups < nblk) tmem_ld8(taddr + (cb + kGroups) * 32, v);
+      const int col0 = cb * 32 + t * 8;
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + col0), b1 = *reinterpret_cast<const float4*>(bias + col0 + 4);
+      float x[8];
+      x[0] = fmaf(a[0], scale, b0.x); x[1] = fmaf(a[1], scale, b0.y); x[2] = fmaf(a[2], scale, b0.z); x[3] = fmaf(a[3], scale, b0.w);
+      x[4] = fmaf(a[4], scale, b1.x); x[5] = fmaf(a[5], scale, b1.y); x[6] = fmaf(a[6], scale, b1.z); x[7] = fmaf(a[7], scale, b1.w);
+      if (RELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+      }
+      acc(col0, x);
+      if (EMIT) ap.store8(t, x);
     }
-    f(col0, x);
-    if (tr) tr->mark(12);                    // 12: one column block drained (and its slot published)
+    if (EMIT) ap.end();
+    if (tr) tr->mark(12);                    // 12: one column block drained (and its chunk published)
   }
+  if (EMIT) ap.base += nblk;
   tc_fence_before_sync();
 }
 
 // One tile (128 rows) through one network, this group's share.  Returns this group's partial
 // (rgb logits, raw sigma) of the thread's row; the four groups' partials add up to the result
-// (biases are added by group 0).  DENSITY: trunk + alpha only.  Contains ONE worker_sync (all 16 worker
-// warps call it) between the view-weight computation and the view chunks.
+// (biases are added by group 0).  DENSITY: trunk + alpha only.
 template <int FMT, bool DENSITY>
 __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe& pp, uint32_t (&d_cnt)[2],
                                                   const RowCtx& rc, const RenderKParams& P, const float* sm,
-                                                  int quarter, int grp, int row, float* wj, Trace* tr = nullptr) {
+                                                  int quarter, int grp, Trace* tr = nullptr) {
   const NetProgram& pg = P.prog;
   const int D = pg.dims.D, W = pg.dims.W;
   float sigma = 0.f;
   const float* wa = sm + pg.sm.alpha_w;
-  // operands of trunk layers 0..D-1 and of feature_linear (l == D): [encoding part] + drain of layer l-1
+  // operands of trunk layers 0..D-1: [encoding part] + drain of layer l-1
 #pragma unroll 1
-  for (int l = 0; l <= D; ++l) {
-    if (l == 0 || ((l - 1) == pg.dims.skip && l < D)) {
+  for (int l = 0; l < D; ++l) {
+    if (l == 0 || (l - 1) == pg.dims.skip) {
       if (tr) tr->mark(20);                  // 20/21: encoding part begin/end
       produce_pts_chunks<FMT>(ap, rc, P, grp);
       if (tr) tr->mark(21);
     }
-    if (l > 0) {
-      const bool last = (l == D);                 // h of the last trunk layer: alpha_linear in fp32 on the way
-      const bool emit = !(DENSITY && last);
-      drain_region<FMT, true>(pp, d_cnt, (l - 1) & 1, W, sm + pg.sm.bias[l - 1], sm[l - 1], quarter, grp,
-                              [&](int col0, const float (&x)[8]) {
-                                if (last) {
-#pragma unroll
-                                  for (int i = 0; i < 8; ++i) sigma = fmaf(x[i], wa[col0 + i], sigma);
-                                }
-                                if (emit) ap.put8(x);
-                              }, tr);
-    }
+    if (l > 0)
+      drain_region<FMT, true, true>(ap, pp, d_cnt, (l - 1) & 1, W, sm + pg.sm.bias[l - 1], sm[l - 1], quarter, grp,
+                                    [](int, const float (&)[8]) {}, tr);
   }
+  // h of the last trunk layer: alpha_linear in fp32 on the way; operand of feature_linear unless DENSITY
+  auto alpha_acc = [&](int col0, const float (&x)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sigma = fmaf(x[i], wa[col0 + i], sigma);
+  };
+  if (DENSITY) {
+    drain_region<FMT, true, false>(ap, pp, d_cnt, (D - 1) & 1, W, sm + pg.sm.bias[D - 1], sm[D - 1], quarter, grp, alpha_acc, tr);
+    if (grp == 0) sigma += sm[pg.sm.alpha_b];
+    return make_float4(0.f, 0.f, 0.f, sigma);
+  }
+  drain_region<FMT, true, true>(ap, pp, d_cnt, (D - 1) & 1, W, sm + pg.sm.bias[D - 1], sm[D - 1], quarter, grp, alpha_acc, tr);
   if (grp == 0) sigma += sm[pg.sm.alpha_b];
-  if (DENSITY) return make_float4(0.f, 0.f, 0.f, sigma);
   // operand of views_linears[0]: view encoding first (independent of feature), then feature (no ReLU)
   if (tr) tr->mark(22);
-  compute_view_weights(rc, P, grp, row, wj);
-  worker_sync();
-  produce_view_chunks<FMT>(ap, rc, P, grp, row, wj);
+  produce_view_chunks<FMT>(ap, rc, P, grp);
   if (tr) tr->mark(23);
-  drain_region<FMT, false>(pp, d_cnt, D & 1, W, sm + pg.sm.bias[D], sm[D], quarter, grp,
-                           [&](int, const float (&x)[8]) { ap.put8(x); }, tr);
+  drain_region<FMT, false, true>(ap, pp, d_cnt, D & 1, W, sm + pg.sm.bias[D], sm[D], quarter, grp,
+                                 [](int, const float (&)[8]) {}, tr);
   // views layer output -> rgb_linear in fp32
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
   const float* wr = sm + pg.sm.rgb_w;
   const int H = W / 2;
-  drain_region<FMT, true>(pp, d_cnt, (D + 1) & 1, H, sm + pg.sm.bias[D + 1], sm[D + 1], quarter, grp,
-                          [&](int col0, const float (&x)[8]) {
+  drain_region<FMT, true, false>(ap, pp, d_cnt, (D + 1) & 1, H, sm + pg.sm.bias[D + 1], sm[D + 1], quarter, grp,
+                                 [&](int col0, const float (&x)[8]) {
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                              r0 = fmaf(x[i], wr[col0 + i], r0);
-                              r1 = fmaf(x[i], wr[H + col0 + i], r1);
-                              r2 = fmaf(x[i], wr[2 * H + col0 + i], r2);
-                            }
-                          }, tr);
+                                   for (int i = 0; i < 8; ++i) {
+                                     r0 = fmaf(x[i], wr[col0 + i], r0);
+                                     r1 = fmaf(x[i], wr[H + col0 + i], r1);
+                                     r2 = fmaf(x[i], wr[2 * H + col0 + i], r2);
+                                   }
+                                 }, tr);
   if (grp == 0) {
     const float* br = sm + pg.sm.rgb_b;
     r0 += br[0]; r1 += br[1]; r2 += br[2];
@@ -630,15 +674,17 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
   const int nl = DENSITY ? pg.dims.D : pg.n_layers;
 
   if (warp == kMmaWarp) {
-    if (lane == 0) {
-      uint32_t a_seq = 0, b_seq = 0;
-      Trace trc; trc.init(P.trace, 0);
+    uint32_t a_seq = 0, b_seq = 0;
+    Trace trc; trc.init(lane == 0 ? P.trace : nullptr, 0);
+    if (pp.rank == 0) {            // leader: the whole warp walks the program, one elected lane issues
       for (int it = 0; it < n_iter; ++it)
         for (int ps = 0; ps < passes; ++ps)
-          for (int l = 0; l < nl; ++l) {
-            if (pp.rank == 0) mma_layer<FMT>(pp, a_seq, b_seq, pg.layer[l].n, pg.layer[l].chunks, l & 1, P.trace ? &trc : nullptr);
-            else relay_layer(pp, b_seq, pg.layer[l].chunks);
-          }
+          for (int l = 0; l < nl; ++l)
+            mma_layer<FMT>(pp, a_seq, b_seq, pg.layer[l].n, pg.layer[l].chunks, l & 1, trc.p ? &trc : nullptr);
+    } else if (lane == 0) {        // peer: relay "my weight half has landed"
+      for (int it = 0; it < n_iter; ++it)
+        for (int ps = 0; ps < passes; ++ps)
+          for (int l = 0; l < nl; ++l) relay_layer(pp, b_seq, pg.layer[l].chunks);
     }
     __syncwarp();
   } else if (warp == kLoadWarp) {
@@ -655,7 +701,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
     // ------------------------------- worker warps (rows) -------------------------------------
     const int grp = warp >> 2, quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    AProducer<FMT> ap(pp, row, grp);
+    AProducer<FMT> ap(pp, row);
     uint32_t d_cnt[2] = {0u, 0u};
     Trace trc; trc.init((quarter == 0 && lane == 0 && grp < 2) ? P.trace : nullptr, 1 + grp);
     Trace* tr = trc.p ? &trc : nullptr;
@@ -667,7 +713,6 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
     float* za_s = reinterpret_cast<float*>(smem + L.z_all);
     float4* raw_s = reinterpret_cast<float4*>(smem + L.raw);
     float4* part_s = reinterpret_cast<float4*>(smem + L.part);
-    float* wj_s = reinterpret_cast<float*>(smem + L.wj);
     float* w_s = reinterpret_cast<float*>(smem + L.wts);
     float* cdf_s = reinterpret_cast<float*>(smem + L.cdf);
     const float* sm0 = reinterpret_cast<const float*>(smem + L.smalls0);
@@ -687,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         RowCtx rc;
         rc.p[0] = P.pts[ci * 3 + 0]; rc.p[1] = P.pts[ci * 3 + 1]; rc.p[2] = P.pts[ci * 3 + 2];
         rc.skt = skt_s; rc.vtab = nullptr; rc.fcode = nullptr;
-        float4 r = worker_net_pass<FMT, true>(ap, pp, d_cnt, rc, P, sm0, quarter, grp, row, wj_s);
+        float4 r = worker_net_pass<FMT, true>(ap, pp, d_cnt, rc, P, sm0, quarter, grp);
         part_s[grp * kTileM + row] = r;
         worker_sync();
         if (grp == 0 && valid)
@@ -767,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
           rc.p[0] = rr[0] + rr[3] * z; rc.p[1] = rr[1] + rr[4] * z; rc.p[2] = rr[2] + rr[5] * z;
           rc.skt = skt_s + r * J * 12; rc.vtab = vtab_s + r * VK; rc.fcode = fc_s + ((is_fine ? R : 0) + r) * 16;
           if (tr) tr->mark(30 + ps);
-          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, is_fine ? sm1 : sm0, quarter, grp, row, wj_s, tr);
+          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, is_fine ? sm1 : sm0, quarter, grp, tr);
           if (tr) tr->mark(40 + ps);
           part_s[grp * kTileM + row] = o;
           worker_sync();
@@ -993,7 +1038,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAStages * kAStageBytes + kBStages * kBStageBytes);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
-  float* zero_bias = reinterpret_cast<float*>(tmem_slot + 4);
+  float* zero_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
   Pipe pp;
   pipe_init(pp, smem, smem + kAStages * kAStageBytes, bars, status);
   if (tid == 0) pipe_init_barriers(pp);
@@ -1007,12 +1052,11 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const 
   const int chunks = K / kKC;
   // two back-to-back "layers" into regions 0 and 1 exercise ring wrap-around and both TMEM regions
   if (warp == kMmaWarp) {
-    if (lane == 0) {
-      uint32_t a_seq = 0, b_seq = 0;
-      for (int rep = 0; rep < 2; ++rep) {
-        if (pp.rank == 0) mma_layer<FMT>(pp, a_seq, b_seq, N, chunks, rep);
-        else relay_layer(pp, b_seq, chunks);
-      }
+    uint32_t a_seq = 0, b_seq = 0;
+    if (pp.rank == 0) {
+      for (int rep = 0; rep < 2; ++rep) mma_layer<FMT>(pp, a_seq, b_seq, N, chunks, rep);
+    } else if (lane == 0) {
+      for (int rep = 0; rep < 2; ++rep) relay_layer(pp, b_seq, chunks);
     }
     __syncwarp();
   } else if (warp == kLoadWarp) {
@@ -1024,18 +1068,23 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_selftest_gemm_kernel(const 
   } else {
     const int grp = warp >> 2, quarter = warp & 3, row = quarter * 32 + lane;
     const size_t grow = (size_t)pp.rank * kTileM + row;          // row of the 256-row problem
-    AProducer<FMT> ap(pp, row, grp);
+    AProducer<FMT> ap(pp, row);
     uint32_t d_cnt[2] = {0u, 0u};
     for (int rep = 0; rep < 2; ++rep) {
-      for (int c = 0; c < chunks; ++c) {
-        float x[8];
+      for (int c = grp; c < chunks; c += kGroups) {
+        ap.begin(c);
+        for (int t = 0; t < 4; ++t) {
+          float x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = A[grow * K + c * kKC + grp * 8 + i];
-        ap.put8(x);
+          for (int i = 0; i < 8; ++i) x[i] = A[grow * K + c * kKC + t * 8 + i];
+          ap.store8(t, x);
+        }
+        ap.end();
       }
+      ap.base += chunks;
     }
     for (int rep = 0; rep < 2; ++rep) {
-      drain_region<1, false>(pp, d_cnt, rep, N, zero_bias, 1.0f, quarter, grp, [&](int col0, const float (&x)[8]) {
+      drain_region<FMT, false, false>(ap, pp, d_cnt, rep, N, zero_bias, 1.0f, quarter, grp, [&](int col0, const float (&x)[8]) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) Dout[(size_t)rep * 2 * kTileM * N + grow * N + col0 + i] = x[i];
       });

@@ -18,7 +18,7 @@ int h_layer_ref_col(int J, int D, int W, int skip, int fc, int l, int k) {
   return layer_ref_col(d, l, k);
 }
 // emission order of produce_pts_chunks: group g encodes joints g, g+4, ... two at a time (36 values + 4 zeros)
-// and its stream fills K elements [8g, 8g+8) of chunk after chunk
+// and its stream fills the chunks g, g+4, g+8, ... of the part
 void h_emit_pts(const float* skt /*[J][12]*/, const float* p, float tau, const float* cut, int J, float* out) {
   NetDims d{J, 8, 256, 4, 0, 0};
   int n = pts_chunks(d) * kKC;
@@ -32,7 +32,7 @@ void h_emit_pts(const float* skt /*[J][12]*/, const float* p, float tau, const f
         int j = g + kGroups * (2 * pair + jj);
         if (j < J) encode_joint_pts(skt + j * 12, p, tau, cut[j], v + jj * kPtsPerJoint);
       }
-      for (int q = 0; q < kPtsPairK; ++q, ++pos) out[(pos / 8) * kKC + g * 8 + pos % 8] = v[q];
+      for (int q = 0; q < kPtsPairK; ++q, ++pos) out[((pos / kKC) * kGroups + g) * kKC + pos % kKC] = v[q];
     }
   }
 }
