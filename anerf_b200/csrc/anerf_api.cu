@@ -309,6 +309,19 @@ int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, con
       o_raw = seg(hout->raw, hout->raw ? (size_t)N * (Si > 0 ? Sf : Sc) * 16 : 0);
   size_t ws_off = off;
   off += al(anerf_render_workspace_bytes(N));
+  {   // keep the stream-ordered pool's memory across calls (the default releases it at every synchronisation)
+    static bool pool_ready = false;
+    if (!pool_ready) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+      pool_ready = true;
+    }
+  }
   uint8_t* arena = nullptr;
   CUDA_TRY(cudaMallocAsync((void**)&arena, off, stream));
   auto up = [&](const Seg& s) -> const float* {
@@ -334,7 +347,7 @@ int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, con
 
 int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t format, void* stream_) {
   if (!A || !B || !D) return fail(ANERF_ERR_INVALID, "null argument");
-  if (K <= 0 || K % kKC != 0) return fail(ANERF_ERR_INVALID, "K must be a positive multiple of 32");
+  if (K <= 0 || K % (kGroups * kKC) != 0) return fail(ANERF_ERR_INVALID, "K must be a positive multiple of 128");
   if (N != 64 && N != 128 && N != 256) return fail(ANERF_ERR_INVALID, "N must be 64, 128 or 256");
   if (format != 0 && format != 1) return fail(ANERF_ERR_INVALID, "format must be 0 (fp16) or 1 (bf16)");
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -57,8 +57,10 @@ ANERF_HD int pts_group_joints(const NetDims& d) { return ceil_div(d.J, kGroups);
 ANERF_HD int pts_pairs(const NetDims& d) { return ceil_div(pts_group_joints(d), 2); }
 ANERF_HD int pts_group_chunks(const NetDims& d) { return ceil_div(pts_pairs(d) * kPtsPairK, kKC); }
 ANERF_HD int pts_chunks(const NetDims& d) { return kGroups * pts_group_chunks(d); }
-ANERF_HD int view_chunks(const NetDims& d) { return d.J + (d.fc_ch > 0 ? 1 : 0); }
-ANERF_HD int hid_chunks(const NetDims& d) { return d.W / kKC; }
+// every part is padded to a multiple of 4 chunks: group g then always fills ring stage g (4 stages), i.e. each
+// group follows the phases of ONE "stage empty" barrier in order (a parity wait is only valid one phase ahead)
+ANERF_HD int view_chunks(const NetDims& d) { return round_up(d.J + (d.fc_ch > 0 ? 1 : 0), kGroups); }
+ANERF_HD int hid_chunks(const NetDims& d) { return round_up(d.W / kKC, kGroups); }
 ANERF_HD int in_pts_ref(const NetDims& d) { return d.J * (1 + 2 * kF) + d.J * 3; }
 ANERF_HD int in_views_ref(const NetDims& d) { return d.J * kViewPerJoint; }
 
@@ -88,7 +90,7 @@ ANERF_HD int pts_part_ref_col(const NetDims& d, int k) {
 }
 ANERF_HD int view_part_ref_col(const NetDims& d, int k) {   // relative to the start of input_views
   int c = k / kKC, q = k % kKC;
-  if (c >= d.J) return (c == d.J && q < d.fc_ch) ? in_views_ref(d) + q : -1;
+  if (c >= d.J) return (c == d.J && d.fc_ch > 0 && q < d.fc_ch) ? in_views_ref(d) + q : -1;
   if (q >= kViewPerJoint) return -1;
   return (q / 3) * 3 * d.J + 3 * c + (q % 3);
 }
@@ -96,12 +98,12 @@ ANERF_HD int layer_ref_col(const NetDims& d, int l, int k) {
   int P = pts_chunks(d) * kKC, V = view_chunks(d) * kKC;
   if (l == 0) return pts_part_ref_col(d, k);
   if (l < d.D) {
-    if ((l - 1) == d.skip) return k < P ? pts_part_ref_col(d, k) : in_pts_ref(d) + (k - P);
-    return k;
+    if ((l - 1) == d.skip) return k < P ? pts_part_ref_col(d, k) : ((k - P) < d.W ? in_pts_ref(d) + (k - P) : -1);
+    return k < d.W ? k : -1;
   }
-  if (l == d.D) return k;
+  if (l == d.D) return k < d.W ? k : -1;
   if (k < V) { int c = view_part_ref_col(d, k); return c < 0 ? -1 : d.W + c; }
-  return k - V;   // feature part
+  return (k - V) < d.W ? k - V : -1;   // feature part
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -399,17 +399,23 @@ __device__ __forceinline__ void produce_view_chunks(AProducer<FMT>& ap, const Ro
     }
     ap.end();
   }
-  if (P.prog.dims.fc_ch > 0 && grp == (J % kGroups)) {
-    ap.begin(J);
+  int c0 = J;                                   // first chunk after the joints
+  if (P.prog.dims.fc_ch > 0) {
+    if (grp == (J % kGroups)) {
+      ap.begin(J);
 #pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float x[8];
+      for (int t = 0; t < 4; ++t) {
+        float x[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = (8 * t + i) < P.prog.dims.fc_ch ? rc.fcode[(8 * t + i) & 15] : 0.f;
-      ap.store8(t, x);
+        for (int i = 0; i < 8; ++i) x[i] = (8 * t + i) < P.prog.dims.fc_ch ? rc.fcode[(8 * t + i) & 15] : 0.f;
+        ap.store8(t, x);
+      }
+      ap.end();
     }
-    ap.end();
+    c0 = J + 1;
   }
+  for (int c = c0; c < view_chunks(P.prog.dims); ++c)      // zero chunks up to a multiple of 4
+    if (grp == (c % kGroups)) { ap.begin(c); for (int t = 0; t < 4; ++t) ap.zero8(t); ap.end(); }
   ap.base += view_chunks(P.prog.dims);
 }
 
@@ -456,7 +462,15 @@ __device__ __forceinline__ void drain_region(AProducer<FMT>& ap, const Pipe& pp,
     if (EMIT) ap.end();
     if (tr) tr->mark(12);                    // 12: one column block drained (and its chunk published)
   }
-  if (EMIT) ap.base += nblk;
+  if (EMIT) {
+    const int padded = round_up(nblk, kGroups);            // hidden parts are padded to a multiple of 4 chunks
+    for (int cb = nblk + ((grp - nblk) % kGroups + kGroups) % kGroups; cb < padded; cb += kGroups) {
+      ap.begin(cb);
+      for (int t = 0; t < 4; ++t) ap.zero8(t);
+      ap.end();
+    }
+    ap.base += padded;
+  }
   tc_fence_before_sync();
 }
 

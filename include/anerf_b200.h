@@ -143,7 +143,7 @@ int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf
                          const float* pts, const float* skts, int64_t n_points, float* sigma, void* stream);
 
 /* Build-time self test of the tensor-core building blocks on one CTA pair: D[256,N] = A[256,K] * B[N,K]^T with
- * the split-precision operand path (A, B fp32 on the device, D [2,256,N] fp32: two passes; K multiple of 64;
+ * the split-precision operand path (A, B fp32 on the device, D [2,256,N] fp32: two passes; K multiple of 128;
  * N in {64,128,256}).
  * format: 1 bf16, 0 fp16. */
 int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t format,
