@@ -144,12 +144,16 @@ ANERF_HD void near_far_cylinder(const float o[3], const float d[3], const float 
 // cutoff_embedder.py:111-174 with dist_inputs=False, cutoff_inputs=True).
 // skt = rows 0..2 of the 4x4 world->bone transform, row-major (12 floats).
 // out[18] = [v w, sin(2^f v) w, cos(2^f v) w (f=0..6), r0, r1, r2];  also returns v.
-// sin/cos of 2^f v: two accurate evaluations (f=0 and f=3) + at most three exact-angle doublings
-// each, which stays within a few ulp of evaluating sinf(2^f v) directly (2^f v is exact in fp32).
 // ------------------------------------------------------------------------------------------------
+// 1 - sigmoid(tau (v - c))  (cutoff_embedder.py:138-146).  Device: ex2/rcp based (relative error ~2^-21 on a
+// factor in [0,1]); host (layout tests): libm.
 ANERF_HD float cutoff_w(float v, float tau, float cut) {
   float a = tau * (v - cut);
+#if defined(__CUDA_ARCH__)
+  return 1.0f - __fdividef(1.0f, 1.0f + __expf(-a));
+#else
   return 1.0f - 1.0f / (1.0f + expf(-a));
+#endif
 }
 
 ANERF_HD void bone_local(const float* skt, const float p[3], float x[3]) {
@@ -158,33 +162,38 @@ ANERF_HD void bone_local(const float* skt, const float p[3], float x[3]) {
   x[2] = skt[8] * p[0] + skt[9] * p[1] + skt[10] * p[2] + skt[11];
 }
 
+// sin and cos of x = 2^f v (exact in fp32), |x| up to a few hundred.  Device: two-term Cody-Waite reduction by
+// 2 pi to [-pi, pi], then the SFU (sin.approx / cos.approx, absolute error <= 2^-20.9 there): ~5e-7 absolute,
+// 5 instructions.  (sincosf costs ~35 instructions per call; two calls + double-angle steps were 1.4e-6.)
+ANERF_HD void sincos_2pi(float x, float& s, float& c) {
+#if defined(__CUDA_ARCH__)
+  float k = rintf(x * 0.15915494309189535f);
+  float r = fmaf(-k, 6.2831854820251465f, x);          // 2 pi, high part (fp32)
+  r = fmaf(-k, -1.7484555314695172e-07f, r);            // 2 pi - high part
+  s = __sinf(r);
+  c = __cosf(r);
+#else
+  s = sinf(x); c = cosf(x);
+#endif
+}
+
 ANERF_HD float encode_joint_pts(const float* skt, const float p[3], float tau, float cut, float* out) {
   float x[3];
   bone_local(skt, p, x);
   float v = sqrtf(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+#if defined(__CUDA_ARCH__)
+  float inv = __frcp_rn(fmaxf(v, 1e-12f));
+#else
   float inv = 1.0f / fmaxf(v, 1e-12f);
+#endif
   float w = cutoff_w(v, tau, cut);
   out[0] = v * w;
-  float s, c;
-#if defined(__CUDA_ARCH__)
-  sincosf(v, &s, &c);
-#else
-  s = sinf(v); c = cosf(v);
-#endif
-  float s3, c3;
-#if defined(__CUDA_ARCH__)
-  sincosf(v * 8.0f, &s3, &c3);
-#else
-  s3 = sinf(v * 8.0f); c3 = cosf(v * 8.0f);
-#endif
 #pragma unroll
   for (int f = 0; f < kF; ++f) {
-    if (f == 3) { s = s3; c = c3; }
+    float s, c;
+    sincos_2pi(v * (float)(1 << f), s, c);
     out[1 + 2 * f] = s * w;
     out[2 + 2 * f] = c * w;
-    float s2 = 2.0f * s * c;
-    float c2 = 1.0f - 2.0f * s * s;
-    s = s2; c = c2;
   }
   out[15] = x[0] * inv;
   out[16] = x[1] * inv;

@@ -264,40 +264,48 @@ __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint3
   const uint32_t dcol = pp.tmem_base + (uint32_t)region * 256u;
   const uint32_t a_base = smem_u32(pp.a_ring), b_base = smem_u32(pp.b_ring);
   const uint32_t NH = (uint32_t)N / 2;           // B rows held by each CTA
+  // Narrow layers (N <= 128: 64-cycle MMAs) take two chunks per iteration so that the fixed cost of an
+  // iteration (barrier probes, commits) stays below the tensor time of what it issues.  Chunk counts are
+  // multiples of 4, so pairs never straddle a layer.
+  const int step = N <= 128 ? 2 : 1;
+  const int lane = threadIdx.x & 31;
 #pragma unroll 1
-  for (int c = 0; c < chunks; ++c) {
-    const uint32_t sa = a_seq % kAStages, sb = b_seq % kBStages;
+  for (int c = 0; c < chunks; c += step) {
     {
-      // the three "operand ready" barriers of this chunk are probed concurrently by different lanes
-      const int which = (threadIdx.x & 31) % 3;
-      uint64_t* bar = which == 0 ? &pp.a_full[sa] : (which == 1 ? &pp.b_full[sb] : &pp.peer_b[sb]);
-      const uint32_t par = which == 0 ? ((a_seq / kAStages) & 1) : ((b_seq / kBStages) & 1);
+      // the "operand ready" barriers of this iteration's chunks are probed concurrently by different lanes
+      const int which = lane % 3, sub = (lane / 3) % step;
+      const uint32_t qa = a_seq + sub, qb = b_seq + sub;
+      uint64_t* bar = which == 0 ? &pp.a_full[qa % kAStages] : (which == 1 ? &pp.b_full[qb % kBStages] : &pp.peer_b[qb % kBStages]);
+      const uint32_t par = which == 0 ? ((qa / kAStages) & 1) : ((qb / kBStages) & 1);
       mbar_wait(bar, par, pp.st, 200 + 100 * which);
       __syncwarp();
     }
     tc_fence_after_sync();
     if (tr) tr->mark(c == 0 ? 1 : 2);        // 1: first chunk of a layer ready, 2: later chunk ready
-    const uint32_t a_hi = a_base + sa * kAStageBytes, a_lo = a_hi + kAHalfBytes;
-    const uint32_t b_hi = b_base + sb * kBStageBytes, b_lo = b_hi + NH * 64u;
     if (elect_one()) {
+      for (int u = 0; u < step; ++u) {
+        const uint32_t sa = (a_seq + u) % kAStages, sb = (b_seq + u) % kBStages;
+        const uint32_t a_hi = a_base + sa * kAStageBytes, a_lo = a_hi + kAHalfBytes;
+        const uint32_t b_hi = b_base + sb * kBStageBytes, b_lo = b_hi + NH * 64u;
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        uint64_t da_hi = smem_desc(a_hi + s * 4096, 2048, 128);
-        uint64_t da_lo = smem_desc(a_lo + s * 4096, 2048, 128);
-        uint64_t db_hi = smem_desc(b_hi + s * NH * 32u, NH * 16u, 128);
-        uint64_t db_lo = smem_desc(b_lo + s * NH * 32u, NH * 16u, 128);
-        // the two small cross terms first, then the dominant one
-        umma_f16(dcol, da_lo, db_hi, id, (c > 0 || s > 0) ? 1u : 0u);
-        umma_f16(dcol, da_hi, db_lo, id, 1u);
-        umma_f16(dcol, da_hi, db_hi, id, 1u);
+        for (int s = 0; s < 2; ++s) {
+          uint64_t da_hi = smem_desc(a_hi + s * 4096, 2048, 128);
+          uint64_t da_lo = smem_desc(a_lo + s * 4096, 2048, 128);
+          uint64_t db_hi = smem_desc(b_hi + s * NH * 32u, NH * 16u, 128);
+          uint64_t db_lo = smem_desc(b_lo + s * NH * 32u, NH * 16u, 128);
+          // the two small cross terms first, then the dominant one
+          umma_f16(dcol, da_lo, db_hi, id, (c + u > 0 || s > 0) ? 1u : 0u);
+          umma_f16(dcol, da_hi, db_lo, id, 1u);
+          umma_f16(dcol, da_hi, db_hi, id, 1u);
+        }
+        umma_commit(&pp.a_empty[sa]);
+        umma_commit(&pp.b_empty[sb]);
       }
-      umma_commit(&pp.a_empty[sa]);
-      umma_commit(&pp.b_empty[sb]);
-      if (c == chunks - 1) umma_commit(&pp.d_full[region]);
+      if (c + step >= chunks) umma_commit(&pp.d_full[region]);
     }
     __syncwarp();
-    ++a_seq;
-    ++b_seq;
+    a_seq += step;
+    b_seq += step;
   }
   if (tr) tr->mark(3);                       // 3: layer fully issued
 }
