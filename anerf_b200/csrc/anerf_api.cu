@@ -67,6 +67,8 @@ struct anerf_plan {
   NetProgram prog;
   int* d_kmap[kMaxLayers];   // device: packed K index -> reference column (-1 = zero)
   int k_in[kMaxLayers];      // reference fan-in of each layer
+  float* d_fold_w;           // [W/2, W + 27J + fc] views_linears[0] with feature_linear folded in
+  float* d_fold_b;           // [W/2]
   int n_sm;
   int max_smem;
 };
@@ -98,6 +100,7 @@ int anerf_plan_create(const anerf_net_config* cfg, anerf_plan** out) {
   p->dims.n_fc = cfg->framecode_ch > 0 ? cfg->n_framecodes : 0;
   p->prog = make_program(p->dims);
   for (int l = 0; l < kMaxLayers; ++l) p->d_kmap[l] = nullptr;
+  p->d_fold_w = p->d_fold_b = nullptr;
   const NetDims& d = p->dims;
   for (int l = 0; l < p->prog.n_layers; ++l) {
     int kp = p->prog.layer[l].chunks * kKC;
@@ -105,13 +108,18 @@ int anerf_plan_create(const anerf_net_config* cfg, anerf_plan** out) {
     for (int k = 0; k < kp; ++k) km[k] = layer_ref_col(d, l, k);
     if (l == 0) p->k_in[l] = in_pts_ref(d);
     else if (l < d.D) p->k_in[l] = d.W + ((l - 1) == d.skip ? in_pts_ref(d) : 0);
-    else if (l == d.D) p->k_in[l] = d.W;
     else p->k_in[l] = d.W + in_views_ref(d) + d.fc_ch;
     for (int k = 0; k < kp; ++k)
       if (km[k] >= p->k_in[l]) { delete p; return fail(ANERF_ERR_INVALID, "internal: kmap out of range"); }
     cudaError_t e = cudaMalloc((void**)&p->d_kmap[l], kp * sizeof(int));
     if (e == cudaSuccess) e = cudaMemcpy(p->d_kmap[l], km.data(), kp * sizeof(int), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { anerf_plan_destroy(p); return fail(ANERF_ERR_CUDA, "plan upload failed: %s", cudaGetErrorString(e)); }
+  }
+  {
+    const size_t cols = (size_t)d.W + in_views_ref(d) + d.fc_ch;
+    cudaError_t e = cudaMalloc((void**)&p->d_fold_w, (size_t)(d.W / 2) * cols * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_fold_b, (size_t)(d.W / 2) * sizeof(float));
+    if (e != cudaSuccess) { anerf_plan_destroy(p); return fail(ANERF_ERR_CUDA, "plan alloc failed: %s", cudaGetErrorString(e)); }
   }
   int dev = 0;
   cudaGetDevice(&dev);
@@ -125,6 +133,8 @@ void anerf_plan_destroy(anerf_plan* p) {
   if (!p) return;
   for (int l = 0; l < kMaxLayers; ++l)
     if (p->d_kmap[l]) cudaFree(p->d_kmap[l]);
+  if (p->d_fold_w) cudaFree(p->d_fold_w);
+  if (p->d_fold_b) cudaFree(p->d_fold_b);
   delete p;
 }
 
@@ -138,9 +148,14 @@ int anerf_pack_net(const anerf_plan* plan, const anerf_net_params* prm, void* pa
   uint8_t* img = (uint8_t*)packed;
   float* smalls = (float*)(img + pg.smalls_off);
   const int fmt = plan->cfg.operand_format;
+  if (!prm->feature_w || !prm->feature_b || !prm->views_w || !prm->views_b) return fail(ANERF_ERR_INVALID, "missing feature/views parameters");
+  // note: the plan's fold buffers make concurrent anerf_pack_net calls on one plan unsafe across streams
+  anerf_fold_views_kernel<<<64, 256, 0, stream>>>(prm->views_w, prm->views_b, prm->feature_w, prm->feature_b, d.W / 2, d.W,
+                                                  in_views_ref(d) + d.fc_ch, plan->d_fold_w, plan->d_fold_b);
+  CUDA_TRY(cudaGetLastError());
   for (int l = 0; l < pg.n_layers; ++l) {
-    const float* w = l < d.D ? prm->pts_w[l] : (l == d.D ? prm->feature_w : prm->views_w);
-    const float* b = l < d.D ? prm->pts_b[l] : (l == d.D ? prm->feature_b : prm->views_b);
+    const float* w = l < d.D ? prm->pts_w[l] : plan->d_fold_w;
+    const float* b = l < d.D ? prm->pts_b[l] : plan->d_fold_b;
     if (!w || !b) return fail(ANERF_ERR_INVALID, "missing parameter pointer for layer %d", l);
     int n = pg.layer[l].n, chunks = pg.layer[l].chunks;
     long long total = (long long)chunks * n * 4;

@@ -64,19 +64,21 @@ ANERF_HD int hid_chunks(const NetDims& d) { return round_up(d.W / kKC, kGroups);
 ANERF_HD int in_pts_ref(const NetDims& d) { return d.J * (1 + 2 * kF) + d.J * 3; }
 ANERF_HD int in_views_ref(const NetDims& d) { return d.J * kViewPerJoint; }
 
-// Layer program: l in [0,D) trunk, l == D feature_linear, l == D+1 views_linears[0].
-ANERF_HD int layer_n(const NetDims& d, int l) { return l <= d.D ? d.W : d.W / 2; }
+// Layer program: l in [0,D) trunk, l == D the views layer.  feature_linear has no activation behind it
+// (nerf.py:121-125), so it is folded into views_linears[0] when the weights are packed:
+//   views(cat[feature(h), x_view]) = (Wv[:, :W] Wf) h + Wv[:, W:] x_view + (bv + Wv[:, :W] bf)
+// -- the same function up to fp32 re-association, one 256x256 GEMM per sample less.
+ANERF_HD int layer_n(const NetDims& d, int l) { return l < d.D ? d.W : d.W / 2; }
 ANERF_HD int layer_chunks(const NetDims& d, int l) {
   if (l == 0) return pts_chunks(d);
   if (l < d.D) return hid_chunks(d) + ((l - 1) == d.skip ? pts_chunks(d) : 0);
-  if (l == d.D) return hid_chunks(d);
   return view_chunks(d) + hid_chunks(d);
 }
 
 // Map packed K index of layer l -> column of the reference weight matrix (or -1 for zero padding).
 // Reference column orders: pts input = [k*J + j (k = 0 raw, 1+2f sin, 2+2f cos) | 15J + 3j + c]
 // (cutoff_embedder.py:147-172, raycasters.py:560-569); skip layer input = cat[pts input, h]
-// (nerf.py:100-101); views layer input = cat[feature, k*3J + 3j + c, framecode] (nerf.py:121-125).
+// (nerf.py:100-101); (folded) views layer input = cat[h, k*3J + 3j + c, framecode] (nerf.py:121-125).
 ANERF_HD int pts_part_ref_col(const NetDims& d, int k) {
   int c = k / kKC, g = c % kGroups;
   int p = (c / kGroups) * kKC + (k % kKC);       // position in group g's value stream
@@ -101,9 +103,8 @@ ANERF_HD int layer_ref_col(const NetDims& d, int l, int k) {
     if ((l - 1) == d.skip) return k < P ? pts_part_ref_col(d, k) : ((k - P) < d.W ? in_pts_ref(d) + (k - P) : -1);
     return k < d.W ? k : -1;
   }
-  if (l == d.D) return k < d.W ? k : -1;
   if (k < V) { int c = view_part_ref_col(d, k); return c < 0 ? -1 : d.W + c; }
-  return (k - V) < d.W ? k - V : -1;   // feature part
+  return (k - V) < d.W ? k - V : -1;   // h part (columns of the folded Wv[:, :W] Wf)
 }
 
 // ------------------------------------------------------------------------------------------------

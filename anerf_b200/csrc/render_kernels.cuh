@@ -58,7 +58,7 @@ struct SmallsLayout {
 
 struct NetProgram {
   NetDims dims;
-  int n_layers;         // D + 2
+  int n_layers;         // D + 1 (trunk layers + the views layer with feature_linear folded in)
   LayerProg layer[kMaxLayers];
   unsigned smalls_off;  // byte offset of the smalls block in the packed image
   SmallsLayout sm;
@@ -70,7 +70,7 @@ inline __host__ __device__ int align_up(int x, int a) { return (x + a - 1) / a *
 inline __host__ NetProgram make_program(const NetDims& d) {
   NetProgram p{};
   p.dims = d;
-  p.n_layers = d.D + 2;
+  p.n_layers = d.D + 1;
   unsigned off = 0;
   for (int l = 0; l < p.n_layers; ++l) {
     p.layer[l].n = layer_n(d, l);
@@ -441,8 +441,13 @@ __device__ __forceinline__ void drain_region(AProducer<FMT>& ap, const Pipe& pp,
   if (tr) tr->mark(11);                      // 11: accumulators ready
   const uint32_t taddr = pp.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)region * 256u;
   const int nblk = N / 32;
+  // TMEM reads run at ~64 B/cycle per SM: if all 16 warps start loading at once, group 0's first chunk (the
+  // one the tensor core is waiting for) gets a quarter of that.  So the groups start in turn: group g begins
+  // loading when group g-1 has pulled its first 32 columns (named barriers 2..4, 128 arrive + 128 sync).
+  if (grp > 0) asm volatile("bar.sync %0, 256;" ::"r"(1 + grp) : "memory");
   uint32_t v[8];
   if (grp < nblk) tmem_ld8(taddr + grp * 32, v);
+  bool handed_over = false;
 #pragma unroll 1
   for (int cb = grp; cb < nblk; cb += kGroups) {
     if (EMIT) ap.begin(cb);
@@ -452,6 +457,10 @@ __device__ __forceinline__ void drain_region(AProducer<FMT>& ap, const Pipe& pp,
       float a[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(v[i]);
+      if (t == 3 && !handed_over) {           // first chunk's columns are in registers: next group may start
+        if (grp < kGroups - 1) asm volatile("bar.arrive %0, 256;" ::"r"(2 + grp) : "memory");
+        handed_over = true;
+      }
       // next 8 columns in flight while these are processed
       if (t < 3) tmem_ld8(taddr + cb * 32 + (t + 1) * 8, v);
       else if (cb + kGroups < nblk) tmem_ld8(taddr + (cb + kGroups) * 32, v);
@@ -470,6 +479,7 @@ __device__ __forceinline__ void drain_region(AProducer<FMT>& ap, const Pipe& pp,
     if (EMIT) ap.end();
     if (tr) tr->mark(12);                    // 12: one column block drained (and its chunk published)
   }
+  if (!handed_over && grp < kGroups - 1) asm volatile("bar.arrive %0, 256;" ::"r"(2 + grp) : "memory");   // no chunk of mine
   if (EMIT) {
     const int padded = round_up(nblk, kGroups);            // hidden parts are padded to a multiple of 4 chunks
     for (int cb = nblk + ((grp - nblk) % kGroups + kGroups) % kGroups; cb < padded; cb += kGroups) {
@@ -515,19 +525,18 @@ __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe
     if (grp == 0) sigma += sm[pg.sm.alpha_b];
     return make_float4(0.f, 0.f, 0.f, sigma);
   }
-  drain_region<FMT, true, true>(ap, pp, d_cnt, (D - 1) & 1, W, sm + pg.sm.bias[D - 1], sm[D - 1], quarter, grp, alpha_acc, tr);
-  if (grp == 0) sigma += sm[pg.sm.alpha_b];
-  // operand of views_linears[0]: view encoding first (independent of feature), then feature (no ReLU)
+  // operand of the views layer (feature_linear folded in): the view encoding first -- it does not depend on the
+  // trunk, so it is produced while the last trunk layer's MMAs run -- then h of the last trunk layer
   if (tr) tr->mark(22);
   produce_view_chunks<FMT>(ap, rc, P, grp);
   if (tr) tr->mark(23);
-  drain_region<FMT, false, true>(ap, pp, d_cnt, D & 1, W, sm + pg.sm.bias[D], sm[D], quarter, grp,
-                                 [](int, const float (&)[8]) {}, tr);
+  drain_region<FMT, true, true>(ap, pp, d_cnt, (D - 1) & 1, W, sm + pg.sm.bias[D - 1], sm[D - 1], quarter, grp, alpha_acc, tr);
+  if (grp == 0) sigma += sm[pg.sm.alpha_b];
   // views layer output -> rgb_linear in fp32
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
   const float* wr = sm + pg.sm.rgb_w;
   const int H = W / 2;
-  drain_region<FMT, true, false>(ap, pp, d_cnt, (D + 1) & 1, H, sm + pg.sm.bias[D + 1], sm[D + 1], quarter, grp,
+  drain_region<FMT, true, false>(ap, pp, d_cnt, D & 1, H, sm + pg.sm.bias[D], sm[D], quarter, grp,
                                  [&](int col0, const float (&x)[8]) {
 #pragma unroll
                                    for (int i = 0; i < 8; ++i) {
@@ -1035,6 +1044,29 @@ __global__ void anerf_pack_layer_kernel(const float* __restrict__ w, int k_in, c
     size_t off = (size_t)g * nh * 16 + (size_t)(r >> 3) * 128 + (size_t)(r & 7) * 16;
     *reinterpret_cast<uint4*>(half + off) = hi;
     *reinterpret_cast<uint4*>(half + (size_t)nh * 64 + off) = lo;
+  }
+}
+
+// feature_linear folded into views_linears[0] (path_math.cuh, layer program):
+//   out_w [H, W + V] = [ Wv[:, :W] * Wf  |  Wv[:, W:] ],   out_b [H] = bv + Wv[:, :W] * bf      (fp64 accumulation)
+__global__ void anerf_fold_views_kernel(const float* __restrict__ wv, const float* __restrict__ bv,
+                                        const float* __restrict__ wf, const float* __restrict__ bf, int H, int W, int V,
+                                        float* __restrict__ out_w, float* __restrict__ out_b) {
+  const int cols = W + V;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * (cols + 1); i += gridDim.x * blockDim.x) {
+    const int n = i / (cols + 1), c = i % (cols + 1);
+    const float* wrow = wv + (size_t)n * cols;
+    if (c == cols) {
+      double acc = (double)bv[n];
+      for (int k = 0; k < W; ++k) acc += (double)wrow[k] * (double)bf[k];
+      out_b[n] = (float)acc;
+    } else if (c < W) {
+      double acc = 0.0;
+      for (int k = 0; k < W; ++k) acc += (double)wrow[k] * (double)wf[(size_t)k * W + c];
+      out_w[(size_t)n * cols + c] = (float)acc;
+    } else {
+      out_w[(size_t)n * cols + c] = wrow[c];
+    }
   }
 }
 

@@ -45,7 +45,7 @@ def test_packed_k_order_inverts_producer_order(harness, J, fc):
     fcode = rng.randn(16).astype(np.float32)
     D, W, skip = 8, 256, 4
     nP = harness.h_layer_chunks(J, D, W, skip, fc, 0) * 32
-    nV = harness.h_layer_chunks(J, D, W, skip, fc, D + 1) * 32 - W
+    nV = harness.h_layer_chunks(J, D, W, skip, fc, D) * 32 - W
     ep = np.zeros(nP, np.float32)
     ev = np.zeros(nV, np.float32)
     harness.h_emit_pts(fptr(skt12), fptr(p), C.c_float(tau), fptr(cut), J, fptr(ep))
@@ -61,15 +61,14 @@ def test_packed_k_order_inverts_producer_order(harness, J, fc):
     cols = [col(l, k) for k in range(nP + W)]
     assert cols[:nP] == [col(0, k) for k in range(nP)]
     assert cols[nP:] == [cfg.in_pts + n for n in range(W)]
-    # plain trunk layer and feature layer: identity
+    # plain trunk layer: identity
     assert [col(2, k) for k in range(W)] == list(range(W))
-    assert [col(D, k) for k in range(W)] == list(range(W))
-    # views layer: [view encoding (+ framecode) | feature]
+    # views layer (feature_linear folded in): [view encoding (+ framecode) | h]
     ref_in = np.concatenate([np.zeros(W), xv, fcode[:fc].astype(np.float64)])
     for k in range(nV):
-        c = col(D + 1, k)
+        c = col(D, k)
         assert (ev[k] == 0.0) if c < 0 else abs(ev[k] - ref_in[c]) < 2e-6, (k, c)
-    cols = [col(D + 1, k) for k in range(nV + W)]
+    cols = [col(D, k) for k in range(nV + W)]
     assert cols[nV:] == list(range(W))
     assert sorted(c for c in cols if c >= 0) == list(range(W + cfg.in_views + fc))
 
