@@ -108,3 +108,28 @@ def test_mesh_density_entry_point():
              render_kwargs=rk['preproc_kwargs'], res=case["res"], netchunk=4096, fwd_type='mesh')
     assert tuple(sig.shape) == (16, 16, 16)
     assert rel_err(sig.cpu().numpy(), gold["ref_sigma"]) < 1e-4
+
+
+def test_sharded_density_grid_and_ragged_point_counts():
+    from anerf_b200 import mesh
+    case, gold = load_golden("mesh_j24_res15")
+    J = case["n_joints"]
+    pose = synthetic.make_pose(11, J)
+    _, rk, _, _, _, _ = create_raycaster(make_args(N_importance=16, no_reload=True), data_attrs(J))
+    rc = rk['ray_caster'].eval()
+    rc.network_fine.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(202).items()})
+    dev = torch.device("cuda")
+    t = lambda a: torch.as_tensor(a).to(dev)
+    kps, skts = t(pose["kps"])[None], t(pose["skts"])[None]
+    sig = mesh.density_grid_sharded(rc, kps, skts, radius=case["radius"], res=case["res"])
+    assert rel_err(sig.cpu().numpy(), gold["ref_sigma"]) < 1e-4
+    # the generated slab points equal the reference's meshgrid, and point counts that are not a multiple of the
+    # 128-row tile (or of the CTA pair) work
+    t_ = np.linspace(-case["radius"], case["radius"], case["res"] + 1)
+    ref_pts = np.stack(np.meshgrid(t_, t_, t_), axis=-1).astype(np.float32).reshape(-1, 3) + pose["kps"][0]
+    pts = mesh.grid_points(kps, case["radius"], case["res"])
+    assert np.abs(pts.cpu().numpy() - ref_pts).max() < 1e-6
+    full = rc.render_pts_density(pts.reshape(-1, 1, 3), kps, skts, None).reshape(-1)
+    for n in (1, 127, 129, 1000):
+        part = rc.render_pts_density(pts[:n].reshape(-1, 1, 3), kps, skts, None).reshape(-1)
+        assert torch.equal(part, full[:n])

@@ -50,3 +50,16 @@ def test_slabs_cover_everything():
             s = [parallel.slab_for_rank(n, r, w) for r in range(w)]
             assert s[0][0] == 0 and s[-1][1] == n and all(s[i][1] == s[i + 1][0] for i in range(w - 1))
             assert sorted(f for r in range(w) for f in parallel.frames_for_rank(n, r, w)) == list(range(n))
+
+
+def test_grid_points_match_reference_meshgrid():
+    import numpy as np
+    from anerf_b200 import mesh
+    res, radius = 6, 0.7
+    kps = torch.tensor([[[0.1, -0.2, 0.3]]])
+    t = np.linspace(-radius, radius, res + 1)
+    ref = np.stack(np.meshgrid(t, t, t), axis=-1).astype(np.float32).reshape(-1, 3) + kps[0, 0].numpy()
+    pts = mesh.grid_points(kps, radius, res).numpy()
+    assert np.abs(pts - ref).max() < 1e-6
+    a, b = parallel.slab_for_rank((res + 1) ** 3, 1, 3)
+    assert np.abs(mesh.grid_points(kps, radius, res, a, b).numpy() - ref[a:b]).max() < 1e-6
