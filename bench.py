@@ -348,6 +348,31 @@ def main():
         parity = {"rays": len(idx), "rgb0_rel": rel(o["rgb0"], ref["rgb0"]), "acc0_rel": rel(o["acc0"], ref["acc0"]),
                   "rgb_map_rel": rel(o["rgb_map"], ref["rgb_map"]),
                   "rgb_map_psnr_db": float(-10 * np.log10(max(mse, 1e-30)))}
+    ref_gpu = None
+    if not opt.no_cpu_baseline and world == 1:
+        # the reference's PyTorch path on the same B200 (fp32, eager, default matmul precision).  The
+        # Python reference cannot travel, so this is its oracle port (same torch ops) run with CUDA tensors.
+        try:
+            from oracle import anerf_oracle as orc
+            torch.backends.cuda.matmul.allow_tf32 = False
+            g = lambda a: a.to(dev)
+            sd0g = {k: g(torch.as_tensor(v)) for k, v in synthetic.make_net_weights(101).items()}
+            sd1g = {k: g(torch.as_tensor(v)) for k, v in synthetic.make_net_weights(202).items()}
+            fr0 = devf[0]
+            sl = slice(128 * 512, 128 * 512 + CHUNK)
+            a = (sd0g, sd1g, orc.PathConfig(), fr0["rays"][sl, 0:3], fr0["rays"][sl, 3:6], fr0["skts"][sl], fr0["cyls"][sl])
+            with torch.no_grad():
+                orc.render_rays(*a)
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    orc.render_rays(*a)
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / 2
+            ref_gpu = {"value": CHUNK / dt, "unit": "rays/s", "kind": "port of the reference's PyTorch path, CUDA tensors, fp32 eager",
+                       "sample": "one 4096-ray chunk, mean of 2 after 1 warm-up"}
+        except Exception as e:  # noqa: BLE001
+            ref_gpu = {"error": repr(e)[:200]}
     line = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": opt.steps, "warmup": max(opt.warmup, 3),
             "ms_per_step": ms / opt.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 via fp16 hi/lo split on tcgen05 (3 MMAs per product, fp32 accumulate)" if rc._operand_format == 0
@@ -357,7 +382,7 @@ def main():
                        "parallelism": f"frame-parallel x{world}, gather of [rays,5] pixels to rank 0" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: 402 MB of per-ray skts per frame, two frames alternated"},
             "clocks": clocks, "gpu_launches": 2 * n_chunks * opt.steps, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu_base, "parity": parity}
+            "cpu_baseline": cpu_base, "reference_gpu_port": ref_gpu, "parity": parity}
     print(json.dumps(line), flush=True)
 
 
