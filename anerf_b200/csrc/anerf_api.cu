@@ -173,6 +173,8 @@ int anerf_pack_net(const anerf_plan* plan, const anerf_net_params* prm, void* pa
   CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.alpha_b, prm->alpha_b, sizeof(float), cudaMemcpyDeviceToDevice, stream));
   CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.rgb_w, prm->rgb_w, 3 * (d.W / 2) * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.rgb_b, prm->rgb_b, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  anerf_pack_view_weights_kernel<<<128, 256, 0, stream>>>(plan->d_fold_w, d.W + in_views_ref(d) + d.fc_ch, d, smalls + pg.sm.gw);
+  CUDA_TRY(cudaGetLastError());
   if (d.fc_ch > 0) {
     if (!prm->framecodes) return fail(ANERF_ERR_INVALID, "framecodes pointer missing");
     anerf_pack_framecodes_kernel<<<1, 32, 0, stream>>>(prm->framecodes, d.n_fc, d.fc_ch, smalls + pg.sm.framecodes);
@@ -274,6 +276,7 @@ int anerf_render_fwd(const anerf_plan* plan, const void* packed_coarse, const vo
     if (P.sl.total <= plan->max_smem || R == 1) break;
   }
   P.R = R;
+  P.slotc = slot_chunks(R);
   P.tilesC = ceil_div(R * Sc, kTileM);
   P.tilesF = Si > 0 ? ceil_div(R * (Sc + Si), kTileM) : 0;
   P.n_items = ceil_div(N, R);
@@ -295,7 +298,7 @@ int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf
   fill_common(plan, o, P);
   P.packed[0] = P.packed[1] = (const uint8_t*)packed;
   P.sl = make_smem_layout(plan->dims, plan->prog.sm.fixed_floats, 1, 4, 4);
-  P.R = 1; P.Sc = 4; P.Sf = 4;
+  P.R = 1; P.Sc = 4; P.Sf = 4; P.slotc = slot_chunks(1);
   P.n_items = (int)((n_points + kTileM - 1) / kTileM);
   P.pts = pts; P.skts = skts; P.sigma = sigma; P.n_points = n_points;
   return launch_fused(plan, P, true, (cudaStream_t)stream_);

@@ -49,8 +49,12 @@ struct NetDims {
 //   pts part : group g encodes joints g, g+4, g+8, ... two at a time (2 x 18 values + 4 zeros = 40
 //              = 5 x 8) into its own value stream, zero padded to `pts_group_chunks` chunks; the
 //              part has 4 x pts_group_chunks chunks;
-//   view part: one chunk per joint (27 per-ray direction features + 5 zeros, times the sample's cutoff
-//              weight), joint j in chunk j; framecodes, if any, add one chunk (16 values + 16 zeros);
+//   view part: contracted per ray.  The 27 J view inputs of a sample are table[ray][j][q] * w_j(sample), so
+//              Wv[:, view] x = sum_j w_j(sample) G[ray][:, j] with G[ray][n][j] = sum_q Wv[n][(j, q)] table[ray][j][q]
+//              (a per-ray 128 x (J+1) matrix; the pseudo joint J carries the framecode with weight 1).  The
+//              operand is one chunk per "ray slot" of the CTA pair (2R slots): a row puts [w_0..w_{J-1}, 1, 0..]
+//              into the chunk of its own ray and zeros elsewhere; the B side of those chunks is G, built
+//              in shared memory per item and network (not streamed from the packed image);
 //   hidden   : chunk cb = accumulator columns [32cb, 32cb+32).
 // ------------------------------------------------------------------------------------------------
 ANERF_HD int pts_group_joints(const NetDims& d) { return ceil_div(d.J, kGroups); }
@@ -59,7 +63,7 @@ ANERF_HD int pts_group_chunks(const NetDims& d) { return ceil_div(pts_pairs(d) *
 ANERF_HD int pts_chunks(const NetDims& d) { return kGroups * pts_group_chunks(d); }
 // every part is padded to a multiple of 4 chunks: group g then always fills ring stage g (4 stages), i.e. each
 // group follows the phases of ONE "stage empty" barrier in order (a parity wait is only valid one phase ahead)
-ANERF_HD int view_chunks(const NetDims& d) { return round_up(d.J + (d.fc_ch > 0 ? 1 : 0), kGroups); }
+ANERF_HD int slot_chunks(int rays_per_item) { return round_up(2 * rays_per_item, kGroups); }   // ray-slot chunks of the views layer
 ANERF_HD int hid_chunks(const NetDims& d) { return round_up(d.W / kKC, kGroups); }
 ANERF_HD int in_pts_ref(const NetDims& d) { return d.J * (1 + 2 * kF) + d.J * 3; }
 ANERF_HD int in_views_ref(const NetDims& d) { return d.J * kViewPerJoint; }
@@ -69,10 +73,11 @@ ANERF_HD int in_views_ref(const NetDims& d) { return d.J * kViewPerJoint; }
 //   views(cat[feature(h), x_view]) = (Wv[:, :W] Wf) h + Wv[:, W:] x_view + (bv + Wv[:, :W] bf)
 // -- the same function up to fp32 re-association, one 256x256 GEMM per sample less.
 ANERF_HD int layer_n(const NetDims& d, int l) { return l < d.D ? d.W : d.W / 2; }
+// chunks of layer l that are streamed from the packed image (the views layer's ray-slot chunks are not)
 ANERF_HD int layer_chunks(const NetDims& d, int l) {
   if (l == 0) return pts_chunks(d);
   if (l < d.D) return hid_chunks(d) + ((l - 1) == d.skip ? pts_chunks(d) : 0);
-  return view_chunks(d) + hid_chunks(d);
+  return hid_chunks(d);
 }
 
 // Map packed K index of layer l -> column of the reference weight matrix (or -1 for zero padding).
@@ -90,21 +95,20 @@ ANERF_HD int pts_part_ref_col(const NetDims& d, int k) {
   if (j >= d.J) return -1;
   return q < 1 + 2 * kF ? q * d.J + j : (1 + 2 * kF) * d.J + 3 * j + (q - (1 + 2 * kF));
 }
-ANERF_HD int view_part_ref_col(const NetDims& d, int k) {   // relative to the start of input_views
-  int c = k / kKC, q = k % kKC;
-  if (c >= d.J) return (c == d.J && d.fc_ch > 0 && q < d.fc_ch) ? in_views_ref(d) + q : -1;
-  if (q >= kViewPerJoint) return -1;
-  return (q / 3) * 3 * d.J + 3 * c + (q % 3);
+// column of the (folded) views weight matrix that multiplies feature q (= 3*kk + c, kk = 0 raw, 1+2f sin,
+// 2+2f cos) of joint j; j == J is the framecode pseudo joint (q < fc_ch).  -1 = no such input.
+ANERF_HD int view_weight_col(const NetDims& d, int j, int q) {
+  if (j < d.J) return q < kViewPerJoint ? d.W + (q / 3) * 3 * d.J + 3 * j + (q % 3) : -1;
+  return (j == d.J && q < d.fc_ch) ? d.W + in_views_ref(d) + q : -1;
 }
 ANERF_HD int layer_ref_col(const NetDims& d, int l, int k) {
-  int P = pts_chunks(d) * kKC, V = view_chunks(d) * kKC;
+  int P = pts_chunks(d) * kKC;
   if (l == 0) return pts_part_ref_col(d, k);
   if (l < d.D) {
     if ((l - 1) == d.skip) return k < P ? pts_part_ref_col(d, k) : ((k - P) < d.W ? in_pts_ref(d) + (k - P) : -1);
     return k < d.W ? k : -1;
   }
-  if (k < V) { int c = view_part_ref_col(d, k); return c < 0 ? -1 : d.W + c; }
-  return (k - V) < d.W ? k - V : -1;   // h part (columns of the folded Wv[:, :W] Wf)
+  return k < d.W ? k : -1;   // views layer, h part (columns of the folded Wv[:, :W] Wf)
 }
 
 // ------------------------------------------------------------------------------------------------

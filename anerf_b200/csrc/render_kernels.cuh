@@ -26,7 +26,7 @@
 namespace anerf {
 
 constexpr int kAStages = 4;
-constexpr int kBStages = 6;
+constexpr int kBStages = 3;
 constexpr int kAHalfBytes = kTileM * kKC * 2;        // 8 KB: hi (or lo) part of one A chunk
 constexpr int kAStageBytes = 2 * kAHalfBytes;        // 16 KB
 constexpr int kBStageBytes = 128 * kKC * 2 * 2;      // 16 KB: this CTA's half (N/2 <= 128 rows) of a weight chunk, hi + lo
@@ -53,6 +53,7 @@ struct SmallsLayout {
   int alpha_w, alpha_b, rgb_w, rgb_b;
   int fixed_floats;     // everything above (copied to shared memory)
   int framecodes;       // [n_fc + 1][fc_ch] (last row = mean code); stays in global memory
+  int gw;               // [W/2][27][J+1] view weights of the folded views layer, regrouped per joint; global memory
   int total_floats;
 };
 
@@ -87,6 +88,7 @@ inline __host__ NetProgram make_program(const NetDims& d) {
   p.sm.rgb_b = f; f += 4;
   p.sm.fixed_floats = f;
   p.sm.framecodes = f; f += (d.n_fc + 1) * d.fc_ch;
+  p.sm.gw = f; f += (d.W / 2) * (d.J + 1) * kViewPerJoint;
   p.sm.total_floats = align_up(f, 4);
   p.packed_bytes = off + (unsigned)p.sm.total_floats * 4u;
   return p;
@@ -96,26 +98,34 @@ inline __host__ NetProgram make_program(const NetDims& d) {
 // shared-memory carve-up of the fused kernel
 // ------------------------------------------------------------------------------------------------
 struct SmemLayout {
-  int a_ring, b_ring, smalls0, smalls1, ray, skt, view_tab, fcode, z_coarse, z_all, raw, part, wts, cdf, bars, tmem_ptr;
+  int a_ring, b_ring, g_buf, smalls0, smalls1, ray, skt, view_tab, fcode, task_ctr, z_coarse, z_all, raw, part, wj, wts, cdf, bars, tmem_ptr;
   int total;
 };
+// view table T[joint][ray slot][kViewPad]: the 27 direction features of (ray, joint) padded to 28 floats so a
+// thread reads them as seven float4; the joint stride is padded by 4 floats, which makes the float4 reads of
+// eight neighbouring joints hit eight different bank groups for every even slot count.
+constexpr int kViewPad = 28;
+inline __host__ __device__ int view_tab_jstride(int R) { return 2 * R * kViewPad + 4; }
 // ray_s: 12 floats per ray: o(3) d(3) near far |d| pad(3)
 inline __host__ __device__ SmemLayout make_smem_layout(const NetDims& d, int smalls_fixed_floats, int R, int Sc, int Sf) {
   SmemLayout L{};
   int off = 0;
   L.a_ring = off; off += kAStages * kAStageBytes;
   L.b_ring = off; off += kBStages * kBStageBytes;
+  L.g_buf = off; off += slot_chunks(R) * (d.W / 2) * 64;   // per-ray view matrices G as B-operand chunks (this CTA's half)
   L.smalls0 = off; off += align_up(smalls_fixed_floats * 4, 16);
   L.smalls1 = off; off += align_up(smalls_fixed_floats * 4, 16);
   L.ray = off; off += R * 12 * 4;
   L.skt = off; off += align_up(R * d.J * 12 * 4, 16);
-  L.view_tab = off; off += R * d.J * kKC * 4;          // [ray][joint][32]
-  L.fcode = off; off += 2 * R * 16 * 4;      // [net][ray][16]
+  L.view_tab = off; off += align_up(d.J * view_tab_jstride(R) * 4, 16);     // [joint][ray slot of the pair][kViewPad]
+  L.fcode = off; off += align_up(2 * R * 4, 16);   // [ray slot] framecode row index
+  L.task_ctr = off; off += 16;                     // work counter of build_view_matrices
   int rows = R * (Sf > Sc ? Sf : Sc);
   L.z_coarse = off; off += align_up(R * Sc * 4, 16);
   L.z_all = off; off += align_up(rows * 4, 16);
   L.raw = off; off += rows * 16;             // network outputs (r,g,b,sigma) of the item's samples
   L.part = off; off += kGroups * kTileM * 16; // per-group partial outputs of the current tile
+  L.wj = off; off += d.J * kTileM * 4;        // view cutoff weights of the current tile [joint][row]
   L.wts = off; off += align_up(rows * 4, 16);
   L.cdf = off; off += align_up(R * Sc * 4, 16);
   L.bars = off; off += 8 * kNumBars;
@@ -128,7 +138,7 @@ struct RenderKParams {
   NetProgram prog;
   const uint8_t* packed[2];
   // problem
-  int n_rays, Sc, Si, Sf, R, tilesC, tilesF, n_items;
+  int n_rays, Sc, Si, Sf, R, tilesC, tilesF, n_items, slotc;
   int lindisp, softplus, eval_mean_fc;
   float B, shift, tau_p, tau_v;
   float cut_p[kMaxJoints], cut_v[kMaxJoints];
@@ -259,7 +269,9 @@ struct Trace {
 // ELECT/BRA.U.ANY loop, ~100 cycles per instruction); one elected lane issues.
 template <int FMT>
 __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint32_t& b_seq, int N, int chunks,
-                                          int region, Trace* tr = nullptr) {
+                                          int region, Trace* tr = nullptr, int g_chunks = 0, uint32_t g_base = 0) {
+  // `chunks` operand chunks in total; the first `g_chunks` take their B operand from shared memory at g_base
+  // (per-ray view matrices, N * 64 bytes each) instead of the weight ring.
   const uint32_t id = make_idesc_f16(fmt_hi(FMT), fmt_hi(FMT), 2 * kTileM, N);
   const uint32_t dcol = pp.tmem_base + (uint32_t)region * 256u;
   const uint32_t a_base = smem_u32(pp.a_ring), b_base = smem_u32(pp.b_ring);
@@ -273,7 +285,7 @@ __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint3
   for (int c = 0; c < chunks; c += step) {
     {
       // the "operand ready" barriers of this iteration's chunks are probed concurrently by different lanes
-      const int which = lane % 3, sub = (lane / 3) % step;
+      const int which = c < g_chunks ? 0 : lane % 3, sub = (lane / 3) % step;
       const uint32_t qa = a_seq + sub, qb = b_seq + sub;
       uint64_t* bar = which == 0 ? &pp.a_full[qa % kAStages] : (which == 1 ? &pp.b_full[qb % kBStages] : &pp.peer_b[qb % kBStages]);
       const uint32_t par = which == 0 ? ((qa / kAStages) & 1) : ((qb / kBStages) & 1);
@@ -283,10 +295,11 @@ __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint3
     tc_fence_after_sync();
     if (tr) tr->mark(c == 0 ? 1 : 2);        // 1: first chunk of a layer ready, 2: later chunk ready
     if (elect_one()) {
+      const bool from_g = c < g_chunks;
       for (int u = 0; u < step; ++u) {
         const uint32_t sa = (a_seq + u) % kAStages, sb = (b_seq + u) % kBStages;
         const uint32_t a_hi = a_base + sa * kAStageBytes, a_lo = a_hi + kAHalfBytes;
-        const uint32_t b_hi = b_base + sb * kBStageBytes, b_lo = b_hi + NH * 64u;
+        const uint32_t b_hi = from_g ? g_base + (uint32_t)(c + u) * NH * 128u : b_base + sb * kBStageBytes, b_lo = b_hi + NH * 64u;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           uint64_t da_hi = smem_desc(a_hi + s * 4096, 2048, 128);
@@ -299,13 +312,13 @@ __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint3
           umma_f16(dcol, da_hi, db_hi, id, 1u);
         }
         umma_commit(&pp.a_empty[sa]);
-        umma_commit(&pp.b_empty[sb]);
+        if (!from_g) umma_commit(&pp.b_empty[sb]);
       }
       if (c + step >= chunks) umma_commit(&pp.d_full[region]);
     }
     __syncwarp();
     a_seq += step;
-    b_seq += step;
+    if (c >= g_chunks) b_seq += step;
   }
   if (tr) tr->mark(3);                       // 3: layer fully issued
 }
@@ -342,8 +355,7 @@ __device__ __forceinline__ void relay_layer(const Pipe& pp, uint32_t& b_seq, int
 struct RowCtx {
   float p[3];          // world position of this row's sample
   const float* skt;    // this row's ray: [J][12] in shared memory
-  const float* vtab;   // this row's ray: view table [J][32]
-  const float* fcode;  // this row's ray: frame code (16)
+  int slot;            // ray slot of this row's ray inside the CTA pair (rank * R + ray index in the item)
 };
 
 // layer-0 / skip-layer part: distance + bone encodings of the row's sample for this group's joints
@@ -389,42 +401,116 @@ __device__ __forceinline__ void produce_pts_chunks(AProducer<FMT>& ap, const Row
   ap.base += pts_chunks(P.prog.dims);
 }
 
-// views-layer part: one chunk per joint = the ray's 27 direction features of that joint (+5 zeros)
-// times the sample's cutoff weight; this group takes joints g, g+4, ...
+// views-layer part (view branch contracted per ray, see path_math.cuh): one chunk per ray slot of the CTA pair.
+// A row writes [w_0 .. w_{J-1}, 1 (framecode pseudo joint), 0 ...] into the chunk of its own ray and zeros into the
+// others; this group takes the chunks g, g+4, ...
 template <int FMT>
-__device__ __forceinline__ void produce_view_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P, int grp) {
+__device__ __forceinline__ void produce_slot_chunks(AProducer<FMT>& ap, const RowCtx& rc, const RenderKParams& P, int grp,
+                                                    int row, const float* wj) {
   const int J = P.prog.dims.J;
 #pragma unroll 1
-  for (int j = grp; j < J; j += kGroups) {
-    const float w = cutoff_w(joint_dist(rc.skt + j * 12, rc.p), P.tau_v, P.cut_v[j]);
-    const float4* tab = reinterpret_cast<const float4*>(rc.vtab + j * kKC);
-    ap.begin(j);
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-      float4 t0 = tab[2 * t], t1 = tab[2 * t + 1];
-      float x[8] = {t0.x * w, t0.y * w, t0.z * w, t0.w * w, t1.x * w, t1.y * w, t1.z * w, t1.w * w};
-      ap.store8(t, x);
-    }
-    ap.end();
-  }
-  int c0 = J;                                   // first chunk after the joints
-  if (P.prog.dims.fc_ch > 0) {
-    if (grp == (J % kGroups)) {
-      ap.begin(J);
-#pragma unroll
+  for (int c = grp; c < P.slotc; c += kGroups) {
+    ap.begin(c);
+    if (c == rc.slot) {
+#pragma unroll 1
       for (int t = 0; t < 4; ++t) {
         float x[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = (8 * t + i) < P.prog.dims.fc_ch ? rc.fcode[(8 * t + i) & 15] : 0.f;
+        for (int i = 0; i < 8; ++i) {
+          const int j = 8 * t + i;
+          x[i] = j < J ? wj[j * kTileM + row] : ((j == J && P.prog.dims.fc_ch > 0) ? 1.0f : 0.0f);
+        }
         ap.store8(t, x);
       }
-      ap.end();
+    } else {
+      for (int t = 0; t < 4; ++t) ap.zero8(t);
     }
-    c0 = J + 1;
+    ap.end();
   }
-  for (int c = c0; c < view_chunks(P.prog.dims); ++c)      // zero chunks up to a multiple of 4
-    if (grp == (c % kGroups)) { ap.begin(c); for (int t = 0; t < 4; ++t) ap.zero8(t); ap.end(); }
-  ap.base += view_chunks(P.prog.dims);
+  ap.base += P.slotc;
+}
+
+// cutoff weights of the view branch for this tile: group g computes joints g, g+4, ... of its row into shared
+// memory (wj[joint][row]); the group that owns the row's ray-slot chunk reads all of them after a barrier
+__device__ __forceinline__ void compute_view_weights(const RowCtx& rc, const RenderKParams& P, int grp, int row, float* wj) {
+  const int J = P.prog.dims.J;
+#pragma unroll 1
+  for (int j = grp; j < J; j += kGroups)
+    wj[j * kTileM + row] = cutoff_w(joint_dist(rc.skt + j * 12, rc.p), P.tau_v, P.cut_v[j]);
+}
+
+// Per-ray view matrices of one network for all 2R ray slots of the CTA pair, written as B-operand chunks
+// (this CTA's half of the N = W/2 output features): G[slot][n][j] = scale * sum_q gw[n][q][j] * T[j][slot][q],
+// T = per-ray direction features (j < J) or the ray's framecode (j == J).  Work is handed out to warps in
+// groups of 32 (n, j) tasks through a shared counter, so warps that arrive late (the ones compositing a ray)
+// simply take fewer groups.  `ctr` must be zero on entry (reset behind a worker barrier); callers
+// worker_sync() afterwards (the proxy fence is inside).
+template <int FMT>
+__device__ __forceinline__ void build_view_matrices(const RenderKParams& P, int net, uint8_t* g_buf, const float* vtab_s,
+                                                    const int* fc_row_s, int* ctr, int rank, float scale) {
+  const NetDims& d = P.prog.dims;
+  const int NH = d.W / 4;                       // rows of the views layer held by this CTA
+  const int J = d.J, J1 = d.J + 1;
+  const int S = 2 * P.R;                        // ray slots (<= 2 * kMaxRaysPerItem), even
+  const int jstride = view_tab_jstride(P.R);
+  const int lane = threadIdx.x & 31;
+  const float* smalls = reinterpret_cast<const float*>(P.packed[net] + P.prog.smalls_off);
+  const float* gw = smalls + P.prog.sm.gw + (size_t)rank * NH * kViewPerJoint * J1;   // [n][q][j], j fastest: coalesced
+  const int n_tasks = NH * J, n_groups = (n_tasks + 31) / 32;
+  auto put = [&](int slot, uint32_t off, float v) {
+    uint32_t hi, lo;
+    Split<FMT>::pair(v * scale, 0.f, hi, lo);
+    uint8_t* chunk = g_buf + (size_t)slot * NH * 128;
+    *reinterpret_cast<uint16_t*>(chunk + off) = (uint16_t)(hi & 0xFFFFu);
+    *reinterpret_cast<uint16_t*>(chunk + NH * 64 + off) = (uint16_t)(lo & 0xFFFFu);
+  };
+  auto chunk_off = [&](int n, int j) {
+    return (uint32_t)(j >> 3) * NH * 16 + (uint32_t)(n >> 3) * 128 + (uint32_t)(n & 7) * 16 + (uint32_t)(j & 7) * 2;
+  };
+#pragma unroll 1
+  for (;;) {
+    int g = 0;
+    if (lane == 0) g = atomicAdd(ctr, 1);
+    g = __shfl_sync(0xFFFFFFFFu, g, 0);
+    if (g >= n_groups) break;
+    const int i = g * 32 + lane;
+    if (i < n_tasks) {
+      const int j = i % J, n = i / J;
+      const float* w = gw + (size_t)n * kViewPerJoint * J1 + j;
+      float wq[kViewPad];                                  // the joint's 27 weights, all loads in flight at once
+#pragma unroll
+      for (int q = 0; q < kViewPerJoint; ++q) wq[q] = __ldg(w + q * J1);
+      wq[kViewPerJoint] = 0.f;
+      const uint32_t off = chunk_off(n, j);
+      const float4* t = reinterpret_cast<const float4*>(vtab_s + j * jstride);
+#pragma unroll 1
+      for (int s = 0; s < S; s += 2) {                     // two ray slots at a time
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+        for (int v = 0; v < kViewPad / 4; ++v) {
+          const float4 x = t[s * (kViewPad / 4) + v], y = t[(s + 1) * (kViewPad / 4) + v];
+          a0 = fmaf(wq[4 * v], x.x, a0); a1 = fmaf(wq[4 * v + 1], x.y, a1);
+          a0 = fmaf(wq[4 * v + 2], x.z, a0); a1 = fmaf(wq[4 * v + 3], x.w, a1);
+          b0 = fmaf(wq[4 * v], y.x, b0); b1 = fmaf(wq[4 * v + 1], y.y, b1);
+          b0 = fmaf(wq[4 * v + 2], y.z, b0); b1 = fmaf(wq[4 * v + 3], y.w, b1);
+        }
+        put(s, off, a0 + a1);
+        put(s + 1, off, b0 + b1);
+      }
+    }
+  }
+  if (d.fc_ch > 0) {                                       // framecode pseudo joint j == J: one (n, slot) per thread
+    const float* codes = smalls + P.prog.sm.framecodes;
+    for (int i = threadIdx.x; i < NH * S; i += kWorkerThreads) {
+      const int n = i / S, s = i % S;
+      const float* w = gw + (size_t)n * kViewPerJoint * J1 + J;
+      const float* c = codes + (size_t)fc_row_s[s] * d.fc_ch;
+      float acc = 0.f;
+      for (int q = 0; q < d.fc_ch; ++q) acc = fmaf(__ldg(w + q * J1), __ldg(c + q), acc);
+      put(s, chunk_off(n, J), acc);
+    }
+  }
+  fence_proxy_async_smem();
 }
 
 // Wait for the accumulators of the layer that used `region`, then walk this group's column blocks
@@ -498,10 +584,11 @@ __device__ __forceinline__ void drain_region(AProducer<FMT>& ap, const Pipe& pp,
 template <int FMT, bool DENSITY>
 __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe& pp, uint32_t (&d_cnt)[2],
                                                   const RowCtx& rc, const RenderKParams& P, const float* sm,
-                                                  int quarter, int grp, Trace* tr = nullptr) {
+                                                  int quarter, int grp, int row, float* wj, Trace* tr = nullptr) {
   const NetProgram& pg = P.prog;
   const int D = pg.dims.D, W = pg.dims.W;
   float sigma = 0.f;
+  if (!DENSITY) compute_view_weights(rc, P, grp, row, wj);     // consumed after the trunk, behind a barrier
   const float* wa = sm + pg.sm.alpha_w;
   // operands of trunk layers 0..D-1: [encoding part] + drain of layer l-1
 #pragma unroll 1
@@ -528,7 +615,8 @@ __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe
   // operand of the views layer (feature_linear folded in): the view encoding first -- it does not depend on the
   // trunk, so it is produced while the last trunk layer's MMAs run -- then h of the last trunk layer
   if (tr) tr->mark(22);
-  produce_view_chunks<FMT>(ap, rc, P, grp);
+  asm volatile("bar.sync 5, 512;" ::: "memory");              // all groups' view weights are in shared memory
+  produce_slot_chunks<FMT>(ap, rc, P, grp, row, wj);
   if (tr) tr->mark(23);
   drain_region<FMT, true, true>(ap, pp, d_cnt, (D - 1) & 1, W, sm + pg.sm.bias[D - 1], sm[D - 1], quarter, grp, alpha_acc, tr);
   if (grp == 0) sigma += sm[pg.sm.alpha_b];
@@ -711,7 +799,11 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
       for (int it = 0; it < n_iter; ++it)
         for (int ps = 0; ps < passes; ++ps)
           for (int l = 0; l < nl; ++l)
-            mma_layer<FMT>(pp, a_seq, b_seq, pg.layer[l].n, pg.layer[l].chunks, l & 1, trc.p ? &trc : nullptr);
+          {
+            const bool views = !DENSITY && l == pg.dims.D;      // leading ray-slot chunks read G from shared memory
+            mma_layer<FMT>(pp, a_seq, b_seq, pg.layer[l].n, pg.layer[l].chunks + (views ? P.slotc : 0), l & 1,
+                           trc.p ? &trc : nullptr, views ? P.slotc : 0, smem_u32(smem + L.g_buf));
+          }
     } else if (lane == 0) {        // peer: relay "my weight half has landed"
       for (int it = 0; it < n_iter; ++it)
         for (int ps = 0; ps < passes; ++ps)
@@ -739,7 +831,10 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
     float* ray_s = reinterpret_cast<float*>(smem + L.ray);
     float* skt_s = reinterpret_cast<float*>(smem + L.skt);
     float* vtab_s = reinterpret_cast<float*>(smem + L.view_tab);
-    float* fc_s = reinterpret_cast<float*>(smem + L.fcode);
+    int* fcrow_s = reinterpret_cast<int*>(smem + L.fcode);
+    int* gctr_s = reinterpret_cast<int*>(smem + L.task_ctr);
+    uint8_t* g_buf = smem + L.g_buf;
+    float* wj_s = reinterpret_cast<float*>(smem + L.wj);
     float* zc_s = reinterpret_cast<float*>(smem + L.z_coarse);
     float* za_s = reinterpret_cast<float*>(smem + L.z_all);
     float4* raw_s = reinterpret_cast<float4*>(smem + L.raw);
@@ -749,7 +844,6 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
     const float* sm0 = reinterpret_cast<const float*>(smem + L.smalls0);
     const float* sm1 = reinterpret_cast<const float*>(smem + L.smalls1);
     const int J = pg.dims.J;
-    const int VK = J * kKC;
 
     if (DENSITY) {
       // one pose for the whole launch
@@ -762,8 +856,8 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         long long ci = valid ? idx : (P.n_points - 1);
         RowCtx rc;
         rc.p[0] = P.pts[ci * 3 + 0]; rc.p[1] = P.pts[ci * 3 + 1]; rc.p[2] = P.pts[ci * 3 + 2];
-        rc.skt = skt_s; rc.vtab = nullptr; rc.fcode = nullptr;
-        float4 r = worker_net_pass<FMT, true>(ap, pp, d_cnt, rc, P, sm0, quarter, grp);
+        rc.skt = skt_s; rc.slot = 0;
+        float4 r = worker_net_pass<FMT, true>(ap, pp, d_cnt, rc, P, sm0, quarter, grp, row, nullptr);
         part_s[grp * kTileM + row] = r;
         worker_sync();
         if (grp == 0 && valid)
@@ -773,6 +867,12 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
     } else {
       const int R = P.R, Sc = P.Sc, Sf = P.Sf, Si = P.Si;
       const bool fine = Si > 0;
+      const int rank = (int)pp.rank;
+      {   // K rows of the ray-slot chunks that no joint uses (and whole padding chunks) stay zero for the whole launch
+        uint4* z = reinterpret_cast<uint4*>(g_buf);
+        for (int i = tid; i < P.slotc * (pg.dims.W / 2) * 4; i += kWorkerThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        fence_proxy_async_smem();
+      }
       for (int it = 0; it < n_iter; ++it) {
         const int item = blockIdx.x + it * gridDim.x;
         const int ray0 = item * R;       // >= n_rays for a dummy item: every load clamps, every store is guarded
@@ -790,24 +890,29 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
           int gr = min(ray0 + r, P.n_rays - 1);
           skt_s[i] = P.skts[(size_t)gr * J * 16 + (e / 12) * 16 + (e % 12)];
         }
-        if (pg.dims.fc_ch > 0) {
-          for (int i = tid; i < 2 * R * 16; i += kWorkerThreads) {
-            int net = i / (R * 16), r = (i / 16) % R, q = i % 16;
-            int gr = min(ray0 + r, P.n_rays - 1);
-            int cam = P.eval_mean_fc ? pg.dims.n_fc : (int)P.cams[gr];
-            cam = min(max(cam, 0), pg.dims.n_fc);
-            const float* codes = reinterpret_cast<const float*>(P.packed[net] + pg.smalls_off) + pg.sm.framecodes;
-            fc_s[i] = q < pg.dims.fc_ch ? codes[cam * pg.dims.fc_ch + q] : 0.f;
-          }
+        // ray slots of the CTA pair: slot = owner rank * R + ray index; the peer's item is the neighbouring one
+        auto slot_ray = [&](int slot) {
+          const int o = slot / R, r = slot % R;
+          const int it_o = (int)blockIdx.x - rank + o + it * (int)gridDim.x;
+          return min(it_o * R + r, P.n_rays - 1);
+        };
+        if (pg.dims.fc_ch > 0 && tid < 2 * R) {
+          int cam = P.eval_mean_fc ? pg.dims.n_fc : (int)P.cams[slot_ray(tid)];
+          fcrow_s[tid] = min(max(cam, 0), pg.dims.n_fc);
         }
+        if (tid == 0) *gctr_s = 0;       // every thread left the previous build long ago (barriers in between)
         worker_sync();
         // ---- (2) per-ray view-direction table, coarse depths --------------------------------
         {
-          for (int u = tid; u < R * J; u += kWorkerThreads) {
-            int r = u / J, j = u % J;
-            float* o = vtab_s + r * VK + j * kKC;
-            encode_joint_viewdir(skt_s + (r * J + j) * 12, ray_s + r * 12 + 3, o);
-            for (int q = kViewPerJoint; q < kKC; ++q) o[q] = 0.f;
+          const int vstride = view_tab_jstride(R);
+          for (int u = tid; u < 2 * R * J; u += kWorkerThreads) {
+            const int slot = u / J, j = u % J;
+            const int gr = slot_ray(slot);
+            float f[kViewPerJoint];
+            encode_joint_viewdir(P.skts + ((size_t)gr * J + j) * 16, P.rays + (size_t)gr * 8 + 3, f);
+#pragma unroll
+            for (int q = 0; q < kViewPerJoint; ++q) vtab_s[j * vstride + slot * kViewPad + q] = f[q];
+            vtab_s[j * vstride + slot * kViewPad + kViewPerJoint] = 0.f;
           }
           for (int i = tid; i < R * Sc; i += kWorkerThreads) {
             int r = i / Sc, s = i % Sc;
@@ -827,6 +932,11 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
           }
         }
         worker_sync();
+        if (tr) tr->mark(50);
+        build_view_matrices<FMT>(P, 0, g_buf, vtab_s, fcrow_s, gctr_s, rank, 1.0f / sm0[pg.dims.D]);
+        if (tr) tr->mark(51);
+        worker_sync();
+        if (tid == 0) *gctr_s = 0;       // for the fine network's build; the passes in between hold many barriers
         // ---- (3)/(6) network passes: tilesC coarse tiles, then tilesF fine tiles; (4)(5)(7) between ------
 #pragma unroll 1
         for (int ps = 0; ps < passes; ++ps) {
@@ -841,9 +951,9 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
           RowCtx rc;
           const float* rr = ray_s + r * 12;
           rc.p[0] = rr[0] + rr[3] * z; rc.p[1] = rr[1] + rr[4] * z; rc.p[2] = rr[2] + rr[5] * z;
-          rc.skt = skt_s + r * J * 12; rc.vtab = vtab_s + r * VK; rc.fcode = fc_s + ((is_fine ? R : 0) + r) * 16;
+          rc.skt = skt_s + r * J * 12; rc.slot = rank * R + r;
           if (tr) tr->mark(30 + ps);
-          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, is_fine ? sm1 : sm0, quarter, grp, tr);
+          float4 o = worker_net_pass<FMT, false>(ap, pp, d_cnt, rc, P, is_fine ? sm1 : sm0, quarter, grp, row, wj_s, tr);
           if (tr) tr->mark(40 + ps);
           part_s[grp * kTileM + row] = o;
           worker_sync();
@@ -869,6 +979,11 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
                 for (int i = lane; i < Sc; i += 32) reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sc + i] = raw_s[q * Sc + i];
               if (fine) importance_cdf(lane, Sc, w_s + q * Sc, cdf_s + q * Sc);
             }
+            // the coarse network's MMAs are all done: the ray-slot B chunks are rebuilt for the fine network by
+            // whichever warps are not compositing a ray
+            if (tr) tr->mark(52);
+            if (fine) build_view_matrices<FMT>(P, 1, g_buf, vtab_s, fcrow_s, gctr_s, rank, 1.0f / sm1[pg.dims.D]);
+            if (tr) tr->mark(53);
             worker_sync();   // raw_s is free from here (scratch for the merge below)
             if (fine) {
               // ---- (5) importance sampling: every worker thread takes samples, then ranks -------------
@@ -1067,6 +1182,17 @@ __global__ void anerf_fold_views_kernel(const float* __restrict__ wv, const floa
     } else {
       out_w[(size_t)n * cols + c] = wrow[c];
     }
+  }
+}
+
+// view weights of the folded views layer regrouped per joint for the per-ray contraction:
+// gw[n][q][j] = fold_w[n][view_weight_col(j, q)] (0 where the joint has no such input); j fastest
+__global__ void anerf_pack_view_weights_kernel(const float* __restrict__ fold_w, int cols, NetDims d, float* __restrict__ gw) {
+  const int H = d.W / 2, JJ = d.J + 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < H * JJ * kViewPerJoint; i += gridDim.x * blockDim.x) {
+    const int j = i % JJ, q = (i / JJ) % kViewPerJoint, n = i / (kViewPerJoint * JJ);     // [n][q][j]
+    const int c = view_weight_col(d, j, q);
+    gw[i] = c >= 0 ? fold_w[(size_t)n * cols + c] : 0.f;
   }
 }
 

@@ -36,20 +36,15 @@ void h_emit_pts(const float* skt /*[J][12]*/, const float* p, float tau, const f
     }
   }
 }
-// emission order of produce_view_chunks: joint j in chunk j (27 values + 5 zeros); framecode chunk after
-void h_emit_view(const float* skt, const float* dir, const float* p, float tau, const float* cut, int J,
-                 const float* fcode, int fc, float* out) {
-  NetDims d{J, 8, 256, 4, fc, fc ? 4 : 0};
-  int n = view_chunks(d) * kKC;
-  memset(out, 0, n * sizeof(float));
-  for (int j = 0; j < J; ++j) {
-    float tab[kViewPerJoint];
-    encode_joint_viewdir(skt + j * 12, dir, tab);
-    float w = cutoff_w(joint_dist(skt + j * 12, p), tau, cut[j]);
-    for (int q = 0; q < kViewPerJoint; ++q) out[j * kKC + q] = tab[q] * w;
-  }
-  for (int q = 0; q < fc; ++q) out[J * kKC + q] = fcode[q];
+int h_view_weight_col(int J, int D, int W, int skip, int fc, int j, int q) {
+  NetDims d{J, D, W, skip, fc, fc ? 4 : 0};
+  return view_weight_col(d, j, q);
 }
+// per-ray direction features of one joint (the table the kernel contracts the view weights with)
+void h_view_table(const float* skt, const float* dir, int J, float* out /*[J][27]*/) {
+  for (int j = 0; j < J; ++j) encode_joint_viewdir(skt + j * 12, dir, out + j * kViewPerJoint);
+}
+float h_cutoff_w(const float* skt12, const float* p, float tau, float cut) { return cutoff_w(joint_dist(skt12, p), tau, cut); }
 float h_linspace01(int i, int n) { return linspace01(i, n); }
 void h_near_far(const float* o, const float* d, const float* cyl, float near, float far, float* out) {
   bool miss;

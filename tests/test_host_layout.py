@@ -45,11 +45,8 @@ def test_packed_k_order_inverts_producer_order(harness, J, fc):
     fcode = rng.randn(16).astype(np.float32)
     D, W, skip = 8, 256, 4
     nP = harness.h_layer_chunks(J, D, W, skip, fc, 0) * 32
-    nV = harness.h_layer_chunks(J, D, W, skip, fc, D) * 32 - W
     ep = np.zeros(nP, np.float32)
-    ev = np.zeros(nV, np.float32)
     harness.h_emit_pts(fptr(skt12), fptr(p), C.c_float(tau), fptr(cut), J, fptr(ep))
-    harness.h_emit_view(fptr(skt12), fptr(dirv), fptr(p), C.c_float(tau), fptr(cut), J, fptr(fcode), fc, fptr(ev))
     col = lambda l, k: harness.h_layer_ref_col(J, D, W, skip, fc, l, k)
     # layer 0: emitted value k must be reference input column col(0,k)
     for k in range(nP):
@@ -61,16 +58,28 @@ def test_packed_k_order_inverts_producer_order(harness, J, fc):
     cols = [col(l, k) for k in range(nP + W)]
     assert cols[:nP] == [col(0, k) for k in range(nP)]
     assert cols[nP:] == [cfg.in_pts + n for n in range(W)]
-    # plain trunk layer: identity
+    # plain trunk layer and the streamed (h) part of the views layer: identity
     assert [col(2, k) for k in range(W)] == list(range(W))
-    # views layer (feature_linear folded in): [view encoding (+ framecode) | h]
+    assert [col(D, k) for k in range(W)] == list(range(W))
+    # view branch contracted per ray: sum_j w_j sum_q Wv[n, col(j,q)] table[j][q] == Wv[n, W:] . x_view
+    wv = rng.randn(5, W + cfg.in_views + fc)
+    tab = np.zeros((J, 27), np.float32)
+    harness.h_view_table(fptr(skt12), fptr(dirv), J, fptr(tab))
+    harness.h_cutoff_w.restype = C.c_float
+    wj = np.array([harness.h_cutoff_w(fptr(np.ascontiguousarray(skt12[j])), fptr(p), C.c_float(tau), C.c_float(0.5)) for j in range(J)])
+    vcol = lambda j, q: harness.h_view_weight_col(J, D, W, skip, fc, j, q)
+    got = np.zeros(5)
+    seen = []
+    for j in range(J + 1):
+        for q in range(27):
+            c = vcol(j, q)
+            if c < 0:
+                continue
+            seen.append(c)
+            got += wv[:, c] * ((tab[j, q] * wj[j]) if j < J else fcode[q])
     ref_in = np.concatenate([np.zeros(W), xv, fcode[:fc].astype(np.float64)])
-    for k in range(nV):
-        c = col(D, k)
-        assert (ev[k] == 0.0) if c < 0 else abs(ev[k] - ref_in[c]) < 2e-6, (k, c)
-    cols = [col(D, k) for k in range(nV + W)]
-    assert cols[nV:] == list(range(W))
-    assert sorted(c for c in cols if c >= 0) == list(range(W + cfg.in_views + fc))
+    assert np.abs(got - wv @ ref_in).max() < 1e-5
+    assert sorted(seen) == list(range(W, W + cfg.in_views + fc))
 
 
 def test_linspace_matches_torch(harness):
