@@ -7,7 +7,9 @@ import os
 
 import torch
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc", "libanerf_b200.so")
+# ANERF_B200_LIB points at an alternative build of the same library (tools/ab_variants.py: kernel A/B runs)
+_LIB_PATH = os.environ.get("ANERF_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc",
+                                                             "libanerf_b200.so")
 _lib = None
 
 SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "anerf_pack_net",

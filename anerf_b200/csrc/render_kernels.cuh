@@ -26,7 +26,10 @@
 namespace anerf {
 
 constexpr int kAStages = 4;
-constexpr int kBStages = 3;
+#ifndef ANERF_B_STAGES
+#define ANERF_B_STAGES 4
+#endif
+constexpr int kBStages = ANERF_B_STAGES;   // weight ring depth (compile-time knob for tools/ab_variants.py)
 constexpr int kAHalfBytes = kTileM * kKC * 2;        // 8 KB: hi (or lo) part of one A chunk
 constexpr int kAStageBytes = 2 * kAHalfBytes;        // 16 KB
 constexpr int kBStageBytes = 128 * kKC * 2 * 2;      // 16 KB: this CTA's half (N/2 <= 128 rows) of a weight chunk, hi + lo
@@ -443,8 +446,8 @@ __device__ __forceinline__ void compute_view_weights(const RowCtx& rc, const Ren
 // (this CTA's half of the N = W/2 output features): G[slot][n][j] = scale * sum_q gw[n][q][j] * T[j][slot][q],
 // T = per-ray direction features (j < J) or the ray's framecode (j == J).  Work is handed out to warps in
 // groups of 32 (n, j) tasks through a shared counter, so warps that arrive late (the ones compositing a ray)
-// simply take fewer groups.  `ctr` must be zero on entry (reset behind a worker barrier); callers
-// worker_sync() afterwards (the proxy fence is inside).
+// simply take fewer groups -- any subset of the worker warps may call this.  `ctr` must be zero on entry (reset
+// behind a barrier); callers synchronise afterwards (the proxy fence is inside).
 template <int FMT>
 __device__ __forceinline__ void build_view_matrices(const RenderKParams& P, int net, uint8_t* g_buf, const float* vtab_s,
                                                     const int* fc_row_s, int* ctr, int rank, float scale) {
@@ -457,6 +460,7 @@ __device__ __forceinline__ void build_view_matrices(const RenderKParams& P, int 
   const float* smalls = reinterpret_cast<const float*>(P.packed[net] + P.prog.smalls_off);
   const float* gw = smalls + P.prog.sm.gw + (size_t)rank * NH * kViewPerJoint * J1;   // [n][q][j], j fastest: coalesced
   const int n_tasks = NH * J, n_groups = (n_tasks + 31) / 32;
+  const int fc_tasks = d.fc_ch > 0 ? NH * S : 0, fc_groups = (fc_tasks + 31) / 32;   // framecode pseudo joint j == J
   auto put = [&](int slot, uint32_t off, float v) {
     uint32_t hi, lo;
     Split<FMT>::pair(v * scale, 0.f, hi, lo);
@@ -472,7 +476,19 @@ __device__ __forceinline__ void build_view_matrices(const RenderKParams& P, int 
     int g = 0;
     if (lane == 0) g = atomicAdd(ctr, 1);
     g = __shfl_sync(0xFFFFFFFFu, g, 0);
-    if (g >= n_groups) break;
+    if (g >= n_groups + fc_groups) break;
+    if (g >= n_groups) {                                   // one (n, slot) of the framecode pseudo joint per lane
+      const int i = (g - n_groups) * 32 + lane;
+      if (i < fc_tasks) {
+        const int n = i / S, sl = i % S;
+        const float* w = gw + (size_t)n * kViewPerJoint * J1 + J;
+        const float* c = smalls + P.prog.sm.framecodes + (size_t)fc_row_s[sl] * d.fc_ch;
+        float acc = 0.f;
+        for (int q = 0; q < d.fc_ch; ++q) acc = fmaf(__ldg(w + q * J1), __ldg(c + q), acc);
+        put(sl, chunk_off(n, J), acc);
+      }
+      continue;
+    }
     const int i = g * 32 + lane;
     if (i < n_tasks) {
       const int j = i % J, n = i / J;
@@ -484,30 +500,19 @@ __device__ __forceinline__ void build_view_matrices(const RenderKParams& P, int 
       const uint32_t off = chunk_off(n, j);
       const float4* t = reinterpret_cast<const float4*>(vtab_s + j * jstride);
 #pragma unroll 1
-      for (int s = 0; s < S; s += 2) {                     // two ray slots at a time
+      for (int sl = 0; sl < S; sl += 2) {                  // two ray slots at a time
         float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
 #pragma unroll
         for (int v = 0; v < kViewPad / 4; ++v) {
-          const float4 x = t[s * (kViewPad / 4) + v], y = t[(s + 1) * (kViewPad / 4) + v];
+          const float4 x = t[sl * (kViewPad / 4) + v], y = t[(sl + 1) * (kViewPad / 4) + v];
           a0 = fmaf(wq[4 * v], x.x, a0); a1 = fmaf(wq[4 * v + 1], x.y, a1);
           a0 = fmaf(wq[4 * v + 2], x.z, a0); a1 = fmaf(wq[4 * v + 3], x.w, a1);
           b0 = fmaf(wq[4 * v], y.x, b0); b1 = fmaf(wq[4 * v + 1], y.y, b1);
           b0 = fmaf(wq[4 * v + 2], y.z, b0); b1 = fmaf(wq[4 * v + 3], y.w, b1);
         }
-        put(s, off, a0 + a1);
-        put(s + 1, off, b0 + b1);
+        put(sl, off, a0 + a1);
+        put(sl + 1, off, b0 + b1);
       }
-    }
-  }
-  if (d.fc_ch > 0) {                                       // framecode pseudo joint j == J: one (n, slot) per thread
-    const float* codes = smalls + P.prog.sm.framecodes;
-    for (int i = threadIdx.x; i < NH * S; i += kWorkerThreads) {
-      const int n = i / S, s = i % S;
-      const float* w = gw + (size_t)n * kViewPerJoint * J1 + J;
-      const float* c = codes + (size_t)fc_row_s[s] * d.fc_ch;
-      float acc = 0.f;
-      for (int q = 0; q < d.fc_ch; ++q) acc = fmaf(__ldg(w + q * J1), __ldg(c + q), acc);
-      put(s, chunk_off(n, J), acc);
     }
   }
   fence_proxy_async_smem();
@@ -873,70 +878,71 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         for (int i = tid; i < P.slotc * (pg.dims.W / 2) * 4; i += kWorkerThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
         fence_proxy_async_smem();
       }
-      for (int it = 0; it < n_iter; ++it) {
-        const int item = blockIdx.x + it * gridDim.x;
-        const int ray0 = item * R;       // >= n_rays for a dummy item: every load clamps, every store is guarded
-        // ---- (1) per-ray inputs -------------------------------------------------------------
-        if (tid < R) {
-          int gr = min(ray0 + tid, P.n_rays - 1);
+      // ---- (1)(2) per-ray inputs of item `it_`: rays, bone transforms, framecode rows, view-direction table of
+      // the pair's 2R ray slots, coarse depths.  Run by threads t0, t0 + nt, ... (all workers before the first
+      // item; afterwards the warps that are not compositing the previous item's rays).  No barrier inside.
+      auto stage_inputs = [&](int it_, int t0, int nt) {
+        const int ray0 = (blockIdx.x + it_ * (int)gridDim.x) * R;   // >= n_rays for a dummy item: every load clamps
+        // ray slots of the CTA pair: slot = owner rank * R + ray index; the peer's item is the neighbouring one
+        auto slot_ray = [&](int slot) {
+          const int o = slot / R, r = slot % R;
+          const int it_o = (int)blockIdx.x - rank + o + it_ * (int)gridDim.x;
+          return min(it_o * R + r, P.n_rays - 1);
+        };
+        if (t0 == 0) gctr_s[1] = 0;        // counter of the fine network's build (mid-item, many barriers away)
+        for (int i = t0; i < R; i += nt) {
+          int gr = min(ray0 + i, P.n_rays - 1);
           const float* rp = P.rays + (size_t)gr * 8;
-          float* d = ray_s + tid * 12;
+          float* d = ray_s + i * 12;
           d[0] = rp[0]; d[1] = rp[1]; d[2] = rp[2]; d[3] = rp[3]; d[4] = rp[4]; d[5] = rp[5];
           d[6] = P.nearfar[gr * 2]; d[7] = P.nearfar[gr * 2 + 1];
           d[8] = sqrtf(rp[3] * rp[3] + rp[4] * rp[4] + rp[5] * rp[5]);
         }
-        for (int i = tid; i < R * J * 12; i += kWorkerThreads) {
+        for (int i = t0; i < R * J * 12; i += nt) {
           int r = i / (J * 12), e = i % (J * 12);
           int gr = min(ray0 + r, P.n_rays - 1);
           skt_s[i] = P.skts[(size_t)gr * J * 16 + (e / 12) * 16 + (e % 12)];
         }
-        // ray slots of the CTA pair: slot = owner rank * R + ray index; the peer's item is the neighbouring one
-        auto slot_ray = [&](int slot) {
-          const int o = slot / R, r = slot % R;
-          const int it_o = (int)blockIdx.x - rank + o + it * (int)gridDim.x;
-          return min(it_o * R + r, P.n_rays - 1);
-        };
-        if (pg.dims.fc_ch > 0 && tid < 2 * R) {
-          int cam = P.eval_mean_fc ? pg.dims.n_fc : (int)P.cams[slot_ray(tid)];
-          fcrow_s[tid] = min(max(cam, 0), pg.dims.n_fc);
-        }
-        if (tid == 0) *gctr_s = 0;       // every thread left the previous build long ago (barriers in between)
-        worker_sync();
-        // ---- (2) per-ray view-direction table, coarse depths --------------------------------
-        {
-          const int vstride = view_tab_jstride(R);
-          for (int u = tid; u < 2 * R * J; u += kWorkerThreads) {
-            const int slot = u / J, j = u % J;
-            const int gr = slot_ray(slot);
-            float f[kViewPerJoint];
-            encode_joint_viewdir(P.skts + ((size_t)gr * J + j) * 16, P.rays + (size_t)gr * 8 + 3, f);
+        if (pg.dims.fc_ch > 0)
+          for (int i = t0; i < 2 * R; i += nt) {
+            int cam = P.eval_mean_fc ? pg.dims.n_fc : (int)P.cams[slot_ray(i)];
+            fcrow_s[i] = min(max(cam, 0), pg.dims.n_fc);
+          }
+        const int vstride = view_tab_jstride(R);
+        for (int u = t0; u < 2 * R * J; u += nt) {
+          const int slot = u / J, j = u % J;
+          const int gr = slot_ray(slot);
+          float f[kViewPerJoint];
+          encode_joint_viewdir(P.skts + ((size_t)gr * J + j) * 16, P.rays + (size_t)gr * 8 + 3, f);
 #pragma unroll
-            for (int q = 0; q < kViewPerJoint; ++q) vtab_s[j * vstride + slot * kViewPad + q] = f[q];
-            vtab_s[j * vstride + slot * kViewPad + kViewPerJoint] = 0.f;
-          }
-          for (int i = tid; i < R * Sc; i += kWorkerThreads) {
-            int r = i / Sc, s = i % Sc;
-            float near = ray_s[r * 12 + 6], far = ray_s[r * 12 + 7];
-            auto zat = [&](int k) {
-              float t = linspace01(k, Sc);
-              return P.lindisp ? 1.f / (1.f / near * (1.f - t) + 1.f / far * t) : near * (1.f - t) + far * t;
-            };
-            float z = zat(s);
-            if (P.t_rand) {
-              int gr = min(ray0 + r, P.n_rays - 1);
-              float lower = s == 0 ? z : 0.5f * (zat(s - 1) + z);
-              float upper = s == Sc - 1 ? z : 0.5f * (z + zat(s + 1));
-              z = lower + (upper - lower) * P.t_rand[(size_t)gr * Sc + s];
-            }
-            zc_s[i] = z;
-          }
+          for (int q = 0; q < kViewPerJoint; ++q) vtab_s[j * vstride + slot * kViewPad + q] = f[q];
+          vtab_s[j * vstride + slot * kViewPad + kViewPerJoint] = 0.f;
         }
-        worker_sync();
-        if (tr) tr->mark(50);
-        build_view_matrices<FMT>(P, 0, g_buf, vtab_s, fcrow_s, gctr_s, rank, 1.0f / sm0[pg.dims.D]);
-        if (tr) tr->mark(51);
-        worker_sync();
-        if (tid == 0) *gctr_s = 0;       // for the fine network's build; the passes in between hold many barriers
+        for (int i = t0; i < R * Sc; i += nt) {
+          int r = i / Sc, sidx = i % Sc;
+          const int gr = min(ray0 + r, P.n_rays - 1);
+          float near = P.nearfar[gr * 2], far = P.nearfar[gr * 2 + 1];
+          auto zat = [&](int k) {
+            float t = linspace01(k, Sc);
+            return P.lindisp ? 1.f / (1.f / near * (1.f - t) + 1.f / far * t) : near * (1.f - t) + far * t;
+          };
+          float z = zat(sidx);
+          if (P.t_rand) {
+            float lower = sidx == 0 ? z : 0.5f * (zat(sidx - 1) + z);
+            float upper = sidx == Sc - 1 ? z : 0.5f * (z + zat(sidx + 1));
+            z = lower + (upper - lower) * P.t_rand[(size_t)gr * Sc + sidx];
+          }
+          zc_s[i] = z;
+        }
+      };
+      if (tid == 0) gctr_s[0] = 0;
+      stage_inputs(0, tid, kWorkerThreads);
+      worker_sync();
+      build_view_matrices<FMT>(P, 0, g_buf, vtab_s, fcrow_s, gctr_s, rank, 1.0f / sm0[pg.dims.D]);
+      worker_sync();
+      for (int it = 0; it < n_iter; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int ray0 = item * R;       // >= n_rays for a dummy item: every load clamps, every store is guarded
         // ---- (3)/(6) network passes: tilesC coarse tiles, then tilesF fine tiles; (4)(5)(7) between ------
 #pragma unroll 1
         for (int ps = 0; ps < passes; ++ps) {
@@ -961,6 +967,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
             raw_s[g] = add4(add4(part_s[row], part_s[kTileM + row]), add4(part_s[2 * kTileM + row], part_s[3 * kTileM + row]));
           if (ps == P.tilesC - 1) {
             worker_sync();
+            if (tid == 0) gctr_s[0] = 0;   // counter of the next item's coarse build (item end, many barriers away)
             // ---- (4) composite coarse: one warp per ray ----------------------------------------------
             for (int q = warp; q < R; q += kWorkerWarps) {
               int gr = ray0 + q;
@@ -982,7 +989,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
             // the coarse network's MMAs are all done: the ray-slot B chunks are rebuilt for the fine network by
             // whichever warps are not compositing a ray
             if (tr) tr->mark(52);
-            if (fine) build_view_matrices<FMT>(P, 1, g_buf, vtab_s, fcrow_s, gctr_s, rank, 1.0f / sm1[pg.dims.D]);
+            if (fine) build_view_matrices<FMT>(P, 1, g_buf, vtab_s, fcrow_s, gctr_s + 1, rank, 1.0f / sm1[pg.dims.D]);
             if (tr) tr->mark(53);
             worker_sync();   // raw_s is free from here (scratch for the merge below)
             if (fine) {
@@ -1020,14 +1027,20 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
             }
           }
         }
+        // ---- item end: (7) composite fine (one warp per ray) while the other warps stage the next item's inputs
+        // and build its coarse-network view matrices (the last pass's MMAs are done: g_buf is free) ----------------
+        const bool has_next = it + 1 < n_iter;
+        static_assert(kMaxRaysPerItem < kWorkerWarps, "one compositing warp per ray, and warps left for staging");
         if (fine) {
+          const float dnorm = warp < R ? ray_s[warp * 12 + 8] : 0.f;    // ray_s is about to be overwritten
           worker_sync();
-          // ---- (7) composite fine ------------------------------------------------------------------
-          for (int q = warp; q < R; q += kWorkerWarps) {
+          if (warp < R) {
+            if (tr) tr->mark(54);
+            const int q = warp;
             int gr = ray0 + q;
             bool live = gr < P.n_rays;
             int grc = min(gr, P.n_rays - 1);
-            composite_ray(lane, Sf, za_s + q * Sf, raw_s + q * Sf, ray_s[q * 12 + 8],
+            composite_ray(lane, Sf, za_s + q * Sf, raw_s + q * Sf, dnorm,
                           P.noise1 ? P.noise1 + (size_t)grc * Sf : nullptr, P, w_s + q * Sf,
                           (live && P.alpha) ? P.alpha + (size_t)gr * Sf : nullptr,
                           (live && P.rgb_map) ? P.rgb_map + (size_t)gr * 3 : nullptr,
@@ -1035,7 +1048,20 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
                           (live && P.acc_map) ? P.acc_map + gr : nullptr);
             if (live && P.raw_out)
               for (int i = lane; i < Sf; i += 32) reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sf + i] = raw_s[q * Sf + i];
+            if (tr) tr->mark(55);
+          } else if (has_next) {
+            const int nt = kWorkerThreads - 32 * R;
+            if (tr) tr->mark(50);
+            stage_inputs(it + 1, tid - 32 * R, nt);
+            asm volatile("bar.sync 6, %0;" ::"r"(nt) : "memory");        // the staging warps only
+            build_view_matrices<FMT>(P, 0, g_buf, vtab_s, fcrow_s, gctr_s, rank, 1.0f / sm0[pg.dims.D]);
+            if (tr) tr->mark(51);
           }
+          worker_sync();
+        } else if (has_next) {
+          stage_inputs(it + 1, tid, kWorkerThreads);
+          worker_sync();
+          build_view_matrices<FMT>(P, 0, g_buf, vtab_s, fcrow_s, gctr_s, rank, 1.0f / sm0[pg.dims.D]);
           worker_sync();
         }
       }
