@@ -48,7 +48,10 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // One probe of the barrier phase.  With the suspend-time hint the thread sleeps in hardware
 // (SASS: TRYWAIT + NANOSLEEP.SYNCS) until the phase completes or ~`kSuspendNs` elapse, so a waiting
 // thread does not burn issue slots of its SM sub-partition.
-constexpr uint32_t kSuspendNs = 100000u;
+#ifndef ANERF_SUSPEND_NS
+#define ANERF_SUSPEND_NS 100000
+#endif
+constexpr uint32_t kSuspendNs = ANERF_SUSPEND_NS;
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(

@@ -295,10 +295,10 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "kernel": "anerf_fused_kernel",
                 "launch_ms": launch_ms, "algorithmic_flop_per_launch": FLOP_PER_RAY * CHUNK,
                 "note": "achieved = algorithmic fp32-equivalent FLOPs (441.25 MFLOP/ray, BASELINE.md). Each product is issued as "
-                        "3 fp16 MMAs (lo*hi+hi*lo+hi*hi); with feature_linear folded into the views layer and K padding "
-                        "the kernel executes 851,968 MACs x 3 per sample against 861,824 algorithmic, so tensor-pipe "
-                        "work is 2.97x `achieved`: issued_frac below",
-                "issued_frac": 2.966 * achieved / peak}
+                        "3 fp16 MMAs (lo*hi+hi*lo+hi*hi); with feature_linear folded into the views layer, the view branch "
+                        "contracted per ray (views layer K 904 -> 384) and K padding the kernel executes 770,048 MACs x 3 "
+                        "per sample against 861,824 algorithmic, so tensor-pipe work is 2.68x `achieved`: issued_frac below",
+                "issued_frac": 2.6805 * achieved / peak}
 
     # ---- e2e: the C-ABI call with HOST buffers, H2D and D2H inside the timed region ------------------------
     e2e = None
