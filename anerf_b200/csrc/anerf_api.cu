@@ -11,6 +11,7 @@
 
 #include "../../include/anerf_b200.h"
 #include "render_kernels.cuh"
+#include "train_path.cuh"
 
 using namespace anerf;
 
@@ -361,6 +362,49 @@ int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, con
   if (rc != ANERF_OK) return rc;
   if (e != cudaSuccess) { check_device_status(); return g_err.empty() ? fail(ANERF_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e)) : ANERF_ERR_DEVICE; }
   return check_device_status();
+}
+
+size_t anerf_render_bwd_workspace_bytes(const anerf_plan* plan, int32_t n_rays, int32_t n_samples, int32_t n_importance) {
+  if (!plan || n_rays <= 0 || n_samples <= 0 || n_importance < 0) return 0;
+  return train::train_workspace_bytes(plan->dims, n_rays, n_samples, n_importance);
+}
+
+int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, const anerf_net_params* fine,
+                     const anerf_render_opts* o, const anerf_render_inputs* in, const float* nearfar, const float* z_all,
+                     const anerf_render_grads* gout, const anerf_net_grads* g_coarse, const anerf_net_grads* g_fine,
+                     float* g_skts, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!plan || !coarse || !o || !in || !gout || !nearfar) return fail(ANERF_ERR_INVALID, "null argument");
+  const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance;
+  if (N == 0) return ANERF_OK;
+  if (N < 0 || Sc < 4 || Si < 0 || Sc + Si > 512) return fail(ANERF_ERR_INVALID, "bad sizes n_rays=%d n_samples=%d n_importance=%d", N, Sc, Si);
+  if (Si > 0 && (!fine || !z_all)) return fail(ANERF_ERR_INVALID, "fine parameters / z_all missing");
+  if (!in->rays || !in->skts) return fail(ANERF_ERR_INVALID, "rays/skts missing");
+  if (plan->dims.fc_ch > 0 && (!in->cams || o->eval_mean_framecode))
+    return fail(ANERF_ERR_INVALID, "backward needs per-ray cams (the eval-time mean framecode has no training path)");
+  if (!(o->density_scale != 0.f)) return fail(ANERF_ERR_INVALID, "density_scale must be non-zero");
+  const anerf_net_params* nets[2] = {coarse, Si > 0 ? fine : coarse};
+  for (int n = 0; n < (Si > 0 ? 2 : 1); ++n) {
+    const anerf_net_params* q = nets[n];
+    for (int l = 0; l < plan->dims.D; ++l)
+      if (!q->pts_w[l] || !q->pts_b[l]) return fail(ANERF_ERR_INVALID, "missing parameter pointer for layer %d", l);
+    if (!q->alpha_w || !q->alpha_b || !q->feature_w || !q->feature_b || !q->views_w || !q->views_b || !q->rgb_w || !q->rgb_b)
+      return fail(ANERF_ERR_INVALID, "missing head parameters");
+    if (plan->dims.fc_ch > 0 && !q->framecodes) return fail(ANERF_ERR_INVALID, "framecodes pointer missing");
+  }
+  const size_t need = train::train_workspace_bytes(plan->dims, N, Sc, Si);
+  if (!workspace || workspace_bytes < need) return fail(ANERF_ERR_INVALID, "workspace too small (%zu < %zu)", workspace_bytes, need);
+  train::TrainCall c{};
+  c.dims = plan->dims;
+  c.n_rays = N; c.Sc = Sc; c.Si = Si;
+  c.opts = o; c.in = in; c.nearfar = nearfar; c.z_all = z_all; c.gout = gout;
+  c.net[0] = coarse; c.net[1] = Si > 0 ? fine : coarse;
+  c.grad[0] = g_coarse; c.grad[1] = g_fine;
+  c.g_skts = g_skts;
+  c.workspace = (float*)workspace;
+  c.workspace_floats = workspace_bytes / sizeof(float);
+  if (train::train_backward(c, (cudaStream_t)stream_) != 0) return fail(ANERF_ERR_INVALID, "internal: workspace layout");
+  CUDA_TRY(cudaGetLastError());
+  return ANERF_OK;
 }
 
 int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t format, void* stream_) {

@@ -121,6 +121,22 @@ ANERF_HD float linspace01(int i, int n) {
   return i < n / 2 ? step * (float)i : 1.0f - step * (float)(n - 1 - i);
 }
 
+// a3 (ray_utils.py:204-251): coarse depth `sidx` of a ray; `t_rand_row` (the ray's Sc draws) switches the
+// stratified jitter on.  Same arithmetic as the fused kernel's stage (2).
+ANERF_HD float coarse_depth(float near, float far, int sidx, int Sc, int lindisp, const float* t_rand_row) {
+  auto zat = [&](int k) {
+    float t = linspace01(k, Sc);
+    return lindisp ? 1.f / (1.f / near * (1.f - t) + 1.f / far * t) : near * (1.f - t) + far * t;
+  };
+  float z = zat(sidx);
+  if (t_rand_row) {
+    float lower = sidx == 0 ? z : 0.5f * (zat(sidx - 1) + z);
+    float upper = sidx == Sc - 1 ? z : 0.5f * (z + zat(sidx + 1));
+    z = lower + (upper - lower) * t_rand_row[sidx];
+  }
+  return z;
+}
+
 // ------------------------------------------------------------------------------------------------
 // a2: ray / bounding-cylinder intersection in the x-z plane (ray_utils.py:292-326).
 // Returns near', far' (NaN when the ray's projection misses the circle) .

@@ -1,0 +1,266 @@
+// Launch sequence of the training backward pass (host side): per network pass and per block of rays,
+//   encodings -> layer-wise forward (activations kept in the workspace) -> compositing backward ->
+//   layer-wise backward (weight / bias gradients accumulated atomically, input gradients masked by the
+//   ReLU derivative) -> encoding backward into the bone transforms / framecodes.
+// Reference autograd graph: core/raycasters.py:361-474 (render_rays), core/networks/nerf.py:94-205.
+//
+// The same code drives the CUDA kernels in the library (anerf_api.cu: anerf_render_bwd) and, in the host
+// tests only, their CPU emulation (tests/host/simt_emu.h) -- the ANERF_TLAUNCH / ANERF_TZERO macros are the
+// only difference.
+#pragma once
+#include "../../include/anerf_b200.h"
+#include "train_kernels.cuh"
+
+#if defined(ANERF_SIMT_EMU)
+#define ANERF_TLAUNCH(kernel, grid, block, stream, ...) simt_emu::launch(grid, block, kernel, __VA_ARGS__)
+#define ANERF_TZERO(ptr, bytes, stream) memset(ptr, 0, bytes)
+typedef void* anerf_tstream;
+#else
+#define ANERF_TLAUNCH(kernel, grid, block, stream, ...) kernel<<<grid, block, 0, stream>>>(__VA_ARGS__)
+#define ANERF_TZERO(ptr, bytes, stream) cudaMemsetAsync(ptr, 0, bytes, stream)
+typedef cudaStream_t anerf_tstream;
+#endif
+
+namespace anerf {
+namespace train {
+
+constexpr long long kRowsTarget = 65536;    // rows (samples) per block of rays: ~1.5 GB of fp32 activations + gradients at W=256
+
+struct TrainCall {
+  NetDims dims;
+  int n_rays, Sc, Si;
+  const anerf_render_opts* opts;
+  const anerf_render_inputs* in;
+  const float* nearfar;          // [N,2] written by the forward pass
+  const float* z_all;            // [N,Sc+Si] sorted depths of the fine pass (forward tap); unused when Si == 0
+  const anerf_render_grads* gout;
+  const anerf_net_params* net[2];
+  const anerf_net_grads* grad[2];
+  float* g_skts;                 // [N,J,16] accumulated, or NULL
+  float* workspace;
+  size_t workspace_floats;
+};
+
+struct Workspace {
+  long long rb;                  // rows per block
+  long long z_coarse, xs, h[8], vin, hv, raw, graw, cs, ga, gb, gxs, gvin, ghv, total;   // offsets in floats
+  int P, LX, LV;                 // encoding width, leading dimension of XS (P + W), of VIN (W + 27J + fc)
+};
+
+inline int rays_per_block(int n_rays, int S) {
+  long long r = kRowsTarget / S;
+  if (r < 1) r = 1;
+  if (r > n_rays) r = n_rays;
+  return (int)r;
+}
+
+inline Workspace make_workspace(const NetDims& d, int n_rays, int Sc, int Si) {
+  Workspace w{};
+  const int Sf = Sc + Si;
+  long long rb = (long long)rays_per_block(n_rays, Sc) * Sc;
+  if (Si > 0) { long long r1 = (long long)rays_per_block(n_rays, Sf) * Sf; if (r1 > rb) rb = r1; }
+  w.rb = rb;
+  w.P = in_pts_ref(d);
+  w.LX = w.P + d.W;
+  w.LV = d.W + in_views_ref(d) + d.fc_ch;
+  long long off = 0;
+  auto take = [&](long long n) { long long o = off; off += (n + 3) / 4 * 4; return o; };
+  w.z_coarse = take((long long)n_rays * Sc);
+  w.xs = take(rb * w.LX);
+  for (int l = 0; l < 8; ++l) w.h[l] = l < d.D ? take(rb * d.W) : 0;
+  w.vin = take(rb * w.LV);
+  w.hv = take(rb * (d.W / 2));
+  w.raw = take(rb * 4);
+  w.graw = take(rb * 4);
+  w.cs = take(rb * 2);
+  w.ga = take(rb * d.W);
+  w.gb = take(rb * d.W);
+  w.gxs = take(rb * w.LX);
+  w.gvin = take(rb * w.LV);
+  w.ghv = take(rb * (d.W / 2));
+  w.total = off;
+  return w;
+}
+
+inline size_t train_workspace_bytes(const NetDims& d, int n_rays, int Sc, int Si) {
+  return (size_t)make_workspace(d, n_rays, Sc, Si).total * sizeof(float);
+}
+
+inline dim3 gemm_grid(int M, int N, int K, int k_chunk) {
+  return dim3((unsigned)ceil_div(N, kBN), (unsigned)ceil_div(M, kBM), (unsigned)ceil_div(K, k_chunk));
+}
+
+// forward / dgrad form: C[rows, N] = A[rows, K] * B (+ bias, relu, mask)
+template <bool BT>
+inline void gemm_rows(anerf_tstream st, const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
+                      long long rows, int N, int K, const float* bias, int relu, const float* mask, long long ldmask, int mode) {
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+  g.M = (int)rows; g.N = N; g.K = K; g.k_chunk = round_up(K, kBK);
+  g.bias = bias; g.relu = relu; g.mask = mask; g.ldmask = ldmask; g.mode = mode;
+  auto k = sgemm_kernel<false, BT>;
+  ANERF_TLAUNCH(k, gemm_grid(g.M, N, K, g.k_chunk), dim3(kGemmThreads), st, g);
+}
+
+// wgrad form: dW[Nout, Kin] += G[rows, Nout]^T * X[rows, Kin], split over the rows
+inline void gemm_wgrad(anerf_tstream st, const float* G, long long ldg, const float* X, long long ldx, float* dW, long long lddw,
+                       long long rows, int Nout, int Kin) {
+  if (!dW) return;
+  GemmArgs g{};
+  g.A = G; g.lda = ldg; g.B = X; g.ldb = ldx; g.C = dW; g.ldc = lddw;
+  g.M = Nout; g.N = Kin; g.K = (int)rows;
+  int kc = round_up(ceil_div((int)rows, 64), kBK);
+  if (kc < 256) kc = 256;
+  g.k_chunk = kc;
+  g.mode = 2;
+  auto k = sgemm_kernel<true, false>;
+  ANERF_TLAUNCH(k, gemm_grid(Nout, Kin, (int)rows, kc), dim3(kGemmThreads), st, g);
+}
+
+inline void colsum(anerf_tstream st, const float* G, long long ld, int N, long long rows, float* db) {
+  if (!db) return;
+  const int rpb = 128;
+  auto k = colsum_kernel;
+  ANERF_TLAUNCH(k, dim3((unsigned)((rows + rpb - 1) / rpb)), dim3((unsigned)round_up(N, 32)), st, G, ld, N, rows, rpb, db);
+}
+
+// One network pass (net 0 on the coarse depths, or net 1 on the sorted fine depths) over all rays.
+inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S, const float* z, const float* noise,
+                          const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_alpha,
+                          anerf_tstream st) {
+  const NetDims& d = c.dims;
+  const anerf_net_params& p = *c.net[net];
+  static const anerf_net_grads no_grads{};
+  const anerf_net_grads& gr = c.grad[net] ? *c.grad[net] : no_grads;
+  const anerf_render_opts& o = *c.opts;
+  float* ws = c.workspace;
+  const int D = d.D, W = d.W, H = d.W / 2, P = w.P, LX = w.LX, LV = w.LV, J = d.J;
+  const bool need_pose = c.g_skts != nullptr;
+  const bool need_fc = d.fc_ch > 0 && gr.framecodes != nullptr;
+  float* XS = ws + w.xs; float* VIN = ws + w.vin; float* HV = ws + w.hv; float* RAW = ws + w.raw;
+  float* GRAW = ws + w.graw; float* GA = ws + w.ga; float* GB = ws + w.gb; float* GXS = ws + w.gxs;
+  float* GVIN = ws + w.gvin; float* GHV = ws + w.ghv;
+  auto out_ptr = [&](int l) -> float* { return l == d.skip ? XS + P : ws + w.h[l]; };
+  auto out_ld = [&](int l) -> long long { return l == d.skip ? LX : W; };
+  auto in_ptr = [&](int l) -> const float* { return (l == 0 || (l - 1) == d.skip) ? XS : out_ptr(l - 1); };
+  auto in_ld = [&](int l) -> long long { return (l == 0 || (l - 1) == d.skip) ? LX : out_ld(l - 1); };
+  auto in_k = [&](int l) -> int { return l == 0 ? P : ((l - 1) == d.skip ? P + W : W); };
+
+  const int rpb = rays_per_block(c.n_rays, S);
+  for (int ray0 = 0; ray0 < c.n_rays; ray0 += rpb) {
+    const int nb = (ray0 + rpb <= c.n_rays) ? rpb : c.n_rays - ray0;
+    const long long rows = (long long)nb * S;
+    // ---- encodings
+    {
+      EncodeArgs e{};
+      e.rays = c.in->rays; e.skts = c.in->skts; e.z = z; e.cams = c.in->cams; e.codes = p.framecodes;
+      e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W; e.fc_ch = d.fc_ch; e.n_fc = d.n_fc;
+      e.tau_p = o.tau_pts; e.tau_v = o.tau_views;
+      for (int j = 0; j < kMaxJoints; ++j) { e.cut_p[j] = o.cutoff_pts[j]; e.cut_v[j] = o.cutoff_views[j]; }
+      e.XS = XS; e.ldxs = LX; e.VIN = VIN; e.ldv = LV;
+      auto k = encode_rows_kernel;
+      ANERF_TLAUNCH(k, dim3((unsigned)((rows * J + 127) / 128)), dim3(128), st, e);
+    }
+    // ---- forward, activations kept
+    for (int l = 0; l < D; ++l)
+      gemm_rows<true>(st, in_ptr(l), in_ld(l), p.pts_w[l], in_k(l), out_ptr(l), out_ld(l), rows, W, in_k(l), p.pts_b[l], 1, nullptr, 0, 0);
+    const float* HL = out_ptr(D - 1);
+    const long long HLld = out_ld(D - 1);
+    {
+      auto k1 = head_fwd_kernel<1>;
+      ANERF_TLAUNCH(k1, dim3((unsigned)((rows + 127) / 128)), dim3(128), st, HL, HLld, W, p.alpha_w, p.alpha_b, rows, RAW + 3, (long long)4);
+      gemm_rows<true>(st, HL, HLld, p.feature_w, W, VIN, LV, rows, W, W, p.feature_b, 0, nullptr, 0, 0);
+      gemm_rows<true>(st, VIN, LV, p.views_w, LV, HV, H, rows, H, LV, p.views_b, 1, nullptr, 0, 0);
+      auto k3 = head_fwd_kernel<3>;
+      ANERF_TLAUNCH(k3, dim3((unsigned)((rows + 127) / 128)), dim3(128), st, (const float*)HV, (long long)H, H, p.rgb_w, p.rgb_b, rows, RAW, (long long)4);
+    }
+    // ---- compositing backward -> dL/d raw
+    {
+      CompositeBwdArgs a{};
+      a.raw = RAW; a.z = z; a.rays = c.in->rays; a.noise = noise;
+      a.g_rgb = g_rgb; a.g_disp = g_disp; a.g_acc = g_acc; a.g_alpha = g_alpha;
+      a.ray0 = ray0; a.n_rays_blk = nb; a.S = S; a.softplus = o.softplus; a.B = o.density_scale; a.shift = o.softplus_shift;
+      a.scratch = ws + w.cs; a.g_raw = GRAW;
+      auto k = composite_bwd_kernel;
+      ANERF_TLAUNCH(k, dim3((unsigned)((nb + 63) / 64)), dim3(64), st, a);
+    }
+    // ---- heads and the views layer
+    {
+      auto k3 = head_bwd_kernel<3>;
+      ANERF_TLAUNCH(k3, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)(H < 32 ? 32 : H)), st, (const float*)GRAW, (long long)4,
+                    (const float*)HV, (long long)H, H, p.rgb_w, rows, 64, 1, GHV, (long long)H, gr.rgb_w, gr.rgb_b);
+    }
+    gemm_wgrad(st, GHV, H, VIN, LV, gr.views_w, LV, rows, H, LV);
+    colsum(st, GHV, H, H, rows, gr.views_b);
+    const int Nv = (need_pose || need_fc) ? LV : W;         // the view-encoding columns only when something consumes them
+    gemm_rows<false>(st, GHV, H, p.views_w, LV, GVIN, LV, rows, Nv, H, nullptr, 0, nullptr, 0, 0);
+    gemm_wgrad(st, GVIN, LV, HL, HLld, gr.feature_w, W, rows, W, W);
+    colsum(st, GVIN, LV, W, rows, gr.feature_b);
+    {
+      auto k1 = head_bwd_kernel<1>;
+      ANERF_TLAUNCH(k1, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)W), st, (const float*)(GRAW + 3), (long long)4, HL, HLld, W,
+                    p.alpha_w, rows, 64, 0, GA, (long long)W, gr.alpha_w, gr.alpha_b);
+    }
+    // dL/dZ of the last trunk layer = (G_feature Wf + g_sigma (x) w_alpha) . (h > 0)
+    gemm_rows<false>(st, GVIN, LV, p.feature_w, W, GA, W, rows, W, W, nullptr, 0, HL, HLld, 1);
+    // ---- trunk, last layer first
+    const float* cur = GA;
+    long long curld = W;
+    for (int l = D - 1; l >= 0; --l) {
+      gemm_wgrad(st, cur, curld, in_ptr(l), in_ld(l), gr.pts_w[l], in_k(l), rows, W, in_k(l));
+      colsum(st, cur, curld, W, rows, gr.pts_b[l]);
+      if (l > 0) {
+        if ((l - 1) == d.skip) {        // input = cat[encoding, h]: h part masked, encoding part kept for the pose gradient
+          gemm_rows<false>(st, cur, curld, p.pts_w[l] + P, in_k(l), GXS + P, LX, rows, W, W, nullptr, 0, XS + P, LX, 0);
+          if (need_pose) gemm_rows<false>(st, cur, curld, p.pts_w[l], in_k(l), GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, 0);
+          cur = GXS + P; curld = LX;
+        } else {
+          float* nxt = (cur == GA) ? GB : GA;
+          gemm_rows<false>(st, cur, curld, p.pts_w[l], in_k(l), nxt, W, rows, W, W, nullptr, 0, out_ptr(l - 1), out_ld(l - 1), 0);
+          cur = nxt; curld = W;
+        }
+      } else if (need_pose) {
+        gemm_rows<false>(st, cur, curld, p.pts_w[0], P, GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, d.skip >= 0 ? 1 : 0);
+      }
+    }
+    // ---- encodings backward
+    if (need_pose) {
+      EncodeBwdArgs e{};
+      e.rays = c.in->rays; e.skts = c.in->skts; e.z = z;
+      e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W;
+      e.tau_p = o.tau_pts; e.tau_v = o.tau_views;
+      for (int j = 0; j < kMaxJoints; ++j) { e.cut_p[j] = o.cutoff_pts[j]; e.cut_v[j] = o.cutoff_views[j]; }
+      e.gXS = GXS; e.ldxs = LX; e.gVIN = GVIN; e.ldv = LV; e.g_skts = c.g_skts;
+      auto k = encode_bwd_kernel;
+      ANERF_TLAUNCH(k, dim3((unsigned)((nb * J + 63) / 64)), dim3(64), st, e);
+    }
+    if (need_fc) {
+      auto k = framecode_bwd_kernel;
+      ANERF_TLAUNCH(k, dim3((unsigned)((nb * d.fc_ch + 127) / 128)), dim3(128), st, (const float*)GVIN, (long long)LV, W + in_views_ref(d),
+                    c.in->cams, ray0, nb, S, d.fc_ch, d.n_fc, gr.framecodes);
+    }
+  }
+}
+
+// Whole backward of one chunk of rays.  Gradient buffers are accumulated into (the caller zero-fills them).
+inline int train_backward(const TrainCall& c, anerf_tstream st) {
+  const Workspace w = make_workspace(c.dims, c.n_rays, c.Sc, c.Si);
+  if ((size_t)w.total > c.workspace_floats) return -1;
+  float* zc = c.workspace + w.z_coarse;
+  {
+    auto k = coarse_depths_kernel;
+    const long long n = (long long)c.n_rays * c.Sc;
+    ANERF_TLAUNCH(k, dim3((unsigned)((n + 255) / 256)), dim3(256), st, c.nearfar, c.in->t_rand, c.n_rays, c.Sc, c.opts->lindisp, zc);
+  }
+  const anerf_render_grads& g = *c.gout;
+  if (c.Si > 0) {
+    backward_pass(c, w, 0, c.Sc, zc, c.in->noise0, g.rgb0, g.disp0, g.acc0, g.alpha0, st);
+    backward_pass(c, w, 1, c.Sc + c.Si, c.z_all, c.in->noise1, g.rgb_map, g.disp_map, g.acc_map, g.alpha, st);
+  } else {
+    backward_pass(c, w, 0, c.Sc, zc, c.in->noise0, g.rgb_map, g.disp_map, g.acc_map, g.alpha, st);
+  }
+  return 0;
+}
+
+}  // namespace train
+}  // namespace anerf

@@ -19,6 +19,12 @@
  *                                          with host buffers (H2D/D2H inside)
  *   anerf_density_points                <- RayCaster.render_pts_density / render_mesh_density
  *                                          (core/raycasters.py:579-648)
+ *   anerf_render_bwd                    <- what loss.backward() does to the graph of render_rays in training
+ *                                          (core/trainer.py:187-203 optimize -> autograd through
+ *                                          core/networks/nerf.py:94-205, core/cutoff_embedder.py:111-174,
+ *                                          core/encoders.py:8-37, core/networks/embedding.py:17-34):
+ *                                          gradients of the network weights, the framecodes and the per-ray
+ *                                          bone transforms (pose refinement, core/pose_opt.py:435)
  */
 #ifndef ANERF_B200_H_
 #define ANERF_B200_H_
@@ -136,6 +142,50 @@ int anerf_render_fwd(const anerf_plan* plan, const void* packed_coarse, const vo
 int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
                           const anerf_render_opts* opts, const anerf_render_inputs* host_in,
                           const anerf_render_outputs* host_out, void* stream);
+
+/* ---- training: backward of one chunk ------------------------------------------------------------------ */
+
+/* Gradient buffers of one network, same shapes as anerf_net_params (fp32, device).  Gradients are ADDED to
+ * the buffers (zero-fill them for a fresh gradient); a NULL entry skips that parameter (frozen layer). */
+typedef struct {
+  float* pts_w[8];
+  float* pts_b[8];
+  float* alpha_w;
+  float* alpha_b;
+  float* feature_w;
+  float* feature_b;
+  float* views_w;
+  float* views_b;
+  float* rgb_w;
+  float* rgb_b;
+  float* framecodes;
+} anerf_net_grads;
+
+/* dL/d(outputs of anerf_render_fwd), device, same shapes as anerf_render_outputs; NULL = zero. */
+typedef struct {
+  const float* rgb_map;
+  const float* disp_map;
+  const float* acc_map;
+  const float* alpha;
+  const float* rgb0;
+  const float* disp0;
+  const float* acc0;
+  const float* alpha0;
+} anerf_render_grads;
+
+size_t anerf_render_bwd_workspace_bytes(const anerf_plan* plan, int32_t n_rays, int32_t n_samples, int32_t n_importance);
+
+/* Backward of anerf_render_fwd for the same opts / inputs.  `nearfar` [N,2] is the forward call's workspace
+ * (the repaired near/far of every ray), `z_all` [N,Sc+Si] its z_all tap (ignored when n_importance == 0); the
+ * sample positions carry no gradient (the reference detaches them, core/utils/ray_utils.py:285).  The pass
+ * recomputes the activations of both networks layer by layer in fp32 from the fp32 parameters (`coarse`,
+ * `fine`: the same pointers that were packed), so no activations have to be kept from the forward call.
+ * g_skts [N,J,4,4] (added to; NULL = the pose needs no gradient). */
+int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, const anerf_net_params* fine,
+                     const anerf_render_opts* opts, const anerf_render_inputs* in, const float* nearfar,
+                     const float* z_all, const anerf_render_grads* grad_out, const anerf_net_grads* g_coarse,
+                     const anerf_net_grads* g_fine, float* g_skts, void* workspace, size_t workspace_bytes,
+                     void* stream);
 
 /* Raw (pre-activation) density of `n_points` world points under ONE pose: pts [P,3], skts [J,4,4],
  * sigma [P].  Uses tau_pts / cutoff_pts of `opts` (other fields ignored). */
