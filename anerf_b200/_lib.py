@@ -14,7 +14,8 @@ _lib = None
 
 SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "anerf_pack_net",
            "anerf_render_workspace_bytes", "anerf_render_fwd", "anerf_render_fwd_host", "anerf_density_points",
-           "anerf_selftest_gemm", "anerf_last_error", "anerf_version", "anerf_debug_set_trace"]
+           "anerf_selftest_gemm", "anerf_last_error", "anerf_version", "anerf_debug_set_trace",
+           "anerf_render_bwd", "anerf_render_bwd_workspace_bytes"]
 
 
 class NetConfig(C.Structure):
@@ -27,6 +28,14 @@ class NetParams(C.Structure):
     _fields_ = [("pts_w", C.c_void_p * 8), ("pts_b", C.c_void_p * 8), ("alpha_w", C.c_void_p), ("alpha_b", C.c_void_p),
                 ("feature_w", C.c_void_p), ("feature_b", C.c_void_p), ("views_w", C.c_void_p), ("views_b", C.c_void_p),
                 ("rgb_w", C.c_void_p), ("rgb_b", C.c_void_p), ("framecodes", C.c_void_p)]
+
+
+class NetGrads(C.Structure):      # same layout as NetParams (gradient buffers, accumulated into)
+    _fields_ = NetParams._fields_
+
+
+class RenderGrads(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0", "alpha0")]
 
 
 class RenderOpts(C.Structure):
@@ -74,6 +83,11 @@ def load():
     lib.anerf_density_points.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p]
     lib.anerf_selftest_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    lib.anerf_render_bwd_workspace_bytes.restype = C.c_size_t
+    lib.anerf_render_bwd_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.anerf_render_bwd.argtypes = [C.c_void_p, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(RenderOpts),
+                                     C.POINTER(RenderInputs), C.c_void_p, C.c_void_p, C.POINTER(RenderGrads),
+                                     C.POINTER(NetGrads), C.POINTER(NetGrads), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.anerf_debug_set_trace.argtypes = [C.c_void_p]
     lib.anerf_debug_set_trace.restype = None
     _lib = lib
@@ -159,7 +173,7 @@ def make_opts(n_rays, n_samples, n_importance, tau_pts=20., tau_views=20., cutof
 
 
 def render_fwd(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, cams=None, t_rand=None, u_rand=None,
-               noise0=None, noise1=None, want_taps=False):
+               noise0=None, noise1=None, want_taps=False, keep_nearfar=False, want_z_all=False):
     """One chunk on the device.  All tensors fp32 contiguous CUDA.  Returns the reference's output dict
     (core/raycasters.py:711-724) plus 'z_all'/'raw' taps when asked."""
     N, Sc, Si = opts.n_rays, opts.n_samples, opts.n_importance
@@ -171,8 +185,8 @@ def render_fwd(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, cams=No
         out.update(rgb0=f(N, 3), disp0=f(N), acc0=f(N), alpha0=f(N, Sc))
     if want_taps:
         out['raw'] = f(N, Sf if Si > 0 else Sc, 4)
-        if Si > 0:
-            out['z_all'] = f(N, Sf)
+    if (want_taps or want_z_all) and Si > 0:
+        out['z_all'] = f(N, Sf)
     ws_bytes = load().anerf_render_workspace_bytes(N)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     for t in (rays, skts, cyls, cams, t_rand, u_rand, noise0, noise1):
@@ -182,6 +196,8 @@ def render_fwd(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, cams=No
                                                       "alpha0", "z_all", "raw")])
     check(load().anerf_render_fwd(plan.handle, _ptr(packed_coarse), _ptr(packed_fine), C.byref(opts), C.byref(rin),
                                   C.byref(rout), _ptr(ws), ws_bytes, _stream()))
+    if keep_nearfar:        # the repaired near/far of every ray [N,2]: what the backward pass resamples from
+        out['nearfar'] = ws.view(torch.float32)[:2 * N].view(N, 2)
     return out
 
 
@@ -202,6 +218,65 @@ def render_fwd_host(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, ca
     check(load().anerf_render_fwd_host(plan.handle, _ptr(packed_coarse), _ptr(packed_fine), C.byref(opts), C.byref(rin),
                                        C.byref(rout), _stream()))
     return out
+
+
+PARAM_ORDER = (["pts_w", "pts_b"], ["alpha_w", "alpha_b", "feature_w", "feature_b", "views_w", "views_b", "rgb_w", "rgb_b"])
+
+
+def param_names(depth, framecodes):
+    """state_dict names of one network in the order the training entry points take them."""
+    names = []
+    for i in range(depth):
+        names += [f'pts_linears.{i}.weight', f'pts_linears.{i}.bias']
+    names += ['alpha_linear.weight', 'alpha_linear.bias', 'feature_linear.weight', 'feature_linear.bias',
+              'views_linears.0.weight', 'views_linears.0.bias', 'rgb_linear.weight', 'rgb_linear.bias']
+    if framecodes:
+        names.append('framecodes.codes.weight')
+    return names
+
+
+def _fill_net_struct(st, depth, tensors, framecodes):
+    """tensors: list in param_names() order (entries may be None) -> NetParams / NetGrads fields."""
+    it = iter(tensors)
+    for i in range(depth):
+        w, b = next(it), next(it)
+        st.pts_w[i] = None if w is None else w.data_ptr()
+        st.pts_b[i] = None if b is None else b.data_ptr()
+    for f in PARAM_ORDER[1]:
+        t = next(it)
+        setattr(st, f, None if t is None else t.data_ptr())
+    if framecodes:
+        t = next(it)
+        st.framecodes = None if t is None else t.data_ptr()
+    return st
+
+
+def render_bwd(plan, opts, params0, params1, rays, skts, cams, t_rand, noise0, noise1, nearfar, z_all, grad_out,
+               want0, want1, want_skts):
+    """Backward of render_fwd (C ABI anerf_render_bwd).  params0/params1: fp32 CUDA tensors of the coarse / fine
+    network in param_names() order; want0/want1: per-parameter flags; grad_out: dict of dL/d(output) tensors (or
+    None).  Returns (grads0, grads1, g_skts): freshly allocated gradients (None where not wanted)."""
+    N, Sc, Si = opts.n_rays, opts.n_samples, opts.n_importance
+    dev = rays.device
+    depth, fc = plan.cfg.depth, plan.cfg.framecode_ch > 0
+    for t in [rays, skts, cams, t_rand, noise0, noise1, nearfar, z_all] + list(params0) + list(params1 or []) + \
+            [g for g in grad_out.values() if g is not None]:
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+    zeros = lambda p, want: torch.zeros_like(p) if want else None
+    g0 = [zeros(p, w) for p, w in zip(params0, want0)]
+    g1 = [zeros(p, w) for p, w in zip(params1, want1)] if params1 is not None else None
+    g_skts = torch.zeros_like(skts) if want_skts else None
+    p0s, g0s = _fill_net_struct(NetParams(), depth, params0, fc), _fill_net_struct(NetGrads(), depth, g0, fc)
+    p1s = _fill_net_struct(NetParams(), depth, params1, fc) if params1 is not None else None
+    g1s = _fill_net_struct(NetGrads(), depth, g1, fc) if params1 is not None else None
+    rin = RenderInputs(_ptr(rays), _ptr(skts), None, _ptr(cams), _ptr(t_rand), None, _ptr(noise0), _ptr(noise1))
+    rg = RenderGrads(*[_ptr(grad_out.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0", "alpha0")])
+    ws_bytes = load().anerf_render_bwd_workspace_bytes(plan.handle, N, Sc, Si)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(load().anerf_render_bwd(plan.handle, C.byref(p0s), None if p1s is None else C.byref(p1s), C.byref(opts),
+                                  C.byref(rin), _ptr(nearfar), _ptr(z_all), C.byref(rg), C.byref(g0s),
+                                  None if g1s is None else C.byref(g1s), _ptr(g_skts), _ptr(ws), ws_bytes, _stream()))
+    return g0, g1, g_skts
 
 
 def density_points(plan, packed, opts, pts, skts):

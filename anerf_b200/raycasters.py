@@ -129,6 +129,50 @@ class _EncoderTag:
 
 
 # ------------------------------------------------------------------------------------------------
+# training: the chunk as one autograd node
+# ------------------------------------------------------------------------------------------------
+OUT_KEYS = ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0", "alpha0")
+
+
+class _RenderRaysFn(torch.autograd.Function):
+    """render_rays as a single autograd node (reference graph: core/raycasters.py:361-474).  forward = the fused
+    kernel (anerf_render_fwd), keeping only the repaired near/far and the sorted fine depths; backward =
+    anerf_render_bwd, which recomputes the activations layer by layer.  Differentiable inputs: `skts` (pose
+    refinement) and the parameters of both networks; sample positions carry no gradient (ray_utils.py:285)."""
+
+    @staticmethod
+    def forward(ctx, caster, opts, aux, skts, *params):
+        plan = caster._get_plan()
+        p0 = caster._packed_image('network')
+        p1 = caster._packed_image('network_fine') if opts.n_importance > 0 else None
+        out = _lib.render_fwd(plan, p0, p1, opts, aux['rays'], skts, aux['cyls'], aux['cams'], aux['t_rand'], aux['u_rand'],
+                              aux['noise0'], aux['noise1'], keep_nearfar=True, want_z_all=True)
+        ctx.caster, ctx.opts, ctx.aux = caster, opts, aux
+        ctx.nearfar, ctx.z_all = out['nearfar'], out.get('z_all')
+        ctx.save_for_backward(skts, *params)
+        ctx.keys = [k for k in OUT_KEYS if k in out]
+        return tuple(out[k] for k in ctx.keys)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        skts, *params = ctx.saved_tensors
+        aux, opts = ctx.aux, ctx.opts
+        n0 = aux['n_params0']
+        params0, params1 = params[:n0], (params[n0:] if len(params) > n0 else None)
+        need = ctx.needs_input_grad
+        want_skts = bool(need[3])
+        want0 = [bool(x) for x in need[4:4 + n0]]
+        want1 = [bool(x) for x in need[4 + n0:]]
+        gout = {k: (None if g is None else g.float().contiguous()) for k, g in zip(ctx.keys, gouts)}
+        with torch.cuda.device(skts.device):
+            g0, g1, g_skts = _lib.render_bwd(ctx.caster._get_plan(), opts, [p.detach() for p in params0],
+                                             None if params1 is None else [p.detach() for p in params1],
+                                             aux['rays'], skts.detach(), aux['cams'], aux['t_rand'], aux['noise0'], aux['noise1'],
+                                             ctx.nearfar, ctx.z_all, gout, want0, want1, want_skts)
+        return (None, None, None, g_skts, *g0, *(g1 or []))
+
+
+# ------------------------------------------------------------------------------------------------
 # the ray caster
 # ------------------------------------------------------------------------------------------------
 class RayCaster(nn.Module):
@@ -228,16 +272,13 @@ class RayCaster(nn.Module):
             raise NotImplementedError("single_net is not supported")
         if subject_idxs is not None:
             raise NotImplementedError("subject_idxs is not supported by the default encoders")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("anerf_b200 round 1 implements the forward path only; call under "
-                                      "torch.no_grad() / .eval() (training backward: see DESIGN.md 'next')")
         dev = ray_batch.device
         if dev.type != 'cuda':
             raise RuntimeError("anerf_b200.RayCaster: inputs must be CUDA tensors (no CPU path)")
         N = ray_batch.shape[0]
         J = self._n_joints()
         rays = ray_batch[:, :8].float().contiguous()
-        skts_c = skts.float().expand(N, J, 4, 4).contiguous()
+        skts_c = skts.float().expand(N, J, 4, 4).contiguous()          # differentiable when the pose is being refined
         cyls_c = cyls.float().expand(N, cyls.shape[-1]).contiguous()
         density_scale = preproc_kwargs.get('density_scale', 1.0)
         density_fn = preproc_kwargs.get('density_fn', None)
@@ -269,10 +310,22 @@ class RayCaster(nn.Module):
                 noise0 = torch.randn(N, Sc, device=dev) * (raw_noise_std * density_scale)
                 noise1 = torch.randn(N, Sc + Si, device=dev) * (raw_noise_std * density_scale) if Si > 0 else None
         opts = self._opts(N, Sc, Si, lindisp, density_scale, density_fn, eval_mean)
+        names = _lib.param_names(self.network.D, use_fc)
+        nets = [self.network] + ([self.network_fine] if Si > 0 else [])
+        params = [dict(n.named_parameters())[k] for n in nets for k in names]
+        if torch.is_grad_enabled() and (skts_c.requires_grad or any(p.requires_grad for p in params)):
+            if eval_mean:
+                raise NotImplementedError("gradients through the eval-time mean framecode are not supported")
+            aux = dict(rays=rays, cyls=cyls_c, cams=cams_c, t_rand=t_rand, u_rand=u_rand, noise0=noise0, noise1=noise1,
+                       n_params0=len(names))
+            with torch.cuda.device(dev):
+                outs = _RenderRaysFn.apply(self, opts, aux, skts_c, *params)
+            keys = [k for k in OUT_KEYS if Si > 0 or not k.endswith('0')]
+            return dict(zip(keys, outs))
         p0 = self._packed_image('network')
         p1 = self._packed_image('network_fine') if Si > 0 else None
         with torch.cuda.device(dev):
-            out = _lib.render_fwd(self._get_plan(), p0, p1, opts, rays, skts_c, cyls_c, cams_c, t_rand, u_rand,
+            out = _lib.render_fwd(self._get_plan(), p0, p1, opts, rays, skts_c.detach(), cyls_c, cams_c, t_rand, u_rand,
                                   noise0, noise1, want_taps=bool(retraw))
         return out
 

@@ -145,7 +145,7 @@ int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, con
 
 /* ---- training: backward of one chunk ------------------------------------------------------------------ */
 
-/* Gradient buffers of one network, same shapes as anerf_net_params (fp32, device).  Gradients are ADDED to
+/* Gradient buffers of one network, same shapes as anerf_net_params, fp32 on the device.  Gradients are ADDED to
  * the buffers (zero-fill them for a fresh gradient); a NULL entry skips that parameter (frozen layer). */
 typedef struct {
   float* pts_w[8];

@@ -1,0 +1,150 @@
+"""Training path on the GPU: gradients of the CUDA backward (C ABI anerf_render_bwd, and the same through the
+Python boundary's autograd node) against the oracle's autograd on identical rays, weights, draws and output
+cotangents, and against the digests of the reference's own autograd in tests/golden/grad_*.npz.
+
+Tolerances (max-norm relative, per tensor): 2e-4 against the oracle evaluated at the kernel's own fine sample
+positions; 2e-3 against the reference's stored gradients (its sample positions differ by the fp32 conditioning
+of the inverse-CDF step)."""
+import numpy as np
+import pytest
+import torch
+
+from anerf_b200 import _lib, synthetic
+from oracle import grad_tools as gt
+from tests.common import build_case, load_golden
+
+pytestmark = pytest.mark.gpu
+
+GRAD_CASES = ["grad_cfg1_j1_s16_i16", "grad_j24_s24_i0", "grad_j24_s16_i8_fc_perturb"]
+
+
+def gpu_grads(scene, sd0, sd1, cfg, draws, cot, need_pose=True):
+    dev = torch.device("cuda")
+    t = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(dev)
+    N = scene["rays_o"].shape[0]
+    fc = cfg.framecode_ch > 0
+    plan = _lib.Plan(cfg.n_joints, cfg.D, cfg.W, cfg.skips, cfg.framecode_ch,
+                     0 if not fc else sd0['framecodes.codes.weight'].shape[0], 0)
+    names = _lib.param_names(cfg.D, fc)
+    d0 = {k: t(v) for k, v in sd0.items()}
+    d1 = None if sd1 is None else {k: t(v) for k, v in sd1.items()}
+    p0 = plan.pack(d0)
+    p1 = None if d1 is None else plan.pack(d1)
+    rays = t(np.concatenate([scene["rays_o"], scene["rays_d"], np.zeros((N, 1), np.float32), np.ones((N, 1), np.float32)], 1))
+    opts = _lib.make_opts(N, cfg.N_samples, cfg.N_importance, tau_pts=cfg.tau, tau_views=cfg.tau_views,
+                          cutoff_pts=cfg.cutoff_dist, cutoff_views=cfg.cutoff_dist, n_joints=cfg.n_joints)
+    d = draws or {}
+    cams = t(scene["cams"].astype(np.float32)) if fc else None
+    skts = t(scene["skts"])
+    out = _lib.render_fwd(plan, p0, p1, opts, rays, skts, t(scene["cyls"]), cams, t(d.get("t_rand")), t(d.get("u_rand")),
+                          t(d.get("noise0")), t(d.get("noise1")), keep_nearfar=True, want_z_all=True)
+    params0 = [d0[k] for k in names]
+    params1 = None if d1 is None else [d1[k] for k in names]
+    g0, g1, g_skts = _lib.render_bwd(plan, opts, params0, params1, rays, skts, cams, t(d.get("t_rand")), t(d.get("noise0")),
+                                     t(d.get("noise1")), out['nearfar'].contiguous(), out.get('z_all'),
+                                     {k: t(v) for k, v in cot.items()}, [True] * len(names), [True] * len(names), need_pose)
+    torch.cuda.synchronize()
+    grads = {f"net0.{k}": g.cpu().numpy() for k, g in zip(names, g0)}
+    if g1 is not None:
+        grads.update({f"net1.{k}": g.cpu().numpy() for k, g in zip(names, g1)})
+    if need_pose:
+        grads["skts"] = g_skts.cpu().numpy()
+    return grads, {k: v.cpu().numpy() for k, v in out.items()}
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_backward_matches_oracle_and_reference_autograd(name):
+    c, gold = load_golden(name)
+    scene, sd0, sd1, cfg, draws = build_case(c)
+    N = scene["rays_o"].shape[0]
+    cot = gt.cotangents(N, cfg.N_samples, cfg.N_importance)
+    g, out = gpu_grads(scene, sd0, sd1, cfg, draws, cot)
+    _, g_orc, _ = gt.oracle_grads(scene, sd0, sd1, cfg, draws, cot, z_all_override=out.get("z_all"))
+    assert set(g) == set(g_orc)
+    errs = {k: gt.rel_err(g[k], g_orc[k]) for k in g}
+    bad = {k: e for k, e in errs.items() if not (e < 2e-4)}
+    assert not bad, bad
+    errs_ref = {k: gt.digest_err(g[k], {f: gold[f"g|{k}|{f}"] for f in ("sum", "norm", "amax", "idx", "val")}) for k in g}
+    bad = {k: e for k, e in errs_ref.items() if not (e < 2e-3)}
+    assert not bad, bad
+
+
+def test_frozen_parameters_and_no_pose_gradient():
+    c, _ = load_golden("grad_j24_s24_i0")
+    scene, sd0, sd1, cfg, draws = build_case(c)
+    cot = gt.cotangents(scene["rays_o"].shape[0], cfg.N_samples, cfg.N_importance)
+    g_full, _ = gpu_grads(scene, sd0, sd1, cfg, draws, cot, need_pose=True)
+    g_nop, _ = gpu_grads(scene, sd0, sd1, cfg, draws, cot, need_pose=False)
+    assert "skts" not in g_nop
+    for k in g_nop:        # weight gradients do not depend on whether the pose gradient was asked for
+        assert gt.rel_err(g_nop[k], g_full[k]) < 1e-5, k
+
+
+def _train_setup(N_importance=16, opt_framecode=False, n_rays=96):
+    from tests.test_gpu_api import data_attrs, make_args
+    from anerf_b200.raycasters import create_raycaster
+    args = make_args(N_importance=N_importance, no_reload=True, perturb=1.0, raw_noise_std=0., opt_framecode=opt_framecode)
+    rk_train, rk_test, _, grad_vars, optimizer, _ = create_raycaster(args, data_attrs(24, n_views=4))
+    rc = rk_test['ray_caster']
+    wk = dict(framecode_ch=16, n_framecodes=4) if opt_framecode else {}
+    rc.network.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(101, **wk).items()})
+    rc.network_fine.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(202, **wk).items()})
+    scene = synthetic.make_scene(seed=3, n_rays=n_rays, H=512, W=512, focal=500., n_joints=24)
+    dev = torch.device("cuda")
+    t = lambda a: torch.as_tensor(a).to(dev)
+    N = scene["rays_o"].shape[0]
+    rays = torch.cat([t(scene["rays_o"]), t(scene["rays_d"]), torch.zeros(N, 1, device=dev), torch.ones(N, 1, device=dev),
+                      torch.nn.functional.normalize(t(scene["rays_d"]), dim=-1)], 1)
+    kw = {k: v for k, v in rk_train.items() if k not in ('ray_caster', 'use_viewdirs')}
+    batch = dict(kp_batch=t(scene["kps"]), skts=t(scene["skts"]), cyls=t(scene["cyls"]), bones=t(scene["bones"]),
+                 cams=(torch.arange(N, device=dev) % 4).float() if opt_framecode else None, subject_idxs=None)
+    return rk_train['ray_caster'], rc, optimizer, grad_vars, rays, batch, kw
+
+
+def test_autograd_through_the_python_boundary():
+    """loss.backward() through RayCaster in training mode fills .grad of every parameter and of a pose tensor that
+    requires grad; an eval-mode call under no_grad gives the same outputs as the training forward (pytest draws)."""
+    holder, rc, optimizer, grad_vars, rays, batch, kw = _train_setup(opt_framecode=True)
+    holder.train()
+    skts = batch['skts'].clone().requires_grad_(True)
+    kw = dict(kw, pytest=True)                    # numpy-seeded draws: the same samples in both calls
+    out = holder(rays, **dict(batch, skts=skts), **kw)
+    target = torch.full_like(out['rgb_map'], 0.5)
+    loss = ((out['rgb_map'] - target) ** 2).mean() + 0.5 * ((out['rgb0'] - target) ** 2).mean() + 0.01 * out['acc_map'].mean()
+    loss.backward()
+    assert skts.grad is not None and torch.isfinite(skts.grad).all() and float(skts.grad.abs().max()) > 0
+    assert float(skts.grad[:, :, 3].abs().max()) == 0.          # bottom row of the transforms carries nothing
+    for p in grad_vars:
+        assert p.grad is not None and torch.isfinite(p.grad).all()
+    assert float(rc.network.framecodes.codes.weight.grad.abs().max()) > 0
+    assert float(rc.network_fine.pts_linears[0].weight.grad.abs().max()) > 0
+    with torch.no_grad():
+        again = holder(rays, **batch, **kw)
+    assert torch.equal(again['rgb_map'], out['rgb_map'].detach())
+    # frozen layers get no gradient (--fix_layer semantics)
+    optimizer.zero_grad(set_to_none=True)
+    for p in rc.network.pts_linears[0].parameters():
+        p.requires_grad_(False)
+    out = holder(rays, **batch, **kw)
+    out['rgb0'].sum().backward()
+    assert rc.network.pts_linears[0].weight.grad is None and rc.network.pts_linears[1].weight.grad is not None
+    assert rc.network_fine.pts_linears[1].weight.grad is None or float(rc.network_fine.pts_linears[1].weight.grad.abs().max()) == 0.
+
+
+def test_adam_steps_reduce_the_loss():
+    """A few optimizer steps on a fixed batch through the boundary: the photometric loss must go down, and the
+    re-packed weights must be what the next forward uses."""
+    holder, rc, optimizer, grad_vars, rays, batch, kw = _train_setup(N_importance=16, n_rays=256)
+    holder.train()
+    torch.manual_seed(0)
+    target = torch.rand(rays.shape[0], 3, device=rays.device) * 0.5 + 0.25
+    losses = []
+    for step in range(12):
+        optimizer.zero_grad()
+        out = holder(rays, **batch, **dict(kw, perturb=0.))
+        loss = ((out['rgb_map'] - target) ** 2).mean() + ((out['rgb0'] - target) ** 2).mean()
+        loss.backward()
+        optimizer.step()
+        losses.append(float(loss))
+    assert all(np.isfinite(losses))
+    assert losses[-1] < 0.9 * losses[0], losses

@@ -44,3 +44,19 @@ def test_oracle_reproduces_reference_density_grid():
 def test_flop_count_matches_baseline():
     # 441.25 MFLOP per ray at 24 joints, 64+128 samples, 8x256
     assert orc.algorithmic_flops_per_ray(orc.PathConfig()) == 256 * 1723648
+
+
+@pytest.mark.parametrize("name", ["grad_cfg1_j1_s16_i16", "grad_j24_s24_i0", "grad_j24_s16_i8_fc_perturb"])
+def test_oracle_autograd_matches_reference_gradient_digests(name):
+    """The oracle's gradients (torch autograd over the restatement) against the digests of the reference's own
+    autograd on the same rays, weights, draws and output cotangents (oracle/make_golden_grad.py)."""
+    from oracle import grad_tools as gt
+    c, gold = load_golden(name)
+    scene, sd0, sd1, cfg, draws = build_case(c)
+    cot = gt.cotangents(scene["rays_o"].shape[0], cfg.N_samples, cfg.N_importance)
+    out, g, _ = gt.oracle_grads(scene, sd0, sd1, cfg, draws, cot)
+    for k in out:
+        assert rel_err(out[k], gold["ref_" + k]) < (2e-3 if k == "alpha" else 2e-5), k
+    for k in g:
+        dg = {f: gold[f"g|{k}|{f}"] for f in ("sum", "norm", "amax", "idx", "val")}
+        assert gt.digest_err(g[k], dg) < 2e-5, k

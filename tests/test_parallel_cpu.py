@@ -20,12 +20,24 @@ def _worker(rank, world, port, q):
     a, b = parallel.slab_for_rank(n, r, w)
     full = parallel.gather_slabs(torch.arange(a, b, dtype=torch.float32)[:, None] * torch.ones(1, 3), n, r, w)
     tmax = parallel.max_over_ranks(10.0 + r, torch.device("cpu"))
+    # training exchange step: one flat all-reduce averages the gradients (a parameter without .grad counts as zero)
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5)), torch.nn.Parameter(torch.randn(2))]
+    ps[0].grad = torch.full((3, 4), float(r + 1))
+    if r == 0:
+        ps[1].grad = torch.arange(5.)
+    ps[2].requires_grad_(False)
+    parallel.allreduce_gradients(ps, w)
+    g_ok = torch.allclose(ps[0].grad, torch.full((3, 4), 1.5)) and torch.allclose(ps[1].grad, torch.arange(5.) / 2) \
+        and ps[2].grad is None
+    a0, b0 = parallel.rays_for_rank(3072, r, w)
+    g_ok = g_ok and (b0 - a0) == 1536 and a0 == r * 1536
     if r == 0:
         ok = all(torch.equal(frames[f], torch.full((7, 5), float(f)) + torch.arange(5.) * 0.1) for f in range(n_frames))
         ok = ok and torch.equal(full, torch.arange(n, dtype=torch.float32)[:, None] * torch.ones(1, 3))
-        q.put((ok, tmax))
+        q.put((ok and g_ok, tmax))
     else:
-        assert frames is None and full is None
+        assert frames is None and full is None and g_ok
     dist.barrier()
     dist.destroy_process_group()
 
