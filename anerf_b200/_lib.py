@@ -15,7 +15,7 @@ _lib = None
 SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "anerf_pack_net",
            "anerf_render_workspace_bytes", "anerf_render_fwd", "anerf_render_fwd_host", "anerf_density_points",
            "anerf_selftest_gemm", "anerf_last_error", "anerf_version", "anerf_debug_set_trace",
-           "anerf_render_bwd", "anerf_render_bwd_workspace_bytes"]
+           "anerf_render_bwd", "anerf_render_bwd_workspace_bytes", "anerf_selftest_tc_gemm"]
 
 
 class NetConfig(C.Structure):
@@ -88,6 +88,9 @@ def load():
     lib.anerf_render_bwd.argtypes = [C.c_void_p, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(RenderOpts),
                                      C.POINTER(RenderInputs), C.c_void_p, C.c_void_p, C.POINTER(RenderGrads),
                                      C.POINTER(NetGrads), C.POINTER(NetGrads), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.anerf_selftest_tc_gemm.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                           C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
+                                           C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.anerf_debug_set_trace.argtypes = [C.c_void_p]
     lib.anerf_debug_set_trace.restype = None
     _lib = lib
@@ -284,6 +287,15 @@ def density_points(plan, packed, opts, pts, skts):
     check(load().anerf_density_points(plan.handle, _ptr(packed), C.byref(opts), _ptr(pts), _ptr(skts), pts.shape[0],
                                       _ptr(sigma), _stream()))
     return sigma
+
+
+def selftest_tc_gemm(A, a_strides, M, K, B, b_strides, N, C, c_strides, bias=None, mask=None, mask_ms=0, relu=False, mode=0,
+                     slice_chunks=0):
+    """C(m,n) (op)= sum_k A(m,k) B(n,k) through the training path's tensor-core GEMM; strides in elements."""
+    check(load().anerf_selftest_tc_gemm(_ptr(A), a_strides[0], a_strides[1], M, K, _ptr(B), b_strides[0], b_strides[1], N,
+                                        _ptr(C), c_strides[0], c_strides[1], _ptr(bias), _ptr(mask), mask_ms, int(relu), mode,
+                                        slice_chunks, _stream()))
+    return C
 
 
 def selftest_gemm(A, B, fmt):

@@ -4,6 +4,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -402,9 +403,50 @@ int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, con
   c.g_skts = g_skts;
   c.workspace = (float*)workspace;
   c.workspace_floats = workspace_bytes / sizeof(float);
+  // GEMM engine: tensor cores (tc_gemm.cuh) unless ANERF_TRAIN_GEMM=simt asks for the fp32 SIMT kernels (debug knob)
+  train::TcEngine tc{};
+  const char* eng = getenv("ANERF_TRAIN_GEMM");
+  if (!(eng && strcmp(eng, "simt") == 0)) {
+    int rc = ensure_status();
+    if (rc) return rc;
+    const train::Workspace w = train::make_workspace(plan->dims, N, Sc, Si);
+    tc.n_sm = plan->n_sm;
+    tc.status = g_status_dev;
+    tc.wpack = (uint8_t*)((float*)workspace + w.tc_w); tc.wpack_bytes = (size_t)w.tc_w_floats * 4; tc.wpack_used = 0;
+    tc.gpack = (uint8_t*)((float*)workspace + w.tc_g); tc.gpack_bytes = (size_t)w.tc_g_floats * 4;
+    tc.error = 0;
+    c.tc = &tc;
+  }
   if (train::train_backward(c, (cudaStream_t)stream_) != 0) return fail(ANERF_ERR_INVALID, "internal: workspace layout");
+  if (tc.error) return fail(ANERF_ERR_INVALID, "internal: tensor-core GEMM engine error %d (scratch size / launch)", tc.error);
   CUDA_TRY(cudaGetLastError());
   return ANERF_OK;
+}
+
+int anerf_selftest_tc_gemm(const float* A, int64_t a_ms, int64_t a_ks, int32_t M, int32_t K, const float* B, int64_t b_ns,
+                           int64_t b_ks, int32_t N, float* C, int64_t c_ms, int64_t c_ns, const float* bias,
+                           const float* mask, int64_t mask_ms, int32_t relu, int32_t mode, int32_t slice_chunks,
+                           void* stream_) {
+  if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return fail(ANERF_ERR_INVALID, "bad argument");
+  if (slice_chunks < 0 || slice_chunks % 4 != 0) return fail(ANERF_ERR_INVALID, "slice_chunks must be a multiple of 4");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int rc = ensure_status();
+  if (rc) return rc;
+  int dev = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  uint8_t* d_pack = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d_pack, tc_packed_bytes(N, K)));
+  train::TcEngine tc{};
+  tc.n_sm = n_sm; tc.status = g_status_dev; tc.error = 0;
+  tc.pack(stream, B, b_ns, b_ks, N, K, d_pack);
+  tc.run(stream, A, a_ms, a_ks, M, K, d_pack, N, C, c_ms, c_ns, bias, relu, mask, mask_ms, mode, slice_chunks);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+  cudaFree(d_pack);
+  if (tc.error) return fail(ANERF_ERR_INVALID, "tensor-core GEMM launch failed (%d)", tc.error);
+  if (e != cudaSuccess) { check_device_status(); return fail(ANERF_ERR_CUDA, "tc gemm failed: %s [%s]", cudaGetErrorString(e), g_err.c_str()); }
+  return check_device_status();
 }
 
 int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t format, void* stream_) {

@@ -11,6 +11,12 @@
 #include "../../include/anerf_b200.h"
 #include "train_kernels.cuh"
 
+#if !defined(ANERF_SIMT_EMU)
+#include <map>
+#include <tuple>
+#include "tc_gemm.cuh"
+#endif
+
 #if defined(ANERF_SIMT_EMU)
 #define ANERF_TLAUNCH(kernel, grid, block, stream, ...) simt_emu::launch(grid, block, kernel, __VA_ARGS__)
 #define ANERF_TZERO(ptr, bytes, stream) memset(ptr, 0, bytes)
@@ -24,7 +30,80 @@ typedef cudaStream_t anerf_tstream;
 namespace anerf {
 namespace train {
 
-constexpr long long kRowsTarget = 65536;    // rows (samples) per block of rays: ~1.5 GB of fp32 activations + gradients at W=256
+constexpr long long kRowsTarget = 262144;   // rows (samples) per block of rays: ~6 GB of fp32 activations + gradients at W=256 (of 180 GB)
+
+#if !defined(ANERF_SIMT_EMU)
+// Tensor-core GEMM engine of the backward pass (tc_gemm.cuh): launch helper + a per-pass cache of packed
+// weight operands.  Not part of the emulated build: the host tests run the SIMT kernels, the GPU tests compare
+// both engines with the oracle.
+struct TcEngine {
+  int n_sm;
+  DeviceStatus* status;
+  uint8_t* wpack; size_t wpack_bytes, wpack_used;      // packed weight operands of the current network pass
+  uint8_t* gpack; size_t gpack_bytes;                   // packed gradient operand of the current wgrad
+  std::map<std::tuple<const float*, long long, long long, int, int>, const uint8_t*> cache;
+  int error;
+
+  const uint8_t* pack(cudaStream_t st, const float* src, long long s_n, long long s_k, int N, int K, uint8_t* dst) {
+    const int nt = tc_n_tiles(N), NT = tc_tile_width(N), ch = tc_chunks(K);
+    const long long total = (long long)nt * ch * 4 * NT;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    tc_pack_b_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(src, s_n, s_k, N, K, NT, nt, ch, dst);
+    return dst;
+  }
+  const uint8_t* packed_weight(cudaStream_t st, const float* src, long long s_n, long long s_k, int N, int K) {
+    auto key = std::make_tuple(src, s_n, s_k, N, K);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    const size_t need = (tc_packed_bytes(N, K) + 255) & ~(size_t)255;
+    if (wpack_used + need > wpack_bytes) { error = 1; return nullptr; }
+    uint8_t* dst = wpack + wpack_used;
+    wpack_used += need;
+    pack(st, src, s_n, s_k, N, K, dst);
+    cache[key] = dst;
+    return dst;
+  }
+  void new_pass() { cache.clear(); wpack_used = 0; }
+
+  void run(cudaStream_t st, const float* A, long long a_ms, long long a_ks, int M, int K, const uint8_t* Bp, int N,
+           float* C, long long c_ms, long long c_ns, const float* bias, int relu, const float* mask, long long mask_ms,
+           int mode, int slice_chunks) {
+    if (!Bp) { error = 1; return; }
+    TcGemmArgs g{};
+    g.A = A; g.a_ms = a_ms; g.a_ks = a_ks; g.M = M; g.K = K;
+    g.Bp = Bp; g.N = N; g.NT = tc_tile_width(N); g.n_tiles = tc_n_tiles(N);
+    g.chunks_total = tc_chunks(K);
+    g.slice_chunks = slice_chunks > 0 ? slice_chunks : g.chunks_total;
+    g.k_slices = ceil_div(g.chunks_total, g.slice_chunks);
+    g.C = C; g.c_ms = c_ms; g.c_ns = c_ns; g.bias = bias; g.mask = mask; g.mask_ms = mask_ms; g.relu = relu; g.mode = mode;
+    g.status = status;
+    const int items = g.k_slices * ceil_div(M, 2 * kTileM) * g.n_tiles;
+    int pairs = n_sm / 2;
+    if (pairs > items) pairs = items;
+    if (pairs < 1) return;
+    const int smem = kAStages * kAStageBytes + kBStages * kBStageBytes + 8 * kNumBars + 16 + 1024 + 16 + kWorkerWarps * 32 * 36 * 4;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr_set = true;
+    }
+    if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, g) != cudaSuccess) error = 2;
+  }
+};
+#else
+struct TcEngine;
+#endif
 
 struct TrainCall {
   NetDims dims;
@@ -39,11 +118,13 @@ struct TrainCall {
   float* g_skts;                 // [N,J,16] accumulated, or NULL
   float* workspace;
   size_t workspace_floats;
+  TcEngine* tc;                  // tensor-core GEMM engine, or NULL: SIMT fp32 GEMMs (debug knob, and the emulated host tests)
 };
 
 struct Workspace {
   long long rb;                  // rows per block
-  long long z_coarse, xs, h[8], vin, hv, raw, graw, cs, ga, gb, gxs, gvin, ghv, total;   // offsets in floats
+  long long z_coarse, xs, h[8], vin, hv, raw, graw, cs, ga, gb, gxs, gvin, ghv, tc_w, tc_g, total;   // offsets in floats
+  long long tc_w_floats, tc_g_floats;
   int P, LX, LV;                 // encoding width, leading dimension of XS (P + W), of VIN (W + 27J + fc)
 };
 
@@ -78,6 +159,24 @@ inline Workspace make_workspace(const NetDims& d, int n_rays, int Sc, int Si) {
   w.gxs = take(rb * w.LX);
   w.gvin = take(rb * w.LV);
   w.ghv = take(rb * (d.W / 2));
+  // tensor-core engine scratch: packed weight operands of one network pass (forward + transposed forms) and the
+  // packed gradient operand of one wgrad (bf16 hi + lo = 4 bytes per element, rows padded to 128)
+#if !defined(ANERF_SIMT_EMU)
+  {
+    auto pb = [](int N, int K) { return (long long)((tc_packed_bytes(N, K) + 255) & ~(size_t)255); };
+    const int W = d.W, H = d.W / 2;
+    long long s = 0;
+    for (int l = 0; l < d.D; ++l) s += pb(W, l == 0 ? w.P : ((l - 1) == d.skip ? w.LX : W));      // forward forms
+    s += pb(W, W) + pb(H, w.LV);
+    s += pb(w.LV, H) + pb(W, H) + pb(W, W);                                                        // transposed (dgrad) forms
+    for (int l = 1; l < d.D; ++l) s += pb(W, W) + ((l - 1) == d.skip ? pb(w.P, W) : 0);
+    s += pb(w.P, W);
+    w.tc_w_floats = (s + 4096) / 4;
+    w.tc_g_floats = (long long)round_up((int)rb, 128) * d.W + 1024;
+  }
+#endif
+  w.tc_w = take(w.tc_w_floats);
+  w.tc_g = take(w.tc_g_floats);
   w.total = off;
   return w;
 }
@@ -92,8 +191,15 @@ inline dim3 gemm_grid(int M, int N, int K, int k_chunk) {
 
 // forward / dgrad form: C[rows, N] = A[rows, K] * B (+ bias, relu, mask)
 template <bool BT>
-inline void gemm_rows(anerf_tstream st, const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
+inline void gemm_rows(TcEngine* tc, anerf_tstream st, const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc,
                       long long rows, int N, int K, const float* bias, int relu, const float* mask, long long ldmask, int mode) {
+#if !defined(ANERF_SIMT_EMU)
+  if (tc) {      // B(n, k): forward W[n*ldb + k], dgrad W[k*ldb + n]
+    const uint8_t* bp = BT ? tc->packed_weight(st, B, ldb, 1, N, K) : tc->packed_weight(st, B, 1, ldb, N, K);
+    tc->run(st, A, lda, 1, (int)rows, K, bp, N, C, ldc, 1, bias, relu, mask, ldmask, mode, 0);
+    return;
+  }
+#endif
   GemmArgs g{};
   g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
   g.M = (int)rows; g.N = N; g.K = K; g.k_chunk = round_up(K, kBK);
@@ -103,9 +209,17 @@ inline void gemm_rows(anerf_tstream st, const float* A, long long lda, const flo
 }
 
 // wgrad form: dW[Nout, Kin] += G[rows, Nout]^T * X[rows, Kin], split over the rows
-inline void gemm_wgrad(anerf_tstream st, const float* G, long long ldg, const float* X, long long ldx, float* dW, long long lddw,
+inline void gemm_wgrad(TcEngine* tc, anerf_tstream st, const float* G, long long ldg, const float* X, long long ldx, float* dW, long long lddw,
                        long long rows, int Nout, int Kin) {
   if (!dW) return;
+#if !defined(ANERF_SIMT_EMU)
+  if (tc) {      // dW^T[k', n] += sum_rows X[row, k'] G[row, n]: A = X^T (rows of the MMA = input features), B = G^T
+    if (tc_packed_bytes(Nout, (int)rows) > tc->gpack_bytes) { tc->error = 1; return; }
+    const uint8_t* bp = tc->pack(st, G, 1, ldg, Nout, (int)rows, tc->gpack);
+    tc->run(st, X, 1, ldx, Kin, (int)rows, bp, Nout, dW, 1, lddw, nullptr, 0, nullptr, 0, 2, 32);
+    return;
+  }
+#endif
   GemmArgs g{};
   g.A = G; g.lda = ldg; g.B = X; g.ldb = ldx; g.C = dW; g.ldc = lddw;
   g.M = Nout; g.N = Kin; g.K = (int)rows;
@@ -146,6 +260,9 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
   auto in_ld = [&](int l) -> long long { return (l == 0 || (l - 1) == d.skip) ? LX : out_ld(l - 1); };
   auto in_k = [&](int l) -> int { return l == 0 ? P : ((l - 1) == d.skip ? P + W : W); };
 
+#if !defined(ANERF_SIMT_EMU)
+  if (c.tc) c.tc->new_pass();
+#endif
   const int rpb = rays_per_block(c.n_rays, S);
   for (int ray0 = 0; ray0 < c.n_rays; ray0 += rpb) {
     const int nb = (ray0 + rpb <= c.n_rays) ? rpb : c.n_rays - ray0;
@@ -163,14 +280,14 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
     }
     // ---- forward, activations kept
     for (int l = 0; l < D; ++l)
-      gemm_rows<true>(st, in_ptr(l), in_ld(l), p.pts_w[l], in_k(l), out_ptr(l), out_ld(l), rows, W, in_k(l), p.pts_b[l], 1, nullptr, 0, 0);
+      gemm_rows<true>(c.tc, st, in_ptr(l), in_ld(l), p.pts_w[l], in_k(l), out_ptr(l), out_ld(l), rows, W, in_k(l), p.pts_b[l], 1, nullptr, 0, 0);
     const float* HL = out_ptr(D - 1);
     const long long HLld = out_ld(D - 1);
     {
       auto k1 = head_fwd_kernel<1>;
       ANERF_TLAUNCH(k1, dim3((unsigned)((rows + 127) / 128)), dim3(128), st, HL, HLld, W, p.alpha_w, p.alpha_b, rows, RAW + 3, (long long)4);
-      gemm_rows<true>(st, HL, HLld, p.feature_w, W, VIN, LV, rows, W, W, p.feature_b, 0, nullptr, 0, 0);
-      gemm_rows<true>(st, VIN, LV, p.views_w, LV, HV, H, rows, H, LV, p.views_b, 1, nullptr, 0, 0);
+      gemm_rows<true>(c.tc, st, HL, HLld, p.feature_w, W, VIN, LV, rows, W, W, p.feature_b, 0, nullptr, 0, 0);
+      gemm_rows<true>(c.tc, st, VIN, LV, p.views_w, LV, HV, H, rows, H, LV, p.views_b, 1, nullptr, 0, 0);
       auto k3 = head_fwd_kernel<3>;
       ANERF_TLAUNCH(k3, dim3((unsigned)((rows + 127) / 128)), dim3(128), st, (const float*)HV, (long long)H, H, p.rgb_w, p.rgb_b, rows, RAW, (long long)4);
     }
@@ -190,11 +307,11 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
       ANERF_TLAUNCH(k3, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)(H < 32 ? 32 : H)), st, (const float*)GRAW, (long long)4,
                     (const float*)HV, (long long)H, H, p.rgb_w, rows, 64, 1, GHV, (long long)H, gr.rgb_w, gr.rgb_b);
     }
-    gemm_wgrad(st, GHV, H, VIN, LV, gr.views_w, LV, rows, H, LV);
+    gemm_wgrad(c.tc, st, GHV, H, VIN, LV, gr.views_w, LV, rows, H, LV);
     colsum(st, GHV, H, H, rows, gr.views_b);
     const int Nv = (need_pose || need_fc) ? LV : W;         // the view-encoding columns only when something consumes them
-    gemm_rows<false>(st, GHV, H, p.views_w, LV, GVIN, LV, rows, Nv, H, nullptr, 0, nullptr, 0, 0);
-    gemm_wgrad(st, GVIN, LV, HL, HLld, gr.feature_w, W, rows, W, W);
+    gemm_rows<false>(c.tc, st, GHV, H, p.views_w, LV, GVIN, LV, rows, Nv, H, nullptr, 0, nullptr, 0, 0);
+    gemm_wgrad(c.tc, st, GVIN, LV, HL, HLld, gr.feature_w, W, rows, W, W);
     colsum(st, GVIN, LV, W, rows, gr.feature_b);
     {
       auto k1 = head_bwd_kernel<1>;
@@ -202,25 +319,25 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
                     p.alpha_w, rows, 64, 0, GA, (long long)W, gr.alpha_w, gr.alpha_b);
     }
     // dL/dZ of the last trunk layer = (G_feature Wf + g_sigma (x) w_alpha) . (h > 0)
-    gemm_rows<false>(st, GVIN, LV, p.feature_w, W, GA, W, rows, W, W, nullptr, 0, HL, HLld, 1);
+    gemm_rows<false>(c.tc, st, GVIN, LV, p.feature_w, W, GA, W, rows, W, W, nullptr, 0, HL, HLld, 1);
     // ---- trunk, last layer first
     const float* cur = GA;
     long long curld = W;
     for (int l = D - 1; l >= 0; --l) {
-      gemm_wgrad(st, cur, curld, in_ptr(l), in_ld(l), gr.pts_w[l], in_k(l), rows, W, in_k(l));
+      gemm_wgrad(c.tc, st, cur, curld, in_ptr(l), in_ld(l), gr.pts_w[l], in_k(l), rows, W, in_k(l));
       colsum(st, cur, curld, W, rows, gr.pts_b[l]);
       if (l > 0) {
         if ((l - 1) == d.skip) {        // input = cat[encoding, h]: h part masked, encoding part kept for the pose gradient
-          gemm_rows<false>(st, cur, curld, p.pts_w[l] + P, in_k(l), GXS + P, LX, rows, W, W, nullptr, 0, XS + P, LX, 0);
-          if (need_pose) gemm_rows<false>(st, cur, curld, p.pts_w[l], in_k(l), GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, 0);
+          gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l] + P, in_k(l), GXS + P, LX, rows, W, W, nullptr, 0, XS + P, LX, 0);
+          if (need_pose) gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l], in_k(l), GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, 0);
           cur = GXS + P; curld = LX;
         } else {
           float* nxt = (cur == GA) ? GB : GA;
-          gemm_rows<false>(st, cur, curld, p.pts_w[l], in_k(l), nxt, W, rows, W, W, nullptr, 0, out_ptr(l - 1), out_ld(l - 1), 0);
+          gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l], in_k(l), nxt, W, rows, W, W, nullptr, 0, out_ptr(l - 1), out_ld(l - 1), 0);
           cur = nxt; curld = W;
         }
       } else if (need_pose) {
-        gemm_rows<false>(st, cur, curld, p.pts_w[0], P, GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, d.skip >= 0 ? 1 : 0);
+        gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[0], P, GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, d.skip >= 0 ? 1 : 0);
       }
     }
     // ---- encodings backward

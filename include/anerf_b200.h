@@ -199,6 +199,15 @@ int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf
 int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t format,
                         void* stream);
 
+/* Self test of the training path's tensor-core GEMM (tc_gemm.cuh) with explicit strides:
+ *   C(m,n) (op)= sum_k A(m,k) B(n,k),  A(m,k) = A[m*a_ms + k*a_ks], B(n,k) = B[n*b_ns + k*b_ks], C(m,n) = C[m*c_ms + n*c_ns]
+ * epilogue: + bias[n], ReLU, zero where mask[m*mask_ms + n] <= 0; mode 0 store, 1 add to C, 2 atomic add;
+ * slice_chunks > 0 splits K into slices of slice_chunks*32 (use with mode 2).  bf16 hi/lo split, 3 MMAs per product. */
+int anerf_selftest_tc_gemm(const float* A, int64_t a_ms, int64_t a_ks, int32_t M, int32_t K, const float* B, int64_t b_ns,
+                           int64_t b_ks, int32_t N, float* C, int64_t c_ms, int64_t c_ns, const float* bias,
+                           const float* mask, int64_t mask_ms, int32_t relu, int32_t mode, int32_t slice_chunks,
+                           void* stream);
+
 /* Debug aid: device buffer of 3 x 1024 int64; while set, launches record a clock64 timeline of CTA 0
  * (stream 0 MMA thread, 1/2 worker groups; entries = tag << 48 | clock).  NULL switches it off. */
 void anerf_debug_set_trace(long long* device_buffer);

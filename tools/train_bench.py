@@ -24,6 +24,7 @@ n_rays = int(sys.argv[1]) if len(sys.argv) > 1 else 3072
 Si = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 pose = bool(int(sys.argv[3])) if len(sys.argv) > 3 else True
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
+with_ref = not (len(sys.argv) > 5 and sys.argv[5] == "noref")
 Sc = 64
 dev = torch.device("cuda")
 
@@ -74,6 +75,20 @@ def timed(fn, n):
 
 ms = timed(step, steps)
 
+# gradient agreement of the two GEMM engines on this batch (tensor cores, bf16 hi/lo split, vs fp32 SIMT kernels)
+def grads_with(engine):
+    os.environ["ANERF_TRAIN_GEMM"] = engine
+    for p in grad_vars:
+        p.grad = None
+    out = holder(rays, kp_batch=t(sc["kps"]), skts=skts0, cyls=t(sc["cyls"]), bones=t(sc["bones"]), cams=None, subject_idxs=None,
+                 **dict(kw, perturb=0., raw_noise_std=0.))
+    (((out["rgb_map"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean()).backward()
+    return [p.grad.double().clone() for p in grad_vars]
+g_tc, g_simt = grads_with("tc"), grads_with("simt")
+os.environ["ANERF_TRAIN_GEMM"] = "tc"
+engine_l2 = max(float((a - b).norm() / b.norm().clamp_min(1e-30)) for a, b in zip(g_tc, g_simt))
+engine_max = max(float((a - b).abs().max() / b.abs().max().clamp_min(1e-30)) for a, b in zip(g_tc, g_simt))
+
 # forward only / backward only split (CUDA events around the two halves)
 def fwd_only():
     with torch.no_grad():
@@ -83,6 +98,8 @@ ms_fwd = timed(fwd_only, steps)
 # the reference's PyTorch path (oracle port) with autograd on the same GPU
 ref_ms = None
 try:
+    if not with_ref:
+        raise RuntimeError("skipped (noref)")
     from oracle import anerf_oracle as orc
     torch.backends.cuda.matmul.allow_tf32 = False
     p0 = {k: t(v).requires_grad_(True) for k, v in sd0.items()}
@@ -106,5 +123,6 @@ rows = N * (Sc + Sc + Si)
 flop = 3 * rows * 1723648            # forward + dgrad + wgrad, MLP only
 print(json.dumps({"n_rays": N, "N_samples": Sc, "N_importance": Si, "pose_grad": pose, "ms_per_step": ms, "ms_forward_only": ms_fwd,
                   "rays_per_s": N / (ms * 1e-3), "algorithmic_tflops": flop / (ms * 1e-3) / 1e12,
+                  "tc_vs_simt_grad_err": {"l2_rel_worst_tensor": engine_l2, "max_rel_worst_tensor": engine_max},
                   "reference_port_ms_per_step": ref_ms,
                   "speedup_vs_reference_port": (ref_ms / ms) if isinstance(ref_ms, float) else None}))
