@@ -45,7 +45,10 @@ inline __host__ __device__ size_t tc_packed_bytes(int N, int K) {
 // group, row of the tile); rows vary fastest so that both the strided reads (s_n == 1) and the 16-byte writes coalesce.
 template <int FMT>
 __global__ void tc_pack_b_kernel(const float* __restrict__ src, long long s_n, long long s_k, int N, int K, int NT,
-                                 int n_tiles, int chunks_total, uint8_t* __restrict__ out) {
+                                 int n_tiles, int chunks_total, uint8_t* __restrict__ out, float* __restrict__ rowsum) {
+  // rowsum (optional, single-tile operands only): rowsum[n] += sum_k B(n, k) -- the bias gradient when B is a
+  // gradient matrix G^T; the launch keeps gridDim*blockDim a multiple of NT, so a thread's row n never changes
+  float acc = 0.f;
   const long long total = (long long)n_tiles * chunks_total * 4 * NT;
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int r = (int)(t % NT);
@@ -59,6 +62,7 @@ __global__ void tc_pack_b_kernel(const float* __restrict__ src, long long s_n, l
       const int k = c * kKC + g * 8 + i;
       x[i] = (n < N && k < K) ? __ldg(src + (long long)n * s_n + (long long)k * s_k) : 0.f;
     }
+    acc += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
     uint4 hi, lo;
     Split<FMT>::pair(x[0], x[1], hi.x, lo.x);
     Split<FMT>::pair(x[2], x[3], hi.y, lo.y);
@@ -73,6 +77,10 @@ __global__ void tc_pack_b_kernel(const float* __restrict__ src, long long s_n, l
     *reinterpret_cast<uint4*>(half + off) = hi;
     *reinterpret_cast<uint4*>(half + (size_t)nh * 64 + off) = lo;
   }
+  if (rowsum) {
+    const int n = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) % NT);
+    if (n < N && acc != 0.f) atomicAdd(rowsum + n, acc);
+  }
 }
 
 template <int FMT>
@@ -85,7 +93,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
   float* stage_all = zero_bias + 256;            // per worker warp: 32 rows x 36 floats (epilogue transpose)
   Pipe pp;
   pipe_init(pp, smem, smem + kAStages * kAStageBytes, bars, g.status);
-  if (tid == 0) pipe_init_barriers(pp);
+  if (tid == 0) {
+    // as pipe_init_barriers(), except that an A chunk is produced by all 16 worker warps of both CTAs here
+    // (in the fused kernel: by one group of 4 warps per CTA)
+    for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 2 * kWorkerWarps); mbar_init(&pp.a_empty[i], 1); }
+    for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); mbar_init(&pp.peer_b[i], 1); }
+    mbar_init(&pp.d_full[0], 1);
+    mbar_init(&pp.d_full[1], 1);
+    fence_mbar_init();
+  }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
   for (int i = tid; i < 256; i += kThreads) zero_bias[i] = 0.f;
   tc_fence_before_sync();
@@ -181,18 +197,34 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
           float* crow = g.C + (long long)(m_warp + r4) * g.c_ms + n;
           const float* mrow = g.mask ? g.mask + (long long)(m_warp + r4) * g.mask_ms + n : nullptr;
           const long long cstep = 4 * g.c_ms, mstep = g.mask ? 4 * g.mask_ms : 0;
-#pragma unroll 2
-          for (int r = r4; r < rmax; r += 4, crow += cstep, mrow += mstep) {
-            float4 v = *reinterpret_cast<const float4*>(stg + r * 36 + (lane & 7) * 4);
-            if (!n_ok) continue;
-            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-            if (g.mode == 1) { const float4 o = *reinterpret_cast<const float4*>(crow); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-            if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (g.mask) {
-              const float4 k = __ldg(reinterpret_cast<const float4*>(mrow));
-              v.x = k.x > 0.f ? v.x : 0.f; v.y = k.y > 0.f ? v.y : 0.f; v.z = k.z > 0.f ? v.z : 0.f; v.w = k.w > 0.f ? v.w : 0.f;
+          const float lo = g.relu ? 0.f : -3.0e38f;          // branch-free ReLU
+          const float* sp = stg + r4 * 36 + (lane & 7) * 4;
+          if (n_ok) {
+            if (!g.mask && g.mode == 0) {                     // forward form: bias, ReLU, store
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                if (r4 + 4 * i < rmax) {
+                  float4 v = *reinterpret_cast<const float4*>(sp + i * 4 * 36);
+                  v.x = fmaxf(v.x + b.x, lo); v.y = fmaxf(v.y + b.y, lo); v.z = fmaxf(v.z + b.z, lo); v.w = fmaxf(v.w + b.w, lo);
+                  *reinterpret_cast<float4*>(crow + i * cstep) = v;
+                }
+              }
+            } else {                                          // dgrad form: optional add to C, ReLU-derivative mask
+#pragma unroll 4
+              for (int i = 0; i < 8; ++i) {
+                if (r4 + 4 * i < rmax) {
+                  float4 v = *reinterpret_cast<const float4*>(sp + i * 4 * 36);
+                  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                  if (g.mode == 1) { const float4 o = *reinterpret_cast<const float4*>(crow + i * cstep); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                  v.x = fmaxf(v.x, lo); v.y = fmaxf(v.y, lo); v.z = fmaxf(v.z, lo); v.w = fmaxf(v.w, lo);
+                  if (g.mask) {
+                    const float4 k = __ldg(reinterpret_cast<const float4*>(mrow + i * mstep));
+                    v.x = k.x > 0.f ? v.x : 0.f; v.y = k.y > 0.f ? v.y : 0.f; v.z = k.z > 0.f ? v.z : 0.f; v.w = k.w > 0.f ? v.w : 0.f;
+                  }
+                  *reinterpret_cast<float4*>(crow + i * cstep) = v;
+                }
+              }
             }
-            *reinterpret_cast<float4*>(crow) = v;
           }
         } else {
           const int n = nb + lane;
@@ -215,73 +247,100 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         __syncwarp();
       });
     };
-    int it = 0, prev = -1;
-    for (int item = pair; item < items; item += n_pairs, ++it) {
+    // ---- A-operand production.  Every worker warp contributes 1/16 of EVERY chunk (8 values per lane), so a lane
+    // holds only 8 registers per chunk and keeps the loads of the next three chunks in flight; loads go to
+    // registers and are issued before the wait for the ring stage, so the global-memory round trip overlaps the
+    // tensor core consuming earlier chunks.  (Each chunk's "full" barrier therefore counts all 16 warps of both CTAs.)
+    //   row-major A (a_ks == 1): lane = (row % 8, 8-wide k group): a warp reads 8 rows x 128 contiguous bytes
+    //   otherwise              : lane = row within a 32-row quarter, warp / 4 = k group (coalesced when a_ms == 1)
+    const int a_t = vec_ok ? (lane & 3) : (warp >> 2);
+    const int a_row = vec_ok ? (warp * 8 + (lane >> 2)) : ((warp & 3) * 32 + lane);
+    const uint32_t a_off = (uint32_t)((a_t >> 1) * 4096 + (a_t & 1) * 2048 + (a_row >> 3) * 128 + (a_row & 7) * 16);
+    uint32_t a_seq = 0;                              // chunks published so far (all items)
+    // per item: pointer to this lane's 8 values of chunk 0 (NULL for a row past M) and the k index they start at
+    const long long a_cstep = (long long)kKC * g.a_ks;      // one chunk further along k
+    auto item_ptr = [&](int item, int& k0) -> const float* {
       const int ks = item / (m_tiles * g.n_tiles);
       const int mt = (item % (m_tiles * g.n_tiles)) / g.n_tiles;
-      const int m = mt * 2 * kTileM + (int)pp.rank * kTileM + row;
-      const int chunks = slice_len(ks);
-      const int k_base = ks * g.slice_chunks * kKC;
-      const bool m_ok = m < g.M;
-      const float* arow = g.A + (long long)(m_ok ? m : 0) * g.a_ms;
-      // ---- this group's chunks of the A operand
-#pragma unroll 1
-      for (int c = grp; c < chunks; c += kGroups) {
-        ap.begin(c);
-        const int k0 = k_base + c * kKC;
-        if (vec_ok) {
-          // row-major A: a warp instruction reads 8 rows x 128 contiguous bytes (lane = (row % 8, 8-wide k group)) and
-          // writes one 128-byte core-matrix row group per k group, instead of 32 scattered 16-byte pieces
-          const int t = lane & 3;
-          const int k = k0 + t * 8;
-          uint8_t* st0 = pp.a_ring + ap.cur * kAStageBytes + (t >> 1) * 4096 + (t & 1) * 2048;
-          const int m_q = mt * 2 * kTileM + (int)pp.rank * kTileM + quarter * 32;
+      const int mrow = mt * 2 * kTileM + (int)pp.rank * kTileM + a_row;
+      k0 = ks * g.slice_chunks * kKC + a_t * 8;
+      return mrow < g.M ? g.A + (long long)mrow * g.a_ms + (long long)k0 * g.a_ks : nullptr;
+    };
+    auto load8 = [&](const float* src, int k, float (&x)[8]) {
+      if (src == nullptr || k >= g.K) {
 #pragma unroll
-          for (int it4 = 0; it4 < 4; ++it4) {
-            const int rl = it4 * 8 + (lane >> 2);            // row inside the warp's 32
-            const int mm = m_q + rl;
-            float x[8];
-            if (mm < g.M && k + 8 <= g.K) {
-              const float4* src = reinterpret_cast<const float4*>(g.A + (long long)mm * g.a_ms + k);
-              const float4 u = __ldg(src), v = __ldg(src + 1);
-              x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
-            } else {
+        for (int i = 0; i < 8; ++i) x[i] = 0.f;
+      } else if (vec_ok && k + 8 <= g.K) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(src)), v = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+      } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) x[i] = (mm < g.M && k + i < g.K) ? __ldg(g.A + (long long)mm * g.a_ms + k + i) : 0.f;
-            }
-            uint4 hi, lo;
-            Split<FMT>::pair(x[0], x[1], hi.x, lo.x);
-            Split<FMT>::pair(x[2], x[3], hi.y, lo.y);
-            Split<FMT>::pair(x[4], x[5], hi.z, lo.z);
-            Split<FMT>::pair(x[6], x[7], hi.w, lo.w);
-            const int rr = quarter * 32 + rl;
-            uint8_t* p = st0 + (rr >> 3) * 128 + (rr & 7) * 16;
-            *reinterpret_cast<uint4*>(p) = hi;
-            *reinterpret_cast<uint4*>(p + kAHalfBytes) = lo;
-          }
-          ap.end();
-          continue;
-        }
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float x[8];
-          const int k = k0 + t * 8;
-          if (!m_ok || k >= g.K) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = 0.f;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = (k + i < g.K) ? __ldg(arow + (long long)(k + i) * g.a_ks) : 0.f;
-          }
-          ap.store8(t, x);
-        }
-        ap.end();
+        for (int i = 0; i < 8; ++i) x[i] = (k + i < g.K) ? __ldg(src + (long long)i * g.a_ks) : 0.f;
       }
-      ap.base += chunks;
+    };
+    // pull a line that will be loaded a few chunks from now into L2 (no register cost)
+    auto prefetch = [&](const float* src, int k) {
+      if (src != nullptr && k < g.K) asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+    };
+    auto emit = [&](const float (&x)[8]) {
+      const uint32_t stage = a_seq % kAStages;
+      mbar_wait_warp(&pp.a_empty[stage], ((a_seq / kAStages) & 1) ^ 1, pp.st, 100 + stage);
+      uint4 hi, lo;
+      Split<FMT>::pair(x[0], x[1], hi.x, lo.x);
+      Split<FMT>::pair(x[2], x[3], hi.y, lo.y);
+      Split<FMT>::pair(x[4], x[5], hi.z, lo.z);
+      Split<FMT>::pair(x[6], x[7], hi.w, lo.w);
+      uint8_t* p = pp.a_ring + stage * kAStageBytes + a_off;
+      *reinterpret_cast<uint4*>(p) = hi;
+      *reinterpret_cast<uint4*>(p + kAHalfBytes) = lo;
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (elect_one()) a_chunk_ready(pp, stage);
+      __syncwarp();
+      ++a_seq;
+    };
+    int it = 0, prev = -1;
+    float x0[8], x1[8], x2[8], x3[8];
+    int k0 = 0, k0n = 0;
+    const float* ap0 = nullptr;                      // this item's lane pointer
+    const float* apn = nullptr;                      // next item's
+    if (pair < items) {                              // first three chunks of the first item
+      ap0 = item_ptr(pair, k0);
+      load8(ap0, k0, x0); load8(ap0 ? ap0 + a_cstep : nullptr, k0 + kKC, x1); load8(ap0 ? ap0 + 2 * a_cstep : nullptr, k0 + 2 * kKC, x2);
+    }
+    for (int item = pair; item < items; item += n_pairs, ++it) {
+      const int ks = item / (m_tiles * g.n_tiles);
+      const int chunks = slice_len(ks);              // multiple of 4
+      const int nxt = item + n_pairs;
+      apn = nxt < items ? item_ptr(nxt, k0n) : nullptr;
+      auto at = [&](int c) -> const float* { return ap0 ? ap0 + (long long)c * a_cstep : nullptr; };
+#pragma unroll 1
+      for (int c = 0; c < chunks; c += 4) {
+        // L2 prefetch two rounds ahead: this item's chunks c+8..c+11, or the head of the next item
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int cc = c + 8 + u;
+          if (cc < chunks) prefetch(at(cc), k0 + cc * kKC);
+          else if (apn && cc - chunks < 8) prefetch(apn + (long long)(cc - chunks) * a_cstep, k0n + (cc - chunks) * kKC);
+        }
+        load8(at(c + 3), k0 + (c + 3) * kKC, x3);
+        emit(x0);
+        if (c + 4 < chunks) load8(at(c + 4), k0 + (c + 4) * kKC, x0);
+        emit(x1);
+        if (c + 5 < chunks) load8(at(c + 5), k0 + (c + 5) * kKC, x1);
+        emit(x2);
+        if (c + 6 < chunks) load8(at(c + 6), k0 + (c + 6) * kKC, x2);
+        emit(x3);
+      }
+      // the next item's first chunks are requested before the epilogue below, which hides their latency
+      if (nxt < items) {
+        load8(apn, k0n, x0); load8(apn ? apn + a_cstep : nullptr, k0n + kKC, x1); load8(apn ? apn + 2 * a_cstep : nullptr, k0n + 2 * kKC, x2);
+      }
+      ap0 = apn; k0 = k0n;
       // ---- epilogue of the previous item while this item's MMAs run
       if (prev >= 0) drain_item(prev, (it - 1) & 1);
       prev = item;
-      // the region of item it+1 is the one just drained: every group must be done with it before any group
+      // the region of item it+1 is the one just drained: every warp must be done with it before any warp
       // publishes a chunk of item it+1 (whose first MMA overwrites that region)
       worker_sync();
     }

@@ -44,12 +44,15 @@ struct TcEngine {
   std::map<std::tuple<const float*, long long, long long, int, int>, const uint8_t*> cache;
   int error;
 
-  const uint8_t* pack(cudaStream_t st, const float* src, long long s_n, long long s_k, int N, int K, uint8_t* dst) {
+  const uint8_t* pack(cudaStream_t st, const float* src, long long s_n, long long s_k, int N, int K, uint8_t* dst,
+                      float* rowsum = nullptr) {
     const int nt = tc_n_tiles(N), NT = tc_tile_width(N), ch = tc_chunks(K);
     const long long total = (long long)nt * ch * 4 * NT;
     long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    tc_pack_b_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(src, s_n, s_k, N, K, NT, nt, ch, dst);
+    const long long cap = rowsum ? 148 * 8 : 148 * 32;   // fewer, longer threads when they also reduce (one atomic each)
+    if (blocks > cap) blocks = cap;
+    if (rowsum && (nt != 1 || (blocks * 256) % NT != 0)) { error = 3; return nullptr; }
+    tc_pack_b_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(src, s_n, s_k, N, K, NT, nt, ch, dst, rowsum);
     return dst;
   }
   const uint8_t* packed_weight(cudaStream_t st, const float* src, long long s_n, long long s_k, int N, int K) {
@@ -208,18 +211,22 @@ inline void gemm_rows(TcEngine* tc, anerf_tstream st, const float* A, long long 
   ANERF_TLAUNCH(k, gemm_grid(g.M, N, K, g.k_chunk), dim3(kGemmThreads), st, g);
 }
 
-// wgrad form: dW[Nout, Kin] += G[rows, Nout]^T * X[rows, Kin], split over the rows
+inline void colsum(anerf_tstream st, const float* G, long long ld, int N, long long rows, float* db);
+
+// wgrad form: dW[Nout, Kin] += G[rows, Nout]^T * X[rows, Kin] and db[Nout] += column sums of G (either may be NULL)
 inline void gemm_wgrad(TcEngine* tc, anerf_tstream st, const float* G, long long ldg, const float* X, long long ldx, float* dW, long long lddw,
-                       long long rows, int Nout, int Kin) {
-  if (!dW) return;
+                       long long rows, int Nout, int Kin, float* db) {
 #if !defined(ANERF_SIMT_EMU)
-  if (tc) {      // dW^T[k', n] += sum_rows X[row, k'] G[row, n]: A = X^T (rows of the MMA = input features), B = G^T
+  if (tc && dW) {   // dW^T[k', n] += sum_rows X[row, k'] G[row, n]: A = X^T (rows of the MMA = input features), B = G^T;
+                    // the pack of G^T reads every gradient once and leaves the bias gradient behind
     if (tc_packed_bytes(Nout, (int)rows) > tc->gpack_bytes) { tc->error = 1; return; }
-    const uint8_t* bp = tc->pack(st, G, 1, ldg, Nout, (int)rows, tc->gpack);
+    const uint8_t* bp = tc->pack(st, G, 1, ldg, Nout, (int)rows, tc->gpack, db);
     tc->run(st, X, 1, ldx, Kin, (int)rows, bp, Nout, dW, 1, lddw, nullptr, 0, nullptr, 0, 2, 32);
     return;
   }
 #endif
+  colsum(st, G, ldg, Nout, rows, db);
+  if (!dW) return;
   GemmArgs g{};
   g.A = G; g.lda = ldg; g.B = X; g.ldb = ldx; g.C = dW; g.ldc = lddw;
   g.M = Nout; g.N = Kin; g.K = (int)rows;
@@ -307,12 +314,10 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
       ANERF_TLAUNCH(k3, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)(H < 32 ? 32 : H)), st, (const float*)GRAW, (long long)4,
                     (const float*)HV, (long long)H, H, p.rgb_w, rows, 64, 1, GHV, (long long)H, gr.rgb_w, gr.rgb_b);
     }
-    gemm_wgrad(c.tc, st, GHV, H, VIN, LV, gr.views_w, LV, rows, H, LV);
-    colsum(st, GHV, H, H, rows, gr.views_b);
+    gemm_wgrad(c.tc, st, GHV, H, VIN, LV, gr.views_w, LV, rows, H, LV, gr.views_b);
     const int Nv = (need_pose || need_fc) ? LV : W;         // the view-encoding columns only when something consumes them
     gemm_rows<false>(c.tc, st, GHV, H, p.views_w, LV, GVIN, LV, rows, Nv, H, nullptr, 0, nullptr, 0, 0);
-    gemm_wgrad(c.tc, st, GVIN, LV, HL, HLld, gr.feature_w, W, rows, W, W);
-    colsum(st, GVIN, LV, W, rows, gr.feature_b);
+    gemm_wgrad(c.tc, st, GVIN, LV, HL, HLld, gr.feature_w, W, rows, W, W, gr.feature_b);
     {
       auto k1 = head_bwd_kernel<1>;
       ANERF_TLAUNCH(k1, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)W), st, (const float*)(GRAW + 3), (long long)4, HL, HLld, W,
@@ -324,8 +329,7 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
     const float* cur = GA;
     long long curld = W;
     for (int l = D - 1; l >= 0; --l) {
-      gemm_wgrad(c.tc, st, cur, curld, in_ptr(l), in_ld(l), gr.pts_w[l], in_k(l), rows, W, in_k(l));
-      colsum(st, cur, curld, W, rows, gr.pts_b[l]);
+      gemm_wgrad(c.tc, st, cur, curld, in_ptr(l), in_ld(l), gr.pts_w[l], in_k(l), rows, W, in_k(l), gr.pts_b[l]);
       if (l > 0) {
         if ((l - 1) == d.skip) {        // input = cat[encoding, h]: h part masked, encoding part kept for the pose gradient
           gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l] + P, in_k(l), GXS + P, LX, rows, W, W, nullptr, 0, XS + P, LX, 0);
