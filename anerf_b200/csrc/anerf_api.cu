@@ -438,7 +438,7 @@ int anerf_selftest_tc_gemm(const float* A, int64_t a_ms, int64_t a_ks, int32_t M
   uint8_t* d_pack = nullptr;
   CUDA_TRY(cudaMalloc((void**)&d_pack, tc_packed_bytes(N, K)));
   train::TcEngine tc{};
-  tc.n_sm = n_sm; tc.status = g_status_dev; tc.error = 0;
+  tc.n_sm = n_sm; tc.status = g_status_dev; tc.error = 0; tc.trace = g_trace;
   tc.pack(stream, B, b_ns, b_ks, N, K, d_pack);
   tc.run(stream, A, a_ms, a_ks, M, K, d_pack, N, C, c_ms, c_ns, bias, relu, mask, mask_ms, mode, slice_chunks);
   cudaError_t e = cudaGetLastError();

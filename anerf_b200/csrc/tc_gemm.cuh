@@ -30,6 +30,7 @@ struct TcGemmArgs {
   const float* mask; long long mask_ms;   // mask(m, n) at mask[m*mask_ms + n]
   int relu, mode;           // mode 0: store, 1: C += r (then relu / mask), 2: atomicAdd
   DeviceStatus* status;
+  long long* trace;         // optional debug timeline of CTA 0 (anerf_debug_set_trace): stream 0 MMA warp, 1 worker warp 0, 2 worker warp 5
 };
 
 inline __host__ __device__ int tc_n_tiles(int N) { return (N + 255) / 256; }
@@ -40,6 +41,10 @@ inline __host__ __device__ size_t tc_packed_bytes(int N, int K) {
 }
 
 #ifdef __CUDACC__
+
+constexpr int kTcProdWarps = 8;    // worker warps 0..7 produce the A operand (two groups of 4)
+constexpr int kTcDrainWarps = 8;   // worker warps 8..15 drain the accumulators
+static_assert(kTcProdWarps + kTcDrainWarps == kWorkerWarps, "worker warp roles");
 
 // B(n, k) = src[n*s_n + k*s_k] (zero outside [0,N) x [0,K)) -> packed tiles.  One thread per (tile, chunk, 8-wide k
 // group, row of the tile); rows vary fastest so that both the strided reads (s_n == 1) and the 16-byte writes coalesce.
@@ -88,22 +93,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAStages * kAStageBytes + kBStages * kBStageBytes);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + kNumBars);
-  float* zero_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
-  float* stage_all = zero_bias + 256;            // per worker warp: 32 rows x 36 floats (epilogue transpose)
+  uint64_t* r_free = bars + kNumBars;            // [2]: the drain warps are done with accumulator region r
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_free + 2);
+  float* stage_all = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
   Pipe pp;
   pipe_init(pp, smem, smem + kAStages * kAStageBytes, bars, g.status);
   if (tid == 0) {
-    // as pipe_init_barriers(), except that an A chunk is produced by all 16 worker warps of both CTAs here
-    // (in the fused kernel: by one group of 4 warps per CTA)
-    for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 2 * kWorkerWarps); mbar_init(&pp.a_empty[i], 1); }
-    for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); mbar_init(&pp.peer_b[i], 1); }
-    mbar_init(&pp.d_full[0], 1);
-    mbar_init(&pp.d_full[1], 1);
+    pipe_init_barriers(pp);                      // an A chunk is produced by one group of 4 warps per CTA, as in the fused kernel
+    mbar_init(&r_free[0], kTcDrainWarps);
+    mbar_init(&r_free[1], kTcDrainWarps);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
-  for (int i = tid; i < 256; i += kThreads) zero_bias[i] = 0.f;
   tc_fence_before_sync();
   __syncthreads();
   cluster_sync_all();
@@ -122,9 +123,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
   if (warp == kMmaWarp) {
     uint32_t a_seq = 0, b_seq = 0;
     int it = 0;
+    Trace trc; trc.init(lane == 0 ? g.trace : nullptr, 0);
     if (pp.rank == 0) {
       for (int item = pair; item < items; item += n_pairs, ++it)
-        mma_layer<FMT>(pp, a_seq, b_seq, NT, slice_len(item / (m_tiles * g.n_tiles)), it & 1);
+        mma_layer<FMT>(pp, a_seq, b_seq, NT, slice_len(item / (m_tiles * g.n_tiles)), it & 1, trc.p ? &trc : nullptr);
     } else if (lane == 0) {
       for (int item = pair; item < items; item += n_pairs) relay_layer(pp, b_seq, slice_len(item / (m_tiles * g.n_tiles)));
     }
@@ -139,54 +141,171 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
       }
     }
     __syncwarp();
-  } else {
-    const int grp = warp >> 2, quarter = warp & 3, row = quarter * 32 + lane;
-    AProducer<FMT> ap(pp, row);
-    uint32_t d_cnt[2] = {0u, 0u};
+  } else if (warp < kTcProdWarps) {
+    // ------------------------------------------------------------------------------------------------------
+    // producers: two groups of 4 warps; group pg fills the chunks c with c % 2 == pg of every item, so two chunks
+    // are in production at any time.  The loads of a chunk go to registers BEFORE the wait for its ring stage and
+    // are consumed before the arrive (whose release semantics would otherwise wait for loads still in flight);
+    // everything further ahead is only pulled into L2 (prefetch.global.L2, no register or ordering cost).
+    //   row-major A (a_ks == 1): lane = (row % 8, 8-wide k group): a warp reads 8 rows x 128 contiguous bytes
+    //   otherwise              : lane = row, 4 k groups per lane (coalesced along the rows when a_ms == 1)
+    // ------------------------------------------------------------------------------------------------------
+    const int pg = warp >> 2;
+    const int lane_g = (warp & 3) * 32 + lane;                       // 0..127 within the group
     const bool vec_ok = g.a_ks == 1 && (g.a_ms & 3) == 0 && ((reinterpret_cast<uintptr_t>(g.A) & 15) == 0);
-    float* stg = stage_all + warp * (32 * 36);
-    // vector epilogue: row-major output whose rows, bias and mask are 16-byte aligned, plain store / add modes
-    const bool vec_out = g.c_ns == 1 && g.mode != 2 && (g.c_ms & 3) == 0 && (g.N & 3) == 0 &&
+    Trace trc; trc.init((lane == 0 && warp == 0) ? g.trace : nullptr, 1);
+    Trace* tr = trc.p ? &trc : nullptr;
+    // slot j (0..3) of this lane: row a_row(j), k group a_t(j)
+    auto a_row = [&](int j) { return vec_ok ? (32 * j + (lane_g >> 2)) : lane_g; };
+    auto a_t = [&](int j) { return vec_ok ? (lane_g & 3) : j; };
+    const long long a_cstep = (long long)kKC * g.a_ks;
+    auto load8 = [&](const float* src, int k, float (&x)[8]) {
+      if (src == nullptr || k >= g.K) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = 0.f;
+      } else if (vec_ok && k + 8 <= g.K) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(src)), v = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x[i] = (k + i < g.K) ? __ldg(src + (long long)i * g.a_ks) : 0.f;
+      }
+    };
+    uint32_t seq_base = 0;
+    int it = 0;
+    for (int item = pair; item < items; item += n_pairs, ++it) {
+      const int ks = item / (m_tiles * g.n_tiles);
+      const int mt = (item % (m_tiles * g.n_tiles)) / g.n_tiles;
+      const int chunks = slice_len(ks);
+      const int m0 = mt * 2 * kTileM + (int)pp.rank * kTileM;
+      const int kbase = ks * g.slice_chunks * kKC;
+      // per slot: pointer to the 8 values of chunk 0 (NULL past the last row) and their k index
+      const float* sp[4];
+      int sk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int mrow = m0 + a_row(j);
+        sk[j] = kbase + a_t(j) * 8;
+        sp[j] = mrow < g.M ? g.A + (long long)mrow * g.a_ms + (long long)sk[j] * g.a_ks : nullptr;
+      }
+      // next item's head, for the L2 prefetch
+      const int nxt = item + n_pairs;
+      const float* np[4] = {nullptr, nullptr, nullptr, nullptr};
+      int nk[4] = {0, 0, 0, 0};
+      if (nxt < items) {
+        const int ks2 = nxt / (m_tiles * g.n_tiles), mt2 = (nxt % (m_tiles * g.n_tiles)) / g.n_tiles;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int mrow2 = mt2 * 2 * kTileM + (int)pp.rank * kTileM + a_row(j);
+          nk[j] = ks2 * g.slice_chunks * kKC + a_t(j) * 8;
+          if (mrow2 < g.M) np[j] = g.A + (long long)mrow2 * g.a_ms + (long long)nk[j] * g.a_ks;
+        }
+      }
+      if (tr) tr->mark(50);
+      // the accumulator region this item's MMAs will overwrite must have been drained (two items ago)
+      if (it >= 2) mbar_wait_warp(&r_free[it & 1], ((it >> 1) - 1) & 1, pp.st, 700 + (it & 1));
+#pragma unroll 1
+      for (int c = pg; c < chunks; c += 2) {
+        float x[4][8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) load8(sp[j] ? sp[j] + (long long)c * a_cstep : nullptr, sk[j] + c * kKC, x[j]);
+        // L2 prefetch, two of this group's rounds ahead (or the head of the next item)
+        {
+          const int cc = c + 4;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float* q = nullptr;
+            if (cc < chunks) { if (sp[j] && sk[j] + cc * kKC < g.K) q = sp[j] + (long long)cc * a_cstep; }
+            else if (np[j] && cc - chunks < 4 && nk[j] + (cc - chunks) * kKC < g.K) q = np[j] + (long long)(cc - chunks) * a_cstep;
+            if (q) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+          }
+        }
+        const uint32_t seq = seq_base + (uint32_t)c;
+        const uint32_t stage = seq % kAStages;
+        mbar_wait_warp(&pp.a_empty[stage], ((seq / kAStages) & 1) ^ 1, pp.st, 100 + stage);
+        uint8_t* st0 = pp.a_ring + stage * kAStageBytes;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 hi, lo;
+          Split<FMT>::pair(x[j][0], x[j][1], hi.x, lo.x);
+          Split<FMT>::pair(x[j][2], x[j][3], hi.y, lo.y);
+          Split<FMT>::pair(x[j][4], x[j][5], hi.z, lo.z);
+          Split<FMT>::pair(x[j][6], x[j][7], hi.w, lo.w);
+          const int rr = a_row(j), tt = a_t(j);
+          uint8_t* q = st0 + (tt >> 1) * 4096 + (tt & 1) * 2048 + (rr >> 3) * 128 + (rr & 7) * 16;
+          *reinterpret_cast<uint4*>(q) = hi;
+          *reinterpret_cast<uint4*>(q + kAHalfBytes) = lo;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (elect_one()) a_chunk_ready(pp, stage);
+        __syncwarp();
+      }
+      seq_base += (uint32_t)chunks;
+      if (tr) tr->mark(51);
+    }
+  } else {
+    // ------------------------------------------------------------------------------------------------------
+    // drain warps (8): warp = (TMEM lane quarter, column half); they take the finished accumulators of item it-1
+    // while the producers and the tensor core work on item it.  A thread holds one row (TMEM lane), 32 columns at
+    // a time; for a row-major output each 32 x 32 block goes through shared memory so that a warp writes (and, for
+    // the add mode and the mask, reads) 4 rows x 128 contiguous bytes per instruction; for the column-major output
+    // of the wgrad form the lanes' rows are already adjacent in memory (coalesced red.global).
+    // ------------------------------------------------------------------------------------------------------
+    const int dw = warp - kTcProdWarps;
+    const int quarter = warp & 3, half = dw >> 2;
+    float* stg = stage_all + dw * (32 * 36);
+    Trace trc; trc.init((lane == 0 && dw == 0) ? g.trace : nullptr, 2);
+    Trace* tr = trc.p ? &trc : nullptr;
+    const bool transposed = g.c_ns == 1;
+    const bool vec_out = transposed && g.mode != 2 && (g.c_ms & 3) == 0 && (g.N & 3) == 0 &&
                          ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) &&
                          (!g.bias || (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0) &&
                          (!g.mask || ((g.mask_ms & 3) == 0 && (reinterpret_cast<uintptr_t>(g.mask) & 15) == 0));
-    // epilogue of one finished item.  A thread holds one row of the accumulator (TMEM lane); when the output is
-    // row-major (c_ns == 1) each 32 x 32 block goes through shared memory so that a warp writes (and, for the add
-    // mode and the mask, reads) 128 contiguous bytes of one row per instruction; when the output is column-major
-    // (wgrad, c_ms == 1) the lanes' rows are already adjacent in memory.
-    auto drain_item = [&](int item, int region) {
+    const int nblk = NT / 32;
+    uint32_t d_cnt[2] = {0u, 0u};
+    int it = 0;
+    for (int item = pair; item < items; item += n_pairs, ++it) {
+      const int region = it & 1;
       const int rem = item % (m_tiles * g.n_tiles);
       const int mt = rem / g.n_tiles, nt = rem % g.n_tiles;
       const int m_warp = mt * 2 * kTileM + (int)pp.rank * kTileM + quarter * 32;
       const int m = m_warp + lane;
       const int n0 = nt * NT;
-      const bool transposed = g.c_ns == 1;
-      drain_region<FMT, false, false>(ap, pp, d_cnt, region, NT, zero_bias, 1.0f, quarter, grp,
-                                      [&](int col0, const float (&x)[8]) {
+      if (tr) tr->mark(10);
+      mbar_wait_warp(&pp.d_full[region], d_cnt[region] & 1, pp.st, 500 + region);
+      ++d_cnt[region];
+      tc_fence_after_sync();
+      if (tr) tr->mark(11);
+      const uint32_t taddr = pp.tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)region * 256u;
+#pragma unroll 1
+      for (int cb = half; cb < nblk; cb += 2) {
+        uint32_t v[32];
+        tmem_ld32(taddr + cb * 32, v);
+        tmem_ld_wait();
+        const int nb = n0 + cb * 32;             // first column of the block
         if (!transposed) {
-          if (m >= g.M) return;
-          float* c = g.C + (long long)m * g.c_ms + (long long)(n0 + col0) * g.c_ns;
+          if (m < g.M) {
+            float* c = g.C + (long long)m * g.c_ms + (long long)nb * g.c_ns;
 #pragma unroll
-          for (int i = 0; i < 8; ++i, c += g.c_ns) {
-            const int n = n0 + col0 + i;
-            if (n >= g.N) continue;
-            float r = x[i];
-            if (g.mode == 2) { atomicAdd(c, r); continue; }
-            if (g.bias) r += __ldg(g.bias + n);
-            if (g.mode == 1) r += *c;
-            if (g.relu) r = fmaxf(r, 0.f);
-            if (g.mask && !(__ldg(g.mask + (long long)m * g.mask_ms + n) > 0.f)) r = 0.f;
-            *c = r;
+            for (int i = 0; i < 32; ++i, c += g.c_ns) {
+              if (nb + i >= g.N) break;
+              float r = __uint_as_float(v[i]);
+              if (g.mode == 2) { atomicAdd(c, r); continue; }
+              if (g.bias) r += __ldg(g.bias + nb + i);
+              if (g.mode == 1) r += *c;
+              if (g.relu) r = fmaxf(r, 0.f);
+              if (g.mask && !(__ldg(g.mask + (long long)m * g.mask_ms + nb + i) > 0.f)) r = 0.f;
+              *c = r;
+            }
           }
-          return;
+          continue;
         }
-        // stage the thread's 8 columns (row stride 36 floats: 16-byte aligned and conflict-free for both phases)
-        const int cin = col0 & 31;
-        *reinterpret_cast<float4*>(stg + lane * 36 + cin) = make_float4(x[0], x[1], x[2], x[3]);
-        *reinterpret_cast<float4*>(stg + lane * 36 + cin + 4) = make_float4(x[4], x[5], x[6], x[7]);
-        if (cin != 24) return;                 // the 32-column block is complete after its fourth call
+#pragma unroll
+        for (int q = 0; q < 8; ++q)              // row stride 36 floats: 16-byte aligned, conflict-free in both phases
+          *reinterpret_cast<float4*>(stg + lane * 36 + 4 * q) =
+              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
         __syncwarp();
-        const int nb = n0 + (col0 - 24);       // first column of the block
         const int rmax = g.M - m_warp < 32 ? g.M - m_warp : 32;
         if (vec_out) {
           // a warp instruction covers 4 rows x 128 contiguous bytes: lane = (row % 4, 4-column group)
@@ -204,24 +323,24 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 if (r4 + 4 * i < rmax) {
-                  float4 v = *reinterpret_cast<const float4*>(sp + i * 4 * 36);
-                  v.x = fmaxf(v.x + b.x, lo); v.y = fmaxf(v.y + b.y, lo); v.z = fmaxf(v.z + b.z, lo); v.w = fmaxf(v.w + b.w, lo);
-                  *reinterpret_cast<float4*>(crow + i * cstep) = v;
+                  float4 w = *reinterpret_cast<const float4*>(sp + i * 4 * 36);
+                  w.x = fmaxf(w.x + b.x, lo); w.y = fmaxf(w.y + b.y, lo); w.z = fmaxf(w.z + b.z, lo); w.w = fmaxf(w.w + b.w, lo);
+                  *reinterpret_cast<float4*>(crow + i * cstep) = w;
                 }
               }
             } else {                                          // dgrad form: optional add to C, ReLU-derivative mask
 #pragma unroll 4
               for (int i = 0; i < 8; ++i) {
                 if (r4 + 4 * i < rmax) {
-                  float4 v = *reinterpret_cast<const float4*>(sp + i * 4 * 36);
-                  v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                  if (g.mode == 1) { const float4 o = *reinterpret_cast<const float4*>(crow + i * cstep); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
-                  v.x = fmaxf(v.x, lo); v.y = fmaxf(v.y, lo); v.z = fmaxf(v.z, lo); v.w = fmaxf(v.w, lo);
+                  float4 w = *reinterpret_cast<const float4*>(sp + i * 4 * 36);
+                  w.x += b.x; w.y += b.y; w.z += b.z; w.w += b.w;
+                  if (g.mode == 1) { const float4 o = *reinterpret_cast<const float4*>(crow + i * cstep); w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
+                  w.x = fmaxf(w.x, lo); w.y = fmaxf(w.y, lo); w.z = fmaxf(w.z, lo); w.w = fmaxf(w.w, lo);
                   if (g.mask) {
                     const float4 k = __ldg(reinterpret_cast<const float4*>(mrow + i * mstep));
-                    v.x = k.x > 0.f ? v.x : 0.f; v.y = k.y > 0.f ? v.y : 0.f; v.z = k.z > 0.f ? v.z : 0.f; v.w = k.w > 0.f ? v.w : 0.f;
+                    w.x = k.x > 0.f ? w.x : 0.f; w.y = k.y > 0.f ? w.y : 0.f; w.z = k.z > 0.f ? w.z : 0.f; w.w = k.w > 0.f ? w.w : 0.f;
                   }
-                  *reinterpret_cast<float4*>(crow + i * cstep) = v;
+                  *reinterpret_cast<float4*>(crow + i * cstep) = w;
                 }
               }
             }
@@ -232,119 +351,28 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
           const float b = (g.bias && n_ok) ? __ldg(g.bias + n) : 0.f;
 #pragma unroll 4
           for (int r = 0; r < rmax; ++r) {
-            float v = stg[r * 36 + lane];
+            float w = stg[r * 36 + lane];
             if (n_ok) {
               float* c = g.C + (long long)(m_warp + r) * g.c_ms + n;
-              if (g.mode == 2) { atomicAdd(c, v); continue; }
-              v += b;
-              if (g.mode == 1) v += *c;
-              if (g.relu) v = fmaxf(v, 0.f);
-              if (g.mask && !(__ldg(g.mask + (long long)(m_warp + r) * g.mask_ms + n) > 0.f)) v = 0.f;
-              *c = v;
+              if (g.mode == 2) { atomicAdd(c, w); continue; }
+              w += b;
+              if (g.mode == 1) w += *c;
+              if (g.relu) w = fmaxf(w, 0.f);
+              if (g.mask && !(__ldg(g.mask + (long long)(m_warp + r) * g.mask_ms + n) > 0.f)) w = 0.f;
+              *c = w;
             }
           }
         }
         __syncwarp();
-      });
-    };
-    // ---- A-operand production.  Every worker warp contributes 1/16 of EVERY chunk (8 values per lane), so a lane
-    // holds only 8 registers per chunk and keeps the loads of the next three chunks in flight; loads go to
-    // registers and are issued before the wait for the ring stage, so the global-memory round trip overlaps the
-    // tensor core consuming earlier chunks.  (Each chunk's "full" barrier therefore counts all 16 warps of both CTAs.)
-    //   row-major A (a_ks == 1): lane = (row % 8, 8-wide k group): a warp reads 8 rows x 128 contiguous bytes
-    //   otherwise              : lane = row within a 32-row quarter, warp / 4 = k group (coalesced when a_ms == 1)
-    const int a_t = vec_ok ? (lane & 3) : (warp >> 2);
-    const int a_row = vec_ok ? (warp * 8 + (lane >> 2)) : ((warp & 3) * 32 + lane);
-    const uint32_t a_off = (uint32_t)((a_t >> 1) * 4096 + (a_t & 1) * 2048 + (a_row >> 3) * 128 + (a_row & 7) * 16);
-    uint32_t a_seq = 0;                              // chunks published so far (all items)
-    // per item: pointer to this lane's 8 values of chunk 0 (NULL for a row past M) and the k index they start at
-    const long long a_cstep = (long long)kKC * g.a_ks;      // one chunk further along k
-    auto item_ptr = [&](int item, int& k0) -> const float* {
-      const int ks = item / (m_tiles * g.n_tiles);
-      const int mt = (item % (m_tiles * g.n_tiles)) / g.n_tiles;
-      const int mrow = mt * 2 * kTileM + (int)pp.rank * kTileM + a_row;
-      k0 = ks * g.slice_chunks * kKC + a_t * 8;
-      return mrow < g.M ? g.A + (long long)mrow * g.a_ms + (long long)k0 * g.a_ks : nullptr;
-    };
-    auto load8 = [&](const float* src, int k, float (&x)[8]) {
-      if (src == nullptr || k >= g.K) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = 0.f;
-      } else if (vec_ok && k + 8 <= g.K) {
-        const float4 u = __ldg(reinterpret_cast<const float4*>(src)), v = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = (k + i < g.K) ? __ldg(src + (long long)i * g.a_ks) : 0.f;
+        if (tr) tr->mark(12);
       }
-    };
-    // pull a line that will be loaded a few chunks from now into L2 (no register cost)
-    auto prefetch = [&](const float* src, int k) {
-      if (src != nullptr && k < g.K) asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
-    };
-    auto emit = [&](const float (&x)[8]) {
-      const uint32_t stage = a_seq % kAStages;
-      mbar_wait_warp(&pp.a_empty[stage], ((a_seq / kAStages) & 1) ^ 1, pp.st, 100 + stage);
-      uint4 hi, lo;
-      Split<FMT>::pair(x[0], x[1], hi.x, lo.x);
-      Split<FMT>::pair(x[2], x[3], hi.y, lo.y);
-      Split<FMT>::pair(x[4], x[5], hi.z, lo.z);
-      Split<FMT>::pair(x[6], x[7], hi.w, lo.w);
-      uint8_t* p = pp.a_ring + stage * kAStageBytes + a_off;
-      *reinterpret_cast<uint4*>(p) = hi;
-      *reinterpret_cast<uint4*>(p + kAHalfBytes) = lo;
-      fence_proxy_async_smem();
+      // hand the region back to the producers (its next MMAs overwrite it)
+      tc_fence_before_sync();
       __syncwarp();
-      if (elect_one()) a_chunk_ready(pp, stage);
+      if (elect_one()) mbar_arrive(&r_free[region]);
       __syncwarp();
-      ++a_seq;
-    };
-    int it = 0, prev = -1;
-    float x0[8], x1[8], x2[8], x3[8];
-    int k0 = 0, k0n = 0;
-    const float* ap0 = nullptr;                      // this item's lane pointer
-    const float* apn = nullptr;                      // next item's
-    if (pair < items) {                              // first three chunks of the first item
-      ap0 = item_ptr(pair, k0);
-      load8(ap0, k0, x0); load8(ap0 ? ap0 + a_cstep : nullptr, k0 + kKC, x1); load8(ap0 ? ap0 + 2 * a_cstep : nullptr, k0 + 2 * kKC, x2);
+      if (tr) tr->mark(61);
     }
-    for (int item = pair; item < items; item += n_pairs, ++it) {
-      const int ks = item / (m_tiles * g.n_tiles);
-      const int chunks = slice_len(ks);              // multiple of 4
-      const int nxt = item + n_pairs;
-      apn = nxt < items ? item_ptr(nxt, k0n) : nullptr;
-      auto at = [&](int c) -> const float* { return ap0 ? ap0 + (long long)c * a_cstep : nullptr; };
-#pragma unroll 1
-      for (int c = 0; c < chunks; c += 4) {
-        // L2 prefetch two rounds ahead: this item's chunks c+8..c+11, or the head of the next item
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int cc = c + 8 + u;
-          if (cc < chunks) prefetch(at(cc), k0 + cc * kKC);
-          else if (apn && cc - chunks < 8) prefetch(apn + (long long)(cc - chunks) * a_cstep, k0n + (cc - chunks) * kKC);
-        }
-        load8(at(c + 3), k0 + (c + 3) * kKC, x3);
-        emit(x0);
-        if (c + 4 < chunks) load8(at(c + 4), k0 + (c + 4) * kKC, x0);
-        emit(x1);
-        if (c + 5 < chunks) load8(at(c + 5), k0 + (c + 5) * kKC, x1);
-        emit(x2);
-        if (c + 6 < chunks) load8(at(c + 6), k0 + (c + 6) * kKC, x2);
-        emit(x3);
-      }
-      // the next item's first chunks are requested before the epilogue below, which hides their latency
-      if (nxt < items) {
-        load8(apn, k0n, x0); load8(apn ? apn + a_cstep : nullptr, k0n + kKC, x1); load8(apn ? apn + 2 * a_cstep : nullptr, k0n + 2 * kKC, x2);
-      }
-      ap0 = apn; k0 = k0n;
-      // ---- epilogue of the previous item while this item's MMAs run
-      if (prev >= 0) drain_item(prev, (it - 1) & 1);
-      prev = item;
-      // the region of item it+1 is the one just drained: every warp must be done with it before any warp
-      // publishes a chunk of item it+1 (whose first MMA overwrites that region)
-      worker_sync();
-    }
-    if (prev >= 0) drain_item(prev, (it - 1) & 1);
   }
   tc_fence_before_sync();
   __syncthreads();

@@ -39,6 +39,7 @@ constexpr long long kRowsTarget = 262144;   // rows (samples) per block of rays:
 struct TcEngine {
   int n_sm;
   DeviceStatus* status;
+  long long* trace;
   uint8_t* wpack; size_t wpack_bytes, wpack_used;      // packed weight operands of the current network pass
   uint8_t* gpack; size_t gpack_bytes;                   // packed gradient operand of the current wgrad
   std::map<std::tuple<const float*, long long, long long, int, int>, const uint8_t*> cache;
@@ -81,11 +82,12 @@ struct TcEngine {
     g.k_slices = ceil_div(g.chunks_total, g.slice_chunks);
     g.C = C; g.c_ms = c_ms; g.c_ns = c_ns; g.bias = bias; g.mask = mask; g.mask_ms = mask_ms; g.relu = relu; g.mode = mode;
     g.status = status;
+    g.trace = trace;
     const int items = g.k_slices * ceil_div(M, 2 * kTileM) * g.n_tiles;
     int pairs = n_sm / 2;
     if (pairs > items) pairs = items;
     if (pairs < 1) return;
-    const int smem = kAStages * kAStageBytes + kBStages * kBStageBytes + 8 * kNumBars + 16 + 1024 + 16 + kWorkerWarps * 32 * 36 * 4;
+    const int smem = kAStages * kAStageBytes + kBStages * kBStageBytes + 8 * (kNumBars + 2) + 16 + 64 + kTcDrainWarps * 32 * 36 * 4;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(kThreads);

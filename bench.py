@@ -187,6 +187,63 @@ def cpu_baseline_sample(n_sample=1024):
                       f"{{8,16,32,64,{os.cpu_count()}}} by a 128-ray probe"}, idx, ref
 
 
+def training_probe(dev, rank, world, n_rays=3072, n_importance=16, steps=5):
+    """Training step through the boundary (create_raycaster's train kwargs, .train() mode): forward (fused kernel) +
+    backward (anerf_render_bwd) + one all-reduce of the flat gradient buffer + Adam.  Weak scaling: n_rays per rank."""
+    import collections
+    import contextlib
+    import io
+    from anerf_b200 import parallel
+    from anerf_b200.raycasters import create_raycaster
+    Skel = collections.namedtuple("Skel", ["joint_names", "joint_trees", "root_id"])
+    data_attrs = dict(skel_type=Skel(synthetic.SMPL_JOINT_NAMES, synthetic.SMPL_PARENTS, 0), near=0., far=1., n_views=1,
+                      joint_coords=np.tile(np.eye(3, dtype=np.float32), (1, N_JOINTS, 1, 1)))
+    args = make_args(N_importance=n_importance, perturb=1.0, raw_noise_std=1.0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        rk_train, rk_test, _, grad_vars, optimizer, _ = create_raycaster(args, data_attrs, device=dev)
+    rc = rk_test["ray_caster"]
+    rc.network.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(101).items()})
+    rc.network_fine.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(202).items()})
+    holder = rk_train["ray_caster"].train()
+    sc = synthetic.make_scene(seed=0, n_rays=n_rays, H=H, W=W, focal=FOCAL, n_joints=N_JOINTS, pixel_offset=rank)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a)).to(dev)
+    N = n_rays
+    rays = torch.cat([t(sc["rays_o"]), t(sc["rays_d"]), torch.zeros(N, 1, device=dev), torch.ones(N, 1, device=dev),
+                      torch.nn.functional.normalize(t(sc["rays_d"]), dim=-1)], 1)
+    skts0, kps, cyls, bones = t(sc["skts"]), t(sc["kps"]), t(sc["cyls"]), t(sc["bones"])
+    kw = {k: v for k, v in rk_train.items() if k not in ("ray_caster", "use_viewdirs")}
+    target = torch.rand(N, 3, device=dev)
+    flat = [None]
+
+    def step():
+        optimizer.zero_grad(set_to_none=True)
+        skts = skts0.clone().requires_grad_(True)           # pose refinement: the bone transforms carry gradient
+        out = holder(rays, kp_batch=kps, skts=skts, cyls=cyls, bones=bones, cams=None, subject_idxs=None, **kw)
+        loss = ((out["rgb_map"] - target) ** 2).mean() + ((out["rgb0"] - target) ** 2).mean()
+        loss.backward()
+        flat[0] = parallel.allreduce_gradients(grad_vars, world, flat[0])
+        optimizer.step()
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        torch.distributed.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = parallel.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+    rows = N * (N_SAMPLES + N_SAMPLES + n_importance)
+    return {"metric": "training rays/sec (fwd + bwd + grad all-reduce + Adam)", "value": N * world / (ms * 1e-3), "unit": "rays/s",
+            "ms_per_step": ms, "rays_per_rank": N, "samples": f"{N_SAMPLES}+{n_importance}", "pose_grad": True,
+            "allreduce_bytes": int(sum(p.numel() for p in grad_vars) * 4) if world > 1 else 0,
+            "algorithmic_tflops": 3 * rows * world * 1723648 / (ms * 1e-3) / 1e12,
+            "gemm_engine": os.environ.get("ANERF_TRAIN_GEMM", "tc") + " (bf16 hi/lo split on tcgen05)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -196,6 +253,7 @@ def main():
     ap.add_argument("--ref-rays", type=int, default=2048, help="rays per step of the CPU reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--format", type=int, default=None, help="operand format override: 0 fp16x3, 1 bf16x3")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement")
     opt = ap.parse_args()
     if opt.impl == "reference":
         return run_reference_arm(opt)
@@ -334,6 +392,12 @@ def main():
         e2e = {"value": n_rays * n_e2e * world / (dt_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "api": "anerf_render_fwd_host (C ABI, pinned host buffers, one call per 4096-ray chunk)"}
 
+    # ---- secondary: one training step per rank (Mixamo-style N_rand 3072, 64 + 16 samples, pose
+    # gradient on): fused forward + CUDA backward + the single flat gradient all-reduce + Adam, through the boundary
+    training = None
+    if not opt.no_train:
+        training = training_probe(dev, rank, world)
+
     if rank != 0:
         return
     cpu_base, parity = None, None
@@ -382,7 +446,7 @@ def main():
                        "parallelism": f"frame-parallel x{world}, gather of [rays,5] pixels to rank 0" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: 402 MB of per-ray skts per frame, two frames alternated"},
             "clocks": clocks, "gpu_launches": 2 * n_chunks * opt.steps, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu_base, "reference_gpu_port": ref_gpu, "parity": parity}
+            "cpu_baseline": cpu_base, "reference_gpu_port": ref_gpu, "parity": parity, "training": training}
     print(json.dumps(line), flush=True)
 
 
