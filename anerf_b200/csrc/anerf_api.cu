@@ -415,6 +415,9 @@ int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, con
     tc.wpack = (uint8_t*)((float*)workspace + w.tc_w); tc.wpack_bytes = (size_t)w.tc_w_floats * 4; tc.wpack_used = 0;
     tc.gpack = (uint8_t*)((float*)workspace + w.tc_g); tc.gpack_bytes = (size_t)w.tc_g_floats * 4;
     tc.error = 0;
+    tc.trace = g_trace;
+    tc.wgrad_slice_chunks = 32;
+    if (const char* sl = getenv("ANERF_WGRAD_SLICE")) { int v = atoi(sl); if (v >= 4 && v % 4 == 0 && v <= 256) tc.wgrad_slice_chunks = v; }
     c.tc = &tc;
   }
   if (train::train_backward(c, (cudaStream_t)stream_) != 0) return fail(ANERF_ERR_INVALID, "internal: workspace layout");

@@ -272,6 +272,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
       const int m_warp = mt * 2 * kTileM + (int)pp.rank * kTileM + quarter * 32;
       const int m = m_warp + lane;
       const int n0 = nt * NT;
+      // while the item's MMAs still run: pull what the epilogue will read (ReLU mask, C in the add mode) into L2
+      if (transposed && (g.mask || g.mode == 1) && m < g.M) {
+        for (int cb = half; cb < nblk; cb += 2) {
+          const int nb = n0 + cb * 32;
+          if (nb < g.N) {
+            if (g.mask) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.mask + (long long)m * g.mask_ms + nb));
+            if (g.mode == 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(g.C + (long long)m * g.c_ms + nb));
+          }
+        }
+      }
       if (tr) tr->mark(10);
       mbar_wait_warp(&pp.d_full[region], d_cnt[region] & 1, pp.st, 500 + region);
       ++d_cnt[region];

@@ -40,6 +40,7 @@ struct TcEngine {
   int n_sm;
   DeviceStatus* status;
   long long* trace;
+  int wgrad_slice_chunks;   // rows per wgrad work item / 32: each item accumulates this many chunks in TMEM, then adds to dW in fp32
   uint8_t* wpack; size_t wpack_bytes, wpack_used;      // packed weight operands of the current network pass
   uint8_t* gpack; size_t gpack_bytes;                   // packed gradient operand of the current wgrad
   std::map<std::tuple<const float*, long long, long long, int, int>, const uint8_t*> cache;
@@ -223,7 +224,7 @@ inline void gemm_wgrad(TcEngine* tc, anerf_tstream st, const float* G, long long
                     // the pack of G^T reads every gradient once and leaves the bias gradient behind
     if (tc_packed_bytes(Nout, (int)rows) > tc->gpack_bytes) { tc->error = 1; return; }
     const uint8_t* bp = tc->pack(st, G, 1, ldg, Nout, (int)rows, tc->gpack, db);
-    tc->run(st, X, 1, ldx, Kin, (int)rows, bp, Nout, dW, 1, lddw, nullptr, 0, nullptr, 0, 2, 32);
+    tc->run(st, X, 1, ldx, Kin, (int)rows, bp, Nout, dW, 1, lddw, nullptr, 0, nullptr, 0, 2, tc->wgrad_slice_chunks);
     return;
   }
 #endif
