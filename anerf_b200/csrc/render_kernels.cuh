@@ -43,6 +43,11 @@ constexpr int kThreads = (kWorkerWarps + 2) * 32;
 constexpr int kTmemCols = 512;
 constexpr int kSmallsHeader = 16;                    // floats: per-layer output scales
 constexpr int kMaxRaysPerItem = 8;
+#ifndef ANERF_SPLIT_FIRST_CHUNK
+#define ANERF_SPLIT_FIRST_CHUNK 1
+#endif
+constexpr bool kSplitFirstChunk = ANERF_SPLIT_FIRST_CHUNK != 0;   // compile-time knob for tools/ab_variants.py
+constexpr int kAFullCount = 32;                      // arrivals (weighted) that complete an A chunk, see pipe_init_barriers
 
 struct LayerProg {
   int n;            // output features (UMMA N)
@@ -190,15 +195,18 @@ __device__ __forceinline__ void pipe_init(Pipe& pp, uint8_t* a_ring, uint8_t* b_
 }
 // thread 0 of each CTA; followed by a cluster-wide sync
 __device__ __forceinline__ void pipe_init_barriers(const Pipe& pp) {
-  for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], 8); mbar_init(&pp.a_empty[i], 1); }   // the 4 warps of the owning group, in both CTAs
+  // an A chunk is complete after kAFullCount arrivals: normally the 4 warps of the owning group in both CTAs, each
+  // arriving with weight 4; a chunk shared by all four groups (first chunk of a drained operand) gets weight 1 from
+  // each of the 16 worker warps of both CTAs
+  for (int i = 0; i < kAStages; ++i) { mbar_init(&pp.a_full[i], kAFullCount); mbar_init(&pp.a_empty[i], 1); }
   for (int i = 0; i < kBStages; ++i) { mbar_init(&pp.b_full[i], 1); mbar_init(&pp.b_empty[i], 1); mbar_init(&pp.peer_b[i], 1); }
   mbar_init(&pp.d_full[0], 1);
   mbar_init(&pp.d_full[1], 1);
   fence_mbar_init();
 }
-// a chunk of this CTA's A rows is complete: tell the leader's MMA thread
-__device__ __forceinline__ void a_chunk_ready(const Pipe& pp, uint32_t stage) {
-  if (pp.rank == 0) mbar_arrive(&pp.a_full[stage]); else mbar_arrive_remote(&pp.a_full[stage], 0);
+// a warp's share of a chunk of this CTA's A rows is complete: tell the leader's MMA thread
+__device__ __forceinline__ void a_chunk_ready(const Pipe& pp, uint32_t stage, uint32_t weight = 4) {
+  if (pp.rank == 0) mbar_arrive_cnt(&pp.a_full[stage], weight); else mbar_arrive_remote_cnt(&pp.a_full[stage], 0, weight);
 }
 
 __device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
@@ -250,6 +258,13 @@ struct AProducer {
     fence_proxy_async_smem();
     __syncwarp();
     if (elect_one()) a_chunk_ready(pp, cur);
+    __syncwarp();
+  }
+  // same for a chunk that all four groups fill together (each warp contributes a quarter of the owner's weight)
+  __device__ __forceinline__ void end_shared() {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one()) a_chunk_ready(pp, cur, 1);
     __syncwarp();
   }
 };
@@ -521,10 +536,13 @@ __device__ __forceinline__ void build_view_matrices(const RenderKParams& P, int 
 // Wait for the accumulators of the layer that used `region`, then walk this group's column blocks
 // (cb = g, g+4, ...; 32 columns each, 8 at a time).  acc(col0, x[8]) sees scale*acc + bias (ReLU applied
 // when RELU); with EMIT the block also becomes chunk cb of the next layer's operand.
+// `split0` (EMIT only): columns [0, 32) -- chunk 0 of the next operand, the one the tensor core is waiting for right after
+// "layer done" -- are drained by all four groups together, 8 columns each, instead of by group 0 alone: the first MMA
+// of the next layer can start after one TMEM load per warp instead of four in sequence.
 template <int FMT, bool RELU, bool EMIT, typename F>
 __device__ __forceinline__ void drain_region(AProducer<FMT>& ap, const Pipe& pp, uint32_t (&d_cnt)[2], int region, int N,
                                              const float* bias, float scale, int quarter, int grp, F&& acc,
-                                             Trace* tr = nullptr) {
+                                             Trace* tr = nullptr, bool split0 = false) {
   if (tr) tr->mark(10);                      // 10: start waiting for the layer's accumulators
   mbar_wait_warp(&pp.d_full[region], d_cnt[region] & 1, pp.st, 500 + region);
   ++d_cnt[region];
@@ -535,9 +553,34 @@ __device__ __forceinline__ void drain_region(AProducer<FMT>& ap, const Pipe& pp,
   // All 16 warps start loading at once (TMEM reads run at ~64 B/cycle per SM; letting the groups start in turn,
   // so that group 0's chunk comes out sooner, measured 1 % slower overall: tools/ab_variants.py, r1 notes).
   uint32_t v[8];
-  if (grp < nblk) tmem_ld8(taddr + grp * 32, v);
+  int cb0 = grp;
+  if (EMIT && split0) {
+    tmem_ld8(taddr + grp * 8, v);
+    ap.begin(0);
+    tmem_ld_wait();
+    float a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = __uint_as_float(v[i]);
+    cb0 = grp == 0 ? kGroups : grp;            // group 0's block 0 is the shared one
+    if (cb0 < nblk) tmem_ld8(taddr + cb0 * 32, v);
+    const int col0 = grp * 8;
+    const float4 b0 = *reinterpret_cast<const float4*>(bias + col0), b1 = *reinterpret_cast<const float4*>(bias + col0 + 4);
+    float x[8];
+    x[0] = fmaf(a[0], scale, b0.x); x[1] = fmaf(a[1], scale, b0.y); x[2] = fmaf(a[2], scale, b0.z); x[3] = fmaf(a[3], scale, b0.w);
+    x[4] = fmaf(a[4], scale, b1.x); x[5] = fmaf(a[5], scale, b1.y); x[6] = fmaf(a[6], scale, b1.z); x[7] = fmaf(a[7], scale, b1.w);
+    if (RELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = fmaxf(x[i], 0.f);
+    }
+    acc(col0, x);
+    ap.store8(grp, x);
+    ap.end_shared();
+    if (tr) tr->mark(12);
+  } else if (grp < nblk) {
+    tmem_ld8(taddr + grp * 32, v);
+  }
 #pragma unroll 1
-  for (int cb = grp; cb < nblk; cb += kGroups) {
+  for (int cb = cb0; cb < nblk; cb += kGroups) {
     if (EMIT) ap.begin(cb);
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
@@ -597,7 +640,7 @@ __device__ __forceinline__ float4 worker_net_pass(AProducer<FMT>& ap, const Pipe
     }
     if (l > 0)
       drain_region<FMT, true, true>(ap, pp, d_cnt, (l - 1) & 1, W, sm + pg.sm.bias[l - 1], sm[l - 1], quarter, grp,
-                                    [](int, const float (&)[8]) {}, tr);
+                                    [](int, const float (&)[8]) {}, tr, /*split0=*/kSplitFirstChunk && (l - 1) != pg.dims.skip);
   }
   // h of the last trunk layer: alpha_linear in fp32 on the way; operand of feature_linear unless DENSITY
   auto alpha_acc = [&](int col0, const float (&x)[8]) {

@@ -45,7 +45,8 @@ def write_case(d, c, scene, sd0, sd1, cfg, draws, cot, taps, need_pose=True):
         if s < c["D"] - 1:
             skip = s
     meta = dict(J=cfg.n_joints, D=cfg.D, W=cfg.W, skip=skip, fc_ch=cfg.framecode_ch, n_fc=c.get("n_framecodes", 0), N=N,
-                Sc=cfg.N_samples, Si=cfg.N_importance, lindisp=0, softplus=0, B=cfg.density_scale, shift=0., tau_p=cfg.tau,
+                Sc=cfg.N_samples, Si=cfg.N_importance, lindisp=int(cfg.lindisp), softplus=int(cfg.density_type == 'softplus'),
+                B=cfg.density_scale, shift=cfg.softplus_shift, tau_p=cfg.tau,
                 tau_v=cfg.tau_views, cut=cfg.cutoff_dist, need_pose=int(need_pose))
     with open(os.path.join(d, "meta.txt"), "w") as f:
         for k, v in meta.items():
@@ -103,3 +104,25 @@ def test_emulated_backward_matches_oracle_autograd(harness, name):
     for k in g_orc:
         dg = {f: gold[f"g|{k}|{f}"] for f in ("sum", "norm", "amax", "idx", "val")}
         assert gt.digest_err(g[k], dg) < 3e-4, k
+
+
+def test_emulated_backward_softplus_density_scale_lindisp(harness):
+    """Options of the path that the fixtures do not exercise: softplus density with a shift, density_scale != 1,
+    sampling linear in disparity, a different cutoff sharpness for the view branch -- against the oracle's autograd."""
+    c, _ = load_golden("grad_j24_s16_i8_fc_perturb")
+    scene, sd0, sd1, cfg, draws = build_case(c)
+    cfg.density_type, cfg.softplus_shift, cfg.density_scale, cfg.lindisp, cfg.tau_views = 'softplus', 0.5, 2.0, True, 35.0
+    # tau 25 rather than the fixture's 20: with lindisp at tau = 20 one pre-activation of the fine network's layer 2 lies
+    # within fp32 rounding of zero and its ReLU derivative differs between two correct fp32 evaluations (1.5e-2 on that
+    # layer's gradient; 2e-6 at tau 21 / 25 / 30)
+    cfg.tau = 25.0
+    N = scene["rays_o"].shape[0]
+    cot = gt.cotangents(N, cfg.N_samples, cfg.N_importance, seed=4)
+    _, g_orc, taps = gt.oracle_grads(scene, sd0, sd1, cfg, draws, cot)
+    with tempfile.TemporaryDirectory(prefix="anerf_train_case_") as d:
+        write_case(d, c, scene, sd0, sd1, cfg, draws, cot, taps)
+        r = subprocess.run([harness, d], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr
+        g = read_grads(d, sd0, sd1, scene)
+    bad = {k: gt.rel_err(g[k], g_orc[k]) for k in g_orc if not (gt.rel_err(g[k], g_orc[k]) < 3e-4)}
+    assert not bad, bad
