@@ -15,7 +15,7 @@ _lib = None
 SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "anerf_pack_net",
            "anerf_render_workspace_bytes", "anerf_render_fwd", "anerf_render_fwd_host", "anerf_density_points",
            "anerf_selftest_gemm", "anerf_last_error", "anerf_version", "anerf_debug_set_trace",
-           "anerf_render_bwd", "anerf_render_bwd_workspace_bytes", "anerf_selftest_tc_gemm"]
+           "anerf_render_bwd", "anerf_render_bwd_workspace_bytes", "anerf_selftest_tc_gemm", "anerf_render_frame"]
 
 
 class NetConfig(C.Structure):
@@ -49,6 +49,13 @@ class RenderInputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("rays", "skts", "cyls", "cams", "t_rand", "u_rand", "noise0", "noise1")]
 
 
+class FrameInputs(C.Structure):
+    _fields_ = [("c2w", C.c_float * 12), ("focal_x", C.c_float), ("focal_y", C.c_float), ("center_x", C.c_float),
+                ("center_y", C.c_float), ("near", C.c_float), ("far", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
+                ("pixel0", C.c_int32), ("pixels", C.c_void_p), ("skts", C.c_void_p), ("cyl", C.c_void_p), ("cam", C.c_float),
+                ("reserved", C.c_int32)]
+
+
 class RenderOutputs(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0", "alpha0",
                                           "z_all", "raw")]
@@ -78,6 +85,8 @@ def load():
     lib.anerf_pack_net.argtypes = [C.c_void_p, C.POINTER(NetParams), C.c_void_p, C.c_void_p]
     lib.anerf_render_fwd.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.POINTER(RenderInputs),
                                      C.POINTER(RenderOutputs), C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.anerf_render_frame.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.POINTER(FrameInputs),
+                                       C.POINTER(RenderOutputs), C.c_void_p, C.c_size_t, C.c_void_p]
     lib.anerf_render_fwd_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RenderOpts),
                                           C.POINTER(RenderInputs), C.POINTER(RenderOutputs), C.c_void_p]
     lib.anerf_density_points.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_void_p,
@@ -202,6 +211,40 @@ def render_fwd(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, cams=No
     if keep_nearfar:        # the repaired near/far of every ray [N,2]: what the backward pass resamples from
         out['nearfar'] = ws.view(torch.float32)[:2 * N].view(N, 2)
     return out
+
+
+def render_frame(plan, packed_coarse, packed_fine, opts, c2w, focal, center, H, W, skts, cyl, pixel0=0, pixels=None, cam=0.,
+                 near=0., far=1., out=None, ray0=0):
+    """A chunk of one frame with rays generated in the kernels (C ABI anerf_render_frame).  c2w: 12 floats (rows 0..2 of
+    the camera-to-world matrix); skts [J,4,4], cyl [5]: fp32 CUDA tensors; pixels: optional int32 CUDA tensor [n_rays].
+    `out`: dict of preallocated full-frame output tensors to write rows [ray0, ray0 + n_rays) of; else fresh tensors."""
+    N, Sc, Si = opts.n_rays, opts.n_samples, opts.n_importance
+    dev = skts.device
+    Sf = Sc + Si
+    if out is None:
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        out = dict(rgb_map=f(N, 3), disp_map=f(N), acc_map=f(N), alpha=f(N, Sf if Si > 0 else Sc))
+        if Si > 0:
+            out.update(rgb0=f(N, 3), disp0=f(N), acc0=f(N), alpha0=f(N, Sc))
+        views = out
+    else:
+        views = {k: v[ray0:ray0 + N] for k, v in out.items()}
+    assert skts.is_cuda and skts.dtype == torch.float32 and skts.is_contiguous() and cyl.is_cuda and cyl.is_contiguous()
+    assert pixels is None or (pixels.is_cuda and pixels.dtype == torch.int32 and pixels.is_contiguous())
+    fr = FrameInputs()
+    for i, v in enumerate(c2w):
+        fr.c2w[i] = float(v)
+    fr.focal_x, fr.focal_y = (float(focal), float(focal)) if not hasattr(focal, '__len__') else (float(focal[0]), float(focal[1]))
+    fr.center_x, fr.center_y = (W * 0.5, H * 0.5) if center is None else (float(center[0]), float(center[1]))
+    fr.near, fr.far, fr.width, fr.height, fr.pixel0 = near, far, W, H, pixel0
+    fr.pixels, fr.skts, fr.cyl, fr.cam = _ptr(pixels), _ptr(skts), _ptr(cyl), float(cam)
+    ws_bytes = load().anerf_render_workspace_bytes(N)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    rout = RenderOutputs(*[_ptr(views.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0",
+                                                        "alpha0", "z_all", "raw")])
+    check(load().anerf_render_frame(plan.handle, _ptr(packed_coarse), _ptr(packed_fine), C.byref(opts), C.byref(fr),
+                                    C.byref(rout), _ptr(ws), ws_bytes, _stream()))
+    return views
 
 
 def render_fwd_host(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, cams=None, out=None):

@@ -248,23 +248,21 @@ static void fill_common(const anerf_plan* plan, const anerf_render_opts* o, Rend
   for (int j = 0; j < kMaxJoints; ++j) { P.cut_p[j] = o->cutoff_pts[j]; P.cut_v[j] = o->cutoff_views[j]; }
 }
 
-int anerf_render_fwd(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
-                     const anerf_render_opts* o, const anerf_render_inputs* in, const anerf_render_outputs* out,
-                     void* workspace, size_t workspace_bytes, void* stream_) {
-  if (!plan || !packed_coarse || !o || !in || !out) return fail(ANERF_ERR_INVALID, "null argument");
-  cudaStream_t stream = (cudaStream_t)stream_;
+// shared by anerf_render_fwd (explicit per-ray inputs) and anerf_render_frame (rays generated per pixel, one pose)
+static int render_common(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine, const anerf_render_opts* o,
+                         const float* rays, const RayGen& gen, const float* skts, long long skt_stride, const float* cyls,
+                         int cyl_stride, const float* cams, float cam_const, const anerf_render_inputs* draws,
+                         const anerf_render_outputs* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
   const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance;
   if (N == 0) return ANERF_OK;
   if (N < 0 || Sc < 4 || Si < 0) return fail(ANERF_ERR_INVALID, "bad sizes n_rays=%d n_samples=%d n_importance=%d", N, Sc, Si);
   if (Sc + Si > 512) return fail(ANERF_ERR_INVALID, "n_samples + n_importance must be <= 512");
   if (Si > 0 && !packed_fine) return fail(ANERF_ERR_INVALID, "packed_fine missing");
-  if (!in->rays || !in->skts || !in->cyls) return fail(ANERF_ERR_INVALID, "rays/skts/cyls missing");
-  if (plan->dims.fc_ch > 0 && !in->cams && !o->eval_mean_framecode) return fail(ANERF_ERR_INVALID, "cams missing (framecodes enabled)");
   if (!out->rgb_map || !out->disp_map || !out->acc_map) return fail(ANERF_ERR_INVALID, "rgb/disp/acc outputs missing");
   if (!workspace || workspace_bytes < anerf_render_workspace_bytes(N)) return fail(ANERF_ERR_INVALID, "workspace too small");
   if (!(o->density_scale != 0.f)) return fail(ANERF_ERR_INVALID, "density_scale must be non-zero");
 
-  anerf_nearfar_kernel<<<1, 1024, 0, stream>>>(in->rays, in->cyls, N, (float*)workspace);
+  anerf_nearfar_kernel<<<1, 1024, 0, stream>>>(rays, gen, cyls, cyl_stride, N, (float*)workspace);
   CUDA_TRY(cudaGetLastError());
 
   RenderKParams P{};
@@ -282,13 +280,43 @@ int anerf_render_fwd(const anerf_plan* plan, const void* packed_coarse, const vo
   P.tilesC = ceil_div(R * Sc, kTileM);
   P.tilesF = Si > 0 ? ceil_div(R * (Sc + Si), kTileM) : 0;
   P.n_items = ceil_div(N, R);
-  P.rays = in->rays; P.skts = in->skts; P.cams = in->cams;
-  P.t_rand = in->t_rand; P.u_rand = in->u_rand; P.noise0 = in->noise0; P.noise1 = in->noise1;
+  P.rays = rays; P.gen = gen; P.skts = skts; P.skt_stride = skt_stride; P.cams = cams; P.cam_const = cam_const;
+  if (draws) { P.t_rand = draws->t_rand; P.u_rand = draws->u_rand; P.noise0 = draws->noise0; P.noise1 = draws->noise1; }
   P.nearfar = (const float*)workspace;
   P.rgb_map = out->rgb_map; P.disp_map = out->disp_map; P.acc_map = out->acc_map; P.alpha = out->alpha;
   P.rgb0 = out->rgb0; P.disp0 = out->disp0; P.acc0 = out->acc0; P.alpha0 = out->alpha0;
   P.z_all_out = out->z_all; P.raw_out = out->raw;
   return launch_fused(plan, P, false, stream);
+}
+
+int anerf_render_fwd(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
+                     const anerf_render_opts* o, const anerf_render_inputs* in, const anerf_render_outputs* out,
+                     void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!plan || !packed_coarse || !o || !in || !out) return fail(ANERF_ERR_INVALID, "null argument");
+  if (o->n_rays == 0) return ANERF_OK;
+  if (!in->rays || !in->skts || !in->cyls) return fail(ANERF_ERR_INVALID, "rays/skts/cyls missing");
+  if (plan->dims.fc_ch > 0 && !in->cams && !o->eval_mean_framecode) return fail(ANERF_ERR_INVALID, "cams missing (framecodes enabled)");
+  return render_common(plan, packed_coarse, packed_fine, o, in->rays, RayGen{}, in->skts, (long long)plan->dims.J * 16, in->cyls, 5,
+                       in->cams, 0.f, in, out, workspace, workspace_bytes, (cudaStream_t)stream_);
+}
+
+int anerf_render_frame(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
+                       const anerf_render_opts* o, const anerf_frame_inputs* fr, const anerf_render_outputs* out,
+                       void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!plan || !packed_coarse || !o || !fr || !out) return fail(ANERF_ERR_INVALID, "null argument");
+  if (o->n_rays == 0) return ANERF_OK;
+  if (!fr->skts || !fr->cyl) return fail(ANERF_ERR_INVALID, "skts/cyl missing");
+  if (fr->width <= 0 || fr->height <= 0 || !(fr->focal_x != 0.f) || !(fr->focal_y != 0.f))
+    return fail(ANERF_ERR_INVALID, "bad camera (width=%d height=%d)", fr->width, fr->height);
+  if (!fr->pixels && (fr->pixel0 < 0 || (long long)fr->pixel0 + o->n_rays > (long long)fr->width * fr->height))
+    return fail(ANERF_ERR_INVALID, "pixel range [%d, %d) outside the %d x %d image", fr->pixel0, fr->pixel0 + o->n_rays, fr->width, fr->height);
+  RayGen g{};
+  for (int i = 0; i < 12; ++i) g.c2w[i] = fr->c2w[i];
+  g.fx = fr->focal_x; g.fy = fr->focal_y; g.cx = fr->center_x; g.cy = fr->center_y;
+  g.near = fr->near; g.far = fr->far;
+  g.W = fr->width; g.pixel0 = fr->pixel0; g.pixels = fr->pixels;
+  return render_common(plan, packed_coarse, packed_fine, o, nullptr, g, fr->skts, 0, fr->cyl, 0, nullptr, fr->cam, nullptr, out,
+                       workspace, workspace_bytes, (cudaStream_t)stream_);
 }
 
 int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf_render_opts* o, const float* pts,

@@ -121,6 +121,35 @@ ANERF_HD float linspace01(int i, int n) {
   return i < n / 2 ? step * (float)i : 1.0f - step * (float)(n - 1 - i);
 }
 
+// get_rays (ray_utils.py:6-28) for one pixel: dirs = [(i - cx) / fx, -(j - cy) / fy, -1], d = c2w[:3,:3] dirs,
+// o = c2w[:3,3].  c2w = rows 0..2 of the camera-to-world matrix, row-major [3][4]; pix = j * W + i.
+struct RayGen {
+  float c2w[12];
+  float fx, fy, cx, cy;
+  float near, far;
+  int W;
+  int pixel0;            // pixel of ray 0 when `pixels` is NULL
+  const int* pixels;     // optional list of flat pixel indices, one per ray
+};
+ANERF_HD void pixel_ray(const RayGen& g, int ray, float r[8]) {
+  const int pix = g.pixels ? g.pixels[ray] : g.pixel0 + ray;
+  const float i = (float)(pix % g.W), j = (float)(pix / g.W);
+  const float dx = (i - g.cx) / g.fx, dy = -(j - g.cy) / g.fy, dz = -1.0f;
+#if defined(__CUDA_ARCH__)       // products and sums rounded separately, as the reference's elementwise torch code does
+#pragma unroll
+  for (int a = 0; a < 3; ++a)
+    r[3 + a] = __fadd_rn(__fadd_rn(__fmul_rn(dx, g.c2w[4 * a]), __fmul_rn(dy, g.c2w[4 * a + 1])), __fmul_rn(dz, g.c2w[4 * a + 2]));
+#else
+  for (int a = 0; a < 3; ++a) {
+    volatile float p0 = dx * g.c2w[4 * a], p1 = dy * g.c2w[4 * a + 1], p2 = dz * g.c2w[4 * a + 2];
+    volatile float s01 = p0 + p1;
+    r[3 + a] = s01 + p2;
+  }
+#endif
+  r[0] = g.c2w[3]; r[1] = g.c2w[7]; r[2] = g.c2w[11];
+  r[6] = g.near; r[7] = g.far;
+}
+
 // a3 (ray_utils.py:204-251): coarse depth `sidx` of a ray; `t_rand_row` (the ray's Sc draws) switches the
 // stratified jitter on.  Same arithmetic as the fused kernel's stage (2).
 ANERF_HD float coarse_depth(float near, float far, int sidx, int Sc, int lindisp, const float* t_rand_row) {

@@ -151,6 +151,10 @@ struct RenderKParams {
   float B, shift, tau_p, tau_v;
   float cut_p[kMaxJoints], cut_v[kMaxJoints];
   const float *rays, *skts, *cams, *t_rand, *u_rand, *noise0, *noise1;
+  // frame mode (anerf_render_frame): rays == NULL, generated per pixel from `gen`; ONE pose / camera index for all rays
+  RayGen gen;
+  long long skt_stride;     // floats between the poses of consecutive rays: J*16, or 0 in frame mode
+  float cam_const;          // frame mode: the frame's camera index (framecodes)
   const float* nearfar;     // [N,2] from the near/far pre-kernel
   float *rgb_map, *disp_map, *acc_map, *alpha, *rgb0, *disp0, *acc0, *alpha0, *z_all_out, *raw_out;
   // density-only mode (mesh grid): one pose, explicit points
@@ -928,7 +932,9 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         if (t0 == 0) gctr_s[1] = 0;        // counter of the fine network's build (mid-item, many barriers away)
         for (int i = t0; i < R; i += nt) {
           int gr = min(ray0 + i, P.n_rays - 1);
-          const float* rp = P.rays + (size_t)gr * 8;
+          float rbuf[8];
+          const float* rp = rbuf;
+          if (P.rays) rp = P.rays + (size_t)gr * 8; else pixel_ray(P.gen, gr, rbuf);
           float* d = ray_s + i * 12;
           d[0] = rp[0]; d[1] = rp[1]; d[2] = rp[2]; d[3] = rp[3]; d[4] = rp[4]; d[5] = rp[5];
           d[6] = P.nearfar[gr * 2]; d[7] = P.nearfar[gr * 2 + 1];
@@ -937,11 +943,11 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         for (int i = t0; i < R * J * 12; i += nt) {
           int r = i / (J * 12), e = i % (J * 12);
           int gr = min(ray0 + r, P.n_rays - 1);
-          skt_s[i] = P.skts[(size_t)gr * J * 16 + (e / 12) * 16 + (e % 12)];
+          skt_s[i] = P.skts[(size_t)gr * P.skt_stride + (e / 12) * 16 + (e % 12)];
         }
         if (pg.dims.fc_ch > 0)
           for (int i = t0; i < 2 * R; i += nt) {
-            int cam = P.eval_mean_fc ? pg.dims.n_fc : (int)P.cams[slot_ray(i)];
+            int cam = P.eval_mean_fc ? pg.dims.n_fc : (int)(P.cams ? P.cams[slot_ray(i)] : P.cam_const);
             fcrow_s[i] = min(max(cam, 0), pg.dims.n_fc);
           }
         const int vstride = view_tab_jstride(R);
@@ -949,7 +955,10 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
           const int slot = u / J, j = u % J;
           const int gr = slot_ray(slot);
           float f[kViewPerJoint];
-          encode_joint_viewdir(P.skts + ((size_t)gr * J + j) * 16, P.rays + (size_t)gr * 8 + 3, f);
+          float rbuf[8];
+          const float* rd = rbuf + 3;
+          if (P.rays) rd = P.rays + (size_t)gr * 8 + 3; else pixel_ray(P.gen, gr, rbuf);
+          encode_joint_viewdir(P.skts + (size_t)gr * P.skt_stride + (size_t)j * 16, rd, f);
 #pragma unroll
           for (int q = 0; q < kViewPerJoint; ++q) vtab_s[j * vstride + slot * kViewPad + q] = f[q];
           vtab_s[j * vstride + slot * kViewPad + kViewPerJoint] = 0.f;
@@ -1113,8 +1122,9 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
 // a2 pre-kernel: near/far of every ray of the chunk + the chunk-wide nanmean repair
 // (ray_utils.py:292-344).  One CTA; the reduction is what makes the result chunk-dependent.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1) anerf_nearfar_kernel(const float* __restrict__ rays,
-                                                                const float* __restrict__ cyls, int n,
+// rays == NULL: frame mode, rays generated per pixel from `gen`; cyl_stride = 5 (per-ray cylinders) or 0 (one per frame)
+__global__ void __launch_bounds__(1024, 1) anerf_nearfar_kernel(const float* __restrict__ rays, const RayGen gen,
+                                                                const float* __restrict__ cyls, int cyl_stride, int n,
                                                                 float* __restrict__ nearfar) {
   __shared__ double s_sum[2][32];
   __shared__ int s_cnt[2][32];
@@ -1124,10 +1134,12 @@ __global__ void __launch_bounds__(1024, 1) anerf_nearfar_kernel(const float* __r
   double sn = 0.0, sf = 0.0;
   int cn = 0, cf = 0;
   for (int i = tid; i < n; i += blockDim.x) {
-    const float* r = rays + (size_t)i * 8;
+    float rbuf[8];
+    const float* r = rbuf;
+    if (rays) r = rays + (size_t)i * 8; else pixel_ray(gen, i, rbuf);
     float nn, ff;
     bool miss;
-    near_far_cylinder(r, r + 3, cyls + (size_t)i * 5, r[6], r[7], nn, ff, miss);
+    near_far_cylinder(r, r + 3, cyls + (size_t)i * cyl_stride, r[6], r[7], nn, ff, miss);
     nearfar[2 * i] = nn;
     nearfar[2 * i + 1] = ff;
     if (nn == nn) { sn += nn; ++cn; }
@@ -1153,10 +1165,12 @@ __global__ void __launch_bounds__(1024, 1) anerf_nearfar_kernel(const float* __r
   if (!s_any) return;
   const float mn = s_mean[0], mf = s_mean[1];
   for (int i = tid; i < n; i += blockDim.x) {
-    const float* r = rays + (size_t)i * 8;
+    float rbuf[8];
+    const float* r = rbuf;
+    if (rays) r = rays + (size_t)i * 8; else pixel_ray(gen, i, rbuf);
     float nn, ff;
     bool miss;
-    near_far_cylinder(r, r + 3, cyls + (size_t)i * 5, r[6], r[7], nn, ff, miss);
+    near_far_cylinder(r, r + 3, cyls + (size_t)i * cyl_stride, r[6], r[7], nn, ff, miss);
     if (miss) {     // rows where Q is NaN get the chunk mean (or the original bound if no ray hit)
       nearfar[2 * i] = (mn == mn) ? mn : r[6];
       nearfar[2 * i + 1] = (mf == mf) ? mf : r[7];

@@ -330,6 +330,51 @@ class RayCaster(nn.Module):
         return out
 
     @torch.no_grad()
+    def render_frame(self, H, W, focal, c2w, skts, cyls, cams=None, pixel_idx=None, chunk=4096, N_samples=64, N_importance=0,
+                     lindisp=False, preproc_kwargs={}, center=None, near=0., far=1., out=None, **unused):
+        """One frame (or the pixels `pixel_idx` of it) of a posed camera, rays generated inside the kernels and the
+        pose read once per frame: the same pixels as the reference's
+            render(H, W, focal, rays=get_rays(H, W, focal, c2w)[pixel_idx], skts=skts.expand(n, ...), cyls=..., chunk=chunk)
+        (core/utils/ray_utils.py:6-28, run_nerf.py:77-98, core/trainer.py:64-143), chunk by chunk -- the near/far repair of
+        rays that miss the cylinder stays a chunk-wide mean -- without materialising rays or per-ray poses.
+        c2w [3,4] or [4,4]; skts [J,4,4] or [1,J,4,4]; cyls [5] or [1,5]; pixel_idx: optional int tensor of flat pixel
+        indices (e.g. from kp_to_valid_rays).  Returns the output dict for those pixels ([n, ...] tensors)."""
+        dev = skts.device
+        if dev.type != 'cuda':
+            raise RuntimeError("anerf_b200.RayCaster: inputs must be CUDA tensors (no CPU path)")
+        J = self._n_joints()
+        skts_c = skts.float().reshape(-1, J, 4, 4)[0].contiguous()
+        cyl_c = cyls.float().reshape(-1, cyls.shape[-1])[0, :5].contiguous()
+        c2w_l = [float(x) for x in torch.as_tensor(c2w, dtype=torch.float32).cpu()[:3, :4].reshape(-1)]
+        pix = None if pixel_idx is None else torch.as_tensor(pixel_idx, device=dev).to(torch.int32).contiguous()
+        n = H * W if pix is None else int(pix.shape[0])
+        Sc, Si = int(N_samples), int(N_importance)
+        use_fc = self.network.use_framecode
+        cam, eval_mean = 0., False
+        if use_fc:
+            if cams is None:
+                raise RuntimeError("opt_framecode networks need `cams`")
+            cam = float(torch.as_tensor(cams).reshape(-1)[0])
+            eval_mean = (not self.training) and cam < 0
+        density_scale = preproc_kwargs.get('density_scale', 1.0)
+        density_fn = preproc_kwargs.get('density_fn', None)
+        p0 = self._packed_image('network')
+        p1 = self._packed_image('network_fine') if Si > 0 else None
+        if out is None:
+            f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+            out = dict(rgb_map=f(n, 3), disp_map=f(n), acc_map=f(n), alpha=f(n, Sc + Si if Si > 0 else Sc))
+            if Si > 0:
+                out.update(rgb0=f(n, 3), disp0=f(n), acc0=f(n), alpha0=f(n, Sc))
+        with torch.cuda.device(dev):
+            for i in range(0, n, chunk):
+                m = min(chunk, n - i)
+                opts = self._opts(m, Sc, Si, lindisp, density_scale, density_fn, eval_mean)
+                _lib.render_frame(self._get_plan(), p0, p1, opts, c2w_l, focal, center, H, W, skts_c, cyl_c,
+                                  pixel0=i if pix is None else 0, pixels=None if pix is None else pix[i:i + m], cam=cam,
+                                  near=near, far=far, out=out, ray0=i)
+        return out
+
+    @torch.no_grad()
     def render_mesh_density(self, kps, skts, bones, subject_idxs=None, radius=1.0, res=64, render_kwargs=None,
                             netchunk=1024 * 64, v=None):
         """[res+1]^3 raw densities around kps[0,0] (reference: core/raycasters.py:579-595)."""

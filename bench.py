@@ -98,7 +98,7 @@ def frame_inputs(frame_idx, n_frames_total=8):
     sc = synthetic.make_scene(seed=0, n_rays=None, H=H, W=W, focal=FOCAL, n_joints=N_JOINTS, cam_angle=ang)
     N = sc["rays_o"].shape[0]
     rays = np.concatenate([sc["rays_o"], sc["rays_d"], np.zeros((N, 1), np.float32), np.ones((N, 1), np.float32)], 1)
-    return dict(rays=rays, skts=sc["skts"], cyls=sc["cyls"], kps=sc["kps"], bones=sc["bones"])
+    return dict(rays=rays, skts=sc["skts"], cyls=sc["cyls"], kps=sc["kps"], bones=sc["bones"], c2w=sc["c2w"], pose=sc["pose"])
 
 
 def pick_cpu_threads(fn):
@@ -290,7 +290,7 @@ def main():
     # two frames per rank, alternated, resident in HBM (402 MB of per-ray skts each: larger than the 126 MB L2)
     my_frames = [rank * 2, rank * 2 + 1]
     host = [frame_inputs(f, n_frames_total=2 * world * 4) for f in my_frames]
-    devf = [{k: torch.as_tensor(v).to(dev) for k, v in fr.items()} for fr in host]
+    devf = [{k: torch.as_tensor(v).to(dev) for k, v in fr.items() if k not in ("c2w", "pose")} for fr in host]
     n_rays = H * W
     n_chunks = (n_rays + CHUNK - 1) // CHUNK
 
@@ -392,6 +392,35 @@ def main():
         e2e = {"value": n_rays * n_e2e * world / (dt_ms * 1e-3), "unit": "rays/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "api": "anerf_render_fwd_host (C ABI, pinned host buffers, one call per 4096-ray chunk)"}
 
+    # ---- the frame API (rays generated in the kernels from the camera, pose passed once per frame):
+    # host -> device per frame = camera + one pose (1.6 KB instead of 416 MB), all eight outputs back to pinned host memory
+    e2e_frame = None
+    if e2e is not None:
+        hp = host[0]
+        c2w = np.asarray(hp["c2w"], np.float32)
+        h_skts, h_cyl = torch.as_tensor(hp["pose"]["skts"]).pin_memory(), torch.as_tensor(hp["pose"]["cyl"]).pin_memory()
+        d_out = {k: torch.empty(v.shape, dtype=torch.float32, device=dev) for k, v in h_out.items()}
+
+        def frame_api():
+            o = rc.render_frame(H, W, FOCAL, c2w, h_skts.to(dev, non_blocking=True)[None], h_cyl.to(dev, non_blocking=True)[None],
+                                chunk=CHUNK, N_samples=N_SAMPLES, N_importance=N_IMPORTANCE, preproc_kwargs=kw["preproc_kwargs"], out=d_out)
+            for k, v in h_out.items():
+                v.copy_(o[k], non_blocking=True)
+        frame_api()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            frame_api()
+        torch.cuda.synchronize()
+        dt_ms = parallel.max_over_ranks((time.perf_counter() - t0) * 1e3, dev)
+        ref_px = render_frame(devf[0])
+        e2e_frame = {"value": n_rays * n_e2e * world / (dt_ms * 1e-3), "unit": "rays/s",
+                     "h2d_bytes_per_step": int(12 * 4 + h_skts.numel() * 4 + h_cyl.numel() * 4), "d2h_bytes_per_step": d2h,
+                     "api": "RayCaster.render_frame -> anerf_render_frame (C ABI), camera + one pose in, all outputs to pinned host memory",
+                     "max_abs_diff_vs_explicit_rays": {k: float((h_out[k].to(dev) - ref_px[k]).abs().max()) for k in ("rgb_map", "acc_map")}}
+
     # ---- secondary: one training step per rank (Mixamo-style N_rand 3072, 64 + 16 samples, pose
     # gradient on): fused forward + CUDA backward + the single flat gradient all-reduce + Adam, through the boundary
     training = None
@@ -446,7 +475,8 @@ def main():
                        "parallelism": f"frame-parallel x{world}, gather of [rays,5] pixels to rank 0" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: 402 MB of per-ray skts per frame, two frames alternated"},
             "clocks": clocks, "gpu_launches": 2 * n_chunks * opt.steps, "e2e": e2e, "roofline": roofline,
-            "cpu_baseline": cpu_base, "reference_gpu_port": ref_gpu, "parity": parity, "training": training}
+            "cpu_baseline": cpu_base, "reference_gpu_port": ref_gpu, "parity": parity, "training": training,
+            "e2e_frame_api": e2e_frame}
     print(json.dumps(line), flush=True)
 
 

@@ -17,6 +17,8 @@
  *                                          NeRF.forward + raw2outputs (core/networks/nerf.py:133-205)
  *   anerf_render_fwd_host               <- the same call as core/trainer.py:64-79 batchify_rays makes it,
  *                                          with host buffers (H2D/D2H inside)
+ *   anerf_render_frame                  <- get_rays (core/utils/ray_utils.py:6-28) + the per-ray expansion of the pose in
+ *                                          run_nerf.render_path (run_nerf.py:77-98) + render_rays, per frame
  *   anerf_density_points                <- RayCaster.render_pts_density / render_mesh_density
  *                                          (core/raycasters.py:579-648)
  *   anerf_render_bwd                    <- what loss.backward() does to the graph of render_rays in training
@@ -136,6 +138,29 @@ size_t anerf_render_workspace_bytes(int32_t n_rays);
 int anerf_render_fwd(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
                      const anerf_render_opts* opts, const anerf_render_inputs* in,
                      const anerf_render_outputs* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* One frame's camera and pose for anerf_render_frame: what run_nerf.render_path hands to render() per frame
+ * (run_nerf.py:77-98) before get_rays (core/utils/ray_utils.py:6-28) and the per-ray replication of the pose
+ * (run_nerf.py:84-90) -- here the rays are generated inside the kernels and the pose is read once. */
+typedef struct {
+  float c2w[12];           /* rows 0..2 of the camera-to-world matrix, row-major [3][4] */
+  float focal_x, focal_y;
+  float center_x, center_y;/* principal point; get_rays' default is (W/2, H/2) */
+  float near, far;         /* ray bounds before the cylinder intersection (the reference passes 0 and 1) */
+  int32_t width, height;
+  int32_t pixel0;          /* ray r of the call is pixel pixel0 + r (row-major j*W + i) when `pixels` is NULL */
+  const int32_t* pixels;   /* device, optional: [n_rays] flat pixel indices (e.g. the pixels inside the skeleton's box) */
+  const float* skts;       /* device: [J,4,4], ONE pose for the frame */
+  const float* cyl;        /* device: [5] bounding cylinder of the frame */
+  float cam;               /* the frame's camera index (framecodes); ignored otherwise */
+  int32_t reserved;
+} anerf_frame_inputs;
+
+/* A chunk of n_rays pixels of one frame: like anerf_render_fwd on the rays get_rays would produce for those pixels with
+ * the pose replicated per ray, without materialising either (no random draws: rendering is deterministic). */
+int anerf_render_frame(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
+                       const anerf_render_opts* opts, const anerf_frame_inputs* frame, const anerf_render_outputs* out,
+                       void* workspace, size_t workspace_bytes, void* stream);
 
 /* Same, with HOST buffers for inputs and outputs (pinned or pageable); copies in and out on
  * `stream` around the kernels and synchronises the stream before returning. */

@@ -46,6 +46,13 @@ void h_view_table(const float* skt, const float* dir, int J, float* out /*[J][27
 }
 float h_cutoff_w(const float* skt12, const float* p, float tau, float cut) { return cutoff_w(joint_dist(skt12, p), tau, cut); }
 float h_linspace01(int i, int n) { return linspace01(i, n); }
+// in-kernel ray generation (frame mode): rays of n consecutive pixels starting at pixel0
+void h_pixel_rays(const float* c2w12, float fx, float fy, float cx, float cy, int W, int pixel0, int n, float* out /*[n][8]*/) {
+  RayGen g{};
+  for (int i = 0; i < 12; ++i) g.c2w[i] = c2w12[i];
+  g.fx = fx; g.fy = fy; g.cx = cx; g.cy = cy; g.near = 0.f; g.far = 1.f; g.W = W; g.pixel0 = pixel0; g.pixels = nullptr;
+  for (int r = 0; r < n; ++r) pixel_ray(g, r, out + 8 * r);
+}
 void h_near_far(const float* o, const float* d, const float* cyl, float near, float far, float* out) {
   bool miss;
   near_far_cylinder(o, d, cyl, near, far, out[0], out[1], miss);

@@ -133,3 +133,41 @@ def test_sharded_density_grid_and_ragged_point_counts():
     for n in (1, 127, 129, 1000):
         part = rc.render_pts_density(pts[:n].reshape(-1, 1, 3), kps, skts, None).reshape(-1)
         assert torch.equal(part, full[:n])
+
+
+def test_render_frame_equals_explicit_rays():
+    """anerf_render_frame (rays generated in the kernels, one pose per frame) against the reference-style call with
+    explicit get_rays rays and the pose replicated per ray: identical pixels, including ragged chunks, chunk-wise
+    near/far repair, a pixel subset and framecodes."""
+    H, W, focal = 40, 56, 55.0
+    J = 24
+    pose = synthetic.make_pose(11, J)
+    c2w = synthetic.orbit_c2w(0.4, 3.0, centre=pose['kps'][0] * np.array([1., 0., 1.])).astype(np.float32)
+    _, rk, _, _, _, _ = create_raycaster(make_args(N_importance=16, no_reload=True, opt_framecode=True), data_attrs(J, n_views=3))
+    rc = rk['ray_caster'].eval()
+    wk = dict(framecode_ch=16, n_framecodes=3)
+    rc.network.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(101, **wk).items()})
+    rc.network_fine.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(202, **wk).items()})
+    dev = torch.device("cuda")
+    t = lambda a: torch.as_tensor(a).to(dev)
+    # the reference's get_rays (core/utils/ray_utils.py:6-28)
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing='ij')
+    i, j = i.t(), j.t()
+    dirs = torch.stack([(i - W * 0.5) / focal, -(j - H * 0.5) / focal, -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * torch.as_tensor(c2w[:3, :3]), -1).reshape(-1, 3)
+    rays_o = torch.as_tensor(c2w[:3, 3]).expand(rays_d.shape)
+    n = H * W
+    rays = torch.cat([rays_o, rays_d, torch.zeros(n, 1), torch.ones(n, 1), torch.nn.functional.normalize(rays_d, dim=-1)], 1).to(dev)
+    skts, cyl, kps, bones = t(pose["skts"]), t(pose["cyl"]), t(pose["kps"]), t(pose["bones"])
+    kw = {k: v for k, v in rk.items() if k not in ('ray_caster', 'use_viewdirs')}
+    chunk = 1000                                          # ragged last chunk; several chunks with missing rays
+    for pix in (None, torch.arange(n)[::3][:777]):
+        sel = slice(None) if pix is None else pix.to(dev)
+        m = n if pix is None else len(pix)
+        ref = batchify_rays(rays[sel], chunk, ray_caster=rc, kp_batch=kps.expand(m, J, 3), skts=skts.expand(m, J, 4, 4),
+                            cyls=cyl.expand(m, 5), bones=bones.expand(m, J, 3), cams=torch.full((m,), 2., device=dev),
+                            subject_idxs=None, **kw)
+        out = rc.render_frame(H, W, focal, c2w, skts[None], cyl[None], cams=torch.tensor([2.]), pixel_idx=pix, chunk=chunk, **kw)
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), (k, float((out[k] - ref[k]).abs().max()))
+    assert float(ref['acc_map'].max()) > 0.5 and float(ref['acc_map'].min()) < 0.01

@@ -125,3 +125,21 @@ def test_library_exports_every_declared_symbol():
     for s in declared:
         assert hasattr(lib, s), s
     assert lib.anerf_version() >= 100
+
+
+def test_pixel_rays_match_reference_get_rays(harness):
+    """The kernels' in-place ray generation (anerf_render_frame) against the reference's get_rays
+    (core/utils/ray_utils.py:6-28), restated here with the same torch ops: bit-exact on the CPU."""
+    H, W, focal = 48, 64, 57.5
+    c2w = synthetic.orbit_c2w(0.7, 3.0)[:3, :4].astype(np.float32)
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing='ij')
+    i, j = i.t(), j.t()
+    dirs = torch.stack([(i - W * 0.5) / focal, -(j - H * 0.5) / focal, -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * torch.as_tensor(c2w[:3, :3]), -1).reshape(-1, 3).numpy()
+    n, p0 = 777, 1234
+    out = np.zeros((n, 8), np.float32)
+    harness.h_pixel_rays(fptr(np.ascontiguousarray(c2w.reshape(-1))), C.c_float(focal), C.c_float(focal), C.c_float(W * 0.5),
+                         C.c_float(H * 0.5), W, p0, n, fptr(out))
+    assert np.array_equal(out[:, 3:6], rays_d[p0:p0 + n])
+    assert np.array_equal(out[:, 0:3], np.broadcast_to(c2w[:, 3], (n, 3)))
+    assert np.all(out[:, 6] == 0.) and np.all(out[:, 7] == 1.)
