@@ -171,3 +171,41 @@ def test_render_frame_equals_explicit_rays():
         for k in ref:
             assert torch.equal(out[k], ref[k]), (k, float((out[k] - ref[k]).abs().max()))
     assert float(ref['acc_map'].max()) > 0.5 and float(ref['acc_map'].min()) < 0.01
+
+
+def test_render_path_frame_composites_like_render_path():
+    """frames.render_path_frame (box of the cylinder -> render_frame on those pixels -> composite over the background,
+    run_nerf.py:77-136) against the same steps done with explicit rays through the reference-style call."""
+    from anerf_b200 import frames
+    H, W, focal, J = 96, 128, 110.0, 24
+    pose = synthetic.make_pose(11, J)
+    c2w = synthetic.orbit_c2w(5.1, 2.6, centre=pose['kps'][0] * np.array([1., 0., 1.])).astype(np.float32)
+    _, rk, _, _, _, _ = create_raycaster(make_args(N_importance=16, no_reload=True), data_attrs(J))
+    rc = rk['ray_caster'].eval()
+    rc.network.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(101).items()})
+    rc.network_fine.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(202).items()})
+    dev = torch.device("cuda")
+    t = lambda a: torch.as_tensor(a).to(dev)
+    skts, cyl, kps, bones = t(pose["skts"]), t(pose["cyl"]), t(pose["kps"]), t(pose["bones"])
+    bg = torch.rand(H, W, 3, device=dev)
+    rgb, disp, acc = frames.render_path_frame(rc, c2w, H, W, focal, skts[None], cyl[None], rk, bg=bg, chunk=4096)
+    assert rgb.shape == (H, W, 3) and disp.shape == (H, W, 1) and acc.shape == (H, W, 1)
+    # the same with explicit rays
+    idx, (tl, br) = frames.valid_pixels(pose["cyl"], H, W, focal, c2w, device=dev)
+    assert 0 < len(idx) < H * W
+    i, j = torch.meshgrid(torch.linspace(0, W - 1, W), torch.linspace(0, H - 1, H), indexing='ij')
+    i, j = i.t(), j.t()
+    dirs = torch.stack([(i - W * 0.5) / focal, -(j - H * 0.5) / focal, -torch.ones_like(i)], -1)
+    rays_d = torch.sum(dirs[..., None, :] * torch.as_tensor(c2w[:3, :3]), -1).reshape(-1, 3)[idx.cpu().long()]
+    m = len(idx)
+    rays = torch.cat([torch.as_tensor(c2w[:3, 3]).expand(m, 3), rays_d, torch.zeros(m, 1), torch.ones(m, 1),
+                      torch.nn.functional.normalize(rays_d, dim=-1)], 1).to(dev)
+    kw = {k: v for k, v in rk.items() if k not in ('ray_caster', 'use_viewdirs')}
+    ref = batchify_rays(rays, 4096, ray_caster=rc, kp_batch=kps.expand(m, J, 3), skts=skts.expand(m, J, 4, 4),
+                        cyls=cyl.expand(m, 5), bones=bones.expand(m, J, 3), cams=None, subject_idxs=None, **kw)
+    img = bg.reshape(-1, 3).clone()
+    img[idx.long()] = ref['rgb_map'] + (1. - ref['acc_map'][..., None]) * img[idx.long()]
+    assert torch.equal(rgb.reshape(-1, 3), img)
+    outside = torch.ones(H * W, dtype=torch.bool, device=dev)
+    outside[idx.long()] = False
+    assert torch.equal(rgb.reshape(-1, 3)[outside], bg.reshape(-1, 3)[outside]) and float(acc.reshape(-1)[outside].abs().max()) == 0.

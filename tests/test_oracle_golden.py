@@ -60,3 +60,19 @@ def test_oracle_autograd_matches_reference_gradient_digests(name):
     for k in g:
         dg = {f: gold[f"g|{k}|{f}"] for f in ("sum", "norm", "amax", "idx", "val")}
         assert gt.digest_err(g[k], dg) < 2e-5, k
+
+
+def test_frame_glue_matches_reference_boxes():
+    """anerf_b200.frames.valid_pixels against the reference's cylinder_to_box_2d / kp_to_valid_rays results stored by
+    oracle/make_golden_frames.py (integer boxes and pixel index lists: exact)."""
+    import ast
+    import os
+    from anerf_b200 import frames
+    from tests.common import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "frames_box2d.npz"))
+    cases = ast.literal_eval(str(z["cases"]))
+    for i, c in enumerate(cases):
+        idx, (tl, br) = frames.valid_pixels(z["cyl"], c["H"], c["W"], c["focal"], z[f"{i}|c2w"])
+        assert np.array_equal(tl, z[f"{i}|tl"]) and np.array_equal(br, z[f"{i}|br"]), i
+        assert len(idx) == int(z[f"{i}|n_valid"])
+        assert np.array_equal(idx[:16].numpy(), z[f"{i}|valid_head"]) and np.array_equal(idx[-16:].numpy(), z[f"{i}|valid_tail"])

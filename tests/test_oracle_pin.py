@@ -21,3 +21,12 @@ def test_oracle_matches_live_reference_on_fresh_inputs():
     ours, _ = mg.run_oracle(scene, sd0, sd1, cfg, None)
     for k in ref:
         assert mg.rel_err(ours[k], ref[k]) < (2e-3 if k == "alpha" else 2e-5), k
+
+
+def test_frame_glue_matches_live_reference():
+    from oracle import make_golden_frames as mf
+    from anerf_b200 import frames
+    pose, ref = mf.reference_boxes()
+    for c, r in zip(mf.CASES, ref):
+        idx, (tl, br) = frames.valid_pixels(pose["cyl"], c["H"], c["W"], c["focal"], r["c2w"])
+        assert np.array_equal(tl, r["tl"]) and np.array_equal(br, r["br"]) and len(idx) == r["n_valid"]
