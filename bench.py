@@ -427,6 +427,24 @@ def main():
     if not opt.no_train:
         training = training_probe(dev, rank, world)
 
+    # ---- secondary: 256^3 density grid for mesh extraction (BASELINE.json configs[4]), voxel slabs over the ranks
+    mesh_grid = None
+    if not opt.no_train:
+        from anerf_b200 import mesh
+        pose = host[0]["pose"]
+        kps_m, skts_m = torch.as_tensor(pose["kps"]).to(dev)[None], torch.as_tensor(pose["skts"]).to(dev)[None]
+        for _ in range(2):
+            mesh.density_grid_sharded(rc, kps_m, skts_m, 1.8, 255, rank, world)
+        torch.cuda.synchronize()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record()
+        mesh.density_grid_sharded(rc, kps_m, skts_m, 1.8, 255, rank, world)
+        m1.record()
+        torch.cuda.synchronize()
+        mms = parallel.max_over_ranks(m0.elapsed_time(m1), dev)
+        mesh_grid = {"metric": "voxels/s, 256^3 density grid (24 joints, 8x256 trunk, fine network)", "value": 256 ** 3 / (mms * 1e-3),
+                     "ms": mms, "algorithmic_tflops": 256 ** 3 * 1.3604e6 / (mms * 1e-3) / 1e12}
+
     if rank != 0:
         return
     cpu_base, parity = None, None
@@ -476,7 +494,7 @@ def main():
                        "l2": "inputs larger than L2: 402 MB of per-ray skts per frame, two frames alternated"},
             "clocks": clocks, "gpu_launches": 2 * n_chunks * opt.steps, "e2e": e2e, "roofline": roofline,
             "cpu_baseline": cpu_base, "reference_gpu_port": ref_gpu, "parity": parity, "training": training,
-            "e2e_frame_api": e2e_frame}
+            "e2e_frame_api": e2e_frame, "mesh_grid": mesh_grid}
     print(json.dumps(line), flush=True)
 
 
