@@ -47,6 +47,11 @@ constexpr int kMaxRaysPerItem = 8;
 #define ANERF_SPLIT_FIRST_CHUNK 1
 #endif
 constexpr bool kSplitFirstChunk = ANERF_SPLIT_FIRST_CHUNK != 0;   // compile-time knob for tools/ab_variants.py
+#ifndef ANERF_SORT_ON_RAY_WARP
+#define ANERF_SORT_ON_RAY_WARP 0
+#endif
+constexpr bool kSortOnRayWarp = ANERF_SORT_ON_RAY_WARP != 0;      // importance sampling + merge by the ray's compositing warp
+                                                                  // (measured 3 % slower than all 512 threads after a barrier: off)
 constexpr int kAFullCount = 32;                      // arrivals (weighted) that complete an A chunk, see pipe_init_barriers
 
 struct LayerProg {
@@ -1029,15 +1034,45 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
                             (live && disp_o) ? disp_o + gr : nullptr, (live && acc_o) ? acc_o + gr : nullptr);
               if (!fine && live && P.raw_out)
                 for (int i = lane; i < Sc; i += 32) reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sc + i] = raw_s[q * Sc + i];
-              if (fine) importance_cdf(lane, Sc, w_s + q * Sc, cdf_s + q * Sc);
+              if (fine) {
+                importance_cdf(lane, Sc, w_s + q * Sc, cdf_s + q * Sc);
+                if (kSortOnRayWarp) {
+                  // ---- (5) importance sampling + sorted merge of this ray by its own warp, while the other warps
+                  // build the fine network's view matrices (part_s is free between the passes: scratch)
+                  __syncwarp();
+                  float* t = reinterpret_cast<float*>(part_s) + q * Sf;
+                  for (int e = lane; e < Sf; e += 32) {
+                    float v;
+                    if (e < Sc) {
+                      v = zc_s[q * Sc + e];
+                    } else {
+                      const int m = e - Sc;
+                      const float u = P.u_rand ? P.u_rand[(size_t)grc * Si + m] : linspace01(m, Si);
+                      v = importance_sample(u, Sc, zc_s + q * Sc, cdf_s + q * Sc);
+                    }
+                    t[e] = v;
+                  }
+                  __syncwarp();
+                  for (int e = lane; e < Sf; e += 32) {        // rank sort (stable) == torch.sort on values
+                    const float x = t[e];
+                    int rk = 0;
+                    for (int k = 0; k < Sf; ++k) {
+                      const float y = t[k];
+                      rk += (y < x || (y == x && k < e)) ? 1 : 0;
+                    }
+                    za_s[q * Sf + rk] = x;
+                  }
+                  __syncwarp();
+                  if (P.z_all_out && live)
+                    for (int e = lane; e < Sf; e += 32) P.z_all_out[(size_t)gr * Sf + e] = za_s[q * Sf + e];
+                }
+              }
             }
-            // the coarse network's MMAs are all done: the ray-slot B chunks are rebuilt for the fine network by
-            // whichever warps are not compositing a ray
             if (tr) tr->mark(52);
             if (fine) build_view_matrices<FMT>(P, 1, g_buf, vtab_s, fcrow_s, gctr_s + 1, rank, 1.0f / sm1[pg.dims.D]);
             if (tr) tr->mark(53);
             worker_sync();   // raw_s is free from here (scratch for the merge below)
-            if (fine) {
+            if (fine && !kSortOnRayWarp) {
               // ---- (5) importance sampling: every worker thread takes samples, then ranks -------------
               float* tmp = reinterpret_cast<float*>(raw_s);
               for (int i = tid; i < R * Sf; i += kWorkerThreads) {
