@@ -42,7 +42,8 @@ class RenderOpts(C.Structure):
     _fields_ = [("n_rays", C.c_int32), ("n_samples", C.c_int32), ("n_importance", C.c_int32), ("lindisp", C.c_int32),
                 ("softplus", C.c_int32), ("eval_mean_framecode", C.c_int32), ("density_scale", C.c_float),
                 ("softplus_shift", C.c_float), ("tau_pts", C.c_float), ("tau_views", C.c_float),
-                ("cutoff_pts", C.c_float * 24), ("cutoff_views", C.c_float * 24)]
+                ("cutoff_pts", C.c_float * 24), ("cutoff_views", C.c_float * 24), ("single_net", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class RenderInputs(C.Structure):
@@ -171,8 +172,9 @@ class Plan:
 
 def make_opts(n_rays, n_samples, n_importance, tau_pts=20., tau_views=20., cutoff_pts=0.5, cutoff_views=0.5,
               n_joints=24, lindisp=False, softplus=False, softplus_shift=0., density_scale=1.,
-              eval_mean_framecode=False):
+              eval_mean_framecode=False, single_net=False):
     o = RenderOpts()
+    o.single_net = int(single_net)
     o.n_rays, o.n_samples, o.n_importance = n_rays, n_samples, n_importance
     o.lindisp, o.softplus, o.eval_mean_framecode = int(lindisp), int(softplus), int(eval_mean_framecode)
     o.density_scale, o.softplus_shift, o.tau_pts, o.tau_views = density_scale, softplus_shift, tau_pts, tau_views

@@ -241,6 +241,7 @@ static void fill_common(const anerf_plan* plan, const anerf_render_opts* o, Rend
   P.lindisp = o->lindisp;
   P.softplus = o->softplus;
   P.eval_mean_fc = o->eval_mean_framecode;
+  P.blur_is = o->single_net;
   P.B = o->density_scale;
   P.shift = o->softplus_shift;
   P.tau_p = o->tau_pts;

@@ -152,7 +152,7 @@ struct RenderKParams {
   const uint8_t* packed[2];
   // problem
   int n_rays, Sc, Si, Sf, R, tilesC, tilesF, n_items, slotc;
-  int lindisp, softplus, eval_mean_fc;
+  int lindisp, softplus, eval_mean_fc, blur_is;
   float B, shift, tau_p, tau_v;
   float cut_p[kMaxJoints], cut_v[kMaxJoints];
   const float *rays, *skts, *cams, *t_rand, *u_rand, *noise0, *noise1;
@@ -759,17 +759,22 @@ __device__ __forceinline__ void composite_ray(int lane, int S, const float* z, c
 
 // a13, first part (ray_utils.py:157-166): cdf of the coarse weights of one ray, by one warp.
 // w: shared [Sc]; cdf: shared [Sc] (Sc-1 entries used).  fp64 running sum like torch's CPU cumsum.
-__device__ __forceinline__ void importance_cdf(int lane, int Sc, const float* w, float* cdf) {
+// `blur` (single_net, ray_utils.py:271-277): the pdf is 0.5 (max(w_l, w_k) + max(w_k, w_u)) + 0.01 instead of w_k.
+__device__ __forceinline__ void importance_cdf(int lane, int Sc, const float* w, float* cdf, int blur) {
   const int nw = Sc - 2;
+  auto wt = [&](int i) {
+    const float wk = blur ? 0.5f * (fmaxf(w[i], w[1 + i]) + fmaxf(w[1 + i], w[2 + i])) + 0.01f : w[1 + i];
+    return wk + 1e-5f;
+  };
   double part = 0.0;
-  for (int i = lane; i < nw; i += 32) part += (double)(w[1 + i] + 1e-5f);
+  for (int i = lane; i < nw; i += 32) part += (double)wt(i);
   const float total = (float)warp_sum(part);
   const int per = (nw + 31) / 32;
   const int i0 = lane * per;
   double loc = 0.0;
   for (int k = 0; k < per; ++k) {
     int i = i0 + k;
-    if (i < nw) loc += (double)((w[1 + i] + 1e-5f) / total);
+    if (i < nw) loc += (double)(wt(i) / total);
   }
   double incl = loc;
 #pragma unroll
@@ -781,7 +786,7 @@ __device__ __forceinline__ void importance_cdf(int lane, int Sc, const float* w,
   for (int k = 0; k < per; ++k) {
     int i = i0 + k;
     if (i < nw) {
-      run += (double)((w[1 + i] + 1e-5f) / total);
+      run += (double)(wt(i) / total);
       cdf[i + 1] = (float)run;
     }
   }
@@ -1035,7 +1040,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
               if (!fine && live && P.raw_out)
                 for (int i = lane; i < Sc; i += 32) reinterpret_cast<float4*>(P.raw_out)[(size_t)gr * Sc + i] = raw_s[q * Sc + i];
               if (fine) {
-                importance_cdf(lane, Sc, w_s + q * Sc, cdf_s + q * Sc);
+                importance_cdf(lane, Sc, w_s + q * Sc, cdf_s + q * Sc, P.blur_is);
                 if (kSortOnRayWarp) {
                   // ---- (5) importance sampling + sorted merge of this ray by its own warp, while the other warps
                   // build the fine network's view matrices (part_s is free between the passes: scratch)

@@ -210,6 +210,8 @@ class RayCaster(nn.Module):
     def _packed_image(self, which):
         """Packed tensor-core image of a network, re-packed whenever a parameter changed in place
         (optimizer step, load_state_dict) -- tracked through the tensors' version counters."""
+        if which == 'network_fine' and self.network_fine is self.network:      # --single_net: one image serves both passes
+            which = 'network'
         net = self.network if which == 'network' else self.network_fine
         params = list(net.parameters())
         sig = tuple((p.data_ptr(), p._version) for p in params)
@@ -240,7 +242,8 @@ class RayCaster(nn.Module):
         return _lib.make_opts(n_rays, n_samples, n_importance, tau_pts=tau_p,
                               tau_views=tau_v, cutoff_pts=cp, cutoff_views=cv,
                               lindisp=bool(lindisp), softplus=softplus, softplus_shift=shift,
-                              density_scale=float(density_scale), eval_mean_framecode=eval_mean)
+                              density_scale=float(density_scale), eval_mean_framecode=eval_mean,
+                              single_net=self.single_net)
 
     # ---- reference API -------------------------------------------------------------------------
     @torch.no_grad()
@@ -268,8 +271,6 @@ class RayCaster(nn.Module):
             raise NotImplementedError("anerf_b200 needs skts and cyls (the reference's skts=None path is unused)")
         if ray_noise_std > 0.:
             raise NotImplementedError("ray_noise_std > 0 is not supported")
-        if self.single_net and N_importance > 0:
-            raise NotImplementedError("single_net is not supported")
         if subject_idxs is not None:
             raise NotImplementedError("subject_idxs is not supported by the default encoders")
         dev = ray_batch.device
@@ -508,7 +509,6 @@ def create_raycaster(args, data_attrs, device=None):
     unsupported(g('multires', 7) != MULTIRES or g('multires_views', 4) != MULTIRES_VIEWS or g('multires_bones', 0) != 0,
                 "multires/multires_views/multires_bones other than 7/4/0")
     unsupported(g('i_embed', 0) != 0, "i_embed != 0")
-    unsupported(g('single_net', False), "single_net")
     unsupported(g('nerf_type', 'nerf') != 'nerf', f"nerf_type={g('nerf_type', None)}")
     if args.density_type not in ('relu', 'softplus'):
         raise NotImplementedError(f'density activation {args.density_type} is undefined')
@@ -529,9 +529,12 @@ def create_raycaster(args, data_attrs, device=None):
                        use_framecode=bool(args.opt_framecode), framecode_ch=args.framecode_size,
                        n_framecodes=n_framecodes, skel_type=skel_type, density_scale=args.density_scale)
     model = NeRF(**nerf_kwargs)
-    model_fine = NeRF(**nerf_kwargs) if args.N_importance > 0 else None
+    single_net = bool(g('single_net', False))
+    model_fine = None
+    if args.N_importance > 0:          # --single_net: the fine pass re-uses the coarse network (core/raycasters.py:100-104)
+        model_fine = model if single_net else NeRF(**nerf_kwargs)
     ray_caster = RayCaster(model, embed_fn, embedbones_fn, embeddirs_fn, network_fine=model_fine,
-                           joint_coords=torch.tensor(data_attrs['joint_coords']), single_net=False).to(device)
+                           joint_coords=torch.tensor(data_attrs['joint_coords']), single_net=single_net).to(device)
 
     # trainable variables, with the reference's --fix_layer freezing (core/raycasters.py:186-228)
     if g('finetune', False) and g('fix_layer', 0) > 0:
@@ -543,7 +546,7 @@ def create_raycaster(args, data_attrs, device=None):
                             p.requires_grad = False
     grad_vars = []
     if g('weight_decay', None) is None:
-        for m in (model, model_fine, embed_fn, embedbones_fn, embeddirs_fn):
+        for m in (model, None if single_net else model_fine, embed_fn, embedbones_fn, embeddirs_fn):
             if m is not None:
                 grad_vars += [p for p in m.parameters() if p.requires_grad]
     optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))

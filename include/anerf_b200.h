@@ -98,6 +98,9 @@ typedef struct {
   float tau_pts, tau_views;  /* CutoffEmbedder.tau of embed_fn / embeddirs_fn */
   float cutoff_pts[24];      /* CutoffEmbedder.cutoff_dist per joint */
   float cutoff_views[24];
+  int32_t single_net;        /* --single_net: one network for both passes (pass the same packed image twice) and the
+                                blurred importance pdf of core/utils/ray_utils.py:271-277 */
+  int32_t reserved;
 } anerf_render_opts;
 
 /* Device inputs.  rays: [N,8] = origin(3), direction(3), near, far (the first 8 columns of the
@@ -134,7 +137,7 @@ typedef struct {
 size_t anerf_render_workspace_bytes(int32_t n_rays);
 
 /* One chunk of rays through the whole path on the device.  packed_fine may equal packed_coarse
- * (single_net is not supported otherwise) and is ignored when n_importance == 0. */
+ * (opts->single_net) and is ignored when n_importance == 0. */
 int anerf_render_fwd(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
                      const anerf_render_opts* opts, const anerf_render_inputs* in,
                      const anerf_render_outputs* out, void* workspace, size_t workspace_bytes, void* stream);

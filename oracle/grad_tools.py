@@ -30,7 +30,7 @@ def oracle_grads(scene, sd0, sd1, cfg, draws, cot, dtype=torch.float32, z_all_ov
     t = lambda a: torch.as_tensor(np.asarray(a)).to(dtype)
     d = {k: t(v) for k, v in (draws or {}).items()}
     p0 = {k: v.requires_grad_(True) for k, v in orc.to_torch(sd0, dtype).items()}
-    p1 = None if sd1 is None else {k: v.requires_grad_(True) for k, v in orc.to_torch(sd1, dtype).items()}
+    p1 = None if (sd1 is None or cfg.single_net) else {k: v.requires_grad_(True) for k, v in orc.to_torch(sd1, dtype).items()}
     skts = t(scene["skts"]).requires_grad_(True)
     cams = torch.as_tensor(scene["cams"]) if cfg.framecode_ch > 0 else None
     taps = {}

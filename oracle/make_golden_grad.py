@@ -29,6 +29,9 @@ GRAD_CASES = {
     # BASELINE.json configs[0] shape: 1 joint, 4x64 (no skip), deterministic sampling
     "grad_cfg1_j1_s16_i16": dict(n_joints=1, n_rays=32, H=32, W=32, focal=40., D=4, W_net=64, skips=(4,),
                                  N_samples=16, N_importance=16),
+    # --single_net: both passes through one network (gradients of the two passes add up), blurred importance pdf
+    "grad_single_j24_s16_i8": dict(n_joints=24, n_rays=10, H=512, W=512, focal=500., D=8, W_net=256, skips=(4,),
+                                   N_samples=16, N_importance=8, single_net=True),
     # coarse pass only
     "grad_j24_s24_i0": dict(n_joints=24, n_rays=8, H=512, W=512, focal=500., D=8, W_net=256, skips=(4,),
                             N_samples=24, N_importance=0),
@@ -73,7 +76,7 @@ def reference_grads(core, c, scene, sd0, sd1, cfg, draws, cot):
     loss.backward()
     grads = {}
     for tag, net in (("net0", rc.network), ("net1", rc.network_fine)):
-        if net is None:
+        if net is None or (tag == "net1" and net is rc.network):
             continue
         for k, p in net.named_parameters():
             grads[f"{tag}.{k}"] = (torch.zeros(1) if p.grad is None else p.grad).numpy()

@@ -11,7 +11,7 @@ from oracle import anerf_oracle as orc
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 RENDER_CASES = ["cfg1_j1_s16_i0", "cfg1_j1_s16_i16", "bench_j24_s64_i128", "surreal_j24_s64_i16_tau200",
-                "mixamo_j24_s64_i16_fc", "train_j24_s64_i32_perturb"]
+                "mixamo_j24_s64_i16_fc", "train_j24_s64_i32_perturb", "single_j24_s64_i48"]
 
 
 def load_golden(name):
@@ -30,8 +30,11 @@ def build_case(c):
               n_framecodes=c.get("n_framecodes", 0))
     sd0 = synthetic.make_net_weights(101, **wk)
     sd1 = synthetic.make_net_weights(202, **wk) if c.get("N_importance", 1) > 0 else None
+    if c.get("single_net") and sd1 is not None:
+        sd1 = sd0                                    # --single_net: the fine pass re-uses the coarse network
     cfg = orc.PathConfig(n_joints=J, D=c["D"], W=c["W_net"], skips=c["skips"], N_samples=c.get("N_samples", 64),
-                         N_importance=c.get("N_importance", 0), tau=c.get("tau", 20.), framecode_ch=fc)
+                         N_importance=c.get("N_importance", 0), tau=c.get("tau", 20.), framecode_ch=fc,
+                         single_net=bool(c.get("single_net", False)))
     N = scene["rays_o"].shape[0]
     if fc > 0:
         scene["cams"] = (np.arange(N) % c["n_framecodes"]).astype(np.int64)

@@ -87,7 +87,7 @@ def test_create_raycaster_contract_and_render():
 
 
 def test_unsupported_flags_raise():
-    for bad in (dict(kp_dist_type='relpos'), dict(view_type='world'), dict(single_net=True), dict(use_viewdirs=False),
+    for bad in (dict(kp_dist_type='relpos'), dict(view_type='world'), dict(use_viewdirs=False),
                 dict(multires=10), dict(cutoff_bones=True)):
         with pytest.raises(NotImplementedError):
             create_raycaster(make_args(**bad), data_attrs())
@@ -209,3 +209,31 @@ def test_render_path_frame_composites_like_render_path():
     outside = torch.ones(H * W, dtype=torch.bool, device=dev)
     outside[idx.long()] = False
     assert torch.equal(rgb.reshape(-1, 3)[outside], bg.reshape(-1, 3)[outside]) and float(acc.reshape(-1)[outside].abs().max()) == 0.
+
+
+def test_single_net_through_the_boundary():
+    """--single_net (configs/surreal/surreal_single.txt): one network for both passes, blurred importance pdf; forward
+    against the reference's golden outputs, and loss.backward() accumulates both passes into the one network."""
+    case, gold = load_golden("single_j24_s64_i48")
+    scene, sd0, sd1, cfg, _ = build_case(case)
+    rk_train, rk, _, grad_vars, _, _ = create_raycaster(make_args(N_importance=48, single_net=True, no_reload=True), data_attrs())
+    rc = rk['ray_caster']
+    assert rc.network_fine is rc.network and len(grad_vars) == 24
+    rc.network.load_state_dict({k: torch.as_tensor(v) for k, v in sd0.items()})
+    rc.eval()
+    dev = torch.device("cuda")
+    t = lambda a: torch.as_tensor(a).to(dev)
+    N = scene["rays_o"].shape[0]
+    rays = torch.cat([t(scene["rays_o"]), t(scene["rays_d"]), torch.zeros(N, 1, device=dev), torch.ones(N, 1, device=dev),
+                      torch.nn.functional.normalize(t(scene["rays_d"]), dim=-1)], 1)
+    kw = {k: v for k, v in rk.items() if k not in ('ray_caster', 'use_viewdirs')}
+    batch = dict(kp_batch=t(scene["kps"]), skts=t(scene["skts"]), cyls=t(scene["cyls"]), bones=t(scene["bones"]), cams=None,
+                 subject_idxs=None)
+    out = rc(rays, **batch, **kw)
+    for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "alpha0"):
+        assert rel_err(out[k].cpu().numpy(), gold["ref_" + k]) < 1e-4, k
+    holder = rk_train['ray_caster'].train()
+    o = holder(rays, **batch, **dict(kw, perturb=0.))
+    (o['rgb_map'].sum() + o['rgb0'].sum()).backward()
+    g = rc.network.pts_linears[3].weight.grad
+    assert g is not None and torch.isfinite(g).all() and float(g.abs().max()) > 0

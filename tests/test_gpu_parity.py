@@ -24,7 +24,7 @@ def gpu_render(scene, sd0, sd1, cfg, draws=None, want_taps=False, fmt=1, n_impor
     p1 = plan.pack({k: t(v) for k, v in sd1.items()}) if sd1 is not None else None
     rays = np.concatenate([scene["rays_o"], scene["rays_d"], np.zeros((N, 1), np.float32), np.ones((N, 1), np.float32)], 1)
     opts = _lib.make_opts(N, cfg.N_samples, Si, tau_pts=cfg.tau, tau_views=cfg.tau_views, cutoff_pts=cfg.cutoff_dist,
-                          cutoff_views=cfg.cutoff_dist, n_joints=cfg.n_joints)
+                          cutoff_views=cfg.cutoff_dist, n_joints=cfg.n_joints, single_net=getattr(cfg, "single_net", False))
     d = draws or {}
     cams = scene.get("cams")
     cams = None if cams is None else cams.astype(np.float32)

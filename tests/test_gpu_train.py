@@ -15,8 +15,8 @@ from tests.common import build_case, load_golden
 
 pytestmark = pytest.mark.gpu
 
-GRAD_CASES = ["grad_cfg1_j1_s16_i16", "grad_j24_s24_i0", "grad_j24_s16_i8_fc_perturb"]
-TC_L2_TOL = {"grad_cfg1_j1_s16_i16": 3e-4, "grad_j24_s24_i0": 1e-3, "grad_j24_s16_i8_fc_perturb": 3e-2}
+GRAD_CASES = ["grad_cfg1_j1_s16_i16", "grad_j24_s24_i0", "grad_j24_s16_i8_fc_perturb", "grad_single_j24_s16_i8"]
+TC_L2_TOL = {"grad_cfg1_j1_s16_i16": 3e-4, "grad_j24_s24_i0": 1e-3, "grad_j24_s16_i8_fc_perturb": 3e-2, "grad_single_j24_s16_i8": 1e-3}
 
 
 def gpu_grads(scene, sd0, sd1, cfg, draws, cot, need_pose=True):
@@ -33,7 +33,8 @@ def gpu_grads(scene, sd0, sd1, cfg, draws, cot, need_pose=True):
     p1 = None if d1 is None else plan.pack(d1)
     rays = t(np.concatenate([scene["rays_o"], scene["rays_d"], np.zeros((N, 1), np.float32), np.ones((N, 1), np.float32)], 1))
     opts = _lib.make_opts(N, cfg.N_samples, cfg.N_importance, tau_pts=cfg.tau, tau_views=cfg.tau_views,
-                          cutoff_pts=cfg.cutoff_dist, cutoff_views=cfg.cutoff_dist, n_joints=cfg.n_joints)
+                          cutoff_pts=cfg.cutoff_dist, cutoff_views=cfg.cutoff_dist, n_joints=cfg.n_joints,
+                          single_net=getattr(cfg, "single_net", False))
     d = draws or {}
     cams = t(scene["cams"].astype(np.float32)) if fc else None
     skts = t(scene["skts"])
@@ -45,6 +46,8 @@ def gpu_grads(scene, sd0, sd1, cfg, draws, cot, need_pose=True):
                                      t(d.get("noise1")), out['nearfar'].contiguous(), out.get('z_all'),
                                      {k: t(v) for k, v in cot.items()}, [True] * len(names), [True] * len(names), need_pose)
     torch.cuda.synchronize()
+    if getattr(cfg, "single_net", False) and g1 is not None:     # one network: the two passes' gradients add up (as autograd does)
+        g0, g1 = [a + b for a, b in zip(g0, g1)], None
     grads = {f"net0.{k}": g.cpu().numpy() for k, g in zip(names, g0)}
     if g1 is not None:
         grads.update({f"net1.{k}": g.cpu().numpy() for k, g in zip(names, g1)})

@@ -15,7 +15,7 @@ from oracle import grad_tools as gt
 from tests.common import build_case, load_golden
 
 HOST = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host")
-GRAD_CASES = ["grad_cfg1_j1_s16_i16", "grad_j24_s24_i0", "grad_j24_s16_i8_fc_perturb"]
+GRAD_CASES = ["grad_cfg1_j1_s16_i16", "grad_j24_s24_i0", "grad_j24_s16_i8_fc_perturb", "grad_single_j24_s16_i8"]
 
 PARAM_FILES = {"alpha_linear.weight": "alpha_w", "alpha_linear.bias": "alpha_b", "feature_linear.weight": "feature_w",
                "feature_linear.bias": "feature_b", "views_linears.0.weight": "views_w", "views_linears.0.bias": "views_b",
@@ -73,6 +73,13 @@ def write_case(d, c, scene, sd0, sd1, cfg, draws, cot, taps, need_pose=True):
 
 def read_grads(d, sd0, sd1, scene):
     out = {}
+    if sd1 is sd0 and sd1 is not None:          # single_net: both passes wrote gradients of the same network
+        for k, v in sd0.items():
+            a = np.fromfile(os.path.join(d, f"out_net0_{param_file(k)}.bin"), np.float32)
+            b = np.fromfile(os.path.join(d, f"out_net1_{param_file(k)}.bin"), np.float32)
+            out[f"net0.{k}"] = (a + b).reshape(v.shape)
+        out["skts"] = np.fromfile(os.path.join(d, "out_g_skts.bin"), np.float32).reshape(scene["skts"].shape)
+        return out
     for n, sd in enumerate([sd0, sd1]):
         if sd is not None:
             for k, v in sd.items():

@@ -46,7 +46,7 @@ def test_flop_count_matches_baseline():
     assert orc.algorithmic_flops_per_ray(orc.PathConfig()) == 256 * 1723648
 
 
-@pytest.mark.parametrize("name", ["grad_cfg1_j1_s16_i16", "grad_j24_s24_i0", "grad_j24_s16_i8_fc_perturb"])
+@pytest.mark.parametrize("name", ["grad_cfg1_j1_s16_i16", "grad_j24_s24_i0", "grad_j24_s16_i8_fc_perturb", "grad_single_j24_s16_i8"])
 def test_oracle_autograd_matches_reference_gradient_digests(name):
     """The oracle's gradients (torch autograd over the restatement) against the digests of the reference's own
     autograd on the same rays, weights, draws and output cotangents (oracle/make_golden_grad.py)."""
