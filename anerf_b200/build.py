@@ -16,21 +16,42 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 
+STAMP = LIB + ".srchash"
+
+
+def _source_hash():
+    """Content hash of everything the library is compiled from (+ the flags): the snapshot that carries the built .so
+    to a GPU box need not preserve modification times, so staleness is decided by content, not by mtime."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for f in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
+    with open(STAMP) as fh:
+        return fh.read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    tmp = f"{LIB}.{os.getpid()}.tmp"           # several ranks may build at once: write aside, then rename atomically
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + SOURCES
     r = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, LIB)
+    with open(f"{STAMP}.{os.getpid()}.tmp", "w") as fh:
+        fh.write(_source_hash())
+    os.replace(f"{STAMP}.{os.getpid()}.tmp", STAMP)
     if verbose:
         print(r.stderr)
     return LIB
