@@ -46,6 +46,10 @@ void h_view_table(const float* skt, const float* dir, int J, float* out /*[J][27
 }
 float h_cutoff_w(const float* skt12, const float* p, float tau, float cut) { return cutoff_w(joint_dist(skt12, p), tau, cut); }
 float h_linspace01(int i, int n) { return linspace01(i, n); }
+// a3: coarse depths of one ray (optionally jittered / linear in disparity), as the training path recomputes them
+void h_coarse_depths(float near, float far, int Sc, int lindisp, const float* t_rand_or_null, float* out) {
+  for (int s = 0; s < Sc; ++s) out[s] = coarse_depth(near, far, s, Sc, lindisp, t_rand_or_null);
+}
 // in-kernel ray generation (frame mode): rays of n consecutive pixels starting at pixel0
 void h_pixel_rays(const float* c2w12, float fx, float fy, float cx, float cy, int W, int pixel0, int n, float* out /*[n][8]*/) {
   RayGen g{};

@@ -143,3 +143,19 @@ def test_pixel_rays_match_reference_get_rays(harness):
     assert np.array_equal(out[:, 3:6], rays_d[p0:p0 + n])
     assert np.array_equal(out[:, 0:3], np.broadcast_to(c2w[:, 3], (n, 3)))
     assert np.all(out[:, 6] == 0.) and np.all(out[:, 7] == 1.)
+
+
+@pytest.mark.parametrize("lindisp", [0, 1])
+@pytest.mark.parametrize("jitter", [False, True])
+def test_coarse_depths_match_oracle(harness, lindisp, jitter):
+    """coarse_depth (path_math.cuh; what the fused kernel and the backward pass sample at) against the oracle's
+    restatement of sample_from_lineseg (ray_utils.py:204-251), incl. stratified jitter and lindisp."""
+    rng = np.random.RandomState(3)
+    for Sc in (16, 64, 65):
+        near, far = np.float32(1.2345), np.float32(4.321)
+        tr = rng.rand(Sc).astype(np.float32) if jitter else None
+        out = np.zeros(Sc, np.float32)
+        harness.h_coarse_depths(C.c_float(near), C.c_float(far), Sc, lindisp, fptr(tr) if jitter else None, fptr(out))
+        ref = orc.coarse_depths(torch.tensor([[near]]), torch.tensor([[far]]), Sc, None if tr is None else torch.as_tensor(tr)[None],
+                                bool(lindisp))[0].numpy()
+        assert np.abs(out - ref).max() <= 5e-7 * far, (Sc, np.abs(out - ref).max())
