@@ -30,6 +30,16 @@ def _worker(rank, world, port, q):
     parallel.allreduce_gradients(ps, w)
     g_ok = torch.allclose(ps[0].grad, torch.full((3, 4), 1.5)) and torch.allclose(ps[1].grad, torch.arange(5.) / 2) \
         and ps[2].grad is None
+    # equal contiguous shares + the averaged gradient == the full-batch gradient of a mean-over-rays loss
+    torch.manual_seed(1)
+    lin = torch.nn.Linear(6, 3)
+    xs, ys = torch.randn(64, 6), torch.randn(64, 3)
+    full_g = torch.autograd.grad(((lin(xs) - ys) ** 2).mean(), list(lin.parameters()))
+    lo, hi = parallel.rays_for_rank(64, r, w)
+    lin.zero_grad()
+    ((lin(xs[lo:hi]) - ys[lo:hi]) ** 2).mean().backward()
+    parallel.allreduce_gradients(list(lin.parameters()), w)
+    g_ok = g_ok and all(torch.allclose(p.grad, f, atol=1e-6) for p, f in zip(lin.parameters(), full_g))
     a0, b0 = parallel.rays_for_rank(3072, r, w)
     g_ok = g_ok and (b0 - a0) == 1536 and a0 == r * 1536
     if r == 0:
