@@ -459,6 +459,23 @@ def main():
         parity = {"rays": len(idx), "rgb0_rel": rel(o["rgb0"], ref["rgb0"]), "acc0_rel": rel(o["acc0"], ref["acc0"]),
                   "rgb_map_rel": rel(o["rgb_map"], ref["rgb_map"]),
                   "rgb_map_psnr_db": float(-10 * np.log10(max(mse, 1e-30)))}
+        try:
+            # fine outputs on IDENTICAL sample positions: the oracle evaluated at the kernel's own sorted depths (the
+            # inverse-CDF step is ill-conditioned in fp32; this is the like-for-like comparison)
+            from oracle import anerf_oracle as orc
+            o2 = rc(sub["rays"], kp_batch=sub["kps"], skts=sub["skts"], cyls=sub["cyls"], bones=sub["bones"], cams=None,
+                    subject_idxs=None, retraw=True, **kw)
+            c = lambda a: a.detach().cpu()
+            with torch.no_grad():
+                ref2 = orc.render_rays({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(101).items()},
+                                       {k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(202).items()},
+                                       orc.PathConfig(), c(sub["rays"][:, 0:3]), c(sub["rays"][:, 3:6]), c(sub["skts"]), c(sub["cyls"]),
+                                       z_all_override=c(o2["z_all"]))
+            parity.update({"rgb_map_rel_same_samples": rel(o2["rgb_map"], ref2["rgb_map"]),
+                           "acc_map_rel_same_samples": rel(o2["acc_map"], ref2["acc_map"]),
+                           "alpha_rel_same_samples": rel(o2["alpha"], ref2["alpha"])})
+        except Exception as e:  # noqa: BLE001
+            parity["same_samples_error"] = repr(e)[:200]
     ref_gpu = None
     if not opt.no_cpu_baseline and world == 1:
         # the reference's PyTorch path on the same B200 (fp32, eager, default matmul precision).  The
