@@ -133,3 +133,21 @@ def test_emulated_backward_softplus_density_scale_lindisp(harness):
         g = read_grads(d, sd0, sd1, scene)
     bad = {k: gt.rel_err(g[k], g_orc[k]) for k in g_orc if not (gt.rel_err(g[k], g_orc[k]) < 3e-4)}
     assert not bad, bad
+
+
+def test_emulated_backward_other_network_shapes(harness):
+    """A network shape none of the fixtures has (5 joints, 6 x 128 with the skip after layer 4: encoding width 90, leading
+    dimensions that are not multiples of 4, so the kernels' unaligned / ragged paths run) against the oracle's autograd."""
+    c = dict(n_joints=5, n_rays=9, H=64, W=64, focal=60., D=6, W_net=128, skips=(4,), N_samples=12, N_importance=7)
+    scene, sd0, sd1, cfg, draws = build_case(c)
+    N = scene["rays_o"].shape[0]
+    cot = gt.cotangents(N, cfg.N_samples, cfg.N_importance, seed=2)
+    _, g_orc, taps = gt.oracle_grads(scene, sd0, sd1, cfg, draws, cot)
+    with tempfile.TemporaryDirectory(prefix="anerf_train_case_") as d:
+        write_case(d, c, scene, sd0, sd1, cfg, draws, cot, taps)
+        r = subprocess.run([harness, d], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr
+        g = read_grads(d, sd0, sd1, scene)
+    assert float(np.abs(g_orc["skts"]).max()) > 0 and float(np.abs(g_orc["net1.pts_linears.5.weight"]).max()) > 0
+    bad = {k: gt.rel_err(g[k], g_orc[k]) for k in g_orc if not (gt.rel_err(g[k], g_orc[k]) < 3e-4)}
+    assert not bad, bad
