@@ -113,11 +113,15 @@ __global__ void __launch_bounds__(kGemmThreads) sgemm_kernel(GemmArgs g) {
         b[i] = Bs[kk][tx * 4 + i];
         b[4 + i] = Bs[kk][64 + tx * 4 + i];
       }
-#if defined(ANERF_EMU_BF16X3)
-      // host experiment only (tests/host): the arithmetic of the tensor-core engine (operands split into bf16 hi + lo,
+#if defined(ANERF_EMU_BF16X3) || defined(ANERF_EMU_FP16X3)
+      // host experiment only (tests/host): the arithmetic of the tensor-core engine (operands split into 16-bit hi + lo,
       // three products, fp32 accumulation) to separate its rounding from bugs when gradients disagree
       {
+#if defined(ANERF_EMU_FP16X3)
+        auto bf = [](float x) { return (float)(_Float16)x; };
+#else
         auto bf = [](float x) { uint32_t u; memcpy(&u, &x, 4); u = (u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u; float r; memcpy(&r, &u, 4); return r; };
+#endif
         for (int i = 0; i < 8; ++i) {
           const float ah = bf(a[i]), al = bf(a[i] - ah);
           for (int j = 0; j < 8; ++j) {
