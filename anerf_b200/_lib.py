@@ -21,7 +21,7 @@ SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "ane
 class NetConfig(C.Structure):
     _fields_ = [("n_joints", C.c_int32), ("depth", C.c_int32), ("width", C.c_int32), ("skip", C.c_int32),
                 ("framecode_ch", C.c_int32), ("n_framecodes", C.c_int32), ("operand_format", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("view_freqs", C.c_int32)]
 
 
 class NetParams(C.Structure):
@@ -123,14 +123,14 @@ def _stream():
 class Plan:
     """Owns an anerf_plan (layer program + K maps of one network configuration)."""
 
-    def __init__(self, n_joints, depth, width, skips=(4,), framecode_ch=0, n_framecodes=0, operand_format=1):
+    def __init__(self, n_joints, depth, width, skips=(4,), framecode_ch=0, n_framecodes=0, operand_format=1, view_freqs=4):
         skip = -1
         for s in skips:
             if s < depth - 1:
                 if skip >= 0:
                     raise NotImplementedError("only one skip connection is supported")
                 skip = int(s)
-        self.cfg = NetConfig(n_joints, depth, width, skip, framecode_ch, n_framecodes, operand_format, 0)
+        self.cfg = NetConfig(n_joints, depth, width, skip, framecode_ch, n_framecodes, operand_format, view_freqs)
         self.handle = C.c_void_p()
         check(load().anerf_plan_create(C.byref(self.cfg), C.byref(self.handle)))
         self.packed_bytes = load().anerf_packed_bytes(self.handle)

@@ -71,6 +71,7 @@ struct anerf_plan {
   int k_in[kMaxLayers];      // reference fan-in of each layer
   float* d_fold_w;           // [W/2, W + 27J + fc] views_linears[0] with feature_linear folded in
   float* d_fold_b;           // [W/2]
+  float* d_scale;            // [kMaxLayers] power-of-two operand scale of each layer (scratch of anerf_pack_net)
   int n_sm;
   int max_smem;
 };
@@ -89,6 +90,7 @@ int anerf_plan_create(const anerf_net_config* cfg, anerf_plan** out) {
   if (cfg->depth < 2 || cfg->depth > 8) return fail(ANERF_ERR_INVALID, "depth must be 2..8");
   if (cfg->framecode_ch != 0 && cfg->framecode_ch != 16) return fail(ANERF_ERR_INVALID, "framecode_ch must be 0 or 16");
   if (cfg->framecode_ch > 0 && cfg->n_framecodes < 1) return fail(ANERF_ERR_INVALID, "n_framecodes must be >= 1");
+  if (cfg->view_freqs != 0 && cfg->view_freqs != kFv) return fail(ANERF_ERR_INVALID, "view_freqs (multires_views) must be 0 or 4");
   if (cfg->operand_format != 0 && cfg->operand_format != 1) return fail(ANERF_ERR_INVALID, "operand_format must be 0 (fp16) or 1 (bf16)");
   if (cfg->skip >= cfg->depth - 1 && cfg->skip != -1)
     return fail(ANERF_ERR_INVALID, "skip=%d: a skip connection after the last trunk layer is not supported (use -1 when skips >= depth-1)", cfg->skip);
@@ -100,9 +102,10 @@ int anerf_plan_create(const anerf_net_config* cfg, anerf_plan** out) {
   p->dims.skip = cfg->skip < 0 ? -1 : cfg->skip;
   p->dims.fc_ch = cfg->framecode_ch;
   p->dims.n_fc = cfg->framecode_ch > 0 ? cfg->n_framecodes : 0;
+  p->dims.fv = cfg->view_freqs;
   p->prog = make_program(p->dims);
   for (int l = 0; l < kMaxLayers; ++l) p->d_kmap[l] = nullptr;
-  p->d_fold_w = p->d_fold_b = nullptr;
+  p->d_fold_w = p->d_fold_b = p->d_scale = nullptr;
   const NetDims& d = p->dims;
   for (int l = 0; l < p->prog.n_layers; ++l) {
     int kp = p->prog.layer[l].chunks * kKC;
@@ -121,6 +124,7 @@ int anerf_plan_create(const anerf_net_config* cfg, anerf_plan** out) {
     const size_t cols = (size_t)d.W + in_views_ref(d) + d.fc_ch;
     cudaError_t e = cudaMalloc((void**)&p->d_fold_w, (size_t)(d.W / 2) * cols * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_fold_b, (size_t)(d.W / 2) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_scale, kMaxLayers * sizeof(float));
     if (e != cudaSuccess) { anerf_plan_destroy(p); return fail(ANERF_ERR_CUDA, "plan alloc failed: %s", cudaGetErrorString(e)); }
   }
   int dev = 0;
@@ -137,6 +141,7 @@ void anerf_plan_destroy(anerf_plan* p) {
     if (p->d_kmap[l]) cudaFree(p->d_kmap[l]);
   if (p->d_fold_w) cudaFree(p->d_fold_w);
   if (p->d_fold_b) cudaFree(p->d_fold_b);
+  if (p->d_scale) cudaFree(p->d_scale);
   delete p;
 }
 
@@ -151,7 +156,9 @@ int anerf_pack_net(const anerf_plan* plan, const anerf_net_params* prm, void* pa
   float* smalls = (float*)(img + pg.smalls_off);
   const int fmt = plan->cfg.operand_format;
   if (!prm->feature_w || !prm->feature_b || !prm->views_w || !prm->views_b) return fail(ANERF_ERR_INVALID, "missing feature/views parameters");
-  // note: the plan's fold buffers make concurrent anerf_pack_net calls on one plan unsafe across streams
+  // note: the plan's fold / scale buffers make concurrent anerf_pack_net calls on one plan unsafe across streams
+  float kappa = fmt == 0 ? kTruncKappaFp16 : kTruncKappaBf16;
+  if (const char* e = getenv("ANERF_TRUNC_KAPPA")) kappa = (float)atof(e);     // calibration knob (tools/parity_dump.py)
   anerf_fold_views_kernel<<<64, 256, 0, stream>>>(prm->views_w, prm->views_b, prm->feature_w, prm->feature_b, d.W / 2, d.W,
                                                   in_views_ref(d) + d.fc_ch, plan->d_fold_w, plan->d_fold_b);
   CUDA_TRY(cudaGetLastError());
@@ -162,11 +169,13 @@ int anerf_pack_net(const anerf_plan* plan, const anerf_net_params* prm, void* pa
     int n = pg.layer[l].n, chunks = pg.layer[l].chunks;
     long long total = (long long)chunks * n * 4;
     int blocks = (int)((total + 255) / 256);
-    anerf_layer_scale_kernel<<<1, 1024, 0, stream>>>(w, (long long)n * plan->k_in[l], fmt, smalls + l);
+    // real input columns of the layer as the kernel feeds it (the views layer: h + the row's own ray-slot chunk)
+    const int k_real = l < d.D ? plan->k_in[l] : d.W + kKC;
+    anerf_layer_scale_kernel<<<1, 1024, 0, stream>>>(w, (long long)n * plan->k_in[l], fmt, trunc_comp(k_real, kappa), plan->d_scale + l, smalls + l);
     if (fmt == 1)
-      anerf_pack_layer_kernel<1><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, smalls + l, img + pg.layer[l].w_off);
+      anerf_pack_layer_kernel<1><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, plan->d_scale + l, img + pg.layer[l].w_off);
     else
-      anerf_pack_layer_kernel<0><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, smalls + l, img + pg.layer[l].w_off);
+      anerf_pack_layer_kernel<0><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, plan->d_scale + l, img + pg.layer[l].w_off);
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.bias[l], b, n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
   }

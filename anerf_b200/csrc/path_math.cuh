@@ -40,7 +40,11 @@ struct NetDims {
   int skip;    // index i such that layer i+1 takes cat[enc, h] (reference skips=[4]); -1 = none
   int fc_ch;   // per-frame appearance code channels appended to the view input (0 or 16)
   int n_fc;    // rows of the framecode table
+  int fv;      // view-direction frequencies of the NETWORK (multires_views): kFv = 4, or 0 (configs/surreal/surreal_single.txt:
+               // the view input is the 3 raw bone-local direction components per joint, times the cutoff weight)
 };
+// view inputs per joint that the network actually has: 3 * (1 + 2 fv) of the kViewPerJoint = 27 the kernels tabulate
+ANERF_HD int view_per_joint(const NetDims& d) { return 3 * (1 + 2 * d.fv); }
 
 // ------------------------------------------------------------------------------------------------
 // K layout of the A operand.  Four worker groups produce the chunks of an operand part concurrently:
@@ -66,7 +70,7 @@ ANERF_HD int pts_chunks(const NetDims& d) { return kGroups * pts_group_chunks(d)
 ANERF_HD int slot_chunks(int rays_per_item) { return round_up(2 * rays_per_item, kGroups); }   // ray-slot chunks of the views layer
 ANERF_HD int hid_chunks(const NetDims& d) { return round_up(d.W / kKC, kGroups); }
 ANERF_HD int in_pts_ref(const NetDims& d) { return d.J * (1 + 2 * kF) + d.J * 3; }
-ANERF_HD int in_views_ref(const NetDims& d) { return d.J * kViewPerJoint; }
+ANERF_HD int in_views_ref(const NetDims& d) { return d.J * view_per_joint(d); }
 
 // Layer program: l in [0,D) trunk, l == D the views layer.  feature_linear has no activation behind it
 // (nerf.py:121-125), so it is folded into views_linears[0] when the weights are packed:
@@ -98,7 +102,7 @@ ANERF_HD int pts_part_ref_col(const NetDims& d, int k) {
 // column of the (folded) views weight matrix that multiplies feature q (= 3*kk + c, kk = 0 raw, 1+2f sin,
 // 2+2f cos) of joint j; j == J is the framecode pseudo joint (q < fc_ch).  -1 = no such input.
 ANERF_HD int view_weight_col(const NetDims& d, int j, int q) {
-  if (j < d.J) return q < kViewPerJoint ? d.W + (q / 3) * 3 * d.J + 3 * j + (q % 3) : -1;
+  if (j < d.J) return q < view_per_joint(d) ? d.W + (q / 3) * 3 * d.J + 3 * j + (q % 3) : -1;
   return (j == d.J && q < d.fc_ch) ? d.W + in_views_ref(d) + q : -1;
 }
 ANERF_HD int layer_ref_col(const NetDims& d, int l, int k) {

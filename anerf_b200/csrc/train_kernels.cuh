@@ -259,7 +259,7 @@ struct EncodeArgs {
   const float* z;         // [N,S] depths of this network's pass
   const float* cams;      // [N] or NULL
   const float* codes;     // [n_fc, fc_ch] or NULL
-  int ray0, n_rays_blk, S, J, W, fc_ch, n_fc;
+  int ray0, n_rays_blk, S, J, W, fc_ch, n_fc, vq;    // vq = view inputs per joint, 3 (1 + 2 multires_views)
   float tau_p, tau_v;
   float cut_p[kMaxJoints], cut_v[kMaxJoints];
   float* XS; long long ldxs;
@@ -289,11 +289,12 @@ __global__ void encode_rows_kernel(EncodeArgs e) {
   const float wv = cutoff_w(v, e.tau_v, e.cut_v[j]);
   float* vin = e.VIN + row * e.ldv + e.W;
 #pragma unroll
-  for (int q = 0; q < kViewPerJoint; ++q) vin[(q / 3) * 3 * J + 3 * j + (q % 3)] = T[q] * wv;
+  for (int q = 0; q < kViewPerJoint; ++q)
+    if (q < e.vq) vin[(q / 3) * 3 * J + 3 * j + (q % 3)] = T[q] * wv;
   if (j == 0 && e.fc_ch > 0) {
     int cam = (int)e.cams[ray];
     cam = cam < 0 ? 0 : (cam >= e.n_fc ? e.n_fc - 1 : cam);
-    for (int q = 0; q < e.fc_ch; ++q) vin[kViewPerJoint * J + q] = e.codes[(long long)cam * e.fc_ch + q];
+    for (int q = 0; q < e.fc_ch; ++q) vin[e.vq * J + q] = e.codes[(long long)cam * e.fc_ch + q];
   }
 }
 
@@ -382,7 +383,7 @@ __global__ void composite_bwd_kernel(CompositeBwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 struct EncodeBwdArgs {
   const float* rays; const float* skts; const float* z;
-  int ray0, n_rays_blk, S, J, W;
+  int ray0, n_rays_blk, S, J, W, vq;
   float tau_p, tau_v;
   float cut_p[kMaxJoints], cut_v[kMaxJoints];
   const float* gXS; long long ldxs;
@@ -435,7 +436,7 @@ __global__ void encode_bwd_kernel(EncodeBwdArgs e) {
     float gwv = 0.f;
 #pragma unroll
     for (int q = 0; q < kViewPerJoint; ++q) {
-      const float gq = gvn[(q / 3) * 3 * J + 3 * j + (q % 3)];
+      const float gq = q < e.vq ? gvn[(q / 3) * 3 * J + 3 * j + (q % 3)] : 0.f;
       gwv = fmaf(gq, T[q], gwv);
       gT[q] = fmaf(gq, wv, gT[q]);
     }

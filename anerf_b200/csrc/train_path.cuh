@@ -281,7 +281,7 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
     {
       EncodeArgs e{};
       e.rays = c.in->rays; e.skts = c.in->skts; e.z = z; e.cams = c.in->cams; e.codes = p.framecodes;
-      e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W; e.fc_ch = d.fc_ch; e.n_fc = d.n_fc;
+      e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W; e.fc_ch = d.fc_ch; e.n_fc = d.n_fc; e.vq = view_per_joint(d);
       e.tau_p = o.tau_pts; e.tau_v = o.tau_views;
       for (int j = 0; j < kMaxJoints; ++j) { e.cut_p[j] = o.cutoff_pts[j]; e.cut_v[j] = o.cutoff_views[j]; }
       e.XS = XS; e.ldxs = LX; e.VIN = VIN; e.ldv = LV;
@@ -351,7 +351,7 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
     if (need_pose) {
       EncodeBwdArgs e{};
       e.rays = c.in->rays; e.skts = c.in->skts; e.z = z;
-      e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W;
+      e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W; e.vq = view_per_joint(d);
       e.tau_p = o.tau_pts; e.tau_v = o.tau_views;
       for (int j = 0; j < kMaxJoints; ++j) { e.cut_p[j] = o.cutoff_pts[j]; e.cut_v[j] = o.cutoff_views[j]; }
       e.gXS = GXS; e.ldxs = LX; e.gVIN = GVIN; e.ldv = LV; e.g_skts = c.g_skts;

@@ -15,7 +15,8 @@ import torch.nn as nn
 
 from . import _lib
 
-MULTIRES, MULTIRES_VIEWS = 7, 4     # the encodings compiled into the kernels (all shipped configs)
+MULTIRES = 7                       # distance frequencies compiled into the kernels (every shipped config)
+MULTIRES_VIEWS = (4, 0)            # view-direction frequencies: 4, or 0 = raw directions (configs/surreal/surreal_single.txt:32)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -204,7 +205,8 @@ class RayCaster(nn.Module):
             net = self.network
             self._plan = _lib.Plan(self._n_joints(), net.D, net.W, net.skips,
                                    net.framecode_ch if net.use_framecode else 0,
-                                   net.n_framecodes if net.use_framecode else 0, self._operand_format)
+                                   net.n_framecodes if net.use_framecode else 0, self._operand_format,
+                                   view_freqs=self.embeddirs_fn.num_freqs)
         return self._plan
 
     def _packed_image(self, which):
@@ -506,8 +508,8 @@ def create_raycaster(args, data_attrs, device=None):
     unsupported(g('normalize_cutoff', False) or g('cut_to_dist', False) or g('cutoff_shift', False)
                 or g('cutoff_bones', False) or g('freq_schedule', False) or g('opt_cutoff', False),
                 "normalize_cutoff / cut_to_dist / cutoff_shift / cutoff_bones / freq_schedule / opt_cutoff")
-    unsupported(g('multires', 7) != MULTIRES or g('multires_views', 4) != MULTIRES_VIEWS or g('multires_bones', 0) != 0,
-                "multires/multires_views/multires_bones other than 7/4/0")
+    unsupported(g('multires', 7) != MULTIRES or g('multires_views', 4) not in MULTIRES_VIEWS or g('multires_bones', 0) != 0,
+                "multires != 7, multires_views not in {4, 0} or multires_bones != 0")
     unsupported(g('i_embed', 0) != 0, "i_embed != 0")
     unsupported(g('nerf_type', 'nerf') != 'nerf', f"nerf_type={g('nerf_type', None)}")
     if args.density_type not in ('relu', 'softplus'):
@@ -520,7 +522,7 @@ def create_raycaster(args, data_attrs, device=None):
     cutoff_dist = args.cutoff_mm * args.ext_scale
     embed_fn = CutoffEmbedder(n_joints, MULTIRES, cutoff_dist, n_joints, dist_inputs=False)
     embedbones_fn = Embedder(n_joints * 3, 0)
-    embeddirs_fn = CutoffEmbedder(n_joints * 3, MULTIRES_VIEWS, cutoff_dist, n_joints, dist_inputs=True)
+    embeddirs_fn = CutoffEmbedder(n_joints * 3, g('multires_views', 4), cutoff_dist, n_joints, dist_inputs=True)
     print(f'KPE: RelDist, BPE: VecNorm, VPE: VecNorm')
 
     output_ch = 5 if args.N_importance > 0 else 4

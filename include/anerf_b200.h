@@ -47,7 +47,8 @@ typedef enum {
 } anerf_status;
 
 /* Shape of one density/radiance MLP and of its encodings (create_raycaster flags,
- * core/raycasters.py:17-104).  multires / multires_views are fixed at 7 / 4 (all shipped configs). */
+ * core/raycasters.py:17-104).  multires is fixed at 7 (all shipped configs); multires_views is 4 or 0
+ * (configs/surreal/surreal_single.txt:32: raw bone-local view directions, no sin/cos features). */
 typedef struct {
   int32_t n_joints;        /* 1..24 */
   int32_t depth;           /* netdepth D (pts_linears), 2..8 */
@@ -55,8 +56,8 @@ typedef struct {
   int32_t skip;            /* reference skips=[4]: layer skip+1 takes cat[encoding, h]; -1 if >= depth-1 */
   int32_t framecode_ch;    /* 0, or 16 when opt_framecode */
   int32_t n_framecodes;    /* rows of the framecode table */
-  int32_t operand_format;  /* 1 = bf16 hi/lo split (default), 0 = fp16 hi/lo split */
-  int32_t reserved;
+  int32_t operand_format;  /* 0 = fp16 hi/lo split (what RayCaster uses by default), 1 = bf16 hi/lo split */
+  int32_t view_freqs;      /* multires_views: 4 or 0 */
 } anerf_net_config;
 
 /* Pointers to one network's fp32 parameters on the device, reference state_dict layout
@@ -68,7 +69,7 @@ typedef struct {
   const float* alpha_b;    /* [1] */
   const float* feature_w;  /* [W, W] */
   const float* feature_b;
-  const float* views_w;    /* [W/2, W + 27*J (+ framecode_ch)] */
+  const float* views_w;    /* [W/2, W + 3*(1 + 2*view_freqs)*J (+ framecode_ch)] */
   const float* views_b;
   const float* rgb_w;      /* [3, W/2] */
   const float* rgb_b;

@@ -10,17 +10,17 @@ using namespace anerf;
 extern "C" {
 
 int h_layer_chunks(int J, int D, int W, int skip, int fc, int l) {
-  NetDims d{J, D, W, skip, fc, fc ? 4 : 0};
+  NetDims d{J, D, W, skip, fc, fc ? 4 : 0, kFv};
   return layer_chunks(d, l);
 }
 int h_layer_ref_col(int J, int D, int W, int skip, int fc, int l, int k) {
-  NetDims d{J, D, W, skip, fc, fc ? 4 : 0};
+  NetDims d{J, D, W, skip, fc, fc ? 4 : 0, kFv};
   return layer_ref_col(d, l, k);
 }
 // emission order of produce_pts_chunks: group g encodes joints g, g+4, ... two at a time (36 values + 4 zeros)
 // and its stream fills the chunks g, g+4, g+8, ... of the part
 void h_emit_pts(const float* skt /*[J][12]*/, const float* p, float tau, const float* cut, int J, float* out) {
-  NetDims d{J, 8, 256, 4, 0, 0};
+  NetDims d{J, 8, 256, 4, 0, 0, kFv};
   int n = pts_chunks(d) * kKC;
   memset(out, 0, n * sizeof(float));
   for (int g = 0; g < kGroups; ++g) {
@@ -37,7 +37,7 @@ void h_emit_pts(const float* skt /*[J][12]*/, const float* p, float tau, const f
   }
 }
 int h_view_weight_col(int J, int D, int W, int skip, int fc, int j, int q) {
-  NetDims d{J, D, W, skip, fc, fc ? 4 : 0};
+  NetDims d{J, D, W, skip, fc, fc ? 4 : 0, kFv};
   return view_weight_col(d, j, q);
 }
 // per-ray direction features of one joint (the table the kernel contracts the view weights with)

@@ -54,7 +54,7 @@ int main(int argc, char** argv) {
     while (f >> k >> v) m[k] = v;
   }
   NetDims d{};
-  d.J = (int)m["J"]; d.D = (int)m["D"]; d.W = (int)m["W"]; d.skip = (int)m["skip"]; d.fc_ch = (int)m["fc_ch"]; d.n_fc = (int)m["n_fc"];
+  d.J = (int)m["J"]; d.D = (int)m["D"]; d.W = (int)m["W"]; d.skip = (int)m["skip"]; d.fc_ch = (int)m["fc_ch"]; d.n_fc = (int)m["n_fc"]; d.fv = m.count("fv") ? (int)m["fv"] : kFv;
   const int N = (int)m["N"], Sc = (int)m["Sc"], Si = (int)m["Si"], Sf = Sc + Si, J = d.J, W = d.W, H = W / 2;
   const int P = in_pts_ref(d), LV = W + in_views_ref(d) + d.fc_ch;
   anerf_render_opts o{};
