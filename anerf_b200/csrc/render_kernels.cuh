@@ -89,10 +89,10 @@ inline __host__ __device__ int align_up(int x, int a) { return (x + a - 1) / a *
 // the fp32 reference's own rounding noise).  The drains multiply by the layer's output scale anyway, so the expected loss
 // is folded into that factor: E[ulp(x)/|x|] ~ 8.6e-8 for log-uniform mantissas, and kappa < 1 accounts for the partial
 // sums being smaller than the final one while they are accumulated.  kappa is calibrated on 4096 rays of the benchmark
-// frame against the fp64 oracle (profiles/r2_parity.md): fp16 operands 0.45 (mean error of sigma -1.9e-5 -> ~0, mean
+// frame against the fp64 oracle (profiles/r2_parity.md): fp16 operands 0.4 (mean error of sigma -1.9e-5 -> -4e-6, mean
 // |error| 4.6e-5 -> 2.1e-5, rgb0 2.3e-5 -> 8e-6; the fp32 reference itself: 1.3e-5 / 5e-6); bf16 operands carry a further
 // systematic shrink of the same form (their 16-bit hi+lo representation) and calibrate to 1.4.
-constexpr float kTruncKappaFp16 = 0.45f;
+constexpr float kTruncKappaFp16 = 0.4f;
 constexpr float kTruncKappaBf16 = 1.4f;
 inline __host__ float trunc_comp(int k_real, float kappa) {
   return 1.0f + kappa * 1.5f * (float)((k_real + 15) / 16) * 8.6e-8f;

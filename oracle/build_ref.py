@@ -37,6 +37,11 @@ FILES = [
     "core/utils/skeleton_utils.py",   # skeletons, cylinders, kinematic helpers
     "core/pose_opt.py",               # PoseOptLayer (the pose chain our fused version is checked against)
     "core/process_spin.py",           # imported by pose_opt.py (SMPL_JOINT_MAPPER)
+    "run_nerf.py",                    # the caller: config_parser() (flag defaults), train(), render_path()
+    # the shipped configurations (tests/test_configs.py: create_raycaster must accept every one of them)
+    "configs/h36m/h36m_prot2.txt", "configs/h36m/h36m_prot2_finetune.txt", "configs/mixamo/mixamo.txt",
+    "configs/mixamo/mixamo_finetune.txt", "configs/perfcap/perfcap.txt", "configs/perfcap/perfcap_finetune.txt",
+    "configs/surreal/surreal.txt", "configs/surreal/surreal_single.txt",
 ]
 
 

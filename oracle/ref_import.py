@@ -1,9 +1,9 @@
 """Import the UNMODIFIED reference hot path from /root/reference (this container only).
 
-TEST INFRASTRUCTURE -- not part of the product path.  Only `oracle/make_golden.py`,
-`oracle/precision_study.py` and the `-m "not gpu"` pinning tests (which skip when
-/root/reference is absent) may use this module.  Nothing on the GPU box may: /root/reference
-does not exist there.
+TEST / MEASUREMENT INFRASTRUCTURE -- not part of the product path.  Users: `oracle/make_golden*.py`,
+`oracle/precision_study.py`, the pinning tests, the tests that drive our boundary through the reference's own callers,
+and bench.py's reference legs.  /root/reference does not exist on the GPU box; there the unmodified copy under
+`oracle/_ref/` (made by `oracle/build_ref.py` in the build container, git-ignored, shipped with the snapshot) is used.
 
 The reference imports plotly / matplotlib / pytorch3d / smplx / h5py at module top
 (core/utils/skeleton_utils.py:1-13, core/pose_opt.py:5, core/dataset.py:2); none of them is
@@ -15,11 +15,30 @@ import sys
 import tempfile
 import types
 
-REF_ROOT = os.environ.get("ANERF_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    """/root/reference in the build container; on the GPU box the unmodified copy under oracle/_ref that
+    oracle/build_ref.py made (it travels with the snapshot like the built .so files)."""
+    for cand in (os.environ.get("ANERF_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "core", "raycasters.py")):
+            return cand
+    return "/root/reference"
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available():
-    return os.path.isdir(os.path.join(REF_ROOT, "core"))
+    if os.environ.get("ANERF_NO_REFERENCE"):       # tests: exercise the fall-back to the oracle port
+        return False
+    return os.path.isfile(os.path.join(REF_ROOT, "core", "raycasters.py"))
+
+
+def reference_kind():
+    """'reference' = the unmodified sources (either location)."""
+    return "reference" if reference_available() else None
 
 
 def _stub(name, **attrs):
@@ -75,3 +94,25 @@ def make_args(**over):
     )
     d.update(over)
     return argparse.Namespace(**d)
+
+
+class reference_on_cuda:
+    """Run the unmodified reference on the GPU the way run_nerf.py does (`torch.set_default_tensor_type(
+    'torch.cuda.FloatTensor')`, run_nerf.py:__main__): several of its tensors are created with the legacy constructors
+    (`torch.Tensor([1e10])`, core/networks/nerf.py:168), which only follow the legacy default type."""
+
+    def __enter__(self):
+        import torch
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            torch.set_default_tensor_type('torch.cuda.FloatTensor')
+        return self
+
+    def __exit__(self, *exc):
+        import torch
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            torch.set_default_tensor_type('torch.FloatTensor')
+        return False

