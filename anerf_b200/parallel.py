@@ -50,28 +50,45 @@ def slab_for_rank(n, rank, world):
     return start, start + base + (1 if rank < rem else 0)
 
 
+def _comm_device():
+    """Where collectives take their tensors: the current CUDA device under NCCL, the host under gloo."""
+    if dist.is_initialized() and dist.get_backend() == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
 def gather_pixels(local_frames, n_frames, rank, world, dst=0):
-    """local_frames: {frame index: tensor [rays, C]} rendered by this rank.  Returns the list of all
-    n_frames tensors on rank `dst` (None elsewhere).  One gather per round of `world` frames."""
+    """local_frames: {frame index: tensor [rays_f, C]} rendered by this rank (fp32).  Returns the list of all
+    n_frames tensors on rank `dst` (None elsewhere).  One gather per round of `world` frames.
+
+    Frames may have DIFFERENT ray counts (per-frame valid-pixel crops: frames.valid_pixels / render_frame(pixel_idx=...))
+    and a rank may own no frame at all (n_frames < world): every round first exchanges the [rows, channels] of each
+    rank's frame (one tiny all_gather), pads the payloads to the round's largest frame and allocates every buffer --
+    placeholders included -- on the communication device with that padded shape."""
     if world == 1:
         return [local_frames[f] for f in range(n_frames)]
     out = [None] * n_frames if rank == dst else None
-    some = next(iter(local_frames.values())) if local_frames else None
+    dev = _comm_device()
     rounds = (n_frames + world - 1) // world
     for r in range(rounds):
         f = r * world + rank
         mine = local_frames.get(f)
-        shape_src = some if some is not None else None
-        if mine is None:
-            # ranks without a frame in the last round still take part with an empty placeholder
-            mine = torch.zeros_like(shape_src) if shape_src is not None else torch.zeros(0)
-        bufs = [torch.empty_like(mine) for _ in range(world)] if rank == dst else None
-        dist.gather(mine.contiguous(), bufs, dst=dst)
+        shape = torch.tensor([0, 0] if mine is None else [mine.shape[0], mine.reshape(mine.shape[0], -1).shape[1]],
+                             dtype=torch.int64, device=dev)
+        shapes = [torch.empty_like(shape) for _ in range(world)]
+        dist.all_gather(shapes, shape)
+        shapes = [tuple(int(x) for x in s.tolist()) for s in shapes]
+        rows, ch = max(s[0] for s in shapes), max(s[1] for s in shapes)
+        pad = torch.zeros((rows, ch), dtype=torch.float32, device=dev)
+        if mine is not None:
+            pad[:mine.shape[0]] = mine.reshape(mine.shape[0], -1).to(dev, torch.float32)
+        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+        dist.gather(pad, bufs, dst=dst)
         if rank == dst:
             for src in range(world):
                 g = r * world + src
                 if g < n_frames:
-                    out[g] = bufs[src]
+                    out[g] = bufs[src][:shapes[src][0], :shapes[src][1]]
     return out
 
 

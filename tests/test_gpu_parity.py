@@ -102,9 +102,8 @@ def test_headline_config_4096_rays(fmt):
     zscale = np.abs(gold["tap_z_all"]).max()
     zerr = np.abs(out["z_all"].astype(np.float64) - gold["tap_z_all"]).max(1) / zscale
     zcond = gold["cond_z_all"].astype(np.float64) / zscale
-    well = zcond < 2e-5
-    assert well.mean() > 0.9
-    assert (zerr[well] < ZTOL).mean() > 0.995, float((zerr[well] < ZTOL).mean())
+    assert (zerr < ZTOL + 8 * zcond).mean() > 0.995, float((zerr < ZTOL + 8 * zcond).mean())
+    assert np.median(zerr) < 2e-6
     assert (zerr < 10 * ZTOL + 8 * zcond).all(), float((zerr - 8 * zcond).max())
 
 

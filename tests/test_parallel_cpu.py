@@ -16,6 +16,11 @@ def _worker(rank, world, port, q):
     n_frames = 5
     mine = {f: torch.full((7, 5), float(f)) + torch.arange(5.) * 0.1 for f in parallel.frames_for_rank(n_frames, r, w)}
     frames = parallel.gather_pixels(mine, n_frames, r, w)
+    # ragged frames (per-frame valid-pixel crops) and fewer frames than ranks: rank 1 owns nothing in the 1-frame case
+    rag = {f: torch.arange((3 + 2 * f) * 5, dtype=torch.float32).reshape(3 + 2 * f, 5) + f for f in parallel.frames_for_rank(3, r, w)}
+    rag_out = parallel.gather_pixels(rag, 3, r, w)
+    one = {f: torch.ones(4, 5) * 9 for f in parallel.frames_for_rank(1, r, w)}
+    one_out = parallel.gather_pixels(one, 1, r, w)
     n = 11
     a, b = parallel.slab_for_rank(n, r, w)
     full = parallel.gather_slabs(torch.arange(a, b, dtype=torch.float32)[:, None] * torch.ones(1, 3), n, r, w)
@@ -45,6 +50,8 @@ def _worker(rank, world, port, q):
     if r == 0:
         ok = all(torch.equal(frames[f], torch.full((7, 5), float(f)) + torch.arange(5.) * 0.1) for f in range(n_frames))
         ok = ok and torch.equal(full, torch.arange(n, dtype=torch.float32)[:, None] * torch.ones(1, 3))
+        ok = ok and all(torch.equal(rag_out[f], torch.arange((3 + 2 * f) * 5, dtype=torch.float32).reshape(3 + 2 * f, 5) + f) for f in range(3))
+        ok = ok and len(one_out) == 1 and torch.equal(one_out[0], torch.ones(4, 5) * 9)
         q.put((ok and g_ok, tmax))
     else:
         assert frames is None and full is None and g_ok
