@@ -15,7 +15,8 @@ _lib = None
 SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "anerf_pack_net",
            "anerf_render_workspace_bytes", "anerf_render_fwd", "anerf_render_fwd_host", "anerf_density_points",
            "anerf_selftest_gemm", "anerf_last_error", "anerf_version", "anerf_debug_set_trace",
-           "anerf_render_bwd", "anerf_render_bwd_workspace_bytes", "anerf_selftest_tc_gemm", "anerf_render_frame"]
+           "anerf_render_bwd", "anerf_render_bwd_workspace_bytes", "anerf_selftest_tc_gemm", "anerf_render_frame",
+           "anerf_check_status"]
 
 
 class NetConfig(C.Structure):
@@ -110,6 +111,11 @@ def load():
 def check(rc):
     if rc != 0:
         raise RuntimeError(f"anerf_b200: {load().anerf_last_error().decode()} (status {rc})")
+
+
+def check_status():
+    """After a stream synchronisation: raises if a kernel recorded a protocol error (anerf_check_status)."""
+    check(load().anerf_check_status())
 
 
 def _ptr(t):

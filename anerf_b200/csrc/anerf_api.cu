@@ -76,14 +76,22 @@ struct anerf_plan {
   int max_smem;
 };
 
+// every entry point starts from a clean error string (a stale message must never be reported for a later failure)
+#define ANERF_ENTRY() g_err.clear()
+
 extern "C" {
 
 const char* anerf_last_error(void) { return g_err.c_str(); }
+/* Device status word of the calling process (pinned host memory the kernels write a protocol error into before they
+ * trap): 0 when clean, ANERF_ERR_DEVICE + message otherwise.  The asynchronous entry points cannot consult it; callers
+ * check it after synchronising the stream (tests, bench). */
+int anerf_check_status(void) { ANERF_ENTRY(); return check_device_status(); }
 int anerf_version(void) { return 100; }
 /* debug: device buffer of 3 x 1024 int64 that the next launches fill with a clock64 timeline of CTA 0 (NULL = off) */
 void anerf_debug_set_trace(long long* device_buffer) { g_trace = device_buffer; }
 
 int anerf_plan_create(const anerf_net_config* cfg, anerf_plan** out) {
+  ANERF_ENTRY();
   if (!cfg || !out) return fail(ANERF_ERR_INVALID, "null argument");
   if (cfg->n_joints < 1 || cfg->n_joints > kMaxJoints) return fail(ANERF_ERR_INVALID, "n_joints must be 1..24");
   if (cfg->width != 64 && cfg->width != 128 && cfg->width != 256) return fail(ANERF_ERR_INVALID, "width must be 64, 128 or 256");
@@ -148,6 +156,7 @@ void anerf_plan_destroy(anerf_plan* p) {
 size_t anerf_packed_bytes(const anerf_plan* plan) { return plan ? plan->prog.packed_bytes : 0; }
 
 int anerf_pack_net(const anerf_plan* plan, const anerf_net_params* prm, void* packed, void* stream_) {
+  ANERF_ENTRY();
   if (!plan || !prm || !packed) return fail(ANERF_ERR_INVALID, "null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   const NetProgram& pg = plan->prog;
@@ -302,6 +311,7 @@ static int render_common(const anerf_plan* plan, const void* packed_coarse, cons
 int anerf_render_fwd(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
                      const anerf_render_opts* o, const anerf_render_inputs* in, const anerf_render_outputs* out,
                      void* workspace, size_t workspace_bytes, void* stream_) {
+  ANERF_ENTRY();
   if (!plan || !packed_coarse || !o || !in || !out) return fail(ANERF_ERR_INVALID, "null argument");
   if (o->n_rays == 0) return ANERF_OK;
   if (!in->rays || !in->skts || !in->cyls) return fail(ANERF_ERR_INVALID, "rays/skts/cyls missing");
@@ -313,6 +323,7 @@ int anerf_render_fwd(const anerf_plan* plan, const void* packed_coarse, const vo
 int anerf_render_frame(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
                        const anerf_render_opts* o, const anerf_frame_inputs* fr, const anerf_render_outputs* out,
                        void* workspace, size_t workspace_bytes, void* stream_) {
+  ANERF_ENTRY();
   if (!plan || !packed_coarse || !o || !fr || !out) return fail(ANERF_ERR_INVALID, "null argument");
   if (o->n_rays == 0) return ANERF_OK;
   if (!fr->skts || !fr->cyl) return fail(ANERF_ERR_INVALID, "skts/cyl missing");
@@ -331,6 +342,7 @@ int anerf_render_frame(const anerf_plan* plan, const void* packed_coarse, const 
 
 int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf_render_opts* o, const float* pts,
                          const float* skts, int64_t n_points, float* sigma, void* stream_) {
+  ANERF_ENTRY();
   if (!plan || !packed || !o || !pts || !skts || !sigma) return fail(ANERF_ERR_INVALID, "null argument");
   if (n_points <= 0) return ANERF_OK;
   if (n_points > (int64_t)1 << 37) return fail(ANERF_ERR_INVALID, "too many points");
@@ -347,6 +359,7 @@ int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf
 int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
                           const anerf_render_opts* o, const anerf_render_inputs* hin,
                           const anerf_render_outputs* hout, void* stream_) {
+  ANERF_ENTRY();
   if (!plan || !o || !hin || !hout) return fail(ANERF_ERR_INVALID, "null argument");
   cudaStream_t stream = (cudaStream_t)stream_;
   const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance, Sf = Sc + Si, J = plan->dims.J;
@@ -368,10 +381,11 @@ int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, con
   size_t ws_off = off;
   off += al(anerf_render_workspace_bytes(N));
   {   // keep the stream-ordered pool's memory across calls (the default releases it at every synchronisation)
-    static bool pool_ready = false;
+    static bool pool_ready_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& pool_ready = pool_ready_dev[(dev >= 0 && dev < 64) ? dev : 0];
     if (!pool_ready) {
-      int dev = 0;
-      cudaGetDevice(&dev);
       cudaMemPool_t pool;
       if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
         unsigned long long keep = ~0ull;
@@ -399,7 +413,10 @@ int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, con
   cudaFreeAsync(arena, stream);
   cudaError_t e = cudaStreamSynchronize(stream);
   if (rc != ANERF_OK) return rc;
-  if (e != cudaSuccess) { check_device_status(); return g_err.empty() ? fail(ANERF_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e)) : ANERF_ERR_DEVICE; }
+  if (e != cudaSuccess) {
+    if (check_device_status() != 0) return ANERF_ERR_DEVICE;      // g_err holds the kernel's protocol error
+    return fail(ANERF_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
+  }
   return check_device_status();
 }
 
@@ -412,6 +429,7 @@ int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, con
                      const anerf_render_opts* o, const anerf_render_inputs* in, const float* nearfar, const float* z_all,
                      const anerf_render_grads* gout, const anerf_net_grads* g_coarse, const anerf_net_grads* g_fine,
                      float* g_skts, void* workspace, size_t workspace_bytes, void* stream_) {
+  ANERF_ENTRY();
   if (!plan || !coarse || !o || !in || !gout || !nearfar) return fail(ANERF_ERR_INVALID, "null argument");
   const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance;
   if (N == 0) return ANERF_OK;
@@ -468,6 +486,7 @@ int anerf_selftest_tc_gemm(const float* A, int64_t a_ms, int64_t a_ks, int32_t M
                            int64_t b_ks, int32_t N, float* C, int64_t c_ms, int64_t c_ns, const float* bias,
                            const float* mask, int64_t mask_ms, int32_t relu, int32_t mode, int32_t slice_chunks,
                            void* stream_) {
+  ANERF_ENTRY();
   if (!A || !B || !C || M <= 0 || N <= 0 || K <= 0) return fail(ANERF_ERR_INVALID, "bad argument");
   if (slice_chunks < 0 || slice_chunks % 4 != 0) return fail(ANERF_ERR_INVALID, "slice_chunks must be a multiple of 4");
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -491,6 +510,7 @@ int anerf_selftest_tc_gemm(const float* A, int64_t a_ms, int64_t a_ks, int32_t M
 }
 
 int anerf_selftest_gemm(const float* A, const float* B, float* D, int32_t N, int32_t K, int32_t format, void* stream_) {
+  ANERF_ENTRY();
   if (!A || !B || !D) return fail(ANERF_ERR_INVALID, "null argument");
   if (K <= 0 || K % (kGroups * kKC) != 0) return fail(ANERF_ERR_INVALID, "K must be a positive multiple of 128");
   if (N != 64 && N != 128 && N != 256) return fail(ANERF_ERR_INVALID, "N must be 64, 128 or 256");

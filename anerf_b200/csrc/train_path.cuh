@@ -99,10 +99,14 @@ struct TcEngine {
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      attr_set = true;
+    {   // function attributes are per device
+      static bool attr_set[64] = {};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+      }
     }
     if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, g) != cudaSuccess) error = 2;
   }

@@ -58,9 +58,14 @@ class CutoffEmbedder(Embedder):
         self.cutoff_dist = nn.Parameter(torch.ones(cutoff_dim) * cutoff_dist, requires_grad=False)
         self.init_tau = 20.
         self.register_buffer('tau', torch.tensor(self.init_tau))
+        self._epoch = 0          # bumped whenever tau / cutoff_dist may have changed (cache key of RayCaster._opts)
 
     def get_tau(self):
         return self.tau.item()
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self._epoch += 1
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def get_cutoff_dist(self):
         return self.cutoff_dist
@@ -71,6 +76,7 @@ class CutoffEmbedder(Embedder):
     def update_tau(self, global_step, step, rate):
         # tau = min(2000, 20 * rate^(step / (cutoff_step * 1000)))   (cutoff_embedder.py:181-183)
         self.tau = (self.init_tau * torch.ones_like(self.tau) * rate ** (global_step / float(step * 1000))).clamp(max=2000.)
+        self._epoch += 1
 
 
 class Optcodes(nn.Module):
@@ -201,12 +207,18 @@ class RayCaster(nn.Module):
         return self.embed_fn.cutoff_dim
 
     def _get_plan(self):
+        """The plan owns device buffers: it is created (and must be used) under the device of the parameters."""
+        dev = next(self.network.parameters()).device
+        if self._plan is not None and self._plan_device != dev:
+            self._plan, self._packed = None, {}
         if self._plan is None:
+            self._plan_device = dev
             net = self.network
-            self._plan = _lib.Plan(self._n_joints(), net.D, net.W, net.skips,
-                                   net.framecode_ch if net.use_framecode else 0,
-                                   net.n_framecodes if net.use_framecode else 0, self._operand_format,
-                                   view_freqs=self.embeddirs_fn.num_freqs)
+            with torch.cuda.device(dev):
+                self._plan = _lib.Plan(self._n_joints(), net.D, net.W, net.skips,
+                                       net.framecode_ch if net.use_framecode else 0,
+                                       net.n_framecodes if net.use_framecode else 0, self._operand_format,
+                                       view_freqs=self.embeddirs_fn.num_freqs)
         return self._plan
 
     def _packed_image(self, which):
@@ -235,8 +247,10 @@ class RayCaster(nn.Module):
             softplus, shift = True, float(density_fn.anerf_shift)
         # embedder scalars live on the device; read them back only when they change (no per-chunk sync)
         e0, e1 = self.embed_fn, self.embeddirs_fn
-        sig = (id(e0.tau), e0.tau._version, id(e1.tau), e1.tau._version, e0.cutoff_dist._version,
-               e1.cutoff_dist._version, e0.cutoff_dist.data_ptr(), e1.cutoff_dist.data_ptr())
+        # key: an explicit epoch (update_tau rebinds `tau` to a fresh tensor whose id / version can repeat) plus the
+        # in-place version counters (tau.fill_(...), cutoff_dist.data edits)
+        sig = (e0._epoch, e1._epoch, e0.tau._version, e1.tau._version, e0.cutoff_dist._version, e1.cutoff_dist._version,
+               e0.tau.data_ptr(), e1.tau.data_ptr(), e0.cutoff_dist.data_ptr(), e1.cutoff_dist.data_ptr())
         if getattr(self, '_embed_cache', (None,))[0] != sig:
             self._embed_cache = (sig, float(e0.tau), float(e1.tau), e0.cutoff_dist.detach().float().cpu().tolist(),
                                  e1.cutoff_dist.detach().float().cpu().tolist())
@@ -325,9 +339,9 @@ class RayCaster(nn.Module):
                 outs = _RenderRaysFn.apply(self, opts, aux, skts_c, *params)
             keys = [k for k in OUT_KEYS if Si > 0 or not k.endswith('0')]
             return dict(zip(keys, outs))
-        p0 = self._packed_image('network')
-        p1 = self._packed_image('network_fine') if Si > 0 else None
-        with torch.cuda.device(dev):
+        with torch.cuda.device(dev):        # plan buffers, packing kernels and the render launch all on the tensors' device
+            p0 = self._packed_image('network')
+            p1 = self._packed_image('network_fine') if Si > 0 else None
             out = _lib.render_fwd(self._get_plan(), p0, p1, opts, rays, skts_c.detach(), cyls_c, cams_c, t_rand, u_rand,
                                   noise0, noise1, want_taps=bool(retraw))
         return out
@@ -361,8 +375,9 @@ class RayCaster(nn.Module):
             eval_mean = (not self.training) and cam < 0
         density_scale = preproc_kwargs.get('density_scale', 1.0)
         density_fn = preproc_kwargs.get('density_fn', None)
-        p0 = self._packed_image('network')
-        p1 = self._packed_image('network_fine') if Si > 0 else None
+        with torch.cuda.device(dev):
+            p0 = self._packed_image('network')
+            p1 = self._packed_image('network_fine') if Si > 0 else None
         if out is None:
             f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
             out = dict(rgb_map=f(n, 3), disp_map=f(n), acc_map=f(n), alpha=f(n, Sc + Si if Si > 0 else Sc))

@@ -243,6 +243,10 @@ void anerf_debug_set_trace(long long* device_buffer);
 
 const char* anerf_last_error(void);
 int anerf_version(void);
+/* The kernels never spin forever: a protocol error is recorded in a pinned status word and the kernel traps.  The
+ * asynchronous entry points cannot see that; call this after synchronising the stream (0 = clean, ANERF_ERR_DEVICE
+ * + anerf_last_error() otherwise).  [the reference drops into pdb on NaNs, core/utils/ray_utils.py:247] */
+int anerf_check_status(void);
 
 #ifdef __cplusplus
 }

@@ -103,7 +103,7 @@ def test_headline_config_4096_rays(fmt):
     zerr = np.abs(out["z_all"].astype(np.float64) - gold["tap_z_all"]).max(1) / zscale
     zcond = gold["cond_z_all"].astype(np.float64) / zscale
     assert (zerr < ZTOL + 8 * zcond).mean() > 0.995, float((zerr < ZTOL + 8 * zcond).mean())
-    assert np.median(zerr) < 2e-6
+    assert np.median(zerr) < (2e-6 if fmt == 0 else 1e-5)
     assert (zerr < 10 * ZTOL + 8 * zcond).all(), float((zerr - 8 * zcond).max())
 
 
