@@ -16,7 +16,7 @@ SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "ane
            "anerf_render_workspace_bytes", "anerf_render_fwd", "anerf_render_fwd_host", "anerf_density_points",
            "anerf_selftest_gemm", "anerf_last_error", "anerf_version", "anerf_debug_set_trace",
            "anerf_render_bwd", "anerf_render_bwd_workspace_bytes", "anerf_selftest_tc_gemm", "anerf_render_frame",
-           "anerf_check_status"]
+           "anerf_check_status", "anerf_density_grid", "anerf_render_fwd_host_chunked"]
 
 
 class NetConfig(C.Structure):
@@ -93,6 +93,10 @@ def load():
                                           C.POINTER(RenderInputs), C.POINTER(RenderOutputs), C.c_void_p]
     lib.anerf_density_points.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p]
+    lib.anerf_density_grid.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_float, C.c_int32, C.c_int64,
+                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.anerf_render_fwd_host_chunked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_int32,
+                                                  C.POINTER(RenderInputs), C.POINTER(RenderOutputs)]
     lib.anerf_selftest_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.anerf_render_bwd_workspace_bytes.restype = C.c_size_t
     lib.anerf_render_bwd_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
@@ -272,6 +276,41 @@ def render_fwd_host(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, ca
     check(load().anerf_render_fwd_host(plan.handle, _ptr(packed_coarse), _ptr(packed_fine), C.byref(opts), C.byref(rin),
                                        C.byref(rout), _stream()))
     return out
+
+
+def render_fwd_host_chunked(plan, packed_coarse, packed_fine, opts, chunk, rays, skts, cyls, cams=None, out=None,
+                            keys=("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0", "alpha0")):
+    """A whole frame (opts.n_rays rays, any number) of host tensors in chunks of `chunk` rays, host<->device copies
+    overlapped with the kernels (C ABI anerf_render_fwd_host_chunked).  `keys`: which outputs to produce on the host."""
+    N, Sc, Si = opts.n_rays, opts.n_samples, opts.n_importance
+    Sf = Sc + Si
+    shapes = dict(rgb_map=(N, 3), disp_map=(N,), acc_map=(N,), alpha=(N, Sf if Si > 0 else Sc), rgb0=(N, 3), disp0=(N,),
+                  acc0=(N,), alpha0=(N, Sc))
+    if out is None:
+        out = {k: torch.empty(*shapes[k], dtype=torch.float32).pin_memory() for k in keys if Si > 0 or not k.endswith("0")}
+    for t in (rays, skts, cyls, cams):
+        assert t is None or (not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+    for k, t in out.items():
+        assert tuple(t.shape) == shapes[k] and not t.is_cuda and t.is_contiguous()
+    rin = RenderInputs(_ptr(rays), _ptr(skts), _ptr(cyls), _ptr(cams), None, None, None, None)
+    rout = RenderOutputs(*[_ptr(out.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0",
+                                                      "alpha0", "z_all", "raw")])
+    check(load().anerf_render_fwd_host_chunked(plan.handle, _ptr(packed_coarse), _ptr(packed_fine), C.byref(opts), int(chunk),
+                                               C.byref(rin), C.byref(rout)))
+    return out
+
+
+def density_grid(plan, packed, opts, origin, radius, res, skts, first=0, count=None):
+    """Raw densities of voxels [first, first+count) of the reference's flattened (res+1)^3 grid around `origin`
+    (CUDA tensor, 3 floats), points generated in the kernel (C ABI anerf_density_grid).  Returns sigma [count]."""
+    total = (res + 1) ** 3
+    count = total - first if count is None else count
+    assert origin.is_cuda and origin.dtype == torch.float32 and origin.is_contiguous() and origin.numel() == 3
+    assert skts.is_cuda and skts.dtype == torch.float32 and skts.is_contiguous()
+    sigma = torch.empty(count, dtype=torch.float32, device=skts.device)
+    check(load().anerf_density_grid(plan.handle, _ptr(packed), C.byref(opts), _ptr(origin), float(radius), int(res), int(first),
+                                    int(count), _ptr(skts), _ptr(sigma), _stream()))
+    return sigma
 
 
 PARAM_ORDER = (["pts_w", "pts_b"], ["alpha_w", "alpha_b", "feature_w", "feature_b", "views_w", "views_b", "rgb_w", "rgb_b"])

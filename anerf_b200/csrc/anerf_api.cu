@@ -356,6 +356,29 @@ int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf
   return launch_fused(plan, P, true, (cudaStream_t)stream_);
 }
 
+int anerf_density_grid(const anerf_plan* plan, const void* packed, const anerf_render_opts* o, const float* origin,
+                       float radius, int32_t res, int64_t first, int64_t count, const float* skts, float* sigma, void* stream_) {
+  ANERF_ENTRY();
+  if (!plan || !packed || !o || !origin || !skts || !sigma) return fail(ANERF_ERR_INVALID, "null argument");
+  if (res < 1 || res > 2047) return fail(ANERF_ERR_INVALID, "res must be 1..2047");
+  const long long total = (long long)(res + 1) * (res + 1) * (res + 1);
+  if (first < 0 || count < 0 || first + count > total) return fail(ANERF_ERR_INVALID, "voxel range outside the grid");
+  if (count == 0) return ANERF_OK;
+  RenderKParams P{};
+  fill_common(plan, o, P);
+  P.packed[0] = P.packed[1] = (const uint8_t*)packed;
+  P.sl = make_smem_layout(plan->dims, plan->prog.sm.fixed_floats, 1, 4, 4);
+  P.R = 1; P.Sc = 4; P.Sf = 4; P.slotc = slot_chunks(1);
+  P.n_items = (int)((count + kTileM - 1) / kTileM);
+  P.pts = nullptr; P.skts = skts; P.sigma = sigma; P.n_points = count;
+  P.grid_first = first; P.grid_n1 = res + 1;
+  // numpy.linspace(-r, r, res + 1) in fp64: step = (stop - start) / res; y[i] = i * step + start; y[-1] = stop
+  P.grid_start = -(double)radius; P.grid_stop = (double)radius;
+  P.grid_step = (P.grid_stop - P.grid_start) / (double)res;
+  P.grid_origin = origin;
+  return launch_fused(plan, P, true, (cudaStream_t)stream_);
+}
+
 int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
                           const anerf_render_opts* o, const anerf_render_inputs* hin,
                           const anerf_render_outputs* hout, void* stream_) {
@@ -415,6 +438,111 @@ int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, con
   if (rc != ANERF_OK) return rc;
   if (e != cudaSuccess) {
     if (check_device_status() != 0) return ANERF_ERR_DEVICE;      // g_err holds the kernel's protocol error
+    return fail(ANERF_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
+  }
+  return check_device_status();
+}
+
+namespace {
+// per-device state of anerf_render_fwd_host_chunked: three streams, two arenas, events
+struct HostPipe {
+  cudaStream_t s_in = nullptr, s_run = nullptr, s_out = nullptr;
+  uint8_t* arena[2] = {nullptr, nullptr};
+  size_t arena_bytes = 0;
+  cudaEvent_t in_done[2] = {}, run_done[2] = {}, out_done[2] = {};
+  bool ready = false;
+};
+HostPipe g_host_pipe[64];
+std::mutex g_host_pipe_mu;
+}  // namespace
+
+int anerf_render_fwd_host_chunked(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
+                                  const anerf_render_opts* o, int32_t chunk, const anerf_render_inputs* hin,
+                                  const anerf_render_outputs* hout) {
+  ANERF_ENTRY();
+  if (!plan || !o || !hin || !hout) return fail(ANERF_ERR_INVALID, "null argument");
+  const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance, Sf = Sc + Si, J = plan->dims.J;
+  if (N <= 0) return ANERF_OK;
+  if (chunk <= 0) return fail(ANERF_ERR_INVALID, "chunk must be positive");
+  if (!hin->rays || !hin->skts || !hin->cyls) return fail(ANERF_ERR_INVALID, "rays/skts/cyls missing");
+  if (!hout->rgb_map || !hout->disp_map || !hout->acc_map) return fail(ANERF_ERR_INVALID, "rgb/disp/acc outputs missing");
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return fail(ANERF_ERR_INVALID, "device index %d not supported", dev);
+  std::lock_guard<std::mutex> lk(g_host_pipe_mu);     // one frame at a time per process: the arenas are shared
+  HostPipe& hp = g_host_pipe[dev];
+  if (!hp.ready) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_in, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_run, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&hp.s_out, cudaStreamNonBlocking));
+    for (int b = 0; b < 2; ++b) {
+      CUDA_TRY(cudaEventCreateWithFlags(&hp.in_done[b], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&hp.run_done[b], cudaEventDisableTiming));
+      CUDA_TRY(cudaEventCreateWithFlags(&hp.out_done[b], cudaEventDisableTiming));
+    }
+    hp.ready = true;
+  }
+  // arena layout for one chunk of `c` rays (offsets independent of the actual chunk length: sized for `chunk`)
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t C = (size_t)(chunk < N ? chunk : N);
+  const int Sa = Si > 0 ? Sf : Sc;
+  struct Seg { size_t off; size_t per_ray; const void* h; };
+  size_t off = 0;
+  auto seg = [&](const void* h, size_t per_ray) { Seg s{off, per_ray, h}; if (h) off += al(C * per_ray); return s; };
+  Seg i_rays = seg(hin->rays, 8 * 4), i_skts = seg(hin->skts, (size_t)J * 64), i_cyls = seg(hin->cyls, 5 * 4), i_cams = seg(hin->cams, 4),
+      i_tr = seg(hin->t_rand, (size_t)Sc * 4), i_ur = seg(hin->u_rand, (size_t)Si * 4), i_n0 = seg(hin->noise0, (size_t)Sc * 4),
+      i_n1 = seg(hin->noise1, (size_t)Sf * 4);
+  Seg o_rgb = seg(hout->rgb_map, 12), o_disp = seg(hout->disp_map, 4), o_acc = seg(hout->acc_map, 4), o_alpha = seg(hout->alpha, (size_t)Sa * 4),
+      o_rgb0 = seg(hout->rgb0, 12), o_disp0 = seg(hout->disp0, 4), o_acc0 = seg(hout->acc0, 4), o_alpha0 = seg(hout->alpha0, (size_t)Sc * 4),
+      o_zall = seg(hout->z_all, (size_t)Sf * 4), o_raw = seg(hout->raw, (size_t)Sa * 16);
+  const size_t ws_off = off;
+  off += al(anerf_render_workspace_bytes((int)C));
+  if (hp.arena_bytes < off) {
+    for (int b = 0; b < 2; ++b) {
+      if (hp.arena[b]) cudaFree(hp.arena[b]);
+      hp.arena[b] = nullptr;
+    }
+    hp.arena_bytes = 0;
+    for (int b = 0; b < 2; ++b) CUDA_TRY(cudaMalloc((void**)&hp.arena[b], off));
+    hp.arena_bytes = off;
+  }
+  const Seg* ins[] = {&i_rays, &i_skts, &i_cyls, &i_cams, &i_tr, &i_ur, &i_n0, &i_n1};
+  const Seg* outs[] = {&o_rgb, &o_disp, &o_acc, &o_alpha, &o_rgb0, &o_disp0, &o_acc0, &o_alpha0, &o_zall, &o_raw};
+  int rc = ANERF_OK;
+  int n_chunks = 0;
+  for (long long r0 = 0; r0 < N && rc == ANERF_OK; r0 += chunk, ++n_chunks) {
+    const int b = n_chunks & 1;
+    const int n = (int)((N - r0) < chunk ? (N - r0) : chunk);
+    uint8_t* A = hp.arena[b];
+    // arena b is free once the device -> host copies of the chunk that used it two rounds ago are done
+    if (n_chunks >= 2) CUDA_TRY(cudaStreamWaitEvent(hp.s_in, hp.out_done[b], 0));
+    for (const Seg* s : ins)
+      if (s->h) CUDA_TRY(cudaMemcpyAsync(A + s->off, (const uint8_t*)s->h + (size_t)r0 * s->per_ray, (size_t)n * s->per_ray, cudaMemcpyHostToDevice, hp.s_in));
+    CUDA_TRY(cudaEventRecord(hp.in_done[b], hp.s_in));
+    CUDA_TRY(cudaStreamWaitEvent(hp.s_run, hp.in_done[b], 0));
+    if (n_chunks >= 2) CUDA_TRY(cudaStreamWaitEvent(hp.s_run, hp.out_done[b], 0));
+    auto dp = [&](const Seg& s) -> float* { return s.h ? (float*)(A + s.off) : nullptr; };
+    anerf_render_inputs din{dp(i_rays), dp(i_skts), dp(i_cyls), dp(i_cams), dp(i_tr), dp(i_ur), dp(i_n0), dp(i_n1)};
+    anerf_render_outputs dout{dp(o_rgb), dp(o_disp), dp(o_acc), dp(o_alpha), dp(o_rgb0), dp(o_disp0), dp(o_acc0), dp(o_alpha0), dp(o_zall), dp(o_raw)};
+    anerf_render_opts oc = *o;
+    oc.n_rays = n;
+    rc = anerf_render_fwd(plan, packed_coarse, packed_fine, &oc, &din, &dout, A + ws_off, anerf_render_workspace_bytes(n), hp.s_run);
+    if (rc != ANERF_OK) break;
+    CUDA_TRY(cudaEventRecord(hp.run_done[b], hp.s_run));
+    CUDA_TRY(cudaStreamWaitEvent(hp.s_out, hp.run_done[b], 0));
+    for (const Seg* s : outs)
+      if (s->h) CUDA_TRY(cudaMemcpyAsync((uint8_t*)s->h + (size_t)r0 * s->per_ray, A + s->off, (size_t)n * s->per_ray, cudaMemcpyDeviceToHost, hp.s_out));
+    CUDA_TRY(cudaEventRecord(hp.out_done[b], hp.s_out));
+  }
+  const std::string keep = g_err;                       // anerf_render_fwd's message, if it failed
+  cudaError_t e = cudaStreamSynchronize(hp.s_in);
+  cudaError_t e2 = cudaStreamSynchronize(hp.s_run);
+  cudaError_t e3 = cudaStreamSynchronize(hp.s_out);
+  if (rc != ANERF_OK) { g_err = keep; return rc; }
+  if (e == cudaSuccess) e = e2;
+  if (e == cudaSuccess) e = e3;
+  if (e != cudaSuccess) {
+    if (check_device_status() != 0) return ANERF_ERR_DEVICE;
     return fail(ANERF_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
   }
   return check_device_status();

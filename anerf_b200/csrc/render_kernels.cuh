@@ -179,10 +179,16 @@ struct RenderKParams {
   float cam_const;          // frame mode: the frame's camera index (framecodes)
   const float* nearfar;     // [N,2] from the near/far pre-kernel
   float *rgb_map, *disp_map, *acc_map, *alpha, *rgb0, *disp0, *acc0, *alpha0, *z_all_out, *raw_out;
-  // density-only mode (mesh grid): one pose, explicit points
+  // density-only mode (mesh grid): one pose; explicit points, or (pts == NULL) the points [grid_first, grid_first +
+  // n_points) of the reference's flattened (res+1)^3 grid generated in the kernel (core/raycasters.py:579-595)
   const float* pts;
   float* sigma;
   long long n_points;
+  long long grid_first;
+  int grid_n1;              // res + 1
+  double grid_start, grid_step;   // np.linspace(-radius, radius, res + 1): start + i * step in fp64, last = radius
+  double grid_stop;
+  const float* grid_origin; // device pointer to kps[0, 0] (3 floats)
   DeviceStatus* status;
   long long* trace;         // optional debug timeline (anerf_debug_set_trace): [3 streams][1024] clock64 stamps of CTA 0
   SmemLayout sl;
@@ -927,7 +933,18 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         bool valid = idx < P.n_points;
         long long ci = valid ? idx : (P.n_points - 1);
         RowCtx rc;
-        rc.p[0] = P.pts[ci * 3 + 0]; rc.p[1] = P.pts[ci * 3 + 1]; rc.p[2] = P.pts[ci * 3 + 2];
+        if (P.pts) {
+          rc.p[0] = P.pts[ci * 3 + 0]; rc.p[1] = P.pts[ci * 3 + 1]; rc.p[2] = P.pts[ci * 3 + 2];
+        } else {
+          // flat index -> (a, b, c) of np.meshgrid(t, t, t) ('xy' indexing: x = t[b], y = t[a], z = t[c]); the
+          // coordinate is np.linspace's fp64 value rounded to fp32, then the fp32 add of the root joint
+          const long long f = P.grid_first + ci;
+          const int n1 = P.grid_n1;
+          const int a = (int)(f / ((long long)n1 * n1)), rem = (int)(f % ((long long)n1 * n1));
+          const int b = rem / n1, c = rem % n1;
+          auto tv = [&](int i) { return i == n1 - 1 ? (float)P.grid_stop : (float)((double)i * P.grid_step + P.grid_start); };
+          rc.p[0] = tv(b) + __ldg(P.grid_origin); rc.p[1] = tv(a) + __ldg(P.grid_origin + 1); rc.p[2] = tv(c) + __ldg(P.grid_origin + 2);
+        }
         rc.skt = skt_s; rc.slot = 0;
         float4 r = worker_net_pass<FMT, true>(ap, pp, d_cnt, rc, P, sm0, quarter, grp, row, nullptr);
         part_s[grp * kTileM + row] = r;

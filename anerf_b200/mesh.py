@@ -13,7 +13,8 @@ from . import parallel
 
 def grid_points(kps, radius, res, start=0, stop=None):
     """World points [start, stop) of the flattened reference grid (np.meshgrid(t, t, t) order, 'xy' indexing)
-    around kps[0, 0], generated on the device without materialising the full grid."""
+    around kps[0, 0] as explicit tensors.  The product path no longer uses this (the kernel generates the points,
+    `RayCaster.render_mesh_density`); tests compare the two."""
     n1 = res + 1
     total = n1 ** 3
     stop = total if stop is None else stop
@@ -32,8 +33,8 @@ def density_grid_sharded(ray_caster, kps, skts, radius=1.0, res=255, rank=0, wor
     n1 = res + 1
     total = n1 ** 3
     a, b = parallel.slab_for_rank(total, rank, world)
-    pts = grid_points(kps, radius, res, a, b)
-    sig = ray_caster.render_pts_density(pts.reshape(-1, 1, 3), kps, skts, None).reshape(-1, 1)
+    # the slab's points are generated inside the density kernel (anerf_density_grid): algorithmic HBM traffic only
+    sig = ray_caster.render_mesh_density(kps, skts, None, radius=radius, res=res, first=a, count=b - a).reshape(-1, 1)
     full = parallel.gather_slabs(sig, total, rank, world, dst=dst)
     if full is None:
         return None

@@ -394,14 +394,27 @@ class RayCaster(nn.Module):
 
     @torch.no_grad()
     def render_mesh_density(self, kps, skts, bones, subject_idxs=None, radius=1.0, res=64, render_kwargs=None,
-                            netchunk=1024 * 64, v=None):
-        """[res+1]^3 raw densities around kps[0,0] (reference: core/raycasters.py:579-595)."""
-        t = np.linspace(-radius, radius, res + 1)
-        grid = np.stack(np.meshgrid(t, t, t), axis=-1).astype(np.float32)
-        sh = grid.shape
-        pts = torch.tensor(grid.reshape(-1, 3), device=kps.device) + kps[0, 0]
-        raw = self.render_pts_density(pts.reshape(-1, 1, 3), kps, skts, bones, render_kwargs, subject_idxs, netchunk)
-        return raw[..., :1].reshape(*sh[:-1]).transpose(1, 0)
+                            netchunk=1024 * 64, v=None, first=0, count=None):
+        """[res+1]^3 raw densities around kps[0,0] (reference: core/raycasters.py:579-595: np.meshgrid(t, t, t) with
+        t = np.linspace(-radius, radius, res+1), + kps[0,0], density of `network_fine`, reshaped and transposed (1,0)).
+        The grid points are generated inside the kernel from (root joint, radius, res): only the densities touch HBM.
+        `first`/`count` (ours): a slab of the flattened grid instead of the whole volume -> flat [count] tensor."""
+        if v is not None:
+            raise NotImplementedError("precomputed v is not supported")
+        if skts.shape[0] != 1:
+            raise NotImplementedError("density queries take one pose (skts [1,J,4,4])")
+        dev = skts.device
+        if dev.type != 'cuda':
+            raise RuntimeError("anerf_b200.RayCaster: inputs must be CUDA tensors (no CPU path)")
+        which = 'network_fine' if self.network_fine is not None else 'network'
+        opts = self._opts(0, 64, 0, False, 1.0, None)
+        with torch.cuda.device(dev):
+            sig = _lib.density_grid(self._get_plan(), self._packed_image(which), opts, kps[0, 0].float().contiguous(), radius, res,
+                                    skts[0].float().contiguous(), first, count)
+        if first != 0 or count is not None:
+            return sig
+        n1 = res + 1
+        return sig.reshape(n1, n1, n1).transpose(1, 0)
 
     @torch.no_grad()
     def render_pts_density(self, pts, kps, skts, bones, render_kwargs=None, subject_idxs=None, netchunk=1024 * 64,

@@ -172,6 +172,16 @@ int anerf_render_fwd_host(const anerf_plan* plan, const void* packed_coarse, con
                           const anerf_render_opts* opts, const anerf_render_inputs* host_in,
                           const anerf_render_outputs* host_out, void* stream);
 
+/* What core/trainer.py:64-79 batchify_rays does with a whole frame of HOST buffers: opts->n_rays rays (any number) are
+ * processed in chunks of `chunk` rays (each chunk exactly as one anerf_render_fwd call, so the near/far repair stays a
+ * chunk-wide mean), with the copies of chunk c+1 (host -> device) and of chunk c-1 (device -> host) overlapping the
+ * kernels of chunk c: three internal streams and two device arenas that are kept across calls.  Pinned host memory
+ * gives real overlap; pageable memory works but serialises.  Outputs that are NULL are neither computed into host memory
+ * nor copied (render_path reads rgb/disp/acc only).  Synchronises before returning. */
+int anerf_render_fwd_host_chunked(const anerf_plan* plan, const void* packed_coarse, const void* packed_fine,
+                                  const anerf_render_opts* opts, int32_t chunk, const anerf_render_inputs* host_in,
+                                  const anerf_render_outputs* host_out);
+
 /* ---- training: backward of one chunk ------------------------------------------------------------------ */
 
 /* Gradient buffers of one network, same shapes as anerf_net_params, fp32 on the device.  Gradients are ADDED to
@@ -220,6 +230,14 @@ int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, con
  * sigma [P].  Uses tau_pts / cutoff_pts of `opts` (other fields ignored). */
 int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf_render_opts* opts,
                          const float* pts, const float* skts, int64_t n_points, float* sigma, void* stream);
+
+/* The same for voxels [first, first + count) of the flattened (res+1)^3 grid that RayCaster.render_mesh_density builds
+ * (core/raycasters.py:579-595: np.meshgrid(t, t, t) with t = np.linspace(-radius, radius, res+1), plus kps[0,0]), with
+ * the points generated inside the kernel: nothing but the densities touches HBM.  origin: DEVICE pointer to the root
+ * joint position (3 floats); sigma [count] in flat grid order. */
+int anerf_density_grid(const anerf_plan* plan, const void* packed, const anerf_render_opts* opts, const float* origin,
+                       float radius, int32_t res, int64_t first, int64_t count, const float* skts, float* sigma,
+                       void* stream);
 
 /* Build-time self test of the tensor-core building blocks on one CTA pair: D[256,N] = A[256,K] * B[N,K]^T with
  * the split-precision operand path (A, B fp32 on the device, D [2,256,N] fp32: two passes; K multiple of 128;

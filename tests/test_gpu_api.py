@@ -133,6 +133,54 @@ def test_sharded_density_grid_and_ragged_point_counts():
     for n in (1, 127, 129, 1000):
         part = rc.render_pts_density(pts[:n].reshape(-1, 1, 3), kps, skts, None).reshape(-1)
         assert torch.equal(part, full[:n])
+    # points generated inside the kernel (anerf_density_grid) == the explicit points, bit for bit, whole grid and slabs;
+    # a radius whose linspace steps are not exact in fp32 exercises the fp64 coordinate arithmetic
+    n1 = case["res"] + 1
+    grid = rc.render_mesh_density(kps, skts, None, radius=case["radius"], res=case["res"])
+    assert torch.equal(grid, full.reshape(n1, n1, n1).transpose(1, 0))
+    for first, count in ((0, 1), (5, 300), (n1 ** 3 - 129, 129)):
+        slab = rc.render_mesh_density(kps, skts, None, radius=case["radius"], res=case["res"], first=first, count=count)
+        assert torch.equal(slab, full[first:first + count])
+    for radius, res in ((1.3, 9), (0.77, 12)):
+        t_ = np.linspace(-radius, radius, res + 1)
+        p_ref = torch.as_tensor(np.stack(np.meshgrid(t_, t_, t_), axis=-1).astype(np.float32).reshape(-1, 3)).to(dev) + kps[0, 0]
+        a = rc.render_pts_density(p_ref.reshape(-1, 1, 3), kps, skts, None).reshape(-1)
+        b = rc.render_mesh_density(kps, skts, None, radius=radius, res=res, first=0, count=(res + 1) ** 3)
+        assert torch.equal(a, b)
+
+
+def test_chunked_host_entry_point_equals_per_chunk_calls():
+    """anerf_render_fwd_host_chunked (a frame of host buffers, copies overlapped with the kernels, optional outputs)
+    against one anerf_render_fwd_host call per chunk: identical results, ragged last chunk, chunk-wise near/far repair."""
+    from anerf_b200 import _lib
+    from tests.common import build_case
+    case, _ = load_golden("surreal_j24_s64_i16_tau200")
+    scene, sd0, sd1, cfg, _ = build_case(case)
+    scene["rays_d"] = scene["rays_d"].copy()
+    scene["rays_d"][3:6, 0] += 2.0                      # rays that miss the cylinder: repaired with their CHUNK's mean
+    dev = torch.device("cuda")
+    N = scene["rays_o"].shape[0]
+    plan = _lib.Plan(cfg.n_joints, cfg.D, cfg.W, cfg.skips, 0, 0, 0)
+    p0 = plan.pack({k: torch.as_tensor(v).to(dev) for k, v in sd0.items()})
+    p1 = plan.pack({k: torch.as_tensor(v).to(dev) for k, v in sd1.items()})
+    pin = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float32).pin_memory()
+    rays = pin(np.concatenate([scene["rays_o"], scene["rays_d"], np.zeros((N, 1), np.float32), np.ones((N, 1), np.float32)], 1))
+    skts, cyls = pin(scene["skts"]), pin(scene["cyls"])
+    mk = lambda n: _lib.make_opts(n, cfg.N_samples, cfg.N_importance, tau_pts=cfg.tau, tau_views=cfg.tau_views)
+    chunk = 24                                           # 64 rays -> 24, 24, 16
+    ref = {}
+    for i in range(0, N, chunk):
+        o = _lib.render_fwd_host(plan, p0, p1, mk(min(chunk, N - i)), rays[i:i + chunk], skts[i:i + chunk], cyls[i:i + chunk])
+        for k, v in o.items():
+            ref.setdefault(k, []).append(v.clone())
+    ref = {k: torch.cat(v) for k, v in ref.items()}
+    for rep in range(2):                                 # second call re-uses the cached arenas / streams
+        out = _lib.render_fwd_host_chunked(plan, p0, p1, mk(N), chunk, rays, skts, cyls)
+        for k in ref:
+            assert torch.equal(out[k], ref[k]), k
+    slim = _lib.render_fwd_host_chunked(plan, p0, p1, mk(N), chunk, rays, skts, cyls, keys=("rgb_map", "disp_map", "acc_map"))
+    assert set(slim) == {"rgb_map", "disp_map", "acc_map"} and all(torch.equal(slim[k], ref[k]) for k in slim)
+    _lib.check_status()
 
 
 def test_render_frame_equals_explicit_rays():
