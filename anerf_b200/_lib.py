@@ -16,7 +16,8 @@ SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "ane
            "anerf_render_workspace_bytes", "anerf_render_fwd", "anerf_render_fwd_host", "anerf_density_points",
            "anerf_selftest_gemm", "anerf_last_error", "anerf_version", "anerf_debug_set_trace",
            "anerf_render_bwd", "anerf_render_bwd_workspace_bytes", "anerf_selftest_tc_gemm", "anerf_render_frame",
-           "anerf_check_status", "anerf_density_grid", "anerf_render_fwd_host_chunked"]
+           "anerf_check_status", "anerf_density_grid", "anerf_render_fwd_host_chunked", "anerf_pose_chain_fwd",
+           "anerf_pose_chain_bwd", "anerf_pose_chain_bwd_scratch_bytes"]
 
 
 class NetConfig(C.Structure):
@@ -48,7 +49,7 @@ class RenderOpts(C.Structure):
 
 
 class RenderInputs(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("rays", "skts", "cyls", "cams", "t_rand", "u_rand", "noise0", "noise1")]
+    _fields_ = [(n, C.c_void_p) for n in ("rays", "skts", "cyls", "cams", "t_rand", "u_rand", "noise0", "noise1", "pose_idx")]
 
 
 class FrameInputs(C.Structure):
@@ -93,10 +94,17 @@ def load():
                                           C.POINTER(RenderInputs), C.POINTER(RenderOutputs), C.c_void_p]
     lib.anerf_density_points.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p]
-    lib.anerf_density_grid.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_float, C.c_int32, C.c_int64,
+    lib.anerf_density_grid.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_void_p, C.c_double, C.c_int32, C.c_int64,
                                        C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.anerf_render_fwd_host_chunked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_int32,
                                                   C.POINTER(RenderInputs), C.POINTER(RenderOutputs)]
+    lib.anerf_pose_chain_fwd.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.anerf_pose_chain_bwd_scratch_bytes.restype = C.c_size_t
+    lib.anerf_pose_chain_bwd_scratch_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.anerf_pose_chain_bwd.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.anerf_selftest_gemm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.anerf_render_bwd_workspace_bytes.restype = C.c_size_t
     lib.anerf_render_bwd_workspace_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
@@ -197,9 +205,11 @@ def make_opts(n_rays, n_samples, n_importance, tau_pts=20., tau_views=20., cutof
 
 
 def render_fwd(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, cams=None, t_rand=None, u_rand=None,
-               noise0=None, noise1=None, want_taps=False, keep_nearfar=False, want_z_all=False):
+               noise0=None, noise1=None, want_taps=False, keep_nearfar=False, want_z_all=False, pose_idx=None):
     """One chunk on the device.  All tensors fp32 contiguous CUDA.  Returns the reference's output dict
-    (core/raycasters.py:711-724) plus 'z_all'/'raw' taps when asked."""
+    (core/raycasters.py:711-724) plus 'z_all'/'raw' taps when asked.  pose_idx (int32 [N]): `skts` is then [P,J,4,4],
+    one set of bone transforms per pose, read through the index."""
+    assert pose_idx is None or (pose_idx.is_cuda and pose_idx.dtype == torch.int32 and pose_idx.is_contiguous())
     N, Sc, Si = opts.n_rays, opts.n_samples, opts.n_importance
     dev = rays.device
     Sf = Sc + Si
@@ -215,7 +225,8 @@ def render_fwd(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, cams=No
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     for t in (rays, skts, cyls, cams, t_rand, u_rand, noise0, noise1):
         assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
-    rin = RenderInputs(_ptr(rays), _ptr(skts), _ptr(cyls), _ptr(cams), _ptr(t_rand), _ptr(u_rand), _ptr(noise0), _ptr(noise1))
+    rin = RenderInputs(_ptr(rays), _ptr(skts), _ptr(cyls), _ptr(cams), _ptr(t_rand), _ptr(u_rand), _ptr(noise0), _ptr(noise1),
+                       _ptr(pose_idx))
     rout = RenderOutputs(*[_ptr(out.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0",
                                                       "alpha0", "z_all", "raw")])
     check(load().anerf_render_fwd(plan.handle, _ptr(packed_coarse), _ptr(packed_fine), C.byref(opts), C.byref(rin),
@@ -345,7 +356,7 @@ def _fill_net_struct(st, depth, tensors, framecodes):
 
 
 def render_bwd(plan, opts, params0, params1, rays, skts, cams, t_rand, noise0, noise1, nearfar, z_all, grad_out,
-               want0, want1, want_skts):
+               want0, want1, want_skts, pose_idx=None):
     """Backward of render_fwd (C ABI anerf_render_bwd).  params0/params1: fp32 CUDA tensors of the coarse / fine
     network in param_names() order; want0/want1: per-parameter flags; grad_out: dict of dL/d(output) tensors (or
     None).  Returns (grads0, grads1, g_skts): freshly allocated gradients (None where not wanted)."""
@@ -362,7 +373,7 @@ def render_bwd(plan, opts, params0, params1, rays, skts, cams, t_rand, noise0, n
     p0s, g0s = _fill_net_struct(NetParams(), depth, params0, fc), _fill_net_struct(NetGrads(), depth, g0, fc)
     p1s = _fill_net_struct(NetParams(), depth, params1, fc) if params1 is not None else None
     g1s = _fill_net_struct(NetGrads(), depth, g1, fc) if params1 is not None else None
-    rin = RenderInputs(_ptr(rays), _ptr(skts), None, _ptr(cams), _ptr(t_rand), None, _ptr(noise0), _ptr(noise1))
+    rin = RenderInputs(_ptr(rays), _ptr(skts), None, _ptr(cams), _ptr(t_rand), None, _ptr(noise0), _ptr(noise1), _ptr(pose_idx))
     rg = RenderGrads(*[_ptr(grad_out.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0", "alpha0")])
     ws_bytes = load().anerf_render_bwd_workspace_bytes(plan.handle, N, Sc, Si)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -370,6 +381,39 @@ def render_bwd(plan, opts, params0, params1, rays, skts, cams, t_rand, noise0, n
                                   C.byref(rin), _ptr(nearfar), _ptr(z_all), C.byref(rg), C.byref(g0s),
                                   None if g1s is None else C.byref(g1s), _ptr(g_skts), _ptr(ws), ws_bytes, _stream()))
     return g0, g1, g_skts
+
+
+def _parents_array(parents):
+    arr = (C.c_int32 * len(parents))(*[int(x) for x in parents])
+    return arr
+
+
+def pose_chain_fwd(rots, rest_pose, pelvis, parents, root_id=0):
+    """PoseOptLayer.calculate_kinematic's chain (C ABI anerf_pose_chain_fwd): rots [P,J,3,3], rest_pose [1|P,J,3],
+    pelvis [P,3] (fp32 CUDA, contiguous) -> (l2ws [P,J,4,4], skts [P,J,4,4], kps [P,J,3])."""
+    P, J = rots.shape[:2]
+    for t in (rots, rest_pose, pelvis):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=rots.device)
+    l2ws, skts, kps = f(P, J, 4, 4), f(P, J, 4, 4), f(P, J, 3)
+    check(load().anerf_pose_chain_fwd(P, J, _parents_array(parents), int(root_id), _ptr(rots), _ptr(rest_pose), rest_pose.shape[0],
+                                      _ptr(pelvis), _ptr(l2ws), _ptr(skts), _ptr(kps), _stream()))
+    return l2ws, skts, kps
+
+
+def pose_chain_bwd(rots, rest_pose, pelvis, parents, root_id, l2ws, skts, g_skts=None, g_l2ws=None, g_kps=None):
+    """-> (g_rots [P,J,3,3], g_pelvis [P,3])."""
+    P, J = rots.shape[:2]
+    for t in (rots, rest_pose, pelvis, l2ws, skts, g_skts, g_l2ws, g_kps):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+    g_rots = torch.empty(P, J, 3, 3, dtype=torch.float32, device=rots.device)
+    g_pelvis = torch.empty(P, 3, dtype=torch.float32, device=rots.device)
+    nb = load().anerf_pose_chain_bwd_scratch_bytes(P, J)
+    scratch = torch.empty(max(nb, 4), dtype=torch.uint8, device=rots.device)
+    check(load().anerf_pose_chain_bwd(P, J, _parents_array(parents), int(root_id), _ptr(rots), _ptr(rest_pose), rest_pose.shape[0],
+                                      _ptr(pelvis), _ptr(l2ws), _ptr(skts), _ptr(g_skts), _ptr(g_l2ws), _ptr(g_kps), _ptr(g_rots),
+                                      _ptr(g_pelvis), _ptr(scratch), nb, _stream()))
+    return g_rots, g_pelvis
 
 
 def density_points(plan, packed, opts, pts, skts):

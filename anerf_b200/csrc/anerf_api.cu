@@ -13,6 +13,7 @@
 #include "../../include/anerf_b200.h"
 #include "render_kernels.cuh"
 #include "train_path.cuh"
+#include "pose_kernels.cuh"
 
 using namespace anerf;
 
@@ -300,7 +301,7 @@ static int render_common(const anerf_plan* plan, const void* packed_coarse, cons
   P.tilesF = Si > 0 ? ceil_div(R * (Sc + Si), kTileM) : 0;
   P.n_items = ceil_div(N, R);
   P.rays = rays; P.gen = gen; P.skts = skts; P.skt_stride = skt_stride; P.cams = cams; P.cam_const = cam_const;
-  if (draws) { P.t_rand = draws->t_rand; P.u_rand = draws->u_rand; P.noise0 = draws->noise0; P.noise1 = draws->noise1; }
+  if (draws) { P.t_rand = draws->t_rand; P.u_rand = draws->u_rand; P.noise0 = draws->noise0; P.noise1 = draws->noise1; P.pose_idx = draws->pose_idx; }
   P.nearfar = (const float*)workspace;
   P.rgb_map = out->rgb_map; P.disp_map = out->disp_map; P.acc_map = out->acc_map; P.alpha = out->alpha;
   P.rgb0 = out->rgb0; P.disp0 = out->disp0; P.acc0 = out->acc0; P.alpha0 = out->alpha0;
@@ -357,7 +358,7 @@ int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf
 }
 
 int anerf_density_grid(const anerf_plan* plan, const void* packed, const anerf_render_opts* o, const float* origin,
-                       float radius, int32_t res, int64_t first, int64_t count, const float* skts, float* sigma, void* stream_) {
+                       double radius, int32_t res, int64_t first, int64_t count, const float* skts, float* sigma, void* stream_) {
   ANERF_ENTRY();
   if (!plan || !packed || !o || !origin || !skts || !sigma) return fail(ANERF_ERR_INVALID, "null argument");
   if (res < 1 || res > 2047) return fail(ANERF_ERR_INVALID, "res must be 1..2047");
@@ -373,7 +374,7 @@ int anerf_density_grid(const anerf_plan* plan, const void* packed, const anerf_r
   P.pts = nullptr; P.skts = skts; P.sigma = sigma; P.n_points = count;
   P.grid_first = first; P.grid_n1 = res + 1;
   // numpy.linspace(-r, r, res + 1) in fp64: step = (stop - start) / res; y[i] = i * step + start; y[-1] = stop
-  P.grid_start = -(double)radius; P.grid_stop = (double)radius;
+  P.grid_start = -radius; P.grid_stop = radius;
   P.grid_step = (P.grid_stop - P.grid_start) / (double)res;
   P.grid_origin = origin;
   return launch_fused(plan, P, true, (cudaStream_t)stream_);
@@ -546,6 +547,62 @@ int anerf_render_fwd_host_chunked(const anerf_plan* plan, const void* packed_coa
     return fail(ANERF_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
   }
   return check_device_status();
+}
+
+static int fill_chain(pose::ChainArgs& a, int32_t n_poses, int32_t n_joints, const int32_t* parents, int32_t root_id,
+                      const float* rots, const float* rest_pose, int32_t n_rest, const float* pelvis) {
+  if (n_poses < 0 || n_joints < 1 || n_joints > pose::kMaxPoseJoints) return fail(ANERF_ERR_INVALID, "bad sizes (n_joints must be 1..%d)", pose::kMaxPoseJoints);
+  if (!parents || !rots || !rest_pose || !pelvis) return fail(ANERF_ERR_INVALID, "null argument");
+  if (root_id < 0 || root_id >= n_joints) return fail(ANERF_ERR_INVALID, "bad root_id");
+  if (n_rest != 1 && n_rest != n_poses) return fail(ANERF_ERR_INVALID, "rest_pose must hold 1 or n_poses skeletons");
+  for (int j = 0; j < n_joints; ++j) {
+    // joints are visited root first, then in index order: every parent must come earlier in that order
+    const int q = parents[j];
+    if (j == root_id) continue;
+    const bool earlier = q == root_id || (q != j && q >= 0 && q < j);
+    if (!earlier) return fail(ANERF_ERR_INVALID, "joint %d: parent %d does not precede it (parents must come first, as in the SMPL tree)", j, q);
+  }
+  a.P = n_poses; a.J = n_joints; a.root = root_id;
+  for (int j = 0; j < n_joints; ++j) a.parent[j] = parents[j];
+  a.rots = rots; a.rest = rest_pose; a.rest_stride = n_rest == 1 ? 0 : (long long)n_joints * 3; a.pelvis = pelvis;
+  return ANERF_OK;
+}
+
+int anerf_pose_chain_fwd(int32_t n_poses, int32_t n_joints, const int32_t* parents, int32_t root_id, const float* rots,
+                         const float* rest_pose, int32_t n_rest, const float* pelvis, float* l2ws, float* skts, float* kps,
+                         void* stream_) {
+  ANERF_ENTRY();
+  pose::ChainArgs a{};
+  int rc = fill_chain(a, n_poses, n_joints, parents, root_id, rots, rest_pose, n_rest, pelvis);
+  if (rc) return rc;
+  if (!l2ws || !skts) return fail(ANERF_ERR_INVALID, "l2ws/skts outputs missing");
+  if (n_poses == 0) return ANERF_OK;
+  a.l2ws = l2ws; a.skts = skts; a.kps = kps;
+  pose::pose_chain_fwd_kernel<<<(n_poses + 63) / 64, 64, 0, (cudaStream_t)stream_>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return ANERF_OK;
+}
+
+size_t anerf_pose_chain_bwd_scratch_bytes(int32_t n_poses, int32_t n_joints) {
+  return (size_t)(n_poses > 0 ? n_poses : 0) * (size_t)(n_joints > 0 ? n_joints : 0) * 12 * sizeof(float);
+}
+
+int anerf_pose_chain_bwd(int32_t n_poses, int32_t n_joints, const int32_t* parents, int32_t root_id, const float* rots,
+                         const float* rest_pose, int32_t n_rest, const float* pelvis, const float* l2ws, const float* skts,
+                         const float* g_skts, const float* g_l2ws, const float* g_kps, float* g_rots, float* g_pelvis,
+                         void* scratch, size_t scratch_bytes, void* stream_) {
+  ANERF_ENTRY();
+  pose::ChainArgs a{};
+  int rc = fill_chain(a, n_poses, n_joints, parents, root_id, rots, rest_pose, n_rest, pelvis);
+  if (rc) return rc;
+  if (!l2ws || !skts || !g_rots || !g_pelvis) return fail(ANERF_ERR_INVALID, "null argument");
+  if (!scratch || scratch_bytes < anerf_pose_chain_bwd_scratch_bytes(n_poses, n_joints)) return fail(ANERF_ERR_INVALID, "scratch too small");
+  if (n_poses == 0) return ANERF_OK;
+  a.l2ws = const_cast<float*>(l2ws); a.skts = const_cast<float*>(skts);
+  a.g_skts = g_skts; a.g_l2ws = g_l2ws; a.g_kps = g_kps; a.g_rots = g_rots; a.g_pelvis = g_pelvis; a.scratch = (float*)scratch;
+  pose::pose_chain_bwd_kernel<<<(n_poses + 63) / 64, 64, 0, (cudaStream_t)stream_>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return ANERF_OK;
 }
 
 size_t anerf_render_bwd_workspace_bytes(const anerf_plan* plan, int32_t n_rays, int32_t n_samples, int32_t n_importance) {

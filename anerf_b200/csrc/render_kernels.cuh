@@ -176,6 +176,7 @@ struct RenderKParams {
   // frame mode (anerf_render_frame): rays == NULL, generated per pixel from `gen`; ONE pose / camera index for all rays
   RayGen gen;
   long long skt_stride;     // floats between the poses of consecutive rays: J*16, or 0 in frame mode
+  const int* pose_idx;      // optional [N]: ray -> row of `skts` (one transform set per pose instead of per ray)
   float cam_const;          // frame mode: the frame's camera index (framecodes)
   const float* nearfar;     // [N,2] from the near/far pre-kernel
   float *rgb_map, *disp_map, *acc_map, *alpha, *rgb0, *disp0, *acc0, *alpha0, *z_all_out, *raw_out;
@@ -942,7 +943,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
           const int n1 = P.grid_n1;
           const int a = (int)(f / ((long long)n1 * n1)), rem = (int)(f % ((long long)n1 * n1));
           const int b = rem / n1, c = rem % n1;
-          auto tv = [&](int i) { return i == n1 - 1 ? (float)P.grid_stop : (float)((double)i * P.grid_step + P.grid_start); };
+          auto tv = [&](int i) { return i == n1 - 1 ? (float)P.grid_stop : (float)__dadd_rn(__dmul_rn((double)i, P.grid_step), P.grid_start); };   // two roundings, like numpy
           rc.p[0] = tv(b) + __ldg(P.grid_origin); rc.p[1] = tv(a) + __ldg(P.grid_origin + 1); rc.p[2] = tv(c) + __ldg(P.grid_origin + 2);
         }
         rc.skt = skt_s; rc.slot = 0;
@@ -987,7 +988,8 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         for (int i = t0; i < R * J * 12; i += nt) {
           int r = i / (J * 12), e = i % (J * 12);
           int gr = min(ray0 + r, P.n_rays - 1);
-          skt_s[i] = P.skts[(size_t)gr * P.skt_stride + (e / 12) * 16 + (e % 12)];
+          const size_t prow = P.pose_idx ? (size_t)__ldg(P.pose_idx + gr) : (size_t)gr;
+          skt_s[i] = P.skts[prow * P.skt_stride + (e / 12) * 16 + (e % 12)];
         }
         if (pg.dims.fc_ch > 0)
           for (int i = t0; i < 2 * R; i += nt) {
@@ -1002,7 +1004,8 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
           float rbuf[8];
           const float* rd = rbuf + 3;
           if (P.rays) rd = P.rays + (size_t)gr * 8 + 3; else pixel_ray(P.gen, gr, rbuf);
-          encode_joint_viewdir(P.skts + (size_t)gr * P.skt_stride + (size_t)j * 16, rd, f);
+          const size_t prow = P.pose_idx ? (size_t)__ldg(P.pose_idx + gr) : (size_t)gr;
+          encode_joint_viewdir(P.skts + prow * P.skt_stride + (size_t)j * 16, rd, f);
 #pragma unroll
           for (int q = 0; q < kViewPerJoint; ++q) vtab_s[j * vstride + slot * kViewPad + q] = f[q];
           vtab_s[j * vstride + slot * kViewPad + kViewPerJoint] = 0.f;

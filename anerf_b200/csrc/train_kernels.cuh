@@ -255,7 +255,8 @@ __global__ void coarse_depths_kernel(const float* __restrict__ nearfar, const fl
 // ------------------------------------------------------------------------------------------------
 struct EncodeArgs {
   const float* rays;      // [N,8]
-  const float* skts;      // [N,J,16]
+  const float* skts;      // [N,J,16], or [P,J,16] read through pose_idx
+  const int* pose_idx;    // optional [N]
   const float* z;         // [N,S] depths of this network's pass
   const float* cams;      // [N] or NULL
   const float* codes;     // [n_fc, fc_ch] or NULL
@@ -276,7 +277,8 @@ __global__ void encode_rows_kernel(EncodeArgs e) {
   const float* rp = e.rays + (long long)ray * 8;
   const float zz = e.z[(long long)ray * e.S + s];
   const float p[3] = {rp[0] + rp[3] * zz, rp[1] + rp[4] * zz, rp[2] + rp[5] * zz};
-  const float* skt = e.skts + ((long long)ray * J + j) * 16;
+  const long long prow = e.pose_idx ? (long long)e.pose_idx[ray] : (long long)ray;
+  const float* skt = e.skts + (prow * J + j) * 16;
   float f[kPtsPerJoint];
   const float v = encode_joint_pts(skt, p, e.tau_p, e.cut_p[j], f);
   float* xs = e.XS + row * e.ldxs;
@@ -383,6 +385,7 @@ __global__ void composite_bwd_kernel(CompositeBwdArgs a) {
 // ------------------------------------------------------------------------------------------------
 struct EncodeBwdArgs {
   const float* rays; const float* skts; const float* z;
+  const int* pose_idx;    // optional [N]: skts / g_skts are then per pose
   int ray0, n_rays_blk, S, J, W, vq;
   float tau_p, tau_v;
   float cut_p[kMaxJoints], cut_v[kMaxJoints];
@@ -397,7 +400,8 @@ __global__ void encode_bwd_kernel(EncodeBwdArgs e) {
   const int rl = idx / e.J, j = idx % e.J, J = e.J, S = e.S;
   const int ray = e.ray0 + rl;
   const float* rp = e.rays + (long long)ray * 8;
-  const float* skt = e.skts + ((long long)ray * J + j) * 16;
+  const long long prow = e.pose_idx ? (long long)e.pose_idx[ray] : (long long)ray;
+  const float* skt = e.skts + (prow * J + j) * 16;
   float T[kViewPerJoint], gT[kViewPerJoint];
   encode_joint_viewdir(skt, rp + 3, T);
 #pragma unroll
@@ -490,9 +494,14 @@ __global__ void encode_bwd_kernel(EncodeBwdArgs e) {
       gs[4 * i + 2] = fmaf(gy, d[2], gs[4 * i + 2]);
     }
   }
-  float* out = e.g_skts + ((long long)ray * J + j) * 16;
+  float* out = e.g_skts + (prow * J + j) * 16;
+  if (e.pose_idx) {         // several rays share the pose: the segment sum of the reference's expand-backward, in place
 #pragma unroll
-  for (int i = 0; i < 12; ++i) out[i] += gs[i];
+    for (int i = 0; i < 12; ++i) atomicAdd(out + i, gs[i]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) out[i] += gs[i];
+  }
 }
 
 // d codes[cam, q] += sum over the ray's samples of gVIN[row, W + 27J + q]; one thread per (ray, q)

@@ -153,7 +153,7 @@ class _RenderRaysFn(torch.autograd.Function):
         p0 = caster._packed_image('network')
         p1 = caster._packed_image('network_fine') if opts.n_importance > 0 else None
         out = _lib.render_fwd(plan, p0, p1, opts, aux['rays'], skts, aux['cyls'], aux['cams'], aux['t_rand'], aux['u_rand'],
-                              aux['noise0'], aux['noise1'], keep_nearfar=True, want_z_all=True)
+                              aux['noise0'], aux['noise1'], keep_nearfar=True, want_z_all=True, pose_idx=aux.get('pose_idx'))
         ctx.caster, ctx.opts, ctx.aux = caster, opts, aux
         ctx.nearfar, ctx.z_all = out['nearfar'], out.get('z_all')
         ctx.save_for_backward(skts, *params)
@@ -175,7 +175,7 @@ class _RenderRaysFn(torch.autograd.Function):
             g0, g1, g_skts = _lib.render_bwd(ctx.caster._get_plan(), opts, [p.detach() for p in params0],
                                              None if params1 is None else [p.detach() for p in params1],
                                              aux['rays'], skts.detach(), aux['cams'], aux['t_rand'], aux['noise0'], aux['noise1'],
-                                             ctx.nearfar, ctx.z_all, gout, want0, want1, want_skts)
+                                             ctx.nearfar, ctx.z_all, gout, want0, want1, want_skts, pose_idx=aux.get('pose_idx'))
         return (None, None, None, g_skts, *g0, *(g1 or []))
 
 
@@ -280,9 +280,13 @@ class RayCaster(nn.Module):
     def render_rays(self, ray_batch, N_samples, kp_batch, skts=None, cyls=None, bones=None, cams=None,
                     subject_idxs=None, retraw=False, lindisp=False, perturb=0., N_importance=0, network_fine=None,
                     raw_noise_std=0., ray_noise_std=0., verbose=False, ext_scale=0.001, pytest=False,
-                    preproc_kwargs={}, nerf_type="nerf", use_viewdirs=True, **unused):
+                    preproc_kwargs={}, nerf_type="nerf", use_viewdirs=True, pose_idx=None, **unused):
         """One chunk of rays -> {'rgb_map','disp_map','acc_map','alpha'[, 'rgb0','disp0','acc0','alpha0']}
-        (reference: core/raycasters.py:361-474, 711-724)."""
+        (reference: core/raycasters.py:361-474, 711-724).
+
+        `pose_idx` (ours, optional int tensor [N]): `skts` then holds one set of bone transforms per POSE ([P,J,4,4], e.g.
+        from anerf_b200.pose_opt.PoseOptLayer.forward_poses) and ray n uses skts[pose_idx[n]]; in training the gradient
+        w.r.t. `skts` comes back per pose, already summed over each pose's rays."""
         if skts is None or cyls is None:
             raise NotImplementedError("anerf_b200 needs skts and cyls (the reference's skts=None path is unused)")
         if ray_noise_std > 0.:
@@ -295,7 +299,14 @@ class RayCaster(nn.Module):
         N = ray_batch.shape[0]
         J = self._n_joints()
         rays = ray_batch[:, :8].float().contiguous()
-        skts_c = skts.float().expand(N, J, 4, 4).contiguous()          # differentiable when the pose is being refined
+        pidx = None
+        if pose_idx is not None:
+            pidx = pose_idx.to(device=dev, dtype=torch.int32).contiguous()
+            if pidx.shape[0] != N:
+                raise ValueError(f"pose_idx has {pidx.shape[0]} entries for {N} rays")
+            skts_c = skts.float().reshape(-1, J, 4, 4).contiguous()     # one transform set per pose, read through the index
+        else:
+            skts_c = skts.float().expand(N, J, 4, 4).contiguous()      # differentiable when the pose is being refined
         cyls_c = cyls.float().expand(N, cyls.shape[-1]).contiguous()
         density_scale = preproc_kwargs.get('density_scale', 1.0)
         density_fn = preproc_kwargs.get('density_fn', None)
@@ -334,7 +345,7 @@ class RayCaster(nn.Module):
             if eval_mean:
                 raise NotImplementedError("gradients through the eval-time mean framecode are not supported")
             aux = dict(rays=rays, cyls=cyls_c, cams=cams_c, t_rand=t_rand, u_rand=u_rand, noise0=noise0, noise1=noise1,
-                       n_params0=len(names))
+                       n_params0=len(names), pose_idx=pidx)
             with torch.cuda.device(dev):
                 outs = _RenderRaysFn.apply(self, opts, aux, skts_c, *params)
             keys = [k for k in OUT_KEYS if Si > 0 or not k.endswith('0')]
@@ -343,7 +354,7 @@ class RayCaster(nn.Module):
             p0 = self._packed_image('network')
             p1 = self._packed_image('network_fine') if Si > 0 else None
             out = _lib.render_fwd(self._get_plan(), p0, p1, opts, rays, skts_c.detach(), cyls_c, cams_c, t_rand, u_rand,
-                                  noise0, noise1, want_taps=bool(retraw))
+                                  noise0, noise1, want_taps=bool(retraw), pose_idx=pidx)
         return out
 
     @torch.no_grad()

@@ -118,6 +118,8 @@ typedef struct {
   const float* u_rand;
   const float* noise0;
   const float* noise1;
+  const int32_t* pose_idx;  /* optional [N]: ray -> pose.  When set, `skts` is [P,J,4,4] (one transform set per POSE, read
+                               through the index) and anerf_render_bwd's g_skts is [P,J,4,4], summed over each pose's rays */
 } anerf_render_inputs;
 
 /* Device outputs ([N,...], fp32).  The *0 entries and z_all may be NULL; with n_importance == 0 the
@@ -236,7 +238,7 @@ int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf
  * the points generated inside the kernel: nothing but the densities touches HBM.  origin: DEVICE pointer to the root
  * joint position (3 floats); sigma [count] in flat grid order. */
 int anerf_density_grid(const anerf_plan* plan, const void* packed, const anerf_render_opts* opts, const float* origin,
-                       float radius, int32_t res, int64_t first, int64_t count, const float* skts, float* sigma,
+                       double radius, int32_t res, int64_t first, int64_t count, const float* skts, float* sigma,
                        void* stream);
 
 /* Build-time self test of the tensor-core building blocks on one CTA pair: D[256,N] = A[256,K] * B[N,K]^T with
@@ -254,6 +256,25 @@ int anerf_selftest_tc_gemm(const float* A, int64_t a_ms, int64_t a_ks, int32_t M
                            int64_t b_ks, int32_t N, float* C, int64_t c_ms, int64_t c_ns, const float* bias,
                            const float* mask, int64_t mask_ms, int32_t relu, int32_t mode, int32_t slice_chunks,
                            void* stream);
+
+/* ---- pose refinement: the kinematic chain ------------------------------------------ */
+
+/* PoseOptLayer.calculate_kinematic (core/pose_opt.py:372-445, with unrolled_kinematic_chain :482-521 and torch.inverse
+ * :435) for n_poses poses: rots [P,J,3,3] per-joint rotations (what rot6d_to_rotmat / axisang_to_rot produce), rest_pose
+ * [n_rest,J,3] with n_rest in {1, P}, pelvis [P,3]  ->  l2ws [P,J,4,4] (pelvis-shifted, as the reference returns them),
+ * skts [P,J,4,4] = l2ws^-1 (closed-form rigid inverse), kps [P,J,3] (may be NULL).  parents: HOST array [J], the
+ * skeleton's joint_trees (parents[root_id] == root_id; every other parent precedes its child).  All tensors on the device. */
+int anerf_pose_chain_fwd(int32_t n_poses, int32_t n_joints, const int32_t* parents, int32_t root_id, const float* rots,
+                         const float* rest_pose, int32_t n_rest, const float* pelvis, float* l2ws, float* skts, float* kps,
+                         void* stream);
+size_t anerf_pose_chain_bwd_scratch_bytes(int32_t n_poses, int32_t n_joints);
+/* Its backward: cotangents of skts / l2ws / kps (each [P,...] or NULL) -> g_rots [P,J,3,3], g_pelvis [P,3] (overwritten).
+ * g_skts is what anerf_render_bwd accumulates per POSE when it is given `pose_idx` (the segment sum over the rays of
+ * each pose happens there, with atomics), so the [N,J,4,4] per-ray gradient of the reference's graph never exists. */
+int anerf_pose_chain_bwd(int32_t n_poses, int32_t n_joints, const int32_t* parents, int32_t root_id, const float* rots,
+                         const float* rest_pose, int32_t n_rest, const float* pelvis, const float* l2ws, const float* skts,
+                         const float* g_skts, const float* g_l2ws, const float* g_kps, float* g_rots, float* g_pelvis,
+                         void* scratch, size_t scratch_bytes, void* stream);
 
 /* Debug aid: device buffer of 3 x 1024 int64; while set, launches record a clock64 timeline of CTA 0
  * (stream 0 MMA thread, 1/2 worker groups; entries = tag << 48 | clock).  NULL switches it off. */

@@ -50,13 +50,25 @@ def test_reference_render_drives_our_caster():
         _, rk_test, _, _, _, _ = create_raycaster(args, _data_attrs(), device=dev)
     _load(rk_test["ray_caster"], sd0, sd1, dev).eval()
     t = lambda a: torch.as_tensor(a).to(dev)
-    out = render(scene["H"], scene["W"], scene["focal"], chunk=40,            # 96 rays in chunks of 40: ragged last chunk
-                 rays=(t(scene["rays_o"]), t(scene["rays_d"])), kp_batch=t(scene["kps"]), skts=t(scene["skts"]),
-                 cyls=t(scene["cyls"]), bones=t(scene["bones"]), cams=None, subject_idxs=None, **rk_test)
-    # chunk-dependent near/far repair aside (every ray of this fixture hits the cylinder), chunking must not matter
+    call = lambda rk, chunk: render(scene["H"], scene["W"], scene["focal"], chunk=chunk, rays=(t(scene["rays_o"]), t(scene["rays_d"])),
+                                    kp_batch=t(scene["kps"]), skts=t(scene["skts"]), cyls=t(scene["cyls"]), bones=t(scene["bones"]),
+                                    cams=None, subject_idxs=None, **rk)
+    out = call(rk_test, 4096)                  # the fixture was rendered as one chunk
     for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "alpha0"):
         assert out[k].shape == gold["ref_" + k].shape
         assert rel_err(out[k].cpu().numpy(), gold["ref_" + k]) < 1e-4, k
+    # 96 rays in chunks of 40 (ragged last chunk; the near/far repair of rays that miss the cylinder is a CHUNK mean,
+    # so the result depends on the chunking): against the reference's own caster on this GPU with the same chunking
+    from core.raycasters import create_raycaster as ref_create
+    with ref_import.reference_on_cuda():
+        with contextlib.redirect_stdout(io.StringIO()):
+            _, ref_test, _, _, _, _ = ref_create(args, _data_attrs())
+        _load(ref_test["ray_caster"], sd0, sd1, dev).eval()
+        with torch.no_grad():
+            want = call(ref_test, 40)
+    got = call(rk_test, 40)
+    for k in ("rgb_map", "disp_map", "acc_map", "rgb0", "disp0", "acc0", "alpha0"):
+        assert rel_err(got[k].cpu().numpy(), want[k].cpu().numpy()) < 1e-4, k
 
 
 def _train_batch(N, dev, seed=3):
@@ -83,20 +95,17 @@ def test_reference_trainer_step_drives_our_caster():
     results = {}
     for who in ("ours", "reference"):
         batch = _train_batch(N, dev)
-        with contextlib.redirect_stdout(io.StringIO()):
+        # the reference's trainer module itself builds tensors with the legacy constructors (core/trainer.py:8), so it
+        # runs the way run_nerf.py runs it: CUDA as the default tensor type -- for both casters
+        with contextlib.redirect_stdout(io.StringIO()), ref_import.reference_on_cuda():
             if who == "ours":
                 rk_train, rk_test, _, grad_vars, optimizer, _ = create_raycaster(args, _data_attrs(), device=dev)
-                _load(rk_test["ray_caster"], sd0, sd1, dev)
-                rk_train["ray_caster"].train()
-                trainer = Trainer(args, _data_attrs(), optimizer, None, rk_train, rk_test, popt_kwargs=None, device=dev)
-                loss, stats = trainer.train_batch(batch, i=1, global_step=1)
             else:
-                with ref_import.reference_on_cuda():
-                    rk_train, rk_test, _, grad_vars, optimizer, _ = ref_create(args, _data_attrs())
-                    _load(rk_test["ray_caster"], sd0, sd1, dev)
-                    rk_train["ray_caster"].train()
-                    trainer = Trainer(args, _data_attrs(), optimizer, None, rk_train, rk_test, popt_kwargs=None, device=dev)
-                    loss, stats = trainer.train_batch(batch, i=1, global_step=1)
+                rk_train, rk_test, _, grad_vars, optimizer, _ = ref_create(args, _data_attrs())
+            _load(rk_test["ray_caster"], sd0, sd1, dev)
+            rk_train["ray_caster"].train()
+            trainer = Trainer(args, _data_attrs(), optimizer, None, rk_train, rk_test, popt_kwargs=None, device=dev)
+            loss, stats = trainer.train_batch(batch, i=1, global_step=1)
         rc = rk_test["ray_caster"]
         results[who] = dict(loss={k: float(v) for k, v in loss.items()}, stats=stats,
                             w={k: v.detach().float().cpu().numpy() for k, v in rc.network_fine.state_dict().items()},
