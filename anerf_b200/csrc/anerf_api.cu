@@ -644,10 +644,12 @@ int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, con
   c.g_skts = g_skts;
   c.workspace = (float*)workspace;
   c.workspace_floats = workspace_bytes / sizeof(float);
-  // GEMM engine: tensor cores (tc_gemm.cuh) unless ANERF_TRAIN_GEMM=simt asks for the fp32 SIMT kernels (debug knob)
+  // GEMM engine: tensor cores (tc_gemm.cuh) with fp16 hi/lo operands and per-matrix scales; ANERF_TRAIN_GEMM=bf16 selects
+  // round 1's bf16 hi/lo operands, ANERF_TRAIN_GEMM=simt the fp32 SIMT kernels (debug knobs)
   train::TcEngine tc{};
   const char* eng = getenv("ANERF_TRAIN_GEMM");
   if (!(eng && strcmp(eng, "simt") == 0)) {
+    tc.fmt = (eng && strcmp(eng, "bf16") == 0) ? 1 : 0;
     int rc = ensure_status();
     if (rc) return rc;
     const train::Workspace w = train::make_workspace(plan->dims, N, Sc, Si);
@@ -655,6 +657,7 @@ int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, con
     tc.status = g_status_dev;
     tc.wpack = (uint8_t*)((float*)workspace + w.tc_w); tc.wpack_bytes = (size_t)w.tc_w_floats * 4; tc.wpack_used = 0;
     tc.gpack = (uint8_t*)((float*)workspace + w.tc_g); tc.gpack_bytes = (size_t)w.tc_g_floats * 4;
+    tc.slots = (float*)workspace + w.tc_slots; tc.w_used = 0; tc.b_used = train::TcEngine::kWeightSlots;
     tc.error = 0;
     tc.trace = g_trace;
     tc.wgrad_slice_chunks = 32;
@@ -684,11 +687,24 @@ int anerf_selftest_tc_gemm(const float* A, int64_t a_ms, int64_t a_ks, int32_t M
   CUDA_TRY(cudaMalloc((void**)&d_pack, tc_packed_bytes(N, K)));
   train::TcEngine tc{};
   tc.n_sm = n_sm; tc.status = g_status_dev; tc.error = 0; tc.trace = g_trace;
-  tc.pack(stream, B, b_ns, b_ks, N, K, d_pack);
-  tc.run(stream, A, a_ms, a_ks, M, K, d_pack, N, C, c_ms, c_ns, bias, relu, mask, mask_ms, mode, slice_chunks);
+  // self test of the GEMM alone: fp16 operands with scales from explicit reductions over A and B
+  const char* eng = getenv("ANERF_TRAIN_GEMM");
+  tc.fmt = (eng && strcmp(eng, "bf16") == 0) ? 1 : 0;
+  float* d_slots = nullptr;
+  CUDA_TRY(cudaMalloc((void**)&d_slots, 4 * sizeof(float)));
+  CUDA_TRY(cudaMemsetAsync(d_slots, 0, 4 * sizeof(float), stream));
+  AmaxRef ra{nullptr, nullptr}, rb{nullptr, nullptr};
+  if (tc.fmt == 0) {
+    tc_absmax_kernel<<<148, 256, 0, stream>>>(A, a_ms, a_ks, M, K, d_slots);
+    tc_absmax_kernel<<<148, 256, 0, stream>>>(B, b_ns, b_ks, N, K, d_slots + 1);
+    ra.p0 = d_slots; rb.p0 = d_slots + 1;
+  }
+  tc.pack(stream, B, b_ns, b_ks, N, K, d_pack, nullptr, rb);
+  tc.run(stream, A, a_ms, a_ks, M, K, d_pack, N, C, c_ms, c_ns, bias, relu, mask, mask_ms, mode, slice_chunks, ra, rb, nullptr);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
   cudaFree(d_pack);
+  cudaFree(d_slots);
   if (tc.error) return fail(ANERF_ERR_INVALID, "tensor-core GEMM launch failed (%d)", tc.error);
   if (e != cudaSuccess) { check_device_status(); return fail(ANERF_ERR_CUDA, "tc gemm failed: %s [%s]", cudaGetErrorString(e), g_err.c_str()); }
   return check_device_status();

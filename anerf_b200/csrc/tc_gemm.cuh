@@ -1,5 +1,10 @@
 // Split-precision tensor-core GEMM for the training path: C (op)= A * B^T with fp32 operands in global
-// memory, each product issued as three bf16 tcgen05 MMAs (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM),
+// memory, each product issued as three 16-bit tcgen05 MMAs (lo*hi + hi*lo + hi*hi, fp32 accumulation in TMEM).
+// Operand format (template FMT): 0 = fp16 hi/lo (22 mantissa bits per value) with a power-of-two scale PER OPERAND
+// MATRIX chosen on the device from the matrix's max |x| (every producer kernel leaves that maximum in an "amax slot",
+// see AmaxRef), so that gradients of any magnitude sit in fp16's range with normal lo parts; 1 = bf16 hi/lo (16 bits,
+// no scaling needed; round 1's engine, kept as ANERF_TRAIN_GEMM=bf16).  The epilogue undoes the scales exactly and
+// multiplies by the expected loss of the tensor core's truncating accumulation (render_kernels.cuh: trunc_comp).  Kernel
 // built from the same pipeline pieces as the fused render kernel (render_kernels.cuh: A-operand ring filled by
 // the 16 worker warps, weight/B ring streamed by one bulk-copy thread per CTA, cta_group::2 MMAs over a CTA
 // pair with M = 256, two TMEM accumulator regions).
@@ -20,8 +25,27 @@
 
 namespace anerf {
 
+// max |x| of an operand matrix, kept on the device (written with atomicMax on the bit pattern by the kernel that
+// produced the matrix); an operand made of two buffers (cat[encoding, h]) takes the larger of two slots
+struct AmaxRef {
+  const float* p0;
+  const float* p1;
+};
+// power of two that brings `amax` into [2^12, 2^13) (exact to apply and to undo); 1 for an empty / non-finite matrix
+inline __host__ __device__ float tc_operand_scale(float amax) {
+  if (!(amax > 0.f) || !(amax < 3.0e38f)) return 1.0f;
+  int e;
+  frexpf(amax, &e);                        // amax = f * 2^e, f in [0.5, 1)
+  int k = 13 - e;
+  k = k < -100 ? -100 : (k > 100 ? 100 : k);
+  return ldexpf(1.0f, k);
+}
+
 struct TcGemmArgs {
   const float* A; long long a_ms, a_ks; int M, K;
+  AmaxRef a_amax, b_amax;   // fp16 format: device maxima the operand scales are derived from (NULL pointers: scale 1)
+  float* c_amax;            // optional: max |C| of what this launch stores (modes 0 / 1) is atomically folded in here
+  float comp;               // epilogue factor: 1 + expected relative loss of the truncating accumulation
   const uint8_t* Bp; int N, NT, n_tiles;
   int chunks_total;         // round_up(K, 128) / 32
   int k_slices, slice_chunks;   // split-K: slice s covers chunks [s*slice_chunks, min((s+1)*slice_chunks, chunks_total)); multiple of 4
@@ -48,9 +72,34 @@ static_assert(kTcProdWarps + kTcDrainWarps == kWorkerWarps, "worker warp roles")
 
 // B(n, k) = src[n*s_n + k*s_k] (zero outside [0,N) x [0,K)) -> packed tiles.  One thread per (tile, chunk, 8-wide k
 // group, row of the tile); rows vary fastest so that both the strided reads (s_n == 1) and the 16-byte writes coalesce.
+__device__ __forceinline__ float amax_value(const AmaxRef& r) {
+  float a = r.p0 ? __ldg(r.p0) : 0.f;
+  if (r.p1) a = fmaxf(a, __ldg(r.p1));
+  return a;
+}
+__device__ __forceinline__ void amax_fold(float* slot, float v) {      // v >= 0: the bit patterns order like the values
+  atomicMax(reinterpret_cast<int*>(slot), __float_as_int(v));
+}
+
+// max |B(n, k)| of a strided matrix -> slot (weights: run once per pack; activations and gradients get theirs from
+// the kernels that produce them)
+__global__ void tc_absmax_kernel(const float* __restrict__ src, long long s_n, long long s_k, int N, int K, float* __restrict__ slot) {
+  float m = 0.f;
+  const long long total = (long long)N * K;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long n = s_k == 1 ? t / K : t % N, k = s_k == 1 ? t % K : t / N;
+    m = fmaxf(m, fabsf(__ldg(src + n * s_n + k * s_k)));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) amax_fold(slot, m);
+}
+
 template <int FMT>
 __global__ void tc_pack_b_kernel(const float* __restrict__ src, long long s_n, long long s_k, int N, int K, int NT,
-                                 int n_tiles, int chunks_total, uint8_t* __restrict__ out, float* __restrict__ rowsum) {
+                                 int n_tiles, int chunks_total, uint8_t* __restrict__ out, float* __restrict__ rowsum,
+                                 AmaxRef amax) {
+  const float sb = FMT == 0 ? tc_operand_scale(amax_value(amax)) : 1.0f;
   // rowsum (optional, single-tile operands only): rowsum[n] += sum_k B(n, k) -- the bias gradient when B is a
   // gradient matrix G^T; the launch keeps gridDim*blockDim a multiple of NT, so a thread's row n never changes
   float acc = 0.f;
@@ -68,6 +117,10 @@ __global__ void tc_pack_b_kernel(const float* __restrict__ src, long long s_n, l
       x[i] = (n < N && k < K) ? __ldg(src + (long long)n * s_n + (long long)k * s_k) : 0.f;
     }
     acc += ((x[0] + x[1]) + (x[2] + x[3])) + ((x[4] + x[5]) + (x[6] + x[7]));
+    if (FMT == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] *= sb;
+    }
     uint4 hi, lo;
     Split<FMT>::pair(x[0], x[1], hi.x, lo.x);
     Split<FMT>::pair(x[2], x[3], hi.y, lo.y);
@@ -110,6 +163,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
   cluster_sync_all();
   tc_fence_after_sync();
   pp.tmem_base = *tmem_slot;
+
+  // operand scales (fp16 format) and the epilogue factor that undoes them
+  const float sa = FMT == 0 ? tc_operand_scale(amax_value(g.a_amax)) : 1.0f;
+  const float out_scale = (FMT == 0 ? (1.0f / sa) * (1.0f / tc_operand_scale(amax_value(g.b_amax))) : 1.0f) * g.comp;
 
   const int m_tiles = ceil_div(g.M, 2 * kTileM);
   const int items = g.k_slices * m_tiles * g.n_tiles;
@@ -226,6 +283,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         uint8_t* st0 = pp.a_ring + stage * kAStageBytes;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+          if (FMT == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) x[j][i] *= sa;
+          }
           uint4 hi, lo;
           Split<FMT>::pair(x[j][0], x[j][1], hi.x, lo.x);
           Split<FMT>::pair(x[j][2], x[j][3], hi.y, lo.y);
@@ -265,6 +326,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     const int nblk = NT / 32;
     uint32_t d_cnt[2] = {0u, 0u};
     int it = 0;
+    float cmax = 0.f;                                  // max |C| of what this thread stored (c_amax)
     for (int item = pair; item < items; item += n_pairs, ++it) {
       const int region = it & 1;
       const int rem = item % (m_tiles * g.n_tiles);
@@ -293,6 +355,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         uint32_t v[32];
         tmem_ld32(taddr + cb * 32, v);
         tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * out_scale);
         const int nb = n0 + cb * 32;             // first column of the block
         if (!transposed) {
           if (m < g.M) {
@@ -307,6 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
               if (g.relu) r = fmaxf(r, 0.f);
               if (g.mask && !(__ldg(g.mask + (long long)m * g.mask_ms + nb + i) > 0.f)) r = 0.f;
               *c = r;
+              cmax = fmaxf(cmax, fabsf(r));
             }
           }
           continue;
@@ -336,6 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                   float4 w = *reinterpret_cast<const float4*>(sp + i * 4 * 36);
                   w.x = fmaxf(w.x + b.x, lo); w.y = fmaxf(w.y + b.y, lo); w.z = fmaxf(w.z + b.z, lo); w.w = fmaxf(w.w + b.w, lo);
                   *reinterpret_cast<float4*>(crow + i * cstep) = w;
+                  cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(w.x), fabsf(w.y))), fmaxf(fabsf(w.z), fabsf(w.w)));
                 }
               }
             } else {                                          // dgrad form: optional add to C, ReLU-derivative mask
@@ -351,6 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
                     w.x = k.x > 0.f ? w.x : 0.f; w.y = k.y > 0.f ? w.y : 0.f; w.z = k.z > 0.f ? w.z : 0.f; w.w = k.w > 0.f ? w.w : 0.f;
                   }
                   *reinterpret_cast<float4*>(crow + i * cstep) = w;
+                  cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(w.x), fabsf(w.y))), fmaxf(fabsf(w.z), fabsf(w.w)));
                 }
               }
             }
@@ -370,6 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
               if (g.relu) w = fmaxf(w, 0.f);
               if (g.mask && !(__ldg(g.mask + (long long)(m_warp + r) * g.mask_ms + n) > 0.f)) w = 0.f;
               *c = w;
+              cmax = fmaxf(cmax, fabsf(w));
             }
           }
         }
@@ -382,6 +450,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
       if (elect_one()) mbar_arrive(&r_free[region]);
       __syncwarp();
       if (tr) tr->mark(61);
+    }
+    if (g.c_amax) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+      if (lane == 0 && cmax > 0.f && cmax < 3.0e38f) amax_fold(g.c_amax, cmax);
     }
   }
   tc_fence_before_sync();

@@ -36,51 +36,116 @@ constexpr long long kRowsTarget = 262144;   // rows (samples) per block of rays:
 // Tensor-core GEMM engine of the backward pass (tc_gemm.cuh): launch helper + a per-pass cache of packed
 // weight operands.  Not part of the emulated build: the host tests run the SIMT kernels, the GPU tests compare
 // both engines with the oracle.
+__global__ void tc_set_slot_kernel(float* slot, float v) { *slot = v; }
+
 struct TcEngine {
   int n_sm;
   DeviceStatus* status;
   long long* trace;
+  int fmt;                  // operand format of the GEMMs: 0 = fp16 hi/lo with per-matrix power-of-two scales, 1 = bf16 hi/lo
   int wgrad_slice_chunks;   // rows per wgrad work item / 32: each item accumulates this many chunks in TMEM, then adds to dW in fp32
   uint8_t* wpack; size_t wpack_bytes, wpack_used;      // packed weight operands of the current network pass
   uint8_t* gpack; size_t gpack_bytes;                   // packed gradient operand of the current wgrad
-  std::map<std::tuple<const float*, long long, long long, int, int>, const uint8_t*> cache;
+  std::map<std::tuple<const float*, long long, long long, int, int>, std::pair<const uint8_t*, float*>> cache;
+  // amax slots (fp16 format): one device float per operand matrix, folded into by the kernel that produces the matrix.
+  // Slots [0, kWeightSlots) belong to the weights of the current pass, the rest to the activation / gradient buffers
+  // of the current block of rays (reset per block).
+  static constexpr int kWeightSlots = 64, kSlots = 256;
+  float* slots;
+  int w_used, b_used;
+  std::map<const float*, float*> amax_of;              // base pointer of a buffer -> slot of its latest contents
   int error;
 
+  float* weight_slot() { if (w_used >= kWeightSlots) { error = 4; return slots; } return slots + w_used++; }
+  // a fresh (zeroed) slot for the buffer starting at `base`, replacing whatever was known about it
+  float* produce(const float* base) {
+    if (fmt != 0) return nullptr;
+    if (b_used >= kSlots) { error = 4; return slots + kWeightSlots; }
+    float* sl = slots + b_used++;
+    amax_of[base] = sl;
+    return sl;
+  }
+  // a buffer whose bound is known analytically (encodings): no reduction needed
+  void produce_const(cudaStream_t st, const float* base, float bound) {
+    float* sl = produce(base);
+    if (sl) tc_set_slot_kernel<<<1, 1, 0, st>>>(sl, bound);
+  }
+  // a buffer written by a kernel that does not fold its maximum: one extra read pass
+  void produce_scan(cudaStream_t st, const float* base, long long ld, int cols, long long rows) {
+    float* sl = produce(base);
+    if (sl) tc_absmax_kernel<<<148 * 4, 256, 0, st>>>(base, ld, 1, (int)rows, cols, sl);
+  }
+  // slots of every buffer that starts inside [p, p + width) of a row: an operand may be cat[encoding, h]
+  AmaxRef ref(const float* p, int width) {
+    AmaxRef r{nullptr, nullptr};
+    if (fmt != 0) return r;
+    for (auto& kv : amax_of)
+      if (kv.first >= p && kv.first < p + width) {
+        if (!r.p0) r.p0 = kv.second; else if (!r.p1) r.p1 = kv.second; else error = 5;
+      }
+    if (!r.p0) error = 6;        // an operand nobody registered: the scale would silently be 1
+    return r;
+  }
+  void new_block(cudaStream_t st) {
+    if (fmt != 0) return;
+    amax_of.clear();
+    b_used = kWeightSlots;
+    cudaMemsetAsync(slots + kWeightSlots, 0, (kSlots - kWeightSlots) * sizeof(float), st);
+  }
+
   const uint8_t* pack(cudaStream_t st, const float* src, long long s_n, long long s_k, int N, int K, uint8_t* dst,
-                      float* rowsum = nullptr) {
+                      float* rowsum, AmaxRef amax) {
     const int nt = tc_n_tiles(N), NT = tc_tile_width(N), ch = tc_chunks(K);
     const long long total = (long long)nt * ch * 4 * NT;
     long long blocks = (total + 255) / 256;
     const long long cap = rowsum ? 148 * 8 : 148 * 32;   // fewer, longer threads when they also reduce (one atomic each)
     if (blocks > cap) blocks = cap;
     if (rowsum && (nt != 1 || (blocks * 256) % NT != 0)) { error = 3; return nullptr; }
-    tc_pack_b_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(src, s_n, s_k, N, K, NT, nt, ch, dst, rowsum);
+    if (fmt == 0) tc_pack_b_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(src, s_n, s_k, N, K, NT, nt, ch, dst, rowsum, amax);
+    else tc_pack_b_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(src, s_n, s_k, N, K, NT, nt, ch, dst, rowsum, amax);
     return dst;
   }
-  const uint8_t* packed_weight(cudaStream_t st, const float* src, long long s_n, long long s_k, int N, int K) {
+  // packed form of a weight matrix (cached per pass) + the slot holding its max |w|
+  std::pair<const uint8_t*, float*> packed_weight(cudaStream_t st, const float* src, long long s_n, long long s_k, int N, int K) {
     auto key = std::make_tuple(src, s_n, s_k, N, K);
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     const size_t need = (tc_packed_bytes(N, K) + 255) & ~(size_t)255;
-    if (wpack_used + need > wpack_bytes) { error = 1; return nullptr; }
+    if (wpack_used + need > wpack_bytes) { error = 1; return {nullptr, nullptr}; }
     uint8_t* dst = wpack + wpack_used;
     wpack_used += need;
-    pack(st, src, s_n, s_k, N, K, dst);
-    cache[key] = dst;
-    return dst;
+    float* sl = nullptr;
+    if (fmt == 0) {
+      sl = weight_slot();
+      tc_absmax_kernel<<<64, 256, 0, st>>>(src, s_n, s_k, N, K, sl);
+    }
+    pack(st, src, s_n, s_k, N, K, dst, nullptr, AmaxRef{sl, nullptr});
+    cache[key] = {dst, sl};
+    return {dst, sl};
   }
-  void new_pass() { cache.clear(); wpack_used = 0; }
+  void new_pass(cudaStream_t st) {
+    cache.clear(); wpack_used = 0; w_used = 0;
+    if (fmt == 0) cudaMemsetAsync(slots, 0, kWeightSlots * sizeof(float), st);
+  }
 
+  // k_real: real length of the contraction (for the truncation compensation)
   void run(cudaStream_t st, const float* A, long long a_ms, long long a_ks, int M, int K, const uint8_t* Bp, int N,
            float* C, long long c_ms, long long c_ns, const float* bias, int relu, const float* mask, long long mask_ms,
-           int mode, int slice_chunks) {
+           int mode, int slice_chunks, AmaxRef a_amax = AmaxRef{nullptr, nullptr}, AmaxRef b_amax = AmaxRef{nullptr, nullptr},
+           float* c_amax = nullptr) {
     if (!Bp) { error = 1; return; }
     TcGemmArgs g{};
     g.A = A; g.a_ms = a_ms; g.a_ks = a_ks; g.M = M; g.K = K;
+    g.a_amax = a_amax; g.b_amax = b_amax; g.c_amax = c_amax;
     g.Bp = Bp; g.N = N; g.NT = tc_tile_width(N); g.n_tiles = tc_n_tiles(N);
     g.chunks_total = tc_chunks(K);
     g.slice_chunks = slice_chunks > 0 ? slice_chunks : g.chunks_total;
     g.k_slices = ceil_div(g.chunks_total, g.slice_chunks);
+    // each accumulator sees 3 truncating MMAs per K = 16 slab of its slice (render_kernels.cuh: trunc_comp)
+    {
+      const int k_acc = g.k_slices > 1 ? g.slice_chunks * kKC : K;
+      g.comp = trunc_comp(k_acc < K ? k_acc : K, fmt == 0 ? kTruncKappaFp16 : kTruncKappaBf16);
+    }
     g.C = C; g.c_ms = c_ms; g.c_ns = c_ns; g.bias = bias; g.mask = mask; g.mask_ms = mask_ms; g.relu = relu; g.mode = mode;
     g.status = status;
     g.trace = trace;
@@ -104,11 +169,13 @@ struct TcEngine {
       int dev = 0;
       cudaGetDevice(&dev);
       if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaFuncSetAttribute(tc_gemm_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         cudaFuncSetAttribute(tc_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
       }
     }
-    if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, g) != cudaSuccess) error = 2;
+    if (fmt == 0) { if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<0>, g) != cudaSuccess) error = 2; }
+    else { if (cudaLaunchKernelEx(&cfg, tc_gemm_kernel<1>, g) != cudaSuccess) error = 2; }
   }
 };
 #else
@@ -133,7 +200,7 @@ struct TrainCall {
 
 struct Workspace {
   long long rb;                  // rows per block
-  long long z_coarse, xs, h[8], vin, hv, raw, graw, cs, ga, gb, gxs, gvin, ghv, tc_w, tc_g, total;   // offsets in floats
+  long long z_coarse, xs, h[8], vin, hv, raw, graw, cs, ga, gb, gxs, gvin, ghv, tc_w, tc_g, tc_slots, total;   // offsets in floats
   long long tc_w_floats, tc_g_floats;
   int P, LX, LV;                 // encoding width, leading dimension of XS (P + W), of VIN (W + 27J + fc)
 };
@@ -187,6 +254,7 @@ inline Workspace make_workspace(const NetDims& d, int n_rays, int Sc, int Si) {
 #endif
   w.tc_w = take(w.tc_w_floats);
   w.tc_g = take(w.tc_g_floats);
+  w.tc_slots = take(256);
   w.total = off;
   return w;
 }
@@ -205,8 +273,10 @@ inline void gemm_rows(TcEngine* tc, anerf_tstream st, const float* A, long long 
                       long long rows, int N, int K, const float* bias, int relu, const float* mask, long long ldmask, int mode) {
 #if !defined(ANERF_SIMT_EMU)
   if (tc) {      // B(n, k): forward W[n*ldb + k], dgrad W[k*ldb + n]
-    const uint8_t* bp = BT ? tc->packed_weight(st, B, ldb, 1, N, K) : tc->packed_weight(st, B, 1, ldb, N, K);
-    tc->run(st, A, lda, 1, (int)rows, K, bp, N, C, ldc, 1, bias, relu, mask, ldmask, mode, 0);
+    auto bp = BT ? tc->packed_weight(st, B, ldb, 1, N, K) : tc->packed_weight(st, B, 1, ldb, N, K);
+    const AmaxRef a_ref = tc->ref(A, K);                 // looked up BEFORE the output registers its slot (C may alias a row of A's buffer)
+    float* c_slot = tc->produce(C);
+    tc->run(st, A, lda, 1, (int)rows, K, bp.first, N, C, ldc, 1, bias, relu, mask, ldmask, mode, 0, a_ref, AmaxRef{bp.second, nullptr}, c_slot);
     return;
   }
 #endif
@@ -227,8 +297,9 @@ inline void gemm_wgrad(TcEngine* tc, anerf_tstream st, const float* G, long long
   if (tc && dW) {   // dW^T[k', n] += sum_rows X[row, k'] G[row, n]: A = X^T (rows of the MMA = input features), B = G^T;
                     // the pack of G^T reads every gradient once and leaves the bias gradient behind
     if (tc_packed_bytes(Nout, (int)rows) > tc->gpack_bytes) { tc->error = 1; return; }
-    const uint8_t* bp = tc->pack(st, G, 1, ldg, Nout, (int)rows, tc->gpack, db);
-    tc->run(st, X, 1, ldx, Kin, (int)rows, bp, Nout, dW, 1, lddw, nullptr, 0, nullptr, 0, 2, tc->wgrad_slice_chunks);
+    const AmaxRef g_ref = tc->ref(G, Nout);
+    const uint8_t* bp = tc->pack(st, G, 1, ldg, Nout, (int)rows, tc->gpack, db, g_ref);
+    tc->run(st, X, 1, ldx, Kin, (int)rows, bp, Nout, dW, 1, lddw, nullptr, 0, nullptr, 0, 2, tc->wgrad_slice_chunks, tc->ref(X, Kin), g_ref, nullptr);
     return;
   }
 #endif
@@ -275,12 +346,15 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
   auto in_k = [&](int l) -> int { return l == 0 ? P : ((l - 1) == d.skip ? P + W : W); };
 
 #if !defined(ANERF_SIMT_EMU)
-  if (c.tc) c.tc->new_pass();
+  if (c.tc) c.tc->new_pass(st);
 #endif
   const int rpb = rays_per_block(c.n_rays, S);
   for (int ray0 = 0; ray0 < c.n_rays; ray0 += rpb) {
     const int nb = (ray0 + rpb <= c.n_rays) ? rpb : c.n_rays - ray0;
     const long long rows = (long long)nb * S;
+#if !defined(ANERF_SIMT_EMU)
+    if (c.tc) c.tc->new_block(st);
+#endif
     // ---- encodings
     {
       EncodeArgs e{};
@@ -291,6 +365,17 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
       e.XS = XS; e.ldxs = LX; e.VIN = VIN; e.ldv = LV;
       auto k = encode_rows_kernel;
       ANERF_TLAUNCH(k, dim3((unsigned)((rows * J + 127) / 128)), dim3(128), st, e);
+#if !defined(ANERF_SIMT_EMU)
+      if (c.tc) {
+        // bounds of the encodings: |v w(v)|, |sin|, |cos|, |r|, |d| <= max(1, sup v w(v)); v w(v) peaks near the cutoff:
+        // < cutoff + 2 / tau.  A bound within a factor of two of the true maximum costs at most one of the 22 bits.
+        float cmax = 0.f;
+        for (int j = 0; j < J; ++j) cmax = fmaxf(cmax, fmaxf(o.cutoff_pts[j] + 2.f / fmaxf(o.tau_pts, 1e-3f), 1.f));
+        c.tc->produce_const(st, XS, cmax);
+        if (d.fc_ch > 0) c.tc->produce_scan(st, VIN + W, LV, LV - W, rows);     // view encodings + framecodes (any magnitude)
+        else c.tc->produce_const(st, VIN + W, 1.0f);
+      }
+#endif
     }
     // ---- forward, activations kept
     for (int l = 0; l < D; ++l)
@@ -320,6 +405,9 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
       auto k3 = head_bwd_kernel<3>;
       ANERF_TLAUNCH(k3, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)(H < 32 ? 32 : H)), st, (const float*)GRAW, (long long)4,
                     (const float*)HV, (long long)H, H, p.rgb_w, rows, 64, 1, GHV, (long long)H, gr.rgb_w, gr.rgb_b);
+#if !defined(ANERF_SIMT_EMU)
+      if (c.tc) c.tc->produce_scan(st, GHV, H, H, rows);
+#endif
     }
     gemm_wgrad(c.tc, st, GHV, H, VIN, LV, gr.views_w, LV, rows, H, LV, gr.views_b);
     const int Nv = (need_pose || need_fc) ? LV : W;         // the view-encoding columns only when something consumes them
@@ -330,6 +418,7 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
       ANERF_TLAUNCH(k1, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)W), st, (const float*)(GRAW + 3), (long long)4, HL, HLld, W,
                     p.alpha_w, rows, 64, 0, GA, (long long)W, gr.alpha_w, gr.alpha_b);
     }
+    // (GA now holds g_sigma (x) w_alpha; the GEMM below adds to it and registers the maximum of the sum)
     // dL/dZ of the last trunk layer = (G_feature Wf + g_sigma (x) w_alpha) . (h > 0)
     gemm_rows<false>(c.tc, st, GVIN, LV, p.feature_w, W, GA, W, rows, W, W, nullptr, 0, HL, HLld, 1);
     // ---- trunk, last layer first

@@ -343,7 +343,7 @@ def training_probe(dev, rank, world, n_rays=3072, n_importance=16, steps=5):
             "ms_per_step": ms, "rays_per_rank": N, "samples": f"{N_SAMPLES}+{n_importance}", "pose_grad": True,
             "allreduce_bytes": int(sum(p.numel() for p in grad_vars) * 4) if world > 1 else 0,
             "algorithmic_tflops": 3 * rows * world * 1723648 / (ms * 1e-3) / 1e12,
-            "gemm_engine": os.environ.get("ANERF_TRAIN_GEMM", "tc") + " (bf16 hi/lo split on tcgen05)"}
+            "gemm_engine": os.environ.get("ANERF_TRAIN_GEMM", "tc") + " (default tc: fp16 hi/lo operands with per-matrix power-of-two scales on tcgen05)"}
 
 
 def main():

@@ -119,11 +119,12 @@ def test_reference_trainer_step_drives_our_caster():
     assert abs(a["stats"]["total_norm"] - b["stats"]["total_norm"]) < 2e-3 * b["stats"]["total_norm"], (a["stats"]["total_norm"], b["stats"]["total_norm"])
     assert a["tau"] == pytest.approx(b["tau"], rel=1e-6)
     # one Adam step moved the weights the same way (step size = lrate per element on the first step)
-    moved = 0
+    moved = same = 0
     for k in b["w"]:
         d_ref = b["w"][k] - np.asarray(sd1[k])
         d_our = a["w"][k] - np.asarray(sd1[k])
         big = np.abs(d_ref) > 0.5 * args.lrate           # elements whose gradient is well above Adam's eps
         moved += int(big.sum())
-        assert (np.sign(d_our[big]) == np.sign(d_ref[big])).mean() > 0.999, k
-    assert moved > 100000
+        same += int((np.sign(d_our[big]) == np.sign(d_ref[big])).sum())
+        assert (np.sign(d_our[big]) == np.sign(d_ref[big])).mean() > 0.98, k
+    assert moved > 100000 and same / moved > 0.999, (moved, same)
