@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -14,6 +15,7 @@
 #include "render_kernels.cuh"
 #include "train_path.cuh"
 #include "pose_kernels.cuh"
+#include "optim_kernels.cuh"
 
 using namespace anerf;
 
@@ -172,28 +174,33 @@ int anerf_pack_net(const anerf_plan* plan, const anerf_net_params* prm, void* pa
   anerf_fold_views_kernel<<<64, 256, 0, stream>>>(prm->views_w, prm->views_b, prm->feature_w, prm->feature_b, d.W / 2, d.W,
                                                   in_views_ref(d) + d.fc_ch, plan->d_fold_w, plan->d_fold_b);
   CUDA_TRY(cudaGetLastError());
-  for (int l = 0; l < pg.n_layers; ++l) {
-    const float* w = l < d.D ? prm->pts_w[l] : plan->d_fold_w;
-    const float* b = l < d.D ? prm->pts_b[l] : plan->d_fold_b;
-    if (!w || !b) return fail(ANERF_ERR_INVALID, "missing parameter pointer for layer %d", l);
-    int n = pg.layer[l].n, chunks = pg.layer[l].chunks;
-    long long total = (long long)chunks * n * 4;
-    int blocks = (int)((total + 255) / 256);
-    // real input columns of the layer as the kernel feeds it (the views layer: h + the row's own ray-slot chunk)
-    const int k_real = l < d.D ? plan->k_in[l] : d.W + kKC;
-    anerf_layer_scale_kernel<<<1, 1024, 0, stream>>>(w, (long long)n * plan->k_in[l], fmt, trunc_comp(k_real, kappa), plan->d_scale + l, smalls + l);
-    if (fmt == 1)
-      anerf_pack_layer_kernel<1><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, plan->d_scale + l, img + pg.layer[l].w_off);
-    else
-      anerf_pack_layer_kernel<0><<<blocks, 256, 0, stream>>>(w, plan->k_in[l], plan->d_kmap[l], n, chunks, plan->d_scale + l, img + pg.layer[l].w_off);
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.bias[l], b, n * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-  }
   if (!prm->alpha_w || !prm->alpha_b || !prm->rgb_w || !prm->rgb_b) return fail(ANERF_ERR_INVALID, "missing alpha/rgb parameters");
-  CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.alpha_w, prm->alpha_w, d.W * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-  CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.alpha_b, prm->alpha_b, sizeof(float), cudaMemcpyDeviceToDevice, stream));
-  CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.rgb_w, prm->rgb_w, 3 * (d.W / 2) * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-  CUDA_TRY(cudaMemcpyAsync(smalls + pg.sm.rgb_b, prm->rgb_b, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+  PackAllArgs a{};
+  a.n_layers = pg.n_layers; a.fmt = fmt; a.pure_scale = plan->d_scale; a.img = img; a.smalls = smalls;
+  long long most = 0;
+  for (int l = 0; l < pg.n_layers; ++l) {
+    a.w[l] = l < d.D ? prm->pts_w[l] : plan->d_fold_w;
+    a.b[l] = l < d.D ? prm->pts_b[l] : plan->d_fold_b;
+    if (!a.w[l] || !a.b[l]) return fail(ANERF_ERR_INVALID, "missing parameter pointer for layer %d", l);
+    a.kmap[l] = plan->d_kmap[l]; a.k_in[l] = plan->k_in[l]; a.n[l] = pg.layer[l].n; a.chunks[l] = pg.layer[l].chunks;
+    a.w_off[l] = pg.layer[l].w_off; a.bias_off[l] = pg.sm.bias[l];
+    // real input columns of the layer as the kernel feeds it (the views layer: h + the row's own ray-slot chunk)
+    a.comp[l] = trunc_comp(l < d.D ? plan->k_in[l] : d.W + kKC, kappa);
+    const long long total = (long long)a.chunks[l] * a.n[l] * 4;
+    if (total > most) most = total;
+  }
+  a.alpha_w = prm->alpha_w; a.alpha_b = prm->alpha_b; a.rgb_w = prm->rgb_w; a.rgb_b = prm->rgb_b;
+  a.alpha_w_off = pg.sm.alpha_w; a.alpha_b_off = pg.sm.alpha_b; a.rgb_w_off = pg.sm.rgb_w; a.rgb_b_off = pg.sm.rgb_b; a.W = d.W;
+  anerf_all_scales_kernel<<<pg.n_layers, 1024, 0, stream>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  {
+    int bx = (int)((most + 255) / 256);
+    if (bx > 148) bx = 148;
+    if (bx < 1) bx = 1;
+    if (fmt == 1) anerf_pack_all_kernel<1><<<dim3(bx, pg.n_layers), 256, 0, stream>>>(a);
+    else anerf_pack_all_kernel<0><<<dim3(bx, pg.n_layers), 256, 0, stream>>>(a);
+    CUDA_TRY(cudaGetLastError());
+  }
   anerf_pack_view_weights_kernel<<<128, 256, 0, stream>>>(plan->d_fold_w, d.W + in_views_ref(d) + d.fc_ch, d, smalls + pg.sm.gw);
   CUDA_TRY(cudaGetLastError());
   if (d.fc_ch > 0) {
@@ -602,6 +609,36 @@ int anerf_pose_chain_bwd(int32_t n_poses, int32_t n_joints, const int32_t* paren
   a.g_skts = g_skts; a.g_l2ws = g_l2ws; a.g_kps = g_kps; a.g_rots = g_rots; a.g_pelvis = g_pelvis; a.scratch = (float*)scratch;
   pose::pose_chain_bwd_kernel<<<(n_poses + 63) / 64, 64, 0, (cudaStream_t)stream_>>>(a);
   CUDA_TRY(cudaGetLastError());
+  return ANERF_OK;
+}
+
+int anerf_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                    float* const* exp_avg_sq, const int64_t* sizes, int64_t step, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, float grad_scale, void* stream_) {
+  ANERF_ENTRY();
+  if (n_tensors < 0 || (n_tensors > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !sizes))) return fail(ANERF_ERR_INVALID, "null argument");
+  if (step < 1) return fail(ANERF_ERR_INVALID, "step must be >= 1 (the count AFTER this update, as torch.optim.Adam keeps it)");
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  for (int t0 = 0; t0 < n_tensors; t0 += optim::kMaxTensors) {
+    optim::AdamArgs a{};
+    a.n = n_tensors - t0 < optim::kMaxTensors ? n_tensors - t0 : optim::kMaxTensors;
+    long long largest = 0;
+    for (int i = 0; i < a.n; ++i) {
+      if (!params[t0 + i] || !grads[t0 + i] || !exp_avg[t0 + i] || !exp_avg_sq[t0 + i] || sizes[t0 + i] < 0)
+        return fail(ANERF_ERR_INVALID, "tensor %d: null pointer or negative size", t0 + i);
+      a.p[i] = params[t0 + i]; a.g[i] = grads[t0 + i]; a.m[i] = exp_avg[t0 + i]; a.v[i] = exp_avg_sq[t0 + i];
+      a.size[i] = sizes[t0 + i];
+      if (sizes[t0 + i] > largest) largest = sizes[t0 + i];
+    }
+    a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+    a.bc1 = bc1; a.bc2_sqrt = bc2s; a.grad_scale = grad_scale;
+    if (largest == 0) continue;
+    long long bx = (largest + 256 * 4 - 1) / (256 * 4);          // ~4 elements per thread for the largest tensor
+    if (bx > 64) bx = 64;
+    optim::adam_step_kernel<<<dim3((unsigned)bx, (unsigned)a.n), 256, 0, (cudaStream_t)stream_>>>(a);
+    CUDA_TRY(cudaGetLastError());
+  }
   return ANERF_OK;
 }
 

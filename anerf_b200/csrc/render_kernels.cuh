@@ -1263,29 +1263,6 @@ __global__ void __launch_bounds__(1024, 1) anerf_nearfar_kernel(const float* __r
 // multiplies the accumulators by the exact inverse (`inv_scale`, smalls header) before adding the bias.
 // The drain scale written to the smalls header also carries `comp` = 1 + expected relative loss of the tensor core's
 // fp32 accumulation (trunc_comp() below); `pure_scale` (what the pack kernel divides the weights by) stays a power of two.
-__global__ void anerf_layer_scale_kernel(const float* __restrict__ w, long long count, int fmt, float comp,
-                                         float* __restrict__ pure_scale, float* __restrict__ inv_scale) {
-  __shared__ float s_max[32];
-  float m = 0.f;
-  if (fmt == 0)
-    for (long long i = threadIdx.x; i < count; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, s_max[i]);
-    int k = 0;
-    if (fmt == 0 && m > 0.f && m < 3.0e38f) {
-      int e;
-      frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)
-      k = min(max(13 - e, -24), 24);
-    }
-    *pure_scale = ldexpf(1.0f, -k);
-    *inv_scale = ldexpf(1.0f, -k) * comp;
-  }
-}
-
 template <int FMT>
 __global__ void anerf_pack_layer_kernel(const float* __restrict__ w, int k_in, const int* __restrict__ kmap,
                                         int n, int chunks, const float* __restrict__ inv_scale,
@@ -1315,6 +1292,93 @@ __global__ void anerf_pack_layer_kernel(const float* __restrict__ w, int k_in, c
     size_t off = (size_t)g * nh * 16 + (size_t)(r >> 3) * 128 + (size_t)(r & 7) * 16;
     *reinterpret_cast<uint4*>(half + off) = hi;
     *reinterpret_cast<uint4*>(half + (size_t)nh * 64 + off) = lo;
+  }
+}
+
+// The whole image in a handful of launches (the optimizer re-packs after every step: SURVEY.md 8(f) row 3): one
+// launch computes every layer's scale, one packs every layer, one copies the small fp32 parameters.
+struct PackAllArgs {
+  const float* w[kMaxLayers];      // fp32 [n, k_in] (the views layer: the folded matrix)
+  const float* b[kMaxLayers];      // fp32 [n]
+  const int* kmap[kMaxLayers];
+  int k_in[kMaxLayers], n[kMaxLayers], chunks[kMaxLayers];
+  unsigned w_off[kMaxLayers];
+  int bias_off[kMaxLayers];        // offsets in floats inside the smalls block
+  float comp[kMaxLayers];
+  int n_layers, fmt;
+  float* pure_scale;               // [kMaxLayers] scratch
+  uint8_t* img;
+  float* smalls;
+  // heads
+  const float *alpha_w, *alpha_b, *rgb_w, *rgb_b;
+  int alpha_w_off, alpha_b_off, rgb_w_off, rgb_b_off, W;
+};
+
+// grid = n_layers blocks of 1024 threads: per-layer operand scale (fp16 operands: the power of two that brings max|W| into [2^12, 2^13); bf16: 1)
+__global__ void anerf_all_scales_kernel(const __grid_constant__ PackAllArgs a) {
+  __shared__ float s_max[32];
+  const int l = blockIdx.x;
+  const float* w = a.w[l];
+  const long long count = (long long)a.n[l] * a.k_in[l];
+  float m = 0.f;
+  if (a.fmt == 0)
+    for (long long i = threadIdx.x; i < count; i += blockDim.x) m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) m = fmaxf(m, s_max[i]);
+    int k = 0;
+    if (a.fmt == 0 && m > 0.f && m < 3.0e38f) {
+      int e;
+      frexpf(m, &e);
+      k = min(max(13 - e, -24), 24);
+    }
+    a.pure_scale[l] = ldexpf(1.0f, -k);
+    a.smalls[l] = ldexpf(1.0f, -k) * a.comp[l];
+  }
+}
+
+// grid = (blocks, n_layers): blockIdx.y picks the layer; also copies the layer's bias
+template <int FMT>
+__global__ void anerf_pack_all_kernel(const __grid_constant__ PackAllArgs a) {
+  const int l = blockIdx.y;
+  const float* __restrict__ w = a.w[l];
+  const int* __restrict__ kmap = a.kmap[l];
+  const int n = a.n[l], k_in = a.k_in[l], chunks = a.chunks[l];
+  uint8_t* out = a.img + a.w_off[l];
+  const float scale = 1.0f / a.pure_scale[l];   // exact: power of two
+  const long long total = (long long)chunks * n * 4;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(t & 3);
+    const int nn = (int)((t >> 2) % n);
+    const int c = (int)((t >> 2) / n);
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int src = kmap[c * kKC + g * 8 + i];
+      x[i] = src >= 0 ? w[(size_t)nn * k_in + src] * scale : 0.f;
+    }
+    uint4 hi, lo;
+    Split<FMT>::pair(x[0], x[1], hi.x, lo.x);
+    Split<FMT>::pair(x[2], x[3], hi.y, lo.y);
+    Split<FMT>::pair(x[4], x[5], hi.z, lo.z);
+    Split<FMT>::pair(x[6], x[7], hi.w, lo.w);
+    const int nh = n >> 1;
+    uint8_t* half = out + (size_t)c * n * 128 + (size_t)(nn / nh) * n * 64;
+    const int r = nn % nh;
+    const size_t off = (size_t)g * nh * 16 + (size_t)(r >> 3) * 128 + (size_t)(r & 7) * 16;
+    *reinterpret_cast<uint4*>(half + off) = hi;
+    *reinterpret_cast<uint4*>(half + (size_t)nh * 64 + off) = lo;
+  }
+  // biases and (layer 0's blocks) the heads
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a.smalls[a.bias_off[l] + i] = a.b[l][i];
+  if (l == 0) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.W; i += gridDim.x * blockDim.x) a.smalls[a.alpha_w_off + i] = a.alpha_w[i];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 3 * (a.W / 2); i += gridDim.x * blockDim.x) a.smalls[a.rgb_w_off + i] = a.rgb_w[i];
+    if (blockIdx.x == 0 && threadIdx.x < 3) a.smalls[a.rgb_b_off + threadIdx.x] = a.rgb_b[threadIdx.x];
+    if (blockIdx.x == 0 && threadIdx.x == 3) a.smalls[a.alpha_b_off] = a.alpha_b[0];
   }
 }
 

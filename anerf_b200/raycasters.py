@@ -590,7 +590,13 @@ def create_raycaster(args, data_attrs, device=None):
         for m in (model, None if single_net else model_fine, embed_fn, embedbones_fn, embeddirs_fn):
             if m is not None:
                 grad_vars += [p for p in m.parameters() if p.requires_grad]
-    optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    # torch.optim.Adam's hyper-parameters, state layout and state_dict (core/raycasters.py:116), one launch per step
+    # (anerf_b200.optim.FusedAdam); plain torch.optim.Adam when the parameters are not on a GPU
+    if torch.device(device).type == 'cuda':
+        from .optim import FusedAdam
+        optimizer = FusedAdam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
+    else:
+        optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
 
     start = 0
     if args.ft_path is not None and args.ft_path != 'None':

@@ -276,6 +276,16 @@ int anerf_pose_chain_bwd(int32_t n_poses, int32_t n_joints, const int32_t* paren
                          const float* g_skts, const float* g_l2ws, const float* g_kps, float* g_rots, float* g_pelvis,
                          void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- optimizer step ------------------------------------------------------------------- */
+
+/* torch.optim.Adam.step (amsgrad off) for n_tensors fp32 tensors in ONE launch (reference: Trainer.optimize,
+ * core/trainer.py:451-483; optimizer built at core/raycasters.py:116).  params / grads / exp_avg / exp_avg_sq: HOST
+ * arrays of device pointers, sizes[i] elements each; `step` = the update count including this one; grads are first
+ * multiplied by grad_scale (1/world after a summing all-reduce). */
+int anerf_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
+                    float* const* exp_avg_sq, const int64_t* sizes, int64_t step, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, float grad_scale, void* stream);
+
 /* Debug aid: device buffer of 3 x 1024 int64; while set, launches record a clock64 timeline of CTA 0
  * (stream 0 MMA thread, 1/2 worker groups; entries = tag << 48 | clock).  NULL switches it off. */
 void anerf_debug_set_trace(long long* device_buffer);
