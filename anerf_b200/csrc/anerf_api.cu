@@ -16,6 +16,7 @@
 #include "train_path.cuh"
 #include "pose_kernels.cuh"
 #include "optim_kernels.cuh"
+#include "mesh_kernels.cuh"
 
 using namespace anerf;
 
@@ -639,6 +640,50 @@ int anerf_adam_step(int32_t n_tensors, float* const* params, const float* const*
     optim::adam_step_kernel<<<dim3((unsigned)bx, (unsigned)a.n), 256, 0, (cudaStream_t)stream_>>>(a);
     CUDA_TRY(cudaGetLastError());
   }
+  return ANERF_OK;
+}
+
+static int mc_fill(mesh::McArgs& a, const float* vol, int32_t n0, int32_t n1, int32_t n2, int64_t s0, int64_t s1, int64_t s2, float iso) {
+  if (!vol) return fail(ANERF_ERR_INVALID, "null argument");
+  if (n0 < 2 || n1 < 2 || n2 < 2 || n0 > 4096 || n1 > 4096 || n2 > 4096) return fail(ANERF_ERR_INVALID, "volume must be 2..4096 voxels per axis");
+  static bool tables[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !tables[dev]) {            // __constant__ memory is per device
+    CUDA_TRY(cudaMemcpyToSymbol(mesh::c_tri_count, mesh::kMcTriCount, sizeof(mesh::kMcTriCount)));
+    CUDA_TRY(cudaMemcpyToSymbol(mesh::c_tri_table, mesh::kMcTriTable, sizeof(mesh::kMcTriTable)));
+    CUDA_TRY(cudaMemcpyToSymbol(mesh::c_edge_corner, mesh::kMcEdgeCorner, sizeof(mesh::kMcEdgeCorner)));
+    CUDA_TRY(cudaMemcpyToSymbol(mesh::c_edge_axis, mesh::kMcEdgeAxis, sizeof(mesh::kMcEdgeAxis)));
+    if (dev >= 0 && dev < 64) tables[dev] = true;
+  }
+  a.vol = vol; a.n0 = n0; a.n1 = n1; a.n2 = n2; a.s0 = s0; a.s1 = s1; a.s2 = s2; a.iso = iso;
+  a.n_cells = (long long)(n0 - 1) * (n1 - 1) * (n2 - 1);
+  return ANERF_OK;
+}
+
+int anerf_mc_count(const float* volume, int32_t n0, int32_t n1, int32_t n2, int64_t s0, int64_t s1, int64_t s2, float iso,
+                   int32_t* counts, void* stream_) {
+  ANERF_ENTRY();
+  mesh::McArgs a{};
+  int rc = mc_fill(a, volume, n0, n1, n2, s0, s1, s2, iso);
+  if (rc) return rc;
+  if (!counts) return fail(ANERF_ERR_INVALID, "null argument");
+  a.counts = counts;
+  mesh::mc_count_kernel<<<(unsigned)((a.n_cells + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return ANERF_OK;
+}
+
+int anerf_mc_emit(const float* volume, int32_t n0, int32_t n1, int32_t n2, int64_t s0, int64_t s1, int64_t s2, float iso,
+                  const int64_t* offsets, float* verts, int64_t* keys, void* stream_) {
+  ANERF_ENTRY();
+  mesh::McArgs a{};
+  int rc = mc_fill(a, volume, n0, n1, n2, s0, s1, s2, iso);
+  if (rc) return rc;
+  if (!offsets || !verts || !keys) return fail(ANERF_ERR_INVALID, "null argument");
+  a.offsets = (const long long*)offsets; a.verts = verts; a.keys = (long long*)keys;
+  mesh::mc_emit_kernel<<<(unsigned)((a.n_cells + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(a);
+  CUDA_TRY(cudaGetLastError());
   return ANERF_OK;
 }
 

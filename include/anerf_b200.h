@@ -276,6 +276,19 @@ int anerf_pose_chain_bwd(int32_t n_poses, int32_t n_joints, const int32_t* paren
                          const float* g_skts, const float* g_l2ws, const float* g_kps, float* g_rots, float* g_pelvis,
                          void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- mesh extraction ------------------------------------------------------------------ */
+
+/* Marching cubes on a density volume resident on the device (reference: mcubes.marching_cubes(sigma, threshold) on a
+ * host copy, run_render.py:983-986).  volume: n0 x n1 x n2 fp32 voxels with element strides s0, s1, s2 (so the
+ * transposed view RayCaster.render_mesh_density returns needs no copy).  Pass 1 writes the number of triangles of each
+ * of the (n0-1)(n1-1)(n2-1) cells (cell index = (i (n1-1) + j)(n2-1) + k); the caller scans them; pass 2 writes, for
+ * triangle t and corner v, the vertex position in index coordinates (verts [T,3,3]) and the id of the volume edge it
+ * lies on (keys [T,3]; equal ids = the same vertex, for welding).  Inside = value > iso; normals point to lower values. */
+int anerf_mc_count(const float* volume, int32_t n0, int32_t n1, int32_t n2, int64_t s0, int64_t s1, int64_t s2, float iso,
+                   int32_t* counts, void* stream);
+int anerf_mc_emit(const float* volume, int32_t n0, int32_t n1, int32_t n2, int64_t s0, int64_t s1, int64_t s2, float iso,
+                  const int64_t* offsets, float* verts, int64_t* keys, void* stream);
+
 /* ---- optimizer step ------------------------------------------------------------------- */
 
 /* torch.optim.Adam.step (amsgrad off) for n_tensors fp32 tensors in ONE launch (reference: Trainer.optimize,

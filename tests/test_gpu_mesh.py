@@ -1,0 +1,123 @@
+"""SURVEY.md 8(f) row 4 on the GPU: marching cubes on a device-resident volume (anerf_mc_count / anerf_mc_emit behind
+anerf_b200.mesh.marching_cubes).  PyMCubes, which the reference calls, is not installed (parity unpinned): the checks are
+geometric -- vertices on the isosurface, closed 2-manifold, Euler characteristic, area / volume of analytic bodies,
+orientation -- plus agreement with a plain numpy walk over the same generated case table."""
+import numpy as np
+import pytest
+import torch
+
+from anerf_b200 import mc_table as mt
+from anerf_b200 import mesh
+
+pytestmark = pytest.mark.gpu
+
+
+def _topology(V, F):
+    und, dirs = {}, {}
+    for a, b, c in F.tolist():
+        for u, v in ((a, b), (b, c), (c, a)):
+            und[(min(u, v), max(u, v))] = und.get((min(u, v), max(u, v)), 0) + 1
+            dirs[(u, v)] = dirs.get((u, v), 0) + 1
+    closed = all(n == 2 for n in und.values())
+    oriented = all(dirs.get((v, u), 0) == 1 and n == 1 for (u, v), n in dirs.items())
+    return closed, oriented, len(V) - len(und) + len(F)
+
+
+def _grid(n):
+    return np.stack(np.meshgrid(*[np.arange(n)] * 3, indexing='ij'), -1).astype(np.float64)
+
+
+def test_sphere_and_torus():
+    dev = torch.device("cuda")
+    N = 48
+    g = _grid(N)
+    c = np.array([23.3, 24.1, 22.7])
+    r = 15.3
+    sphere = (r - np.linalg.norm(g - c, axis=-1)).astype(np.float32)
+    V, F = mesh.marching_cubes(torch.as_tensor(sphere).to(dev), 0.0)
+    V, F = V.cpu().numpy().astype(np.float64), F.cpu().numpy()
+    closed, oriented, chi = _topology(V, F)
+    assert closed and oriented and chi == 2
+    assert np.abs(np.linalg.norm(V - c, axis=1) - r).max() < 0.02          # linear interpolation of a smooth field
+    vol = sum(np.dot(V[a], np.cross(V[b], V[d])) for a, b, d in F) / 6
+    area = sum(np.linalg.norm(np.cross(V[b] - V[a], V[d] - V[a])) / 2 for a, b, d in F)
+    assert abs(vol / (4 / 3 * np.pi * r ** 3) - 1) < 0.01 and vol > 0        # normals point out of the body
+    assert abs(area / (4 * np.pi * r ** 2) - 1) < 0.01
+    R, a_ = 13.0, 5.2
+    q = np.sqrt((g[..., 0] - c[0]) ** 2 + (g[..., 1] - c[1]) ** 2) - R
+    torus = (a_ - np.sqrt(q ** 2 + (g[..., 2] - c[2]) ** 2)).astype(np.float32)
+    V, F = mesh.marching_cubes(torch.as_tensor(torus).to(dev), 0.0)
+    closed, oriented, chi = _topology(V.cpu().numpy(), F.cpu().numpy())
+    assert closed and oriented and chi == 0
+
+
+def test_noise_volume_strided_view_and_reference_walk():
+    """Random volume (every ambiguous configuration occurs), passed as a transposed NON-contiguous view like the one
+    render_mesh_density returns: watertight, and the same triangles as a numpy walk over the generated table."""
+    dev = torch.device("cuda")
+    rng = np.random.RandomState(3)
+    vol = rng.randn(13, 11, 12).astype(np.float32)
+    vol[0] = vol[-1] = -9
+    vol[:, 0] = vol[:, -1] = -9
+    vol[:, :, 0] = vol[:, :, -1] = -9
+    base = torch.as_tensor(np.ascontiguousarray(vol.transpose(1, 0, 2))).to(dev)     # stored [11,13,12]
+    view = base.transpose(1, 0)                                                       # logical [13,11,12], strided
+    assert not view.is_contiguous()
+    V, F = mesh.marching_cubes(view, 0.25)
+    V, F = V.cpu().numpy(), F.cpu().numpy()
+    closed, oriented, _ = _topology(V, F)
+    assert closed and oriented
+    # numpy walk
+    tris = []
+    n = vol.shape
+    for i in range(n[0] - 1):
+        for j in range(n[1] - 1):
+            for k in range(n[2] - 1):
+                case = sum(1 << c_ for c_, (di, dj, dk) in enumerate(mt.CORNER_OFFSETS) if vol[i + di, j + dj, k + dk] > 0.25)
+                for t in range(mt.TRI_COUNT[case]):
+                    tri = []
+                    for e in mt.TRI_TABLE[case, t]:
+                        a, b = mt.EDGE_CORNERS[e]
+                        pa, pb = np.array([i, j, k]) + mt.CORNER_OFFSETS[a], np.array([i, j, k]) + mt.CORNER_OFFSETS[b]
+                        fa, fb = vol[tuple(pa)], vol[tuple(pb)]
+                        tri.append(pa + (np.float32(0.25) - fa) / (fb - fa) * (pb - pa))
+                    tris.append(tri)
+    want = np.asarray(tris, np.float32)
+    got = V[F]
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() < 1e-5                # same cells in the same order, same triangles
+    # an empty volume
+    V0, F0 = mesh.marching_cubes(torch.full((5, 5, 5), -1.0, device=dev), 0.0)
+    assert V0.shape == (0, 3) and F0.shape == (0, 3)
+
+
+def test_render_mesh_writes_ply_of_the_density_surface(tmp_path):
+    """run_render.render_mesh's flow on the device: density grid -> max(raw, 0) -> marching cubes at threshold 10 ->
+    vertices / res - 0.5 -> .ply; the surface separates voxels above / below the threshold."""
+    import contextlib
+    import io
+    from anerf_b200 import synthetic
+    from anerf_b200.raycasters import create_raycaster
+    from tests.test_gpu_api import data_attrs, make_args
+    dev = torch.device("cuda")
+    with contextlib.redirect_stdout(io.StringIO()):
+        _, rk, *_ = create_raycaster(make_args(N_importance=16, no_reload=True), data_attrs(24))
+    rc = rk['ray_caster'].eval()
+    rc.network_fine.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(202).items()})
+    pose = synthetic.make_pose(11, 24)
+    t = lambda a: torch.as_tensor(a).to(dev)
+    data = dict(kp=t(pose["kps"])[None], skts=t(pose["skts"])[None], bones=t(pose["bones"])[None])
+    res = 31
+    out = mesh.render_mesh(str(tmp_path), rk, data, radius=1.2, res=res, threshold=10.)
+    assert len(out) == 1 and (tmp_path / "meshes" / "000.ply").exists()
+    V, F = out[0]
+    assert F.shape[0] > 100 and float(V.min()) >= -0.5 and float(V.max()) <= 0.5
+    raw = rc(kps=data["kp"], skts=data["skts"], bones=None, radius=1.2, res=res, fwd_type='mesh').clamp_min(0.)
+    # every vertex lies on a volume edge whose end points straddle the threshold
+    idx = (V + .5) * res
+    lo = idx.floor().long().clamp(0, res)
+    hi = idx.ceil().long().clamp(0, res)
+    f_lo, f_hi = raw[lo[:, 0], lo[:, 1], lo[:, 2]], raw[hi[:, 0], hi[:, 1], hi[:, 2]]
+    assert bool((((f_lo > 10.) != (f_hi > 10.)) | (f_lo == f_hi)).all())
+    head = (tmp_path / "meshes" / "000.ply").read_bytes().split(b"end_header\n")[0]
+    assert f"element vertex {V.shape[0]}".encode() in head and f"element face {F.shape[0]}".encode() in head

