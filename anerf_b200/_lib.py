@@ -17,7 +17,7 @@ SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "ane
            "anerf_selftest_gemm", "anerf_last_error", "anerf_version", "anerf_debug_set_trace",
            "anerf_render_bwd", "anerf_render_bwd_workspace_bytes", "anerf_selftest_tc_gemm", "anerf_render_frame",
            "anerf_check_status", "anerf_density_grid", "anerf_render_fwd_host_chunked", "anerf_pose_chain_fwd",
-           "anerf_pose_chain_bwd", "anerf_pose_chain_bwd_scratch_bytes", "anerf_adam_step", "anerf_mc_count", "anerf_mc_emit"]
+           "anerf_pose_chain_bwd", "anerf_pose_chain_bwd_scratch_bytes", "anerf_adam_step", "anerf_mc_count", "anerf_mc_emit", "anerf_sample_rays"]
 
 
 class NetConfig(C.Structure):
@@ -105,8 +105,8 @@ def load():
     lib.anerf_pose_chain_bwd.argtypes = [C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.c_void_p, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
-    lib.anerf_adam_step.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
-                                    C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p]
+    lib.anerf_adam_step.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double,
+                                    C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
     lib.anerf_mc_count.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p, C.c_void_p]
     lib.anerf_mc_emit.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_float, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p]

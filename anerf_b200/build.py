@@ -11,7 +11,7 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "csrc")
 LIB = os.path.join(CSRC, "libanerf_b200.so")
 SOURCES = ["anerf_api.cu"]
-HEADERS = ["render_kernels.cuh", "tc_sm100.cuh", "path_math.cuh", "train_kernels.cuh", "train_path.cuh", "tc_gemm.cuh", "pose_kernels.cuh", "optim_kernels.cuh", "mesh_kernels.cuh", "mc_table.inc", os.path.join("..", "..", "include", "anerf_b200.h")]
+HEADERS = ["render_kernels.cuh", "tc_sm100.cuh", "path_math.cuh", "train_kernels.cuh", "train_path.cuh", "tc_gemm.cuh", "pose_kernels.cuh", "optim_kernels.cuh", "mesh_kernels.cuh", "mc_table.inc", "sampler_kernels.cuh", os.path.join("..", "..", "include", "anerf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 

@@ -17,6 +17,7 @@
 #include "pose_kernels.cuh"
 #include "optim_kernels.cuh"
 #include "mesh_kernels.cuh"
+#include "sampler_kernels.cuh"
 
 using namespace anerf;
 
@@ -614,13 +615,14 @@ int anerf_pose_chain_bwd(int32_t n_poses, int32_t n_joints, const int32_t* paren
 }
 
 int anerf_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
-                    float* const* exp_avg_sq, const int64_t* sizes, int64_t step, float lr, float beta1, float beta2, float eps,
-                    float weight_decay, float grad_scale, void* stream_) {
+                    float* const* exp_avg_sq, const int64_t* sizes, int64_t step, double lr_d, double beta1_d, double beta2_d, double eps_d,
+                    double weight_decay_d, double grad_scale_d, void* stream_) {
+  const float lr = (float)lr_d, beta1 = (float)beta1_d, beta2 = (float)beta2_d, eps = (float)eps_d, weight_decay = (float)weight_decay_d, grad_scale = (float)grad_scale_d;
   ANERF_ENTRY();
   if (n_tensors < 0 || (n_tensors > 0 && (!params || !grads || !exp_avg || !exp_avg_sq || !sizes))) return fail(ANERF_ERR_INVALID, "null argument");
   if (step < 1) return fail(ANERF_ERR_INVALID, "step must be >= 1 (the count AFTER this update, as torch.optim.Adam keeps it)");
-  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
-  const float bc2s = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  const float bc1 = (float)(1.0 - pow(beta1_d, (double)step));
+  const float bc2s = (float)sqrt(1.0 - pow(beta2_d, (double)step));
   for (int t0 = 0; t0 < n_tensors; t0 += optim::kMaxTensors) {
     optim::AdamArgs a{};
     a.n = n_tensors - t0 < optim::kMaxTensors ? n_tensors - t0 : optim::kMaxTensors;
@@ -633,6 +635,7 @@ int anerf_adam_step(int32_t n_tensors, float* const* params, const float* const*
       if (sizes[t0 + i] > largest) largest = sizes[t0 + i];
     }
     a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+    a.omb1 = (float)(1.0 - beta1_d); a.omb2 = (float)(1.0 - beta2_d);
     a.bc1 = bc1; a.bc2_sqrt = bc2s; a.grad_scale = grad_scale;
     if (largest == 0) continue;
     long long bx = (largest + 256 * 4 - 1) / (256 * 4);          // ~4 elements per thread for the largest tensor
@@ -683,6 +686,27 @@ int anerf_mc_emit(const float* volume, int32_t n0, int32_t n1, int32_t n2, int64
   if (!offsets || !verts || !keys) return fail(ANERF_ERR_INVALID, "null argument");
   a.offsets = (const long long*)offsets; a.verts = verts; a.keys = (long long*)keys;
   mesh::mc_emit_kernel<<<(unsigned)((a.n_cells + 255) / 256), 256, 0, (cudaStream_t)stream_>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return ANERF_OK;
+}
+
+int anerf_sample_rays(const anerf_sampler_inputs* in, const int32_t* frames, int32_t n_images, int32_t rays_per_image,
+                      uint64_t seed, const anerf_sampler_outputs* out, int32_t* n_valid, void* stream_) {
+  ANERF_ENTRY();
+  if (!in || !frames || !out || !n_valid) return fail(ANERF_ERR_INVALID, "null argument");
+  if (!in->masks || !in->imgs || !in->c2ws || !in->focals) return fail(ANERF_ERR_INVALID, "masks / imgs / c2ws / focals missing");
+  if (!out->rays || !out->target || !out->pixel_idx || !out->frame_of_ray) return fail(ANERF_ERR_INVALID, "rays / target / pixel_idx / frame_of_ray outputs missing");
+  if (in->height < 1 || in->width < 1 || (long long)in->height * in->width > (1 << 26)) return fail(ANERF_ERR_INVALID, "bad image size");
+  if (n_images < 0 || rays_per_image < 1) return fail(ANERF_ERR_INVALID, "bad sizes");
+  if (n_images == 0) return ANERF_OK;
+  sampler::SampleArgs a{};
+  a.masks = in->masks; a.imgs = in->imgs; a.fgs = in->fgs; a.bgs = in->bgs; a.bg_idx = in->bg_idx;
+  a.c2ws = in->c2ws; a.focals = in->focals; a.centers = in->centers;
+  a.frames = frames; a.n_img = n_images; a.k = rays_per_image; a.H = in->height; a.W = in->width;
+  a.seed = seed; a.fg_scale = in->fg_is_255 ? 1.0f / 255.0f : 1.0f; a.mask_img = in->mask_img;
+  a.rays = out->rays; a.target = out->target; a.fg_out = out->fg; a.bg_out = out->bg; a.pixel_idx = out->pixel_idx;
+  a.frame_of_ray = out->frame_of_ray; a.status = n_valid;
+  sampler::sample_rays_kernel<<<n_images, 1024, 0, (cudaStream_t)stream_>>>(a);
   CUDA_TRY(cudaGetLastError());
   return ANERF_OK;
 }

@@ -21,6 +21,7 @@ struct AdamArgs {
   long long size[kMaxTensors];
   int n;
   float lr, beta1, beta2, eps, weight_decay;
+  float omb1, omb2;                // 1 - beta1, 1 - beta2 rounded from double (what torch's lerp_ / addcmul_ receive)
   float bc1, bc2_sqrt;             // 1 - beta1^t, sqrt(1 - beta2^t)
   float grad_scale;                // gradients are multiplied by this first (1/world after a sum all-reduce; 1 otherwise)
 };
@@ -38,8 +39,8 @@ __global__ void adam_step_kernel(const __grid_constant__ AdamArgs a) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < size; i += (long long)gridDim.x * blockDim.x) {
     const float pi = p[i];
     const float gi = fmaf(a.weight_decay, pi, g[i] * a.grad_scale);
-    const float mi = fmaf(a.beta1, m[i] - gi, gi);                 // b1 m + (1 - b1) g
-    const float vi = fmaf(a.beta2, v[i], (1.f - a.beta2) * gi * gi);
+    const float mi = fmaf(a.omb1, gi - m[i], m[i]);                // exp_avg.lerp_(grad, 1 - beta1)
+    const float vi = fmaf(a.omb2 * gi, gi, a.beta2 * v[i]);        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
     m[i] = mi;
     v[i] = vi;
     p[i] = pi - step_size * (mi / (sqrtf(vi) / a.bc2_sqrt + a.eps));

@@ -289,15 +289,51 @@ int anerf_mc_count(const float* volume, int32_t n0, int32_t n1, int32_t n2, int6
 int anerf_mc_emit(const float* volume, int32_t n0, int32_t n1, int32_t n2, int64_t s0, int64_t s1, int64_t s2, float iso,
                   const int64_t* offsets, float* verts, int64_t* keys, void* stream);
 
+/* ---- training-ray sampler ----------------------------------------------------------- */
+
+/* The dataset tensors of BaseH5Dataset (core/dataset.py:108-160 init_meta / the .h5 layout), resident on the device. */
+typedef struct {
+  const uint8_t* masks;    /* [F, H*W] sampling masks: a pixel may be drawn when > 0 ('sampling_masks') */
+  const uint8_t* imgs;     /* [F, H*W, 3] ('imgs') */
+  const uint8_t* fgs;      /* [F, H*W] foreground masks ('masks') or NULL */
+  const uint8_t* bgs;      /* [B, H*W, 3] backgrounds or NULL */
+  const int32_t* bg_idx;   /* [F] background of each image or NULL */
+  const float* c2ws;       /* [F, 3, 4] */
+  const float* focals;     /* [F, 2] (fx, fy) */
+  const float* centers;    /* [F, 2] principal points or NULL (image centre) */
+  int32_t height, width;
+  int32_t fg_is_255;       /* foreground masks stored as 0/255 instead of 0/1 */
+  int32_t mask_img;        /* target = img * fg + (1 - fg) * bg (the reference's mask_img) */
+} anerf_sampler_inputs;
+
+typedef struct {
+  float* rays;             /* [N, 8] origin, direction, near = 0, far = 1   (N = n_images * rays_per_image) */
+  float* target;           /* [N, 3] colours in [0, 1] */
+  float* fg;               /* [N] or NULL */
+  float* bg;               /* [N, 3] or NULL */
+  int32_t* pixel_idx;      /* [N] flat pixel index (row-major), increasing within an image */
+  int32_t* frame_of_ray;   /* [N] image index of every ray (-> camera index / pose index) */
+} anerf_sampler_outputs;
+
+/* BaseH5Dataset.__getitem__ for a batch of images (core/dataset.py:57-105: sample_pixels :277-322 with patch_size 1 and
+ * no box sampling, get_rays :346-362, get_img_data :258-275) on the device: for each of the n_images images listed in
+ * `frames` (DEVICE int32 array), rays_per_image DISTINCT pixels drawn uniformly from its sampling mask, in increasing
+ * pixel order.  n_valid (DEVICE [n_images]) receives each image's number of valid pixels; images with fewer than
+ * rays_per_image valid pixels produce no rows (the caller checks).  The random stream is a counter-based hash of
+ * (seed, image, pixel), not numpy's generator. */
+int anerf_sample_rays(const anerf_sampler_inputs* in, const int32_t* frames, int32_t n_images, int32_t rays_per_image,
+                      uint64_t seed, const anerf_sampler_outputs* out, int32_t* n_valid, void* stream);
+
 /* ---- optimizer step ------------------------------------------------------------------- */
 
 /* torch.optim.Adam.step (amsgrad off) for n_tensors fp32 tensors in ONE launch (reference: Trainer.optimize,
  * core/trainer.py:451-483; optimizer built at core/raycasters.py:116).  params / grads / exp_avg / exp_avg_sq: HOST
  * arrays of device pointers, sizes[i] elements each; `step` = the update count including this one; grads are first
- * multiplied by grad_scale (1/world after a summing all-reduce). */
+ * multiplied by grad_scale (1/world after a summing all-reduce).  Hyper-parameters are doubles (Python floats): 1 - beta is
+ * formed in double like torch does before it reaches the fp32 kernel. */
 int anerf_adam_step(int32_t n_tensors, float* const* params, const float* const* grads, float* const* exp_avg,
-                    float* const* exp_avg_sq, const int64_t* sizes, int64_t step, float lr, float beta1, float beta2, float eps,
-                    float weight_decay, float grad_scale, void* stream);
+                    float* const* exp_avg_sq, const int64_t* sizes, int64_t step, double lr, double beta1, double beta2, double eps,
+                    double weight_decay, double grad_scale, void* stream);
 
 /* Debug aid: device buffer of 3 x 1024 int64; while set, launches record a clock64 timeline of CTA 0
  * (stream 0 MMA thread, 1/2 worker groups; entries = tag << 48 | clock).  NULL switches it off. */
