@@ -19,7 +19,8 @@ def _dataset(F=6, H=40, W=56, seed=0):
     masks = np.zeros((F, H, W), np.uint8)
     for f in range(F):
         masks[f, 5 + f:30, 8:40 + f] = 1
-    masks[1, 12, 20] = 0
+    if F > 1:
+        masks[1, 12, 20] = 0
     fgs = (rng.rand(F, H, W) > 0.5).astype(np.uint8)
     c2ws = np.stack([synthetic.orbit_c2w(0.3 * f, 3.0) for f in range(F)]).astype(np.float32)
     focals = (50. + 3 * np.arange(F)).astype(np.float32)
