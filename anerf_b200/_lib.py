@@ -361,19 +361,37 @@ def _fill_net_struct(st, depth, tensors, framecodes):
 
 
 def render_bwd(plan, opts, params0, params1, rays, skts, cams, t_rand, noise0, noise1, nearfar, z_all, grad_out,
-               want0, want1, want_skts, pose_idx=None):
+               want0, want1, want_skts, pose_idx=None, into0=None, into1=None):
     """Backward of render_fwd (C ABI anerf_render_bwd).  params0/params1: fp32 CUDA tensors of the coarse / fine
     network in param_names() order; want0/want1: per-parameter flags; grad_out: dict of dL/d(output) tensors (or
-    None).  Returns (grads0, grads1, g_skts): freshly allocated gradients (None where not wanted)."""
+    None).  Returns (grads0, grads1, g_skts): gradients (None where not wanted).  into0 / into1: optional lists of
+    existing fp32 buffers the kernels ADD the parameter gradients into (entries may be None); everything else comes
+    zero-filled out of ONE flat allocation."""
     N, Sc, Si = opts.n_rays, opts.n_samples, opts.n_importance
     dev = rays.device
     depth, fc = plan.cfg.depth, plan.cfg.framecode_ch > 0
     for t in [rays, skts, cams, t_rand, noise0, noise1, nearfar, z_all] + list(params0) + list(params1 or []) + \
             [g for g in grad_out.values() if g is not None]:
         assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
-    zeros = lambda p, want: torch.zeros_like(p) if want else None
-    g0 = [zeros(p, w) for p, w in zip(params0, want0)]
-    g1 = [zeros(p, w) for p, w in zip(params1, want1)] if params1 is not None else None
+    into0 = into0 or [None] * len(params0)
+    into1 = into1 or [None] * len(params1 or [])
+    need = [(p, w, t) for p, w, t in list(zip(params0, want0, into0)) + list(zip(params1 or [], want1 or [], into1))]
+    n_new = sum(-(-p.numel() // 4) * 4 for p, w, t in need if w and t is None)
+    flat = torch.zeros(n_new, dtype=torch.float32, device=dev) if n_new else None
+    off = [0]
+
+    def target(p, want, into):
+        if not want:
+            return None
+        if into is not None:
+            assert into.is_cuda and into.dtype == torch.float32 and into.is_contiguous() and into.shape == p.shape
+            return into
+        k = p.numel()
+        g = flat[off[0]:off[0] + k].view_as(p)
+        off[0] += -(-k // 4) * 4                      # 16-byte aligned pieces
+        return g
+    g0 = [target(p, w, t) for p, w, t in zip(params0, want0, into0)]
+    g1 = [target(p, w, t) for p, w, t in zip(params1, want1, into1)] if params1 is not None else None
     g_skts = torch.zeros_like(skts) if want_skts else None
     p0s, g0s = _fill_net_struct(NetParams(), depth, params0, fc), _fill_net_struct(NetGrads(), depth, g0, fc)
     p1s = _fill_net_struct(NetParams(), depth, params1, fc) if params1 is not None else None

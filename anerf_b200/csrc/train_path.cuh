@@ -54,6 +54,7 @@ struct TcEngine {
   float* slots;
   int w_used, b_used;
   std::map<const float*, float*> amax_of;              // base pointer of a buffer -> slot of its latest contents
+  std::map<std::tuple<const float*, long long>, float*> wmax;   // (weight base pointer, elements) -> slot of max |w| (this pass)
   int error;
 
   float* weight_slot() { if (w_used >= kWeightSlots) { error = 4; return slots; } return slots + w_used++; }
@@ -116,15 +117,23 @@ struct TcEngine {
     wpack_used += need;
     float* sl = nullptr;
     if (fmt == 0) {
-      sl = weight_slot();
-      tc_absmax_kernel<<<64, 256, 0, st>>>(src, s_n, s_k, N, K, sl);
+      // max |w| does not depend on the form (W or W^T share it): one reduction per weight buffer and pass.  Sub-blocks
+      // of a weight (the skip layer's [encoding | h] column ranges) have other base pointers and get their own.
+      auto key2 = std::make_tuple(src, N * (long long)K);
+      auto f = wmax.find(key2);
+      if (f != wmax.end()) sl = f->second;
+      else {
+        sl = weight_slot();
+        tc_absmax_kernel<<<64, 256, 0, st>>>(src, s_n, s_k, N, K, sl);
+        wmax[key2] = sl;
+      }
     }
     pack(st, src, s_n, s_k, N, K, dst, nullptr, AmaxRef{sl, nullptr});
     cache[key] = {dst, sl};
     return {dst, sl};
   }
   void new_pass(cudaStream_t st) {
-    cache.clear(); wpack_used = 0; w_used = 0;
+    cache.clear(); wmax.clear(); wpack_used = 0; w_used = 0;
     if (fmt == 0) cudaMemsetAsync(slots, 0, kWeightSlots * sizeof(float), st);
   }
 

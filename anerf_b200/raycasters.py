@@ -171,18 +171,43 @@ class _RenderRaysFn(torch.autograd.Function):
         want0 = [bool(x) for x in need[4:4 + n0]]
         want1 = [bool(x) for x in need[4 + n0:]]
         gout = {k: (None if g is None else g.float().contiguous()) for k, g in zip(ctx.keys, gouts)}
+        # Parameter gradients: the kernels ADD into buffers, so an existing contiguous fp32 .grad is used as it is and
+        # missing ones are carved out of one zero-filled allocation and installed as .grad -- autograd's AccumulateGrad
+        # (one clone or add per tensor, ~90 tiny launches per step for two networks) is bypassed by returning None for
+        # those inputs.  RayCaster.accumulate_param_grads_in_place = False restores the returned-gradient behaviour
+        # (needed only by torch.autograd.grad(..., network_parameters)).
+        direct = ctx.caster.accumulate_param_grads_in_place
+        usable = lambda p, w: direct and w and p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.device == p.device
+        into0 = [p.grad if usable(p, w) else None for p, w in zip(params0, want0)]
+        into1 = None if params1 is None else [p.grad if usable(p, w) else None for p, w in zip(params1, want1)]
         with torch.cuda.device(skts.device):
             g0, g1, g_skts = _lib.render_bwd(ctx.caster._get_plan(), opts, [p.detach() for p in params0],
                                              None if params1 is None else [p.detach() for p in params1],
                                              aux['rays'], skts.detach(), aux['cams'], aux['t_rand'], aux['noise0'], aux['noise1'],
-                                             ctx.nearfar, ctx.z_all, gout, want0, want1, want_skts, pose_idx=aux.get('pose_idx'))
-        return (None, None, None, g_skts, *g0, *(g1 or []))
+                                             ctx.nearfar, ctx.z_all, gout, want0, want1, want_skts, pose_idx=aux.get('pose_idx'),
+                                             into0=into0, into1=into1)
+        if not direct:
+            return (None, None, None, g_skts, *g0, *(g1 or []))
+        seen = {}
+        for p, g, w in list(zip(params0, g0, want0)) + list(zip(params1 or [], g1 or [], want1)):
+            if not w:
+                continue
+            if p.grad is None:
+                if id(p) in seen:                       # --single_net: the same parameter in both passes
+                    seen[id(p)].add_(g)
+                else:
+                    p.grad = g
+                    seen[id(p)] = g
+            elif p.grad is not g:                       # an unusable .grad (other dtype / layout): add the usual way
+                p.grad.add_(g.to(p.grad.dtype))
+        return (None, None, None, g_skts) + (None,) * (len(params0) + len(params1 or []))
 
 
 # ------------------------------------------------------------------------------------------------
 # the ray caster
 # ------------------------------------------------------------------------------------------------
 class RayCaster(nn.Module):
+    accumulate_param_grads_in_place = True       # see _RenderRaysFn.backward
 
     def __init__(self, network, embed_fn, embedbones_fn, embeddirs_fn, network_fine=None, joint_coords=None,
                  single_net=False, operand_format=None):
