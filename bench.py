@@ -443,12 +443,15 @@ def main():
     launch_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     peak, peak_src = load_peaks()
     achieved = FLOP_PER_RAY * CHUNK / (launch_ms * 1e-3) / 1e12
-    traffic = None
+    # DRAM traffic of one launch cannot be measured outside a profiler: it is the figure of the committed ncu capture
+    # (profiles/fused_kernel_traffic.json says which build and command it comes from)
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "fused_kernel_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), f"{tj.get('build')}; {tj.get('source')}"
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "anerf_fused_kernel",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "anerf_fused_kernel",
                 "launch_ms": launch_ms, "algorithmic_flop_per_launch": FLOP_PER_RAY * CHUNK,
                 "note": "achieved = algorithmic fp32-equivalent FLOPs (441.25 MFLOP/ray, BASELINE.md). Each product is issued as "
                         "3 fp16 MMAs (lo*hi+hi*lo+hi*hi); with feature_linear folded into the views layer, the view branch "
