@@ -56,7 +56,9 @@ def _worker(rank, world, port, q):
     # ---- training: equal contiguous ray shares + one all-reduce == the full-batch gradient
     holder = rk_train["ray_caster"].train()
     N = 128
-    sc = synthetic.make_scene(seed=5, n_rays=N, H=256, W=256, focal=250., n_joints=24)
+    # a narrow field of view: every ray crosses the bounding cylinder, so the near/far repair (a CHUNK-wide mean that
+    # would differ between the full batch and its halves) is not involved
+    sc = synthetic.make_scene(seed=5, n_rays=N, H=64, W=64, focal=250., n_joints=24)
     rays = torch.cat([t(sc["rays_o"]), t(sc["rays_d"]), torch.zeros(N, 1, device=dev), torch.ones(N, 1, device=dev),
                       torch.nn.functional.normalize(t(sc["rays_d"]), dim=-1)], 1)
     target = t(np.random.RandomState(9).rand(N, 3).astype(np.float32))
