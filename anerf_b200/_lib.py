@@ -17,7 +17,7 @@ SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "ane
            "anerf_selftest_gemm", "anerf_last_error", "anerf_version", "anerf_debug_set_trace",
            "anerf_render_bwd", "anerf_render_bwd_workspace_bytes", "anerf_selftest_tc_gemm", "anerf_render_frame",
            "anerf_check_status", "anerf_density_grid", "anerf_render_fwd_host_chunked", "anerf_pose_chain_fwd",
-           "anerf_pose_chain_bwd", "anerf_pose_chain_bwd_scratch_bytes", "anerf_adam_step", "anerf_mc_count", "anerf_mc_emit", "anerf_sample_rays"]
+           "anerf_pose_chain_bwd", "anerf_pose_chain_bwd_scratch_bytes", "anerf_adam_step", "anerf_mc_count", "anerf_mc_emit", "anerf_sample_rays", "anerf_render_bwd_pass", "anerf_loss_seed"]
 
 
 class NetConfig(C.Structure):
@@ -116,6 +116,11 @@ def load():
     lib.anerf_render_bwd.argtypes = [C.c_void_p, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(RenderOpts),
                                      C.POINTER(RenderInputs), C.c_void_p, C.c_void_p, C.POINTER(RenderGrads),
                                      C.POINTER(NetGrads), C.POINTER(NetGrads), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.anerf_render_bwd_pass.argtypes = [C.c_void_p, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(RenderOpts),
+                                          C.POINTER(RenderInputs), C.c_void_p, C.c_void_p, C.POINTER(RenderGrads),
+                                          C.POINTER(NetGrads), C.POINTER(NetGrads), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]
+    lib.anerf_loss_seed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.anerf_selftest_tc_gemm.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
                                            C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64,
                                            C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
@@ -361,7 +366,7 @@ def _fill_net_struct(st, depth, tensors, framecodes):
 
 
 def render_bwd(plan, opts, params0, params1, rays, skts, cams, t_rand, noise0, noise1, nearfar, z_all, grad_out,
-               want0, want1, want_skts, pose_idx=None, into0=None, into1=None):
+               want0, want1, want_skts, pose_idx=None, into0=None, into1=None, pass_mask=3, g_skts=None, workspace=None):
     """Backward of render_fwd (C ABI anerf_render_bwd).  params0/params1: fp32 CUDA tensors of the coarse / fine
     network in param_names() order; want0/want1: per-parameter flags; grad_out: dict of dL/d(output) tensors (or
     None).  Returns (grads0, grads1, g_skts): gradients (None where not wanted).  into0 / into1: optional lists of
@@ -392,18 +397,39 @@ def render_bwd(plan, opts, params0, params1, rays, skts, cams, t_rand, noise0, n
         return g
     g0 = [target(p, w, t) for p, w, t in zip(params0, want0, into0)]
     g1 = [target(p, w, t) for p, w, t in zip(params1, want1, into1)] if params1 is not None else None
-    g_skts = torch.zeros_like(skts) if want_skts else None
+    if want_skts and g_skts is None:
+        g_skts = torch.zeros_like(skts)
     p0s, g0s = _fill_net_struct(NetParams(), depth, params0, fc), _fill_net_struct(NetGrads(), depth, g0, fc)
     p1s = _fill_net_struct(NetParams(), depth, params1, fc) if params1 is not None else None
     g1s = _fill_net_struct(NetGrads(), depth, g1, fc) if params1 is not None else None
     rin = RenderInputs(_ptr(rays), _ptr(skts), None, _ptr(cams), _ptr(t_rand), None, _ptr(noise0), _ptr(noise1), _ptr(pose_idx))
     rg = RenderGrads(*[_ptr(grad_out.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0", "alpha0")])
     ws_bytes = load().anerf_render_bwd_workspace_bytes(plan.handle, N, Sc, Si)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    check(load().anerf_render_bwd(plan.handle, C.byref(p0s), None if p1s is None else C.byref(p1s), C.byref(opts),
-                                  C.byref(rin), _ptr(nearfar), _ptr(z_all), C.byref(rg), C.byref(g0s),
-                                  None if g1s is None else C.byref(g1s), _ptr(g_skts), _ptr(ws), ws_bytes, _stream()))
+    ws = workspace if workspace is not None and workspace.numel() >= ws_bytes else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    check(load().anerf_render_bwd_pass(plan.handle, C.byref(p0s), None if p1s is None else C.byref(p1s), C.byref(opts),
+                                       C.byref(rin), _ptr(nearfar), _ptr(z_all), C.byref(rg), C.byref(g0s),
+                                       None if g1s is None else C.byref(g1s), _ptr(g_skts) if want_skts else None, _ptr(ws), ws_bytes,
+                                       int(pass_mask), _stream()))
     return g0, g1, g_skts
+
+
+def bwd_workspace(plan, opts, device):
+    """A reusable workspace tensor for render_bwd (the same size every step of a training loop)."""
+    nb = load().anerf_render_bwd_workspace_bytes(plan.handle, opts.n_rays, opts.n_samples, opts.n_importance)
+    return torch.empty(nb, dtype=torch.uint8, device=device)
+
+
+def loss_seed(rgb, acc, target, bg, use_background, mse, weight, sums):
+    """Trainer._compute_nerf_loss + its gradient in one launch (C ABI anerf_loss_seed).  bg: [N,3] tensor or a float.
+    Returns (d loss / d rgb [N,3], d loss / d acc [N]); adds (sum of loss terms, sum of squared errors) to sums[0:2]."""
+    N = rgb.shape[0]
+    g_rgb, g_acc = torch.empty_like(rgb), torch.empty_like(acc)
+    bg_t = bg if torch.is_tensor(bg) else None
+    for t in (rgb, acc, target, bg_t, sums):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+    check(load().anerf_loss_seed(_ptr(rgb), _ptr(acc), _ptr(target), _ptr(bg_t), 0.0 if bg_t is not None else float(bg), int(use_background),
+                                 int(mse), N, float(weight), _ptr(g_rgb), _ptr(g_acc), _ptr(sums), _stream()))
+    return g_rgb, g_acc
 
 
 def _parents_array(parents):

@@ -711,6 +711,21 @@ int anerf_sample_rays(const anerf_sampler_inputs* in, const int32_t* frames, int
   return ANERF_OK;
 }
 
+int anerf_loss_seed(const float* rgb, const float* acc, const float* target, const float* bg, float bg_const, int32_t use_background,
+                    int32_t mse, int32_t n_rays, float weight, float* g_rgb, float* g_acc, float* sums, void* stream_) {
+  ANERF_ENTRY();
+  if (!rgb || !acc || !target || !g_rgb || !g_acc || !sums) return fail(ANERF_ERR_INVALID, "null argument");
+  if (n_rays <= 0) return ANERF_OK;
+  optim::LossArgs a{};
+  a.rgb = rgb; a.acc = acc; a.target = target; a.bg = bg; a.bg_const = bg_const; a.use_bg = use_background; a.mse = mse; a.N = n_rays;
+  a.weight = weight; a.g_rgb = g_rgb; a.g_acc = g_acc; a.sums = sums;
+  int blocks = (n_rays + 255) / 256;
+  if (blocks > 296) blocks = 296;
+  optim::loss_seed_kernel<<<blocks, 256, 0, (cudaStream_t)stream_>>>(a);
+  CUDA_TRY(cudaGetLastError());
+  return ANERF_OK;
+}
+
 size_t anerf_render_bwd_workspace_bytes(const anerf_plan* plan, int32_t n_rays, int32_t n_samples, int32_t n_importance) {
   if (!plan || n_rays <= 0 || n_samples <= 0 || n_importance < 0) return 0;
   return train::train_workspace_bytes(plan->dims, n_rays, n_samples, n_importance);
@@ -720,7 +735,15 @@ int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, con
                      const anerf_render_opts* o, const anerf_render_inputs* in, const float* nearfar, const float* z_all,
                      const anerf_render_grads* gout, const anerf_net_grads* g_coarse, const anerf_net_grads* g_fine,
                      float* g_skts, void* workspace, size_t workspace_bytes, void* stream_) {
+  return anerf_render_bwd_pass(plan, coarse, fine, o, in, nearfar, z_all, gout, g_coarse, g_fine, g_skts, workspace, workspace_bytes, 3, stream_);
+}
+
+int anerf_render_bwd_pass(const anerf_plan* plan, const anerf_net_params* coarse, const anerf_net_params* fine,
+                          const anerf_render_opts* o, const anerf_render_inputs* in, const float* nearfar, const float* z_all,
+                          const anerf_render_grads* gout, const anerf_net_grads* g_coarse, const anerf_net_grads* g_fine,
+                          float* g_skts, void* workspace, size_t workspace_bytes, int32_t pass_mask, void* stream_) {
   ANERF_ENTRY();
+  if (pass_mask < 1 || pass_mask > 3) return fail(ANERF_ERR_INVALID, "pass_mask must be 1 (coarse), 2 (fine) or 3 (both)");
   if (!plan || !coarse || !o || !in || !gout || !nearfar) return fail(ANERF_ERR_INVALID, "null argument");
   const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance;
   if (N == 0) return ANERF_OK;
@@ -748,6 +771,7 @@ int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, con
   c.net[0] = coarse; c.net[1] = Si > 0 ? fine : coarse;
   c.grad[0] = g_coarse; c.grad[1] = g_fine;
   c.g_skts = g_skts;
+  c.pass_mask = pass_mask;
   c.workspace = (float*)workspace;
   c.workspace_floats = workspace_bytes / sizeof(float);
   // GEMM engine: tensor cores (tc_gemm.cuh) with fp16 hi/lo operands and per-matrix scales; ANERF_TRAIN_GEMM=bf16 selects

@@ -205,6 +205,8 @@ struct TrainCall {
   float* workspace;
   size_t workspace_floats;
   TcEngine* tc;                  // tensor-core GEMM engine, or NULL: SIMT fp32 GEMMs (debug knob, and the emulated host tests)
+  int pass_mask;                 // bit 0: coarse pass, bit 1: fine pass (0 = both): lets the caller exchange the coarse
+                                 // network's gradients while the fine pass still runs
 };
 
 struct Workspace {
@@ -479,9 +481,10 @@ inline int train_backward(const TrainCall& c, anerf_tstream st) {
     ANERF_TLAUNCH(k, dim3((unsigned)((n + 255) / 256)), dim3(256), st, c.nearfar, c.in->t_rand, c.n_rays, c.Sc, c.opts->lindisp, zc);
   }
   const anerf_render_grads& g = *c.gout;
+  const int pm = c.pass_mask ? c.pass_mask : 3;
   if (c.Si > 0) {
-    backward_pass(c, w, 0, c.Sc, zc, c.in->noise0, g.rgb0, g.disp0, g.acc0, g.alpha0, st);
-    backward_pass(c, w, 1, c.Sc + c.Si, c.z_all, c.in->noise1, g.rgb_map, g.disp_map, g.acc_map, g.alpha, st);
+    if (pm & 1) backward_pass(c, w, 0, c.Sc, zc, c.in->noise0, g.rgb0, g.disp0, g.acc0, g.alpha0, st);
+    if (pm & 2) backward_pass(c, w, 1, c.Sc + c.Si, c.z_all, c.in->noise1, g.rgb_map, g.disp_map, g.acc_map, g.alpha, st);
   } else {
     backward_pass(c, w, 0, c.Sc, zc, c.in->noise0, g.rgb_map, g.disp_map, g.acc_map, g.alpha, st);
   }

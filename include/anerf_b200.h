@@ -228,6 +228,14 @@ int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, con
                      const anerf_net_grads* g_fine, float* g_skts, void* workspace, size_t workspace_bytes,
                      void* stream);
 
+/* The same, one network pass at a time: pass_mask 1 = the coarse network's pass, 2 = the fine network's, 3 = both.  Lets a
+ * trainer exchange the coarse network's gradients (NCCL, another stream) while the fine pass still runs. */
+int anerf_render_bwd_pass(const anerf_plan* plan, const anerf_net_params* coarse, const anerf_net_params* fine,
+                          const anerf_render_opts* opts, const anerf_render_inputs* in, const float* nearfar,
+                          const float* z_all, const anerf_render_grads* grad_out, const anerf_net_grads* g_coarse,
+                          const anerf_net_grads* g_fine, float* g_skts, void* workspace, size_t workspace_bytes,
+                          int32_t pass_mask, void* stream);
+
 /* Raw (pre-activation) density of `n_points` world points under ONE pose: pts [P,3], skts [J,4,4],
  * sigma [P].  Uses tau_pts / cutoff_pts of `opts` (other fields ignored). */
 int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf_render_opts* opts,
@@ -325,6 +333,15 @@ int anerf_sample_rays(const anerf_sampler_inputs* in, const int32_t* frames, int
                       uint64_t seed, const anerf_sampler_outputs* out, int32_t* n_valid, void* stream);
 
 /* ---- optimizer step ------------------------------------------------------------------- */
+
+/* Photometric loss of the reference's trainer and its gradient seed in one launch (Trainer._compute_nerf_loss,
+ * core/trainer.py:352-381 with img2l1 / img2mse :9-41): pred = rgb + (1 - acc) bg when use_background (bg [N,3] or, when
+ * NULL, bg_const), loss = weight * mean(|pred - target|) (mse = 0) or weight * mean((pred - target)^2) (mse = 1).
+ * Writes d loss / d rgb [N,3] and d loss / d acc [N]; ADDS the un-normalised sum of loss terms and the sum of squared
+ * errors (for the PSNR) to sums[0..1]. */
+int anerf_loss_seed(const float* rgb, const float* acc, const float* target, const float* bg, float bg_const,
+                    int32_t use_background, int32_t mse, int32_t n_rays, float weight, float* g_rgb, float* g_acc,
+                    float* sums, void* stream);
 
 /* torch.optim.Adam.step (amsgrad off) for n_tensors fp32 tensors in ONE launch (reference: Trainer.optimize,
  * core/trainer.py:451-483; optimizer built at core/raycasters.py:116).  params / grads / exp_avg / exp_avg_sq: HOST
