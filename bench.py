@@ -289,17 +289,21 @@ def headline_parity(rc, kw, dev):
     return par
 
 
-def training_probe(dev, rank, world, n_rays=3072, n_importance=16, steps=5):
-    """Training step through the boundary (create_raycaster's train kwargs, .train() mode): forward (fused kernel) +
-    backward (anerf_render_bwd) + one all-reduce of the flat gradient buffer + Adam.  Weak scaling: n_rays per rank."""
-    import collections
+def training_probe(dev, rank, world, n_rays=3072, n_importance=16, steps=5, n_poses=256):
+    """Training step through the boundary, weak scaling (n_rays per rank), two routes:
+    `fused_step` (primary): anerf_b200.train.FusedTrainStep -- fused forward, loss seed, per-pass backward with the coarse
+        network's gradient all-reduce overlapping the fine pass, FusedAdam; pose refinement ON with the transforms coming
+        from anerf_b200.pose_opt.PoseOptLayer once per POSE (n_poses poses, rays -> pose index; the reference's
+        image_batching: N_sample_images 256, configs/mixamo/mixamo.txt) and d/d skts reduced per pose in the backward;
+    `autograd_route`: create_raycaster's train kwargs in .train() mode with per-RAY transforms that require grad, torch loss,
+        loss.backward(), gradient all-reduce, optimizer.step() -- what the reference's Trainer does through the boundary."""
     import contextlib
     import io
     from anerf_b200 import parallel
+    from anerf_b200.pose_opt import PoseOptLayer
     from anerf_b200.raycasters import create_raycaster
-    Skel = collections.namedtuple("Skel", ["joint_names", "joint_trees", "root_id"])
-    data_attrs = dict(skel_type=Skel(synthetic.SMPL_JOINT_NAMES, synthetic.SMPL_PARENTS, 0), near=0., far=1., n_views=1,
-                      joint_coords=np.tile(np.eye(3, dtype=np.float32), (1, N_JOINTS, 1, 1)))
+    from anerf_b200.train import FusedTrainStep
+    data_attrs = _data_attrs()
     args = make_args(N_importance=n_importance, perturb=1.0, raw_noise_std=1.0)
     with contextlib.redirect_stdout(io.StringIO()):
         rk_train, rk_test, _, grad_vars, optimizer, _ = create_raycaster(args, data_attrs, device=dev)
@@ -316,8 +320,28 @@ def training_probe(dev, rank, world, n_rays=3072, n_importance=16, steps=5):
     kw = {k: v for k, v in rk_train.items() if k not in ("ray_caster", "use_viewdirs")}
     target = torch.rand(N, 3, device=dev)
     flat = [None]
+    # pose layer: n_poses copies of the scene's pose (slightly perturbed), every ray assigned to one of them
+    pose = sc["pose"]
+    rng = np.random.RandomState(1)
+    layer = PoseOptLayer(torch.as_tensor(np.tile(pose["kps"][None], (n_poses, 1, 1))),
+                         torch.as_tensor(np.tile(pose["bones"][None], (n_poses, 1, 1)) + 0.01 * rng.randn(n_poses, N_JOINTS, 3).astype(np.float32)),
+                         torch.as_tensor(synthetic.humanoid_rest_pose()[None]), use_rot6d=True, parents=synthetic.SMPL_PARENTS, root_id=0).to(dev)
+    pose_optimizer = torch.optim.Adam(layer.parameters(), lr=5e-4)
+    kp_idx = np.sort(rng.randint(0, n_poses, size=N))
+    fused = FusedTrainStep(rc, optimizer, loss_fn="L1", use_background=True, world=world)
+    it = [0]
 
-    def step():
+    def step_fused():
+        (kps_p, bones_p, skts_p, _, _), pose_idx = layer.forward_poses(kp_idx)
+        fused(rays, target, kp_batch=kps_p, skts=skts_p, cyls=cyls, bones=bones_p, cams=None, pose_idx=pose_idx, **kw)
+        it[0] += 1
+        if it[0] % 20 == 0:                                  # opt_pose_step (configs/mixamo/mixamo.txt): gradients accumulate in between
+            if world > 1:
+                parallel.allreduce_gradients(list(layer.parameters()), world)
+            pose_optimizer.step()
+            pose_optimizer.zero_grad()
+
+    def step_autograd():
         optimizer.zero_grad(set_to_none=True)
         skts = skts0.clone().requires_grad_(True)           # pose refinement: the bone transforms carry gradient
         out = holder(rays, kp_batch=kps, skts=skts, cyls=cyls, bones=bones, cams=None, subject_idxs=None, **kw)
@@ -326,23 +350,31 @@ def training_probe(dev, rank, world, n_rays=3072, n_importance=16, steps=5):
         flat[0] = parallel.allreduce_gradients(grad_vars, world, flat[0])
         optimizer.step()
 
-    for _ in range(3):
-        step()
-    torch.cuda.synchronize()
-    if world > 1:
-        torch.distributed.barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms = parallel.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return parallel.max_over_ranks(e0.elapsed_time(e1) / steps, dev)
+    ms_auto = timed(step_autograd)
+    for p in grad_vars:
+        p.grad = None
+    ms = timed(step_fused)
     rows = N * (N_SAMPLES + N_SAMPLES + n_importance)
-    return {"metric": "training rays/sec (fwd + bwd + grad all-reduce + Adam)", "value": N * world / (ms * 1e-3), "unit": "rays/s",
-            "ms_per_step": ms, "rays_per_rank": N, "samples": f"{N_SAMPLES}+{n_importance}", "pose_grad": True,
+    return {"metric": "training rays/sec (fwd + loss + bwd + grad all-reduce + Adam, pose refinement on)", "value": N * world / (ms * 1e-3),
+            "unit": "rays/s", "ms_per_step": ms, "route": "FusedTrainStep, per-pose transforms from PoseOptLayer (%d poses), d/dskts reduced per pose" % n_poses,
+            "rays_per_rank": N, "samples": f"{N_SAMPLES}+{n_importance}", "pose_grad": True,
             "allreduce_bytes": int(sum(p.numel() for p in grad_vars) * 4) if world > 1 else 0,
             "algorithmic_tflops": 3 * rows * world * 1723648 / (ms * 1e-3) / 1e12,
+            "autograd_route": {"ms_per_step": ms_auto, "value": N * world / (ms_auto * 1e-3),
+                               "what": "RayCaster.train() + torch loss + loss.backward() + all-reduce + FusedAdam.step(), per-ray transforms [N,24,4,4] requiring grad"},
             "gemm_engine": os.environ.get("ANERF_TRAIN_GEMM", "tc") + " (default tc: fp16 hi/lo operands with per-matrix power-of-two scales on tcgen05)"}
 
 
