@@ -129,11 +129,16 @@ class PoseOptLayer(nn.Module):
             idxs = idxs.cpu().numpy()
         idxs = np.atleast_1d(np.asarray(idxs))
         unique_idxs, inverse_idxs = np.unique(idxs, return_inverse=True)
-        pelvis, bone = self.idx_to_params(unique_idxs)
+        dev = self.pelvis.device
+        # index uploads through pinned memory, non-blocking: a pageable host->device copy would stall the host until the
+        # previous step's kernels have drained and put the launch overhead of this step on the critical path
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).pin_memory().to(dev, non_blocking=True)
+        uidx = up(unique_idxs, np.int64) if dev.type == 'cuda' else torch.from_numpy(np.ascontiguousarray(unique_idxs, dtype=np.int64))
+        pelvis, bone = self.pelvis.index_select(0, uidx), self.bones.index_select(0, uidx)
         rots = self._rots(bone)
         rest = self.get_rest_pose(unique_idxs, rest_pose_idxs)
         l2ws, skts, kps = pose_chain(rots, rest, pelvis, self.parents, self.root_id)
-        pose_idx = torch.as_tensor(inverse_idxs.reshape(-1).astype(np.int32), device=skts.device)
+        pose_idx = up(inverse_idxs.reshape(-1), np.int32)
         return (kps, bone, skts, l2ws, rots), pose_idx
 
     def calculate_kinematic(self, idxs, rest_pose_idxs=None):

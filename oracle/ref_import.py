@@ -2,8 +2,9 @@
 
 TEST / MEASUREMENT INFRASTRUCTURE -- not part of the product path.  Users: `oracle/make_golden*.py`,
 `oracle/precision_study.py`, the pinning tests, the tests that drive our boundary through the reference's own callers,
-and bench.py's reference legs.  /root/reference does not exist on the GPU box; there the unmodified copy under
-`oracle/_ref/` (made by `oracle/build_ref.py` in the build container, git-ignored, shipped with the snapshot) is used.
+and bench.py's reference legs.  /root/reference does not exist on the GPU box; there the archive of unmodified files under
+`oracle/_ref/` (packed by `oracle/build_ref.py` in the build container, git-ignored, shipped with the snapshot) is unpacked
+into a temporary directory and used.
 
 The reference imports plotly / matplotlib / pytorch3d / smplx / h5py at module top
 (core/utils/skeleton_utils.py:1-13, core/pose_opt.py:5, core/dataset.py:2); none of them is
@@ -19,11 +20,22 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def _find_root():
-    """/root/reference in the build container; on the GPU box the unmodified copy under oracle/_ref that
-    oracle/build_ref.py made (it travels with the snapshot like the built .so files)."""
-    for cand in (os.environ.get("ANERF_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+    """/root/reference in the build container; on the GPU box the unmodified files packed by oracle/build_ref.py into
+    oracle/_ref/reference_src.tar.gz (it travels with the snapshot like the built .so files), unpacked -- checksums
+    verified -- into a temporary directory outside the repository."""
+    for cand in (os.environ.get("ANERF_REFERENCE_ROOT"), "/root/reference"):
         if cand and os.path.isfile(os.path.join(cand, "core", "raycasters.py")):
             return cand
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_anerf_build_ref", os.path.join(_HERE, "build_ref.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        d = mod.unpack()
+        if d and os.path.isfile(os.path.join(d, "core", "raycasters.py")):
+            return d
+    except Exception:  # noqa: BLE001
+        pass
     return "/root/reference"
 
 
