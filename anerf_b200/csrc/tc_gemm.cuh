@@ -85,10 +85,23 @@ __device__ __forceinline__ void amax_fold(float* slot, float v) {      // v >= 0
 // the kernels that produce them)
 __global__ void tc_absmax_kernel(const float* __restrict__ src, long long s_n, long long s_k, int N, int K, float* __restrict__ slot) {
   float m = 0.f;
-  const long long total = (long long)N * K;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const long long n = s_k == 1 ? t / K : t % N, k = s_k == 1 ? t % K : t / N;
-    m = fmaxf(m, fabsf(__ldg(src + n * s_n + k * s_k)));
+  const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  if (s_k == 1 && (K & 3) == 0 && (s_n & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    // rows of K contiguous floats: 16-byte loads, one division per four elements
+    const int k4 = K >> 2;
+    const long long total = (long long)N * k4;
+    for (long long t = gid; t < total; t += gsz) {
+      const long long n = t / k4;
+      const int q = (int)(t - n * k4);
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + n * s_n) + q);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+  } else {
+    const long long total = (long long)N * K;
+    for (long long t = gid; t < total; t += gsz) {
+      const long long n = s_k == 1 ? t / K : t % N, k = s_k == 1 ? t % K : t / N;
+      m = fmaxf(m, fabsf(__ldg(src + n * s_n + k * s_k)));
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));

@@ -175,7 +175,23 @@ __global__ void head_fwd_kernel(const float* __restrict__ H, long long ldh, int 
 #pragma unroll
   for (int i = 0; i < NO; ++i) acc[i] = 0.f;
   const float* h = H + row * ldh;
-  for (int k = 0; k < K; ++k) {
+  int k = 0;
+  // 16-byte loads when the row is aligned (it is for every buffer of the training workspace): a thread walks its own
+  // row, so wide loads cut the load instructions per row by four; same summation order as the scalar loop
+  if ((ldh & 3) == 0 && (K & 3) == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
+    const float4* h4 = reinterpret_cast<const float4*>(h);
+    for (; k < K; k += 4) {
+      const float4 x = h4[k >> 2];
+#pragma unroll
+      for (int i = 0; i < NO; ++i) {
+        acc[i] = fmaf(x.x, __ldg(W + i * K + k), acc[i]);
+        acc[i] = fmaf(x.y, __ldg(W + i * K + k + 1), acc[i]);
+        acc[i] = fmaf(x.z, __ldg(W + i * K + k + 2), acc[i]);
+        acc[i] = fmaf(x.w, __ldg(W + i * K + k + 3), acc[i]);
+      }
+    }
+  }
+  for (; k < K; ++k) {
     const float x = h[k];
 #pragma unroll
     for (int i = 0; i < NO; ++i) acc[i] = fmaf(x, __ldg(W + i * K + k), acc[i]);
