@@ -49,7 +49,8 @@ class RenderOpts(C.Structure):
 
 
 class RenderInputs(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("rays", "skts", "cyls", "cams", "t_rand", "u_rand", "noise0", "noise1", "pose_idx")]
+    _fields_ = [(n, C.c_void_p) for n in ("rays", "skts", "cyls", "cams", "t_rand", "u_rand", "noise0", "noise1", "pose_idx")] + \
+               [("n_poses", C.c_int32), ("reserved", C.c_int32)]
 
 
 class FrameInputs(C.Structure):
@@ -236,7 +237,7 @@ def render_fwd(plan, packed_coarse, packed_fine, opts, rays, skts, cyls, cams=No
     for t in (rays, skts, cyls, cams, t_rand, u_rand, noise0, noise1):
         assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
     rin = RenderInputs(_ptr(rays), _ptr(skts), _ptr(cyls), _ptr(cams), _ptr(t_rand), _ptr(u_rand), _ptr(noise0), _ptr(noise1),
-                       _ptr(pose_idx))
+                       _ptr(pose_idx), 0 if pose_idx is None else int(skts.shape[0]), 0)
     rout = RenderOutputs(*[_ptr(out.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0",
                                                       "alpha0", "z_all", "raw")])
     check(load().anerf_render_fwd(plan.handle, _ptr(packed_coarse), _ptr(packed_fine), C.byref(opts), C.byref(rin),
@@ -402,7 +403,8 @@ def render_bwd(plan, opts, params0, params1, rays, skts, cams, t_rand, noise0, n
     p0s, g0s = _fill_net_struct(NetParams(), depth, params0, fc), _fill_net_struct(NetGrads(), depth, g0, fc)
     p1s = _fill_net_struct(NetParams(), depth, params1, fc) if params1 is not None else None
     g1s = _fill_net_struct(NetGrads(), depth, g1, fc) if params1 is not None else None
-    rin = RenderInputs(_ptr(rays), _ptr(skts), None, _ptr(cams), _ptr(t_rand), None, _ptr(noise0), _ptr(noise1), _ptr(pose_idx))
+    rin = RenderInputs(_ptr(rays), _ptr(skts), None, _ptr(cams), _ptr(t_rand), None, _ptr(noise0), _ptr(noise1), _ptr(pose_idx),
+                       0 if pose_idx is None else int(skts.shape[0]), 0)
     rg = RenderGrads(*[_ptr(grad_out.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0", "alpha0")])
     ws_bytes = load().anerf_render_bwd_workspace_bytes(plan.handle, N, Sc, Si)
     ws = workspace if workspace is not None and workspace.numel() >= ws_bytes else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)

@@ -310,7 +310,7 @@ static int render_common(const anerf_plan* plan, const void* packed_coarse, cons
   P.tilesF = Si > 0 ? ceil_div(R * (Sc + Si), kTileM) : 0;
   P.n_items = ceil_div(N, R);
   P.rays = rays; P.gen = gen; P.skts = skts; P.skt_stride = skt_stride; P.cams = cams; P.cam_const = cam_const;
-  if (draws) { P.t_rand = draws->t_rand; P.u_rand = draws->u_rand; P.noise0 = draws->noise0; P.noise1 = draws->noise1; P.pose_idx = draws->pose_idx; }
+  if (draws) { P.t_rand = draws->t_rand; P.u_rand = draws->u_rand; P.noise0 = draws->noise0; P.noise1 = draws->noise1; P.pose_idx = draws->pose_idx; P.n_poses = draws->n_poses; }
   P.nearfar = (const float*)workspace;
   P.rgb_map = out->rgb_map; P.disp_map = out->disp_map; P.acc_map = out->acc_map; P.alpha = out->alpha;
   P.rgb0 = out->rgb0; P.disp0 = out->disp0; P.acc0 = out->acc0; P.alpha0 = out->alpha0;
@@ -702,7 +702,7 @@ int anerf_sample_rays(const anerf_sampler_inputs* in, const int32_t* frames, int
   sampler::SampleArgs a{};
   a.masks = in->masks; a.imgs = in->imgs; a.fgs = in->fgs; a.bgs = in->bgs; a.bg_idx = in->bg_idx;
   a.c2ws = in->c2ws; a.focals = in->focals; a.centers = in->centers;
-  a.frames = frames; a.n_img = n_images; a.k = rays_per_image; a.H = in->height; a.W = in->width;
+  a.frames = frames; a.n_img = n_images; a.k = rays_per_image; a.H = in->height; a.W = in->width; a.n_frames = in->n_frames;
   a.seed = seed; a.fg_scale = in->fg_is_255 ? 1.0f / 255.0f : 1.0f; a.mask_img = in->mask_img;
   a.rays = out->rays; a.target = out->target; a.fg_out = out->fg; a.bg_out = out->bg; a.pixel_idx = out->pixel_idx;
   a.frame_of_ray = out->frame_of_ray; a.status = n_valid;

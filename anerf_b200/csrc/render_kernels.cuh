@@ -1,24 +1,25 @@
 // The fused A-NeRF ray-marching kernel for sm_100a and its helpers.
 //
-// One persistent CTA per SM processes "items" of R rays.  Per item:
+// One persistent CTA per SM, CTAs paired (cluster of 2, cta_group::2), processes "items" of R rays.  Per item:
 //   sample coarse depths -> [coarse net over R*Sc rows] -> composite -> inverse-CDF importance
 //   sampling + merge -> [fine net over R*(Sc+Si) rows] -> composite -> outputs.
 // A "net pass" over one tile of 128 rows (samples) runs the whole 8x256 MLP with activations never
 // leaving the SM:
-//   * 8 worker warps in two groups of 4 (thread == row == TMEM lane; the two groups share the rows and
-//     own the operand chunks of even / odd index) produce the A operand in 32-wide K chunks, either
-//     by computing the encodings of their sample (bone-local transform, cutoff positional encoding)
-//     or by draining the previous layer's accumulators from TMEM (bias, ReLU), split every value into
-//     hi + lo 16-bit parts and store them in the UMMA K-major core-matrix layout (A ring);
+//   * 16 worker warps in four groups of 4 (thread == row == TMEM lane; the groups share the rows and own the operand
+//     chunks c with c % 4 == group) produce the A operand in 32-wide K chunks, either by computing the encodings of
+//     their sample (bone-local transform, cutoff positional encoding) or by draining the previous layer's accumulators
+//     from TMEM (scale incl. the truncation compensation, bias, ReLU), split every value into hi + lo 16-bit parts and
+//     store them in the UMMA K-major core-matrix layout (A ring, 4 stages);
 //   * 1 loader thread per CTA streams this CTA's half (N/2 rows) of the pre-packed weight chunks
 //     (same layout, hi + lo) from L2 with 1-D bulk TMA copies into the B ring;
-//   * CTAs run as pairs (cluster of 2, cta_group::2): 1 MMA thread in the leader CTA issues, per chunk,
-//     2 K-slabs x 3 tcgen05.mma (lo*hi + hi*lo + hi*hi) of shape M=256 (both CTAs' 128 rows) x N into
-//     128 x N fp32 accumulators in each CTA's TMEM; every SM reads its own A rows and only half of B
-//     from its shared memory.  Accumulators ping-pong between two 256-column regions so the drain of
-//     layer l overlaps the MMAs of layer l+1 chunk by chunk.  The peer CTA's spare warp relays
-//     "my weight half has landed" to the leader.
-// Layer program and K layout: path_math.cuh.  Protocol: mbarrier full/empty rings, bounded waits.
+//   * the MMA warp of the leader CTA issues, per chunk, 2 K-slabs x 3 tcgen05.mma (lo*hi + hi*lo + hi*hi) of shape
+//     M=256 (both CTAs' 128 rows) x N into 128 x N fp32 accumulators in each CTA's TMEM; every SM reads its own A rows
+//     and only half of B from its shared memory.  Accumulators ping-pong between two 256-column regions so the drain
+//     of layer l overlaps the MMAs of layer l+1 chunk by chunk.  The peer CTA's spare warp relays "my weight half has
+//     landed" to the leader.
+// The view branch is contracted per ray (per-ray matrices G as a B operand built in shared memory, path_math.cuh).
+// Layer program and K layout: path_math.cuh.  Protocol: mbarrier full/empty rings, bounded waits (a protocol bug
+// records a site id in pinned host memory and traps; anerf_check_status reports it).
 #pragma once
 #include "tc_sm100.cuh"
 #include "path_math.cuh"
@@ -177,6 +178,7 @@ struct RenderKParams {
   RayGen gen;
   long long skt_stride;     // floats between the poses of consecutive rays: J*16, or 0 in frame mode
   const int* pose_idx;      // optional [N]: ray -> row of `skts` (one transform set per pose instead of per ray)
+  int n_poses;              // rows of `skts` when pose_idx is set (indices are clamped); 0 = unchecked
   float cam_const;          // frame mode: the frame's camera index (framecodes)
   const float* nearfar;     // [N,2] from the near/far pre-kernel
   float *rgb_map, *disp_map, *acc_map, *alpha, *rgb0, *disp0, *acc0, *alpha0, *z_all_out, *raw_out;
@@ -196,6 +198,14 @@ struct RenderKParams {
 };
 
 #ifdef __CUDACC__
+
+// row of `skts` that ray `gr` reads: the ray itself, or its pose through the (clamped) index
+__device__ __forceinline__ size_t pose_row(const RenderKParams& P, int gr) {
+  if (!P.pose_idx) return (size_t)gr;
+  int p = __ldg(P.pose_idx + gr);
+  if (P.n_poses > 0) p = min(max(p, 0), P.n_poses - 1);
+  return (size_t)p;
+}
 
 // ------------------------------------------------------------------------------------------------
 // pipeline context shared by the three roles
@@ -988,7 +998,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
         for (int i = t0; i < R * J * 12; i += nt) {
           int r = i / (J * 12), e = i % (J * 12);
           int gr = min(ray0 + r, P.n_rays - 1);
-          const size_t prow = P.pose_idx ? (size_t)__ldg(P.pose_idx + gr) : (size_t)gr;
+          const size_t prow = pose_row(P, gr);
           skt_s[i] = P.skts[prow * P.skt_stride + (e / 12) * 16 + (e % 12)];
         }
         if (pg.dims.fc_ch > 0)
@@ -1004,7 +1014,7 @@ __global__ void __launch_bounds__(kThreads, 1) anerf_fused_kernel(const __grid_c
           float rbuf[8];
           const float* rd = rbuf + 3;
           if (P.rays) rd = P.rays + (size_t)gr * 8 + 3; else pixel_ray(P.gen, gr, rbuf);
-          const size_t prow = P.pose_idx ? (size_t)__ldg(P.pose_idx + gr) : (size_t)gr;
+          const size_t prow = pose_row(P, gr);
           encode_joint_viewdir(P.skts + prow * P.skt_stride + (size_t)j * 16, rd, f);
 #pragma unroll
           for (int q = 0; q < kViewPerJoint; ++q) vtab_s[j * vstride + slot * kViewPad + q] = f[q];

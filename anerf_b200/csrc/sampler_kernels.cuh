@@ -26,7 +26,7 @@ struct SampleArgs {
   const float* focals;        // [F, 2] (fx, fy)
   const float* centers;       // [F, 2] or NULL (image centre)
   const int* frames;          // [n_img] selected image indices
-  int n_img, k, H, W;
+  int n_img, k, H, W, n_frames;
   unsigned long long seed;
   float fg_scale;             // 1/255 when masks are stored as 0/255, 1 when 0/1
   int mask_img;               // compose img * fg + (1 - fg) * bg like the reference's mask_img option
@@ -67,6 +67,10 @@ __global__ void __launch_bounds__(1024, 1) sample_rays_kernel(const SampleArgs a
   __shared__ int s_scan[1024];
   const int img = blockIdx.x, tid = threadIdx.x;
   const int frame = a.frames[img];
+  if (a.n_frames > 0 && (frame < 0 || frame >= a.n_frames)) {      // a bad image index: report, touch nothing
+    if (tid == 0) a.status[img] = -1;
+    return;
+  }
   const int HW = a.H * a.W;
   const int per = (HW + blockDim.x - 1) / blockDim.x;
   const int p0 = tid * per, p1 = min(p0 + per, HW);

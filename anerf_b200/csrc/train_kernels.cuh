@@ -273,6 +273,7 @@ struct EncodeArgs {
   const float* rays;      // [N,8]
   const float* skts;      // [N,J,16], or [P,J,16] read through pose_idx
   const int* pose_idx;    // optional [N]
+  int n_poses;            // rows of skts when pose_idx is set (indices are clamped); 0 = unchecked
   const float* z;         // [N,S] depths of this network's pass
   const float* cams;      // [N] or NULL
   const float* codes;     // [n_fc, fc_ch] or NULL
@@ -293,7 +294,8 @@ __global__ void encode_rows_kernel(EncodeArgs e) {
   const float* rp = e.rays + (long long)ray * 8;
   const float zz = e.z[(long long)ray * e.S + s];
   const float p[3] = {rp[0] + rp[3] * zz, rp[1] + rp[4] * zz, rp[2] + rp[5] * zz};
-  const long long prow = e.pose_idx ? (long long)e.pose_idx[ray] : (long long)ray;
+  long long prow = e.pose_idx ? (long long)e.pose_idx[ray] : (long long)ray;
+  if (e.pose_idx && e.n_poses > 0) prow = prow < 0 ? 0 : (prow >= e.n_poses ? e.n_poses - 1 : prow);
   const float* skt = e.skts + (prow * J + j) * 16;
   float f[kPtsPerJoint];
   const float v = encode_joint_pts(skt, p, e.tau_p, e.cut_p[j], f);
@@ -402,6 +404,7 @@ __global__ void composite_bwd_kernel(CompositeBwdArgs a) {
 struct EncodeBwdArgs {
   const float* rays; const float* skts; const float* z;
   const int* pose_idx;    // optional [N]: skts / g_skts are then per pose
+  int n_poses;
   int ray0, n_rays_blk, S, J, W, vq;
   float tau_p, tau_v;
   float cut_p[kMaxJoints], cut_v[kMaxJoints];
@@ -416,7 +419,8 @@ __global__ void encode_bwd_kernel(EncodeBwdArgs e) {
   const int rl = idx / e.J, j = idx % e.J, J = e.J, S = e.S;
   const int ray = e.ray0 + rl;
   const float* rp = e.rays + (long long)ray * 8;
-  const long long prow = e.pose_idx ? (long long)e.pose_idx[ray] : (long long)ray;
+  long long prow = e.pose_idx ? (long long)e.pose_idx[ray] : (long long)ray;
+  if (e.pose_idx && e.n_poses > 0) prow = prow < 0 ? 0 : (prow >= e.n_poses ? e.n_poses - 1 : prow);
   const float* skt = e.skts + (prow * J + j) * 16;
   float T[kViewPerJoint], gT[kViewPerJoint];
   encode_joint_viewdir(skt, rp + 3, T);

@@ -369,7 +369,7 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
     // ---- encodings
     {
       EncodeArgs e{};
-      e.rays = c.in->rays; e.skts = c.in->skts; e.z = z; e.cams = c.in->cams; e.codes = p.framecodes; e.pose_idx = c.in->pose_idx;
+      e.rays = c.in->rays; e.skts = c.in->skts; e.z = z; e.cams = c.in->cams; e.codes = p.framecodes; e.pose_idx = c.in->pose_idx; e.n_poses = c.in->n_poses;
       e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W; e.fc_ch = d.fc_ch; e.n_fc = d.n_fc; e.vq = view_per_joint(d);
       e.tau_p = o.tau_pts; e.tau_v = o.tau_views;
       for (int j = 0; j < kMaxJoints; ++j) { e.cut_p[j] = o.cutoff_pts[j]; e.cut_v[j] = o.cutoff_views[j]; }
@@ -454,7 +454,7 @@ inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S
     // ---- encodings backward
     if (need_pose) {
       EncodeBwdArgs e{};
-      e.rays = c.in->rays; e.skts = c.in->skts; e.z = z; e.pose_idx = c.in->pose_idx;
+      e.rays = c.in->rays; e.skts = c.in->skts; e.z = z; e.pose_idx = c.in->pose_idx; e.n_poses = c.in->n_poses;
       e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W; e.vq = view_per_joint(d);
       e.tau_p = o.tau_pts; e.tau_v = o.tau_views;
       for (int j = 0; j < kMaxJoints; ++j) { e.cut_p[j] = o.cutoff_pts[j]; e.cut_v[j] = o.cutoff_views[j]; }

@@ -23,7 +23,7 @@ from . import _lib
 class _SamplerInputs(C.Structure):
     _fields_ = [("masks", C.c_void_p), ("imgs", C.c_void_p), ("fgs", C.c_void_p), ("bgs", C.c_void_p), ("bg_idx", C.c_void_p),
                 ("c2ws", C.c_void_p), ("focals", C.c_void_p), ("centers", C.c_void_p), ("height", C.c_int32), ("width", C.c_int32),
-                ("fg_is_255", C.c_int32), ("mask_img", C.c_int32)]
+                ("n_frames", C.c_int32), ("fg_is_255", C.c_int32), ("mask_img", C.c_int32)]
 
 
 class _SamplerOutputs(C.Structure):
@@ -75,7 +75,7 @@ class RaySampler:
         n_valid = torch.empty(n_images, dtype=torch.int32, device=dev)
         p = _lib._ptr
         sin = _SamplerInputs(p(self.masks), p(self.imgs), p(self.fgs), p(self.bgs), p(self.bg_idx), p(self.c2ws), p(self.focals),
-                             p(self.centers), self.H, self.W, int(self.fg_is_255), int(self.mask_img))
+                             p(self.centers), self.H, self.W, self.F, int(self.fg_is_255), int(self.mask_img))
         sout = _SamplerOutputs(p(rays), p(target), p(fg), p(bg), p(pix), p(fr))
         self._calls += 1
         seed = (self._seed * 0x9E3779B97F4A7C15 + self._calls * 0xD1B54A32D192ED03) & 0xFFFFFFFFFFFFFFFF
@@ -84,6 +84,8 @@ class RaySampler:
                                           C.POINTER(_SamplerOutputs), C.c_void_p, C.c_void_p]
         with torch.cuda.device(dev):
             _lib.check(lib.anerf_sample_rays(C.byref(sin), p(frames_t), n_images, k, C.c_uint64(seed), C.byref(sout), p(n_valid), _lib._stream()))
+        if bool((n_valid < 0).any()):
+            raise IndexError(f"image index outside [0, {self.F}): {[int(x) for x in frames_t[n_valid < 0][:8]]}")
         if bool((n_valid < k).any()):
             bad = int(torch.nonzero(n_valid < k)[0])
             raise ValueError(f"image {int(frames_t[bad])} has {int(n_valid[bad])} valid pixels, fewer than the {k} rays asked for")

@@ -120,6 +120,9 @@ typedef struct {
   const float* noise1;
   const int32_t* pose_idx;  /* optional [N]: ray -> pose.  When set, `skts` is [P,J,4,4] (one transform set per POSE, read
                                through the index) and anerf_render_bwd's g_skts is [P,J,4,4], summed over each pose's rays */
+  int32_t n_poses;          /* P (rows of `skts`) when pose_idx is set: indices are clamped to [0, P) on the device, so a bad
+                               index can never read or write outside the buffers; 0 = unchecked */
+  int32_t reserved;
 } anerf_render_inputs;
 
 /* Device outputs ([N,...], fp32).  The *0 entries and z_all may be NULL; with n_importance == 0 the
@@ -310,6 +313,7 @@ typedef struct {
   const float* focals;     /* [F, 2] (fx, fy) */
   const float* centers;    /* [F, 2] principal points or NULL (image centre) */
   int32_t height, width;
+  int32_t n_frames;        /* F: entries of `frames` outside [0, F) make their image report -1 valid pixels and produce no rows */
   int32_t fg_is_255;       /* foreground masks stored as 0/255 instead of 0/1 */
   int32_t mask_img;        /* target = img * fg + (1 - fg) * bg (the reference's mask_img) */
 } anerf_sampler_inputs;

@@ -104,6 +104,13 @@ def test_render_with_pose_index_equals_per_ray_transforms():
     assert gsb.shape == (skts_pose.shape[0], cfg.n_joints, 4, 4)
     seg = torch.zeros_like(gsb).index_add_(0, pidx.long(), gsa)
     assert rel_err(gsb.cpu().numpy(), seg.cpu().numpy()) < 1e-5
+    # an out-of-range pose index is clamped on the device (never an out-of-bounds access)
+    bad = pidx.clone()
+    bad[0], bad[1] = 10 ** 6, -5
+    out = _lib.render_fwd(plan, p0, p1, opts, rays, t(skts_pose), t(scene["cyls"][:N]), cams, dr["t_rand"], dr["u_rand"], dr["noise0"],
+                          dr["noise1"], pose_idx=bad)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out["rgb_map"]).all()
     _lib.check_status()
 
 

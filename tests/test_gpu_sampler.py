@@ -78,6 +78,8 @@ def test_draws_are_uniform_and_exhaustive():
     assert np.array_equal(b["pixel_idx"].cpu().numpy(), valid)
     with pytest.raises(ValueError, match="valid pixels"):
         s.sample(N_rand=len(valid) + 1, n_images=1, frames=[0])
+    with pytest.raises(IndexError, match="image index"):
+        s.sample(N_rand=8, n_images=1, frames=[3])
     # many batches: every valid pixel is drawn about equally often
     hits = np.zeros(d["H"] * d["W"])
     n_batches, k = 400, 50

@@ -156,6 +156,51 @@ def test_autograd_through_the_python_boundary():
     assert rc.network_fine.pts_linears[1].weight.grad is None or float(rc.network_fine.pts_linears[1].weight.grad.abs().max()) == 0.
 
 
+@pytest.mark.parametrize("single_net", [False, True])
+def test_in_place_gradient_accumulation_equals_returned_gradients(single_net):
+    """The autograd node adds parameter gradients straight into .grad (one flat allocation, AccumulateGrad bypassed);
+    RayCaster.accumulate_param_grads_in_place = False returns them to autograd instead.  Same numbers either way, also with
+    --single_net (one parameter set used by both passes), with existing .grad buffers (accumulation over two backward
+    calls) and after zero_grad(set_to_none=False)."""
+    from tests.test_gpu_api import data_attrs, make_args
+    from anerf_b200.raycasters import RayCaster, create_raycaster
+    dev = torch.device("cuda")
+    args = make_args(N_importance=16, no_reload=True, single_net=single_net)
+    got = {}
+    for mode in (True, False):
+        rk_train, rk_test, _, grad_vars, optimizer, _ = create_raycaster(args, data_attrs(24))
+        rc = rk_test['ray_caster']
+        rc.network.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(101).items()})
+        if not single_net:
+            rc.network_fine.load_state_dict({k: torch.as_tensor(v) for k, v in synthetic.make_net_weights(202).items()})
+        assert (rc.network_fine is rc.network) == single_net
+        rc.accumulate_param_grads_in_place = mode
+        holder = rk_train['ray_caster'].train()
+        scene = synthetic.make_scene(seed=3, n_rays=64, H=512, W=512, focal=500., n_joints=24)
+        t = lambda a: torch.as_tensor(a).to(dev)
+        N = 64
+        rays = torch.cat([t(scene["rays_o"]), t(scene["rays_d"]), torch.zeros(N, 1, device=dev), torch.ones(N, 1, device=dev),
+                          torch.nn.functional.normalize(t(scene["rays_d"]), dim=-1)], 1)
+        kw = {k: v for k, v in rk_train.items() if k not in ('ray_caster', 'use_viewdirs')}
+        kw.update(perturb=0., raw_noise_std=0.)
+        batch = dict(kp_batch=t(scene["kps"]), skts=t(scene["skts"]), cyls=t(scene["cyls"]), bones=t(scene["bones"]), cams=None, subject_idxs=None)
+        target = torch.full((N, 3), 0.4, device=dev)
+        snaps = []
+        for rep in range(3):                     # 1: fresh .grad; 2: accumulate into it; 3: after an in-place zero_grad
+            if rep == 2:
+                optimizer.zero_grad(set_to_none=False)
+            out = holder(rays, **batch, **kw)
+            (((out['rgb_map'] - target) ** 2).mean() + ((out['rgb0'] - target) ** 2).mean()).backward()
+            snaps.append([p.grad.clone() for p in grad_vars])
+        got[mode] = snaps
+    RayCaster.accumulate_param_grads_in_place = True
+    for a_rep, b_rep in zip(got[True], got[False]):
+        for a, b in zip(a_rep, b_rep):
+            assert float((a - b).abs().max()) <= 1e-5 * max(float(b.abs().max()), 1e-30)      # fp32 summation order of the two passes
+    for g1, g2 in zip(got[True][0], got[True][1]):   # the second backward doubled the gradients
+        assert float((g2 - 2 * g1).abs().max()) <= 1e-5 * max(float(g1.abs().max()), 1e-30)
+
+
 def test_adam_steps_reduce_the_loss():
     """A few optimizer steps on a fixed batch through the boundary: the photometric loss must go down, and the
     re-packed weights must be what the next forward uses."""
