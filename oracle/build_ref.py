@@ -121,7 +121,7 @@ def unpack(dst=None):
             for m in tar.getmembers():
                 if m.name not in files or not m.isfile():
                     raise RuntimeError(f"unexpected member {m.name} in {ARCHIVE}")
-            tar.extractall(stage)
+            tar.extractall(stage, filter="data")
         for f, h in files.items():
             if _sha(os.path.join(stage, f)) != h:
                 raise RuntimeError(f"{f}: checksum differs from MANIFEST.json")

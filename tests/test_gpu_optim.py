@@ -38,6 +38,7 @@ def test_fused_adam_matches_torch_adam():
         ob.step()
         assert all(p._version > v for p, v in zip(pb, v0) if p.grad is not None)      # re-pack trigger of RayCaster
     for a, b in zip(pa, pb):
+        a, b = a.detach(), b.detach()
         assert float((a - b).abs().max()) <= 1e-6 * max(1.0, float(a.abs().max()))
     sa, sb = oa.state_dict(), ob.state_dict()
     assert sa['state'].keys() == sb['state'].keys()
