@@ -17,7 +17,8 @@ SYMBOLS = ["anerf_plan_create", "anerf_plan_destroy", "anerf_packed_bytes", "ane
            "anerf_selftest_gemm", "anerf_last_error", "anerf_version", "anerf_debug_set_trace",
            "anerf_render_bwd", "anerf_render_bwd_workspace_bytes", "anerf_selftest_tc_gemm", "anerf_render_frame",
            "anerf_check_status", "anerf_density_grid", "anerf_render_fwd_host_chunked", "anerf_pose_chain_fwd",
-           "anerf_pose_chain_bwd", "anerf_pose_chain_bwd_scratch_bytes", "anerf_adam_step", "anerf_mc_count", "anerf_mc_emit", "anerf_sample_rays", "anerf_render_bwd_pass", "anerf_loss_seed"]
+           "anerf_pose_chain_bwd", "anerf_pose_chain_bwd_scratch_bytes", "anerf_adam_step", "anerf_mc_count", "anerf_mc_emit", "anerf_sample_rays", "anerf_render_bwd_pass", "anerf_loss_seed",
+           "anerf_train_state_bytes", "anerf_render_fwd_train", "anerf_render_bwd_saved"]
 
 
 class NetConfig(C.Structure):
@@ -120,6 +121,13 @@ def load():
     lib.anerf_render_bwd_pass.argtypes = [C.c_void_p, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(RenderOpts),
                                           C.POINTER(RenderInputs), C.c_void_p, C.c_void_p, C.POINTER(RenderGrads),
                                           C.POINTER(NetGrads), C.POINTER(NetGrads), C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]
+    lib.anerf_train_state_bytes.restype = C.c_size_t
+    lib.anerf_train_state_bytes.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32]
+    lib.anerf_render_fwd_train.argtypes = [C.c_void_p, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(RenderOpts),
+                                           C.POINTER(RenderInputs), C.POINTER(RenderOutputs), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.anerf_render_bwd_saved.argtypes = [C.c_void_p, C.POINTER(NetParams), C.POINTER(NetParams), C.POINTER(RenderOpts),
+                                           C.POINTER(RenderInputs), C.POINTER(RenderGrads), C.POINTER(NetGrads), C.POINTER(NetGrads),
+                                           C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_void_p]
     lib.anerf_loss_seed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_float,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.anerf_selftest_tc_gemm.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
@@ -367,12 +375,14 @@ def _fill_net_struct(st, depth, tensors, framecodes):
 
 
 def render_bwd(plan, opts, params0, params1, rays, skts, cams, t_rand, noise0, noise1, nearfar, z_all, grad_out,
-               want0, want1, want_skts, pose_idx=None, into0=None, into1=None, pass_mask=3, g_skts=None, workspace=None):
+               want0, want1, want_skts, pose_idx=None, into0=None, into1=None, pass_mask=3, g_skts=None, workspace=None,
+               state=None):
     """Backward of render_fwd (C ABI anerf_render_bwd).  params0/params1: fp32 CUDA tensors of the coarse / fine
     network in param_names() order; want0/want1: per-parameter flags; grad_out: dict of dL/d(output) tensors (or
     None).  Returns (grads0, grads1, g_skts): gradients (None where not wanted).  into0 / into1: optional lists of
     existing fp32 buffers the kernels ADD the parameter gradients into (entries may be None); everything else comes
-    zero-filled out of ONE flat allocation."""
+    zero-filled out of ONE flat allocation.  state: the buffer render_fwd_train filled for these very inputs -- the
+    backward then starts from the kept activations (anerf_render_bwd_saved; nearfar / z_all / workspace are not used)."""
     N, Sc, Si = opts.n_rays, opts.n_samples, opts.n_importance
     dev = rays.device
     depth, fc = plan.cfg.depth, plan.cfg.framecode_ch > 0
@@ -406,6 +416,12 @@ def render_bwd(plan, opts, params0, params1, rays, skts, cams, t_rand, noise0, n
     rin = RenderInputs(_ptr(rays), _ptr(skts), None, _ptr(cams), _ptr(t_rand), None, _ptr(noise0), _ptr(noise1), _ptr(pose_idx),
                        0 if pose_idx is None else int(skts.shape[0]), 0)
     rg = RenderGrads(*[_ptr(grad_out.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0", "alpha0")])
+    if state is not None:
+        assert state.is_cuda and state.dtype == torch.uint8 and state.is_contiguous()
+        check(load().anerf_render_bwd_saved(plan.handle, C.byref(p0s), None if p1s is None else C.byref(p1s), C.byref(opts),
+                                            C.byref(rin), C.byref(rg), C.byref(g0s), None if g1s is None else C.byref(g1s),
+                                            _ptr(g_skts) if want_skts else None, _ptr(state), state.numel(), int(pass_mask), _stream()))
+        return g0, g1, g_skts
     ws_bytes = load().anerf_render_bwd_workspace_bytes(plan.handle, N, Sc, Si)
     ws = workspace if workspace is not None and workspace.numel() >= ws_bytes else torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     check(load().anerf_render_bwd_pass(plan.handle, C.byref(p0s), None if p1s is None else C.byref(p1s), C.byref(opts),
@@ -413,6 +429,39 @@ def render_bwd(plan, opts, params0, params1, rays, skts, cams, t_rand, noise0, n
                                        None if g1s is None else C.byref(g1s), _ptr(g_skts) if want_skts else None, _ptr(ws), ws_bytes,
                                        int(pass_mask), _stream()))
     return g0, g1, g_skts
+
+
+def train_state_bytes(plan, opts):
+    """Bytes of the saved-activation state for this batch shape; 0 = too large to keep resident (use render_fwd + render_bwd)."""
+    return int(load().anerf_train_state_bytes(plan.handle, opts.n_rays, opts.n_samples, opts.n_importance))
+
+
+def render_fwd_train(plan, opts, params0, params1, rays, skts, cyls, state, cams=None, t_rand=None, u_rand=None, noise0=None,
+                     noise1=None, pose_idx=None):
+    """Forward of a training step that keeps its activations in `state` (uint8 CUDA tensor of train_state_bytes()):
+    C ABI anerf_render_fwd_train.  params0 / params1: fp32 CUDA parameter tensors in param_names() order (no packed
+    image involved).  Returns render_fwd's dict + 'nearfar' [N,2] + 'z_all' [N,Sc+Si]."""
+    assert pose_idx is None or (pose_idx.is_cuda and pose_idx.dtype == torch.int32 and pose_idx.is_contiguous())
+    assert state.is_cuda and state.dtype == torch.uint8 and state.is_contiguous()
+    N, Sc, Si = opts.n_rays, opts.n_samples, opts.n_importance
+    dev = rays.device
+    Sf = Sc + Si
+    depth, fc = plan.cfg.depth, plan.cfg.framecode_ch > 0
+    for t in [rays, skts, cyls, cams, t_rand, u_rand, noise0, noise1] + list(params0) + list(params1 or []):
+        assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous())
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+    out = dict(rgb_map=f(N, 3), disp_map=f(N), acc_map=f(N), alpha=f(N, Sf if Si > 0 else Sc), nearfar=f(N, 2))
+    if Si > 0:
+        out.update(rgb0=f(N, 3), disp0=f(N), acc0=f(N), alpha0=f(N, Sc), z_all=f(N, Sf))
+    p0s = _fill_net_struct(NetParams(), depth, params0, fc)
+    p1s = _fill_net_struct(NetParams(), depth, params1, fc) if params1 is not None else None
+    rin = RenderInputs(_ptr(rays), _ptr(skts), _ptr(cyls), _ptr(cams), _ptr(t_rand), _ptr(u_rand), _ptr(noise0), _ptr(noise1),
+                       _ptr(pose_idx), 0 if pose_idx is None else int(skts.shape[0]), 0)
+    rout = RenderOutputs(*[_ptr(out.get(k)) for k in ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0",
+                                                      "alpha0", "z_all", "raw")])
+    check(load().anerf_render_fwd_train(plan.handle, C.byref(p0s), None if p1s is None else C.byref(p1s), C.byref(opts),
+                                        C.byref(rin), C.byref(rout), _ptr(out['nearfar']), _ptr(state), state.numel(), _stream()))
+    return out
 
 
 def bwd_workspace(plan, opts, device):

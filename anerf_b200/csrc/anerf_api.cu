@@ -738,20 +738,16 @@ int anerf_render_bwd(const anerf_plan* plan, const anerf_net_params* coarse, con
   return anerf_render_bwd_pass(plan, coarse, fine, o, in, nearfar, z_all, gout, g_coarse, g_fine, g_skts, workspace, workspace_bytes, 3, stream_);
 }
 
-int anerf_render_bwd_pass(const anerf_plan* plan, const anerf_net_params* coarse, const anerf_net_params* fine,
-                          const anerf_render_opts* o, const anerf_render_inputs* in, const float* nearfar, const float* z_all,
-                          const anerf_render_grads* gout, const anerf_net_grads* g_coarse, const anerf_net_grads* g_fine,
-                          float* g_skts, void* workspace, size_t workspace_bytes, int32_t pass_mask, void* stream_) {
-  ANERF_ENTRY();
-  if (pass_mask < 1 || pass_mask > 3) return fail(ANERF_ERR_INVALID, "pass_mask must be 1 (coarse), 2 (fine) or 3 (both)");
-  if (!plan || !coarse || !o || !in || !gout || !nearfar) return fail(ANERF_ERR_INVALID, "null argument");
+// argument checks shared by the training entry points
+static int check_train_args(const anerf_plan* plan, const anerf_net_params* coarse, const anerf_net_params* fine,
+                            const anerf_render_opts* o, const anerf_render_inputs* in) {
+  if (!plan || !coarse || !o || !in) return fail(ANERF_ERR_INVALID, "null argument");
   const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance;
-  if (N == 0) return ANERF_OK;
   if (N < 0 || Sc < 4 || Si < 0 || Sc + Si > 512) return fail(ANERF_ERR_INVALID, "bad sizes n_rays=%d n_samples=%d n_importance=%d", N, Sc, Si);
-  if (Si > 0 && (!fine || !z_all)) return fail(ANERF_ERR_INVALID, "fine parameters / z_all missing");
-  if (!in->rays || !in->skts) return fail(ANERF_ERR_INVALID, "rays/skts missing");
+  if (Si > 0 && !fine) return fail(ANERF_ERR_INVALID, "fine parameters missing");
+  if (N > 0 && (!in->rays || !in->skts)) return fail(ANERF_ERR_INVALID, "rays/skts missing");
   if (plan->dims.fc_ch > 0 && (!in->cams || o->eval_mean_framecode))
-    return fail(ANERF_ERR_INVALID, "backward needs per-ray cams (the eval-time mean framecode has no training path)");
+    return fail(ANERF_ERR_INVALID, "the training path needs per-ray cams (the eval-time mean framecode has no training path)");
   if (!(o->density_scale != 0.f)) return fail(ANERF_ERR_INVALID, "density_scale must be non-zero");
   const anerf_net_params* nets[2] = {coarse, Si > 0 ? fine : coarse};
   for (int n = 0; n < (Si > 0 ? 2 : 1); ++n) {
@@ -762,6 +758,41 @@ int anerf_render_bwd_pass(const anerf_plan* plan, const anerf_net_params* coarse
       return fail(ANERF_ERR_INVALID, "missing head parameters");
     if (plan->dims.fc_ch > 0 && !q->framecodes) return fail(ANERF_ERR_INVALID, "framecodes pointer missing");
   }
+  return ANERF_OK;
+}
+
+// GEMM engine of the training path bound to one workspace: tensor cores (tc_gemm.cuh) with fp16 hi/lo operands and
+// per-matrix scales; ANERF_TRAIN_GEMM=bf16 selects round 1's bf16 hi/lo operands, ANERF_TRAIN_GEMM=simt the fp32 SIMT
+// kernels (debug knobs).  Returns false for the SIMT engine (tc untouched).
+static bool bind_engine(train::TcEngine& tc, const anerf_plan* plan, float* workspace, const train::Workspace& w) {
+  const char* eng = getenv("ANERF_TRAIN_GEMM");
+  if (eng && strcmp(eng, "simt") == 0) return false;
+  tc.fmt = (eng && strcmp(eng, "bf16") == 0) ? 1 : 0;
+  tc.n_sm = plan->n_sm;
+  tc.status = g_status_dev;
+  tc.wpack = (uint8_t*)(workspace + w.tc_w); tc.wpack_bytes = (size_t)w.tc_w_floats * 4; tc.wpack_used = 0;
+  tc.gpack = (uint8_t*)(workspace + w.tc_g); tc.gpack_bytes = (size_t)w.tc_g_floats * 4;
+  tc.slots = workspace + w.tc_slots; tc.w_used = 0; tc.b_used = train::TcEngine::kWeightSlots;
+  tc.error = 0;
+  tc.dry = false;
+  tc.trace = g_trace;
+  tc.wgrad_slice_chunks = 32;
+  if (const char* sl = getenv("ANERF_WGRAD_SLICE")) { int v = atoi(sl); if (v >= 4 && v % 4 == 0 && v <= 256) tc.wgrad_slice_chunks = v; }
+  return true;
+}
+
+int anerf_render_bwd_pass(const anerf_plan* plan, const anerf_net_params* coarse, const anerf_net_params* fine,
+                          const anerf_render_opts* o, const anerf_render_inputs* in, const float* nearfar, const float* z_all,
+                          const anerf_render_grads* gout, const anerf_net_grads* g_coarse, const anerf_net_grads* g_fine,
+                          float* g_skts, void* workspace, size_t workspace_bytes, int32_t pass_mask, void* stream_) {
+  ANERF_ENTRY();
+  if (pass_mask < 1 || pass_mask > 3) return fail(ANERF_ERR_INVALID, "pass_mask must be 1 (coarse), 2 (fine) or 3 (both)");
+  if (!gout || !nearfar) return fail(ANERF_ERR_INVALID, "null argument");
+  int rc = check_train_args(plan, coarse, fine, o, in);
+  if (rc) return rc;
+  const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance;
+  if (N == 0) return ANERF_OK;
+  if (Si > 0 && !z_all) return fail(ANERF_ERR_INVALID, "z_all missing");
   const size_t need = train::train_workspace_bytes(plan->dims, N, Sc, Si);
   if (!workspace || workspace_bytes < need) return fail(ANERF_ERR_INVALID, "workspace too small (%zu < %zu)", workspace_bytes, need);
   train::TrainCall c{};
@@ -774,28 +805,95 @@ int anerf_render_bwd_pass(const anerf_plan* plan, const anerf_net_params* coarse
   c.pass_mask = pass_mask;
   c.workspace = (float*)workspace;
   c.workspace_floats = workspace_bytes / sizeof(float);
-  // GEMM engine: tensor cores (tc_gemm.cuh) with fp16 hi/lo operands and per-matrix scales; ANERF_TRAIN_GEMM=bf16 selects
-  // round 1's bf16 hi/lo operands, ANERF_TRAIN_GEMM=simt the fp32 SIMT kernels (debug knobs)
+  rc = ensure_status();
+  if (rc) return rc;
   train::TcEngine tc{};
-  const char* eng = getenv("ANERF_TRAIN_GEMM");
-  if (!(eng && strcmp(eng, "simt") == 0)) {
-    tc.fmt = (eng && strcmp(eng, "bf16") == 0) ? 1 : 0;
-    int rc = ensure_status();
-    if (rc) return rc;
-    const train::Workspace w = train::make_workspace(plan->dims, N, Sc, Si);
-    tc.n_sm = plan->n_sm;
-    tc.status = g_status_dev;
-    tc.wpack = (uint8_t*)((float*)workspace + w.tc_w); tc.wpack_bytes = (size_t)w.tc_w_floats * 4; tc.wpack_used = 0;
-    tc.gpack = (uint8_t*)((float*)workspace + w.tc_g); tc.gpack_bytes = (size_t)w.tc_g_floats * 4;
-    tc.slots = (float*)workspace + w.tc_slots; tc.w_used = 0; tc.b_used = train::TcEngine::kWeightSlots;
-    tc.error = 0;
-    tc.trace = g_trace;
-    tc.wgrad_slice_chunks = 32;
-    if (const char* sl = getenv("ANERF_WGRAD_SLICE")) { int v = atoi(sl); if (v >= 4 && v % 4 == 0 && v <= 256) tc.wgrad_slice_chunks = v; }
-    c.tc = &tc;
-  }
+  if (bind_engine(tc, plan, (float*)workspace, train::make_workspace(plan->dims, N, Sc, Si))) c.tc = &tc;
   if (train::train_backward(c, (cudaStream_t)stream_) != 0) return fail(ANERF_ERR_INVALID, "internal: workspace layout");
   if (tc.error) return fail(ANERF_ERR_INVALID, "internal: tensor-core GEMM engine error %d (scratch size / launch)", tc.error);
+  CUDA_TRY(cudaGetLastError());
+  return ANERF_OK;
+}
+
+size_t anerf_train_state_bytes(const anerf_plan* plan, int32_t n_rays, int32_t n_samples, int32_t n_importance) {
+  if (!plan || n_rays <= 0 || n_samples <= 0 || n_importance < 0) return 0;
+  const train::TrainState t = train::make_train_state(plan->dims, n_rays, n_samples, n_importance);
+  return t.fits ? (size_t)t.total * sizeof(float) : 0;
+}
+
+int anerf_render_fwd_train(const anerf_plan* plan, const anerf_net_params* coarse, const anerf_net_params* fine,
+                           const anerf_render_opts* o, const anerf_render_inputs* in, const anerf_render_outputs* out,
+                           float* nearfar_out, void* state, size_t state_bytes, void* stream_) {
+  ANERF_ENTRY();
+  if (!out) return fail(ANERF_ERR_INVALID, "null argument");
+  int rc = check_train_args(plan, coarse, fine, o, in);
+  if (rc) return rc;
+  const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance;
+  if (N == 0) return ANERF_OK;
+  if (!in->cyls) return fail(ANERF_ERR_INVALID, "cyls missing");
+  if (!out->rgb_map || !out->disp_map || !out->acc_map) return fail(ANERF_ERR_INVALID, "rgb/disp/acc outputs missing");
+  if (Si > 0 && (!out->rgb0 || !out->disp0 || !out->acc0)) return fail(ANERF_ERR_INVALID, "rgb0/disp0/acc0 outputs missing");
+  const train::TrainState t = train::make_train_state(plan->dims, N, Sc, Si);
+  if (!t.fits) return fail(ANERF_ERR_INVALID, "batch too large to keep its activations (anerf_train_state_bytes == 0): use anerf_render_fwd + anerf_render_bwd");
+  if (!state || state_bytes < (size_t)t.total * sizeof(float)) return fail(ANERF_ERR_INVALID, "state too small (%zu < %zu)", state_bytes, (size_t)t.total * sizeof(float));
+  rc = ensure_status();
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream_;
+  float* base = (float*)state;
+  anerf_nearfar_kernel<<<1, 1024, 0, st>>>(in->rays, RayGen{}, in->cyls, 5, N, base + t.nearfar);
+  CUDA_TRY(cudaGetLastError());
+  train::TrainCall c{};
+  c.dims = plan->dims;
+  c.n_rays = N; c.Sc = Sc; c.Si = Si;
+  c.opts = o; c.in = in; c.nearfar = base + t.nearfar;
+  c.net[0] = coarse; c.net[1] = Si > 0 ? fine : coarse;
+  c.workspace = base;
+  c.workspace_floats = state_bytes / sizeof(float);
+  train::TcEngine tc0{}, tc1{};
+  const bool use_tc = bind_engine(tc0, plan, base, t.w);
+  if (use_tc && Si > 0) bind_engine(tc1, plan, base + t.ws1, t.w);
+  train::TrainFwdOut fo{out->rgb_map, out->disp_map, out->acc_map, out->alpha, out->rgb0, out->disp0, out->acc0, out->alpha0};
+  if (train::train_forward(c, t, use_tc ? &tc0 : nullptr, use_tc ? &tc1 : nullptr, fo, st) != 0)
+    return fail(ANERF_ERR_INVALID, "internal: per-ray stage launch");
+  if (tc0.error || tc1.error) return fail(ANERF_ERR_INVALID, "internal: tensor-core GEMM engine error %d (scratch size / launch)", tc0.error ? tc0.error : tc1.error);
+  if (nearfar_out) CUDA_TRY(cudaMemcpyAsync(nearfar_out, base + t.nearfar, (size_t)N * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (out->z_all && Si > 0) CUDA_TRY(cudaMemcpyAsync(out->z_all, base + t.z_all, (size_t)N * (Sc + Si) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(cudaGetLastError());
+  return ANERF_OK;
+}
+
+int anerf_render_bwd_saved(const anerf_plan* plan, const anerf_net_params* coarse, const anerf_net_params* fine,
+                           const anerf_render_opts* o, const anerf_render_inputs* in, const anerf_render_grads* gout,
+                           const anerf_net_grads* g_coarse, const anerf_net_grads* g_fine, float* g_skts, void* state,
+                           size_t state_bytes, int32_t pass_mask, void* stream_) {
+  ANERF_ENTRY();
+  if (pass_mask < 1 || pass_mask > 3) return fail(ANERF_ERR_INVALID, "pass_mask must be 1 (coarse), 2 (fine) or 3 (both)");
+  if (!gout) return fail(ANERF_ERR_INVALID, "null argument");
+  int rc = check_train_args(plan, coarse, fine, o, in);
+  if (rc) return rc;
+  const int N = o->n_rays, Sc = o->n_samples, Si = o->n_importance;
+  if (N == 0) return ANERF_OK;
+  const train::TrainState t = train::make_train_state(plan->dims, N, Sc, Si);
+  if (!t.fits) return fail(ANERF_ERR_INVALID, "batch too large for a saved-activation state");
+  if (!state || state_bytes < (size_t)t.total * sizeof(float)) return fail(ANERF_ERR_INVALID, "state too small (%zu < %zu)", state_bytes, (size_t)t.total * sizeof(float));
+  rc = ensure_status();
+  if (rc) return rc;
+  float* base = (float*)state;
+  train::TrainCall c{};
+  c.dims = plan->dims;
+  c.n_rays = N; c.Sc = Sc; c.Si = Si;
+  c.opts = o; c.in = in; c.nearfar = base + t.nearfar; c.z_all = base + t.z_all; c.gout = gout;
+  c.net[0] = coarse; c.net[1] = Si > 0 ? fine : coarse;
+  c.grad[0] = g_coarse; c.grad[1] = g_fine;
+  c.g_skts = g_skts;
+  c.pass_mask = pass_mask;
+  c.workspace = base;
+  c.workspace_floats = state_bytes / sizeof(float);
+  train::TcEngine tc0{}, tc1{};
+  const bool use_tc = bind_engine(tc0, plan, base, t.w);
+  if (use_tc && Si > 0) bind_engine(tc1, plan, base + t.ws1, t.w);
+  train::train_backward_saved(c, t, use_tc ? &tc0 : nullptr, use_tc ? &tc1 : nullptr, (cudaStream_t)stream_);
+  if (tc0.error || tc1.error) return fail(ANERF_ERR_INVALID, "internal: tensor-core GEMM engine error %d (scratch size / launch)", tc0.error ? tc0.error : tc1.error);
   CUDA_TRY(cudaGetLastError());
   return ANERF_OK;
 }

@@ -739,8 +739,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
 // a12 (nerf.py:150-205): alpha compositing of one ray by one warp.  z, raw: shared [S]; wts: shared [S] (out).
+// P: anything with the density options B (density_scale), softplus, shift (the fused kernel passes its parameter block)
+template <typename PT>
 __device__ __forceinline__ void composite_ray(int lane, int S, const float* z, const float4* raw,
-                                              float dnorm, const float* noise, const RenderKParams& P, float* wts,
+                                              float dnorm, const float* noise, const PT& P, float* wts,
                                               float* alpha_out, float* rgb_out, float* disp_out, float* acc_out) {
   const int per = (S + 31) / 32;
   const int i0 = lane * per;

@@ -31,6 +31,7 @@ namespace anerf {
 namespace train {
 
 constexpr long long kRowsTarget = 262144;   // rows (samples) per block of rays: ~6 GB of fp32 activations + gradients at W=256 (of 180 GB)
+constexpr long long kStateRowsTarget = 524288;   // saved-activation training state: one block per pass up to this many rows (2 x 12 GB)
 
 #if !defined(ANERF_SIMT_EMU)
 // Tensor-core GEMM engine of the backward pass (tc_gemm.cuh): launch helper + a per-pass cache of packed
@@ -56,6 +57,8 @@ struct TcEngine {
   std::map<const float*, float*> amax_of;              // base pointer of a buffer -> slot of its latest contents
   std::map<std::tuple<const float*, long long>, float*> wmax;   // (weight base pointer, elements) -> slot of max |w| (this pass)
   int error;
+  bool dry;                 // replay of the host-side bookkeeping only (slots, packed-operand offsets), no launches: how the
+                            // backward of anerf_render_fwd_train finds what its forward left in the state buffer
 
   float* weight_slot() { if (w_used >= kWeightSlots) { error = 4; return slots; } return slots + w_used++; }
   // a fresh (zeroed) slot for the buffer starting at `base`, replacing whatever was known about it
@@ -69,12 +72,12 @@ struct TcEngine {
   // a buffer whose bound is known analytically (encodings): no reduction needed
   void produce_const(cudaStream_t st, const float* base, float bound) {
     float* sl = produce(base);
-    if (sl) tc_set_slot_kernel<<<1, 1, 0, st>>>(sl, bound);
+    if (sl && !dry) tc_set_slot_kernel<<<1, 1, 0, st>>>(sl, bound);
   }
   // a buffer written by a kernel that does not fold its maximum: one extra read pass
   void produce_scan(cudaStream_t st, const float* base, long long ld, int cols, long long rows) {
     float* sl = produce(base);
-    if (sl) tc_absmax_kernel<<<148 * 4, 256, 0, st>>>(base, ld, 1, (int)rows, cols, sl);
+    if (sl && !dry) tc_absmax_kernel<<<148 * 4, 256, 0, st>>>(base, ld, 1, (int)rows, cols, sl);
   }
   // slots of every buffer that starts inside [p, p + width) of a row: an operand may be cat[encoding, h]
   AmaxRef ref(const float* p, int width) {
@@ -91,7 +94,13 @@ struct TcEngine {
     if (fmt != 0) return;
     amax_of.clear();
     b_used = kWeightSlots;
-    cudaMemsetAsync(slots + kWeightSlots, 0, (kSlots - kWeightSlots) * sizeof(float), st);
+    if (!dry) cudaMemsetAsync(slots + kWeightSlots, 0, (kSlots - kWeightSlots) * sizeof(float), st);
+  }
+  // after a dry replay of the forward: the slots the backward is about to hand out start from zero again
+  void reset_unused_slots(cudaStream_t st) {
+    if (fmt != 0) return;
+    if (w_used < kWeightSlots) cudaMemsetAsync(slots + w_used, 0, (kWeightSlots - w_used) * sizeof(float), st);
+    if (b_used < kSlots) cudaMemsetAsync(slots + b_used, 0, (kSlots - b_used) * sizeof(float), st);
   }
 
   const uint8_t* pack(cudaStream_t st, const float* src, long long s_n, long long s_k, int N, int K, uint8_t* dst,
@@ -102,6 +111,7 @@ struct TcEngine {
     const long long cap = rowsum ? 148 * 8 : 148 * 32;   // fewer, longer threads when they also reduce (one atomic each)
     if (blocks > cap) blocks = cap;
     if (rowsum && (nt != 1 || (blocks * 256) % NT != 0)) { error = 3; return nullptr; }
+    if (dry) return dst;
     if (fmt == 0) tc_pack_b_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(src, s_n, s_k, N, K, NT, nt, ch, dst, rowsum, amax);
     else tc_pack_b_kernel<1><<<(unsigned)blocks, 256, 0, st>>>(src, s_n, s_k, N, K, NT, nt, ch, dst, rowsum, amax);
     return dst;
@@ -124,7 +134,7 @@ struct TcEngine {
       if (f != wmax.end()) sl = f->second;
       else {
         sl = weight_slot();
-        tc_absmax_kernel<<<64, 256, 0, st>>>(src, s_n, s_k, N, K, sl);
+        if (!dry) tc_absmax_kernel<<<64, 256, 0, st>>>(src, s_n, s_k, N, K, sl);
         wmax[key2] = sl;
       }
     }
@@ -134,7 +144,7 @@ struct TcEngine {
   }
   void new_pass(cudaStream_t st) {
     cache.clear(); wmax.clear(); wpack_used = 0; w_used = 0;
-    if (fmt == 0) cudaMemsetAsync(slots, 0, kWeightSlots * sizeof(float), st);
+    if (fmt == 0 && !dry) cudaMemsetAsync(slots, 0, kWeightSlots * sizeof(float), st);
   }
 
   // k_real: real length of the contraction (for the truncation compensation)
@@ -143,6 +153,7 @@ struct TcEngine {
            int mode, int slice_chunks, AmaxRef a_amax = AmaxRef{nullptr, nullptr}, AmaxRef b_amax = AmaxRef{nullptr, nullptr},
            float* c_amax = nullptr) {
     if (!Bp) { error = 1; return; }
+    if (dry) return;
     TcGemmArgs g{};
     g.A = A; g.a_ms = a_ms; g.a_ks = a_ks; g.M = M; g.K = K;
     g.a_amax = a_amax; g.b_amax = b_amax; g.c_amax = c_amax;
@@ -216,18 +227,18 @@ struct Workspace {
   int P, LX, LV;                 // encoding width, leading dimension of XS (P + W), of VIN (W + 27J + fc)
 };
 
-inline int rays_per_block(int n_rays, int S) {
-  long long r = kRowsTarget / S;
+inline int rays_per_block(int n_rays, int S, long long rows_target = kRowsTarget) {
+  long long r = rows_target / S;
   if (r < 1) r = 1;
   if (r > n_rays) r = n_rays;
   return (int)r;
 }
 
-inline Workspace make_workspace(const NetDims& d, int n_rays, int Sc, int Si) {
+inline Workspace make_workspace(const NetDims& d, int n_rays, int Sc, int Si, long long rows_target = kRowsTarget) {
   Workspace w{};
   const int Sf = Sc + Si;
-  long long rb = (long long)rays_per_block(n_rays, Sc) * Sc;
-  if (Si > 0) { long long r1 = (long long)rays_per_block(n_rays, Sf) * Sf; if (r1 > rb) rb = r1; }
+  long long rb = (long long)rays_per_block(n_rays, Sc, rows_target) * Sc;
+  if (Si > 0) { long long r1 = (long long)rays_per_block(n_rays, Sf, rows_target) * Sf; if (r1 > rb) rb = r1; }
   w.rb = rb;
   w.P = in_pts_ref(d);
   w.LX = w.P + d.W;
@@ -334,139 +345,177 @@ inline void colsum(anerf_tstream st, const float* G, long long ld, int N, long l
   ANERF_TLAUNCH(k, dim3((unsigned)((rows + rpb - 1) / rpb)), dim3((unsigned)round_up(N, 32)), st, G, ld, N, rows, rpb, db);
 }
 
-// One network pass (net 0 on the coarse depths, or net 1 on the sorted fine depths) over all rays.
-inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S, const float* z, const float* noise,
+// Buffers of one network pass inside a workspace (the skip layer's output lives inside XS, next to the encoding)
+struct PassView {
+  const NetDims& d;
+  const Workspace& w;
+  float* ws;
+  int D, W, H, P, LX, LV, J;
+  float *XS, *VIN, *HV, *RAW;
+  PassView(const NetDims& dims, const Workspace& wk, float* base)
+      : d(dims), w(wk), ws(base), D(dims.D), W(dims.W), H(dims.W / 2), P(wk.P), LX(wk.LX), LV(wk.LV), J(dims.J),
+        XS(base + wk.xs), VIN(base + wk.vin), HV(base + wk.hv), RAW(base + wk.raw) {}
+  float* out_ptr(int l) const { return l == d.skip ? XS + P : ws + w.h[l]; }
+  long long out_ld(int l) const { return l == d.skip ? LX : W; }
+  const float* in_ptr(int l) const { return (l == 0 || (l - 1) == d.skip) ? XS : out_ptr(l - 1); }
+  long long in_ld(int l) const { return (l == 0 || (l - 1) == d.skip) ? LX : out_ld(l - 1); }
+  int in_k(int l) const { return l == 0 ? P : ((l - 1) == d.skip ? P + W : W); }
+};
+
+// Forward half of one network pass over the rays [ray0, ray0 + nb): encodings, layer-wise forward with the
+// activations kept in the workspace, heads -> RAW [rows,4].  `dry` (tensor-core engine only): nothing is launched, the
+// engine's host-side bookkeeping (amax slots, packed-weight offsets) is replayed for a workspace that already holds
+// the results of this very sequence (anerf_render_bwd_saved).
+inline void pass_forward(const TrainCall& c, const Workspace& w, int net, int S, const float* z, int ray0, int nb,
+                         anerf_tstream st, bool dry) {
+  const NetDims& d = c.dims;
+  const anerf_net_params& p = *c.net[net];
+  const anerf_render_opts& o = *c.opts;
+  const PassView v(d, w, c.workspace);
+  const int D = v.D, W = v.W, H = v.H, LX = v.LX, LV = v.LV, J = v.J;
+  float* XS = v.XS; float* VIN = v.VIN; float* HV = v.HV; float* RAW = v.RAW;
+  const long long rows = (long long)nb * S;
+  if (dry && !c.tc) return;
+  // ---- encodings
+  {
+    EncodeArgs e{};
+    e.rays = c.in->rays; e.skts = c.in->skts; e.z = z; e.cams = c.in->cams; e.codes = p.framecodes; e.pose_idx = c.in->pose_idx; e.n_poses = c.in->n_poses;
+    e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W; e.fc_ch = d.fc_ch; e.n_fc = d.n_fc; e.vq = view_per_joint(d);
+    e.tau_p = o.tau_pts; e.tau_v = o.tau_views;
+    for (int j = 0; j < kMaxJoints; ++j) { e.cut_p[j] = o.cutoff_pts[j]; e.cut_v[j] = o.cutoff_views[j]; }
+    e.XS = XS; e.ldxs = LX; e.VIN = VIN; e.ldv = LV;
+    auto k = encode_rows_kernel;
+    if (!dry) ANERF_TLAUNCH(k, dim3((unsigned)((rows * J + 127) / 128)), dim3(128), st, e);
+#if !defined(ANERF_SIMT_EMU)
+    if (c.tc) {
+      // bounds of the encodings: |v w(v)|, |sin|, |cos|, |r|, |d| <= max(1, sup v w(v)); v w(v) peaks near the cutoff:
+      // < cutoff + 2 / tau.  A bound within a factor of two of the true maximum costs at most one of the 22 bits.
+      float cmax = 0.f;
+      for (int j = 0; j < J; ++j) cmax = fmaxf(cmax, fmaxf(o.cutoff_pts[j] + 2.f / fmaxf(o.tau_pts, 1e-3f), 1.f));
+      c.tc->produce_const(st, XS, cmax);
+      if (d.fc_ch > 0) c.tc->produce_scan(st, VIN + W, LV, LV - W, rows);     // view encodings + framecodes (any magnitude)
+      else c.tc->produce_const(st, VIN + W, 1.0f);
+    }
+#endif
+  }
+  // ---- forward, activations kept
+  for (int l = 0; l < D; ++l)
+    gemm_rows<true>(c.tc, st, v.in_ptr(l), v.in_ld(l), p.pts_w[l], v.in_k(l), v.out_ptr(l), v.out_ld(l), rows, W, v.in_k(l), p.pts_b[l], 1, nullptr, 0, 0);
+  const float* HL = v.out_ptr(D - 1);
+  const long long HLld = v.out_ld(D - 1);
+  auto k1 = head_fwd_kernel<1>;
+  if (!dry) ANERF_TLAUNCH(k1, dim3((unsigned)((rows + 127) / 128)), dim3(128), st, HL, HLld, W, p.alpha_w, p.alpha_b, rows, RAW + 3, (long long)4);
+  gemm_rows<true>(c.tc, st, HL, HLld, p.feature_w, W, VIN, LV, rows, W, W, p.feature_b, 0, nullptr, 0, 0);
+  gemm_rows<true>(c.tc, st, VIN, LV, p.views_w, LV, HV, H, rows, H, LV, p.views_b, 1, nullptr, 0, 0);
+  auto k3 = head_fwd_kernel<3>;
+  if (!dry) ANERF_TLAUNCH(k3, dim3((unsigned)((rows + 127) / 128)), dim3(128), st, (const float*)HV, (long long)H, H, p.rgb_w, p.rgb_b, rows, RAW, (long long)4);
+}
+
+// Backward half: compositing backward -> heads -> trunk (last layer first) -> encodings, on the activations
+// pass_forward left in the workspace.
+inline void pass_backward(const TrainCall& c, const Workspace& w, int net, int S, const float* z, const float* noise,
                           const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_alpha,
-                          anerf_tstream st) {
+                          int ray0, int nb, anerf_tstream st) {
   const NetDims& d = c.dims;
   const anerf_net_params& p = *c.net[net];
   static const anerf_net_grads no_grads{};
   const anerf_net_grads& gr = c.grad[net] ? *c.grad[net] : no_grads;
   const anerf_render_opts& o = *c.opts;
   float* ws = c.workspace;
-  const int D = d.D, W = d.W, H = d.W / 2, P = w.P, LX = w.LX, LV = w.LV, J = d.J;
+  const PassView v(d, w, ws);
+  const int D = v.D, W = v.W, H = v.H, P = v.P, LX = v.LX, LV = v.LV, J = v.J;
   const bool need_pose = c.g_skts != nullptr;
   const bool need_fc = d.fc_ch > 0 && gr.framecodes != nullptr;
-  float* XS = ws + w.xs; float* VIN = ws + w.vin; float* HV = ws + w.hv; float* RAW = ws + w.raw;
+  float* XS = v.XS; float* VIN = v.VIN; float* HV = v.HV; float* RAW = v.RAW;
   float* GRAW = ws + w.graw; float* GA = ws + w.ga; float* GB = ws + w.gb; float* GXS = ws + w.gxs;
   float* GVIN = ws + w.gvin; float* GHV = ws + w.ghv;
-  auto out_ptr = [&](int l) -> float* { return l == d.skip ? XS + P : ws + w.h[l]; };
-  auto out_ld = [&](int l) -> long long { return l == d.skip ? LX : W; };
-  auto in_ptr = [&](int l) -> const float* { return (l == 0 || (l - 1) == d.skip) ? XS : out_ptr(l - 1); };
-  auto in_ld = [&](int l) -> long long { return (l == 0 || (l - 1) == d.skip) ? LX : out_ld(l - 1); };
-  auto in_k = [&](int l) -> int { return l == 0 ? P : ((l - 1) == d.skip ? P + W : W); };
+  const long long rows = (long long)nb * S;
+  const float* HL = v.out_ptr(D - 1);
+  const long long HLld = v.out_ld(D - 1);
+  // ---- compositing backward -> dL/d raw
+  {
+    CompositeBwdArgs a{};
+    a.raw = RAW; a.z = z; a.rays = c.in->rays; a.noise = noise;
+    a.g_rgb = g_rgb; a.g_disp = g_disp; a.g_acc = g_acc; a.g_alpha = g_alpha;
+    a.ray0 = ray0; a.n_rays_blk = nb; a.S = S; a.softplus = o.softplus; a.B = o.density_scale; a.shift = o.softplus_shift;
+    a.scratch = ws + w.cs; a.g_raw = GRAW;
+    auto k = composite_bwd_kernel;
+    ANERF_TLAUNCH(k, dim3((unsigned)((nb + 63) / 64)), dim3(64), st, a);
+  }
+  // ---- heads and the views layer
+  {
+    auto k3 = head_bwd_kernel<3>;
+    ANERF_TLAUNCH(k3, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)(H < 32 ? 32 : H)), st, (const float*)GRAW, (long long)4,
+                  (const float*)HV, (long long)H, H, p.rgb_w, rows, 64, 1, GHV, (long long)H, gr.rgb_w, gr.rgb_b);
+#if !defined(ANERF_SIMT_EMU)
+    if (c.tc) c.tc->produce_scan(st, GHV, H, H, rows);
+#endif
+  }
+  gemm_wgrad(c.tc, st, GHV, H, VIN, LV, gr.views_w, LV, rows, H, LV, gr.views_b);
+  const int Nv = (need_pose || need_fc) ? LV : W;         // the view-encoding columns only when something consumes them
+  gemm_rows<false>(c.tc, st, GHV, H, p.views_w, LV, GVIN, LV, rows, Nv, H, nullptr, 0, nullptr, 0, 0);
+  gemm_wgrad(c.tc, st, GVIN, LV, HL, HLld, gr.feature_w, W, rows, W, W, gr.feature_b);
+  {
+    auto k1 = head_bwd_kernel<1>;
+    ANERF_TLAUNCH(k1, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)W), st, (const float*)(GRAW + 3), (long long)4, HL, HLld, W,
+                  p.alpha_w, rows, 64, 0, GA, (long long)W, gr.alpha_w, gr.alpha_b);
+  }
+  // (GA now holds g_sigma (x) w_alpha; the GEMM below adds to it and registers the maximum of the sum)
+  // dL/dZ of the last trunk layer = (G_feature Wf + g_sigma (x) w_alpha) . (h > 0)
+  gemm_rows<false>(c.tc, st, GVIN, LV, p.feature_w, W, GA, W, rows, W, W, nullptr, 0, HL, HLld, 1);
+  // ---- trunk, last layer first
+  const float* cur = GA;
+  long long curld = W;
+  for (int l = D - 1; l >= 0; --l) {
+    gemm_wgrad(c.tc, st, cur, curld, v.in_ptr(l), v.in_ld(l), gr.pts_w[l], v.in_k(l), rows, W, v.in_k(l), gr.pts_b[l]);
+    if (l > 0) {
+      if ((l - 1) == d.skip) {        // input = cat[encoding, h]: h part masked, encoding part kept for the pose gradient
+        gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l] + P, v.in_k(l), GXS + P, LX, rows, W, W, nullptr, 0, XS + P, LX, 0);
+        if (need_pose) gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l], v.in_k(l), GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, 0);
+        cur = GXS + P; curld = LX;
+      } else {
+        float* nxt = (cur == GA) ? GB : GA;
+        gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l], v.in_k(l), nxt, W, rows, W, W, nullptr, 0, v.out_ptr(l - 1), v.out_ld(l - 1), 0);
+        cur = nxt; curld = W;
+      }
+    } else if (need_pose) {
+      gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[0], P, GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, d.skip >= 0 ? 1 : 0);
+    }
+  }
+  // ---- encodings backward
+  if (need_pose) {
+    EncodeBwdArgs e{};
+    e.rays = c.in->rays; e.skts = c.in->skts; e.z = z; e.pose_idx = c.in->pose_idx; e.n_poses = c.in->n_poses;
+    e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W; e.vq = view_per_joint(d);
+    e.tau_p = o.tau_pts; e.tau_v = o.tau_views;
+    for (int j = 0; j < kMaxJoints; ++j) { e.cut_p[j] = o.cutoff_pts[j]; e.cut_v[j] = o.cutoff_views[j]; }
+    e.gXS = GXS; e.ldxs = LX; e.gVIN = GVIN; e.ldv = LV; e.g_skts = c.g_skts;
+    auto k = encode_bwd_kernel;
+    ANERF_TLAUNCH(k, dim3((unsigned)((nb * J + 63) / 64)), dim3(64), st, e);
+  }
+  if (need_fc) {
+    auto k = framecode_bwd_kernel;
+    ANERF_TLAUNCH(k, dim3((unsigned)((nb * d.fc_ch + 127) / 128)), dim3(128), st, (const float*)GVIN, (long long)LV, W + in_views_ref(d),
+                  c.in->cams, ray0, nb, S, d.fc_ch, d.n_fc, gr.framecodes);
+  }
+}
 
+// One network pass (net 0 on the coarse depths, or net 1 on the sorted fine depths) over all rays, block by block:
+// forward recomputed, then backward.
+inline void backward_pass(const TrainCall& c, const Workspace& w, int net, int S, const float* z, const float* noise,
+                          const float* g_rgb, const float* g_disp, const float* g_acc, const float* g_alpha,
+                          anerf_tstream st) {
 #if !defined(ANERF_SIMT_EMU)
   if (c.tc) c.tc->new_pass(st);
 #endif
   const int rpb = rays_per_block(c.n_rays, S);
   for (int ray0 = 0; ray0 < c.n_rays; ray0 += rpb) {
     const int nb = (ray0 + rpb <= c.n_rays) ? rpb : c.n_rays - ray0;
-    const long long rows = (long long)nb * S;
 #if !defined(ANERF_SIMT_EMU)
     if (c.tc) c.tc->new_block(st);
 #endif
-    // ---- encodings
-    {
-      EncodeArgs e{};
-      e.rays = c.in->rays; e.skts = c.in->skts; e.z = z; e.cams = c.in->cams; e.codes = p.framecodes; e.pose_idx = c.in->pose_idx; e.n_poses = c.in->n_poses;
-      e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W; e.fc_ch = d.fc_ch; e.n_fc = d.n_fc; e.vq = view_per_joint(d);
-      e.tau_p = o.tau_pts; e.tau_v = o.tau_views;
-      for (int j = 0; j < kMaxJoints; ++j) { e.cut_p[j] = o.cutoff_pts[j]; e.cut_v[j] = o.cutoff_views[j]; }
-      e.XS = XS; e.ldxs = LX; e.VIN = VIN; e.ldv = LV;
-      auto k = encode_rows_kernel;
-      ANERF_TLAUNCH(k, dim3((unsigned)((rows * J + 127) / 128)), dim3(128), st, e);
-#if !defined(ANERF_SIMT_EMU)
-      if (c.tc) {
-        // bounds of the encodings: |v w(v)|, |sin|, |cos|, |r|, |d| <= max(1, sup v w(v)); v w(v) peaks near the cutoff:
-        // < cutoff + 2 / tau.  A bound within a factor of two of the true maximum costs at most one of the 22 bits.
-        float cmax = 0.f;
-        for (int j = 0; j < J; ++j) cmax = fmaxf(cmax, fmaxf(o.cutoff_pts[j] + 2.f / fmaxf(o.tau_pts, 1e-3f), 1.f));
-        c.tc->produce_const(st, XS, cmax);
-        if (d.fc_ch > 0) c.tc->produce_scan(st, VIN + W, LV, LV - W, rows);     // view encodings + framecodes (any magnitude)
-        else c.tc->produce_const(st, VIN + W, 1.0f);
-      }
-#endif
-    }
-    // ---- forward, activations kept
-    for (int l = 0; l < D; ++l)
-      gemm_rows<true>(c.tc, st, in_ptr(l), in_ld(l), p.pts_w[l], in_k(l), out_ptr(l), out_ld(l), rows, W, in_k(l), p.pts_b[l], 1, nullptr, 0, 0);
-    const float* HL = out_ptr(D - 1);
-    const long long HLld = out_ld(D - 1);
-    {
-      auto k1 = head_fwd_kernel<1>;
-      ANERF_TLAUNCH(k1, dim3((unsigned)((rows + 127) / 128)), dim3(128), st, HL, HLld, W, p.alpha_w, p.alpha_b, rows, RAW + 3, (long long)4);
-      gemm_rows<true>(c.tc, st, HL, HLld, p.feature_w, W, VIN, LV, rows, W, W, p.feature_b, 0, nullptr, 0, 0);
-      gemm_rows<true>(c.tc, st, VIN, LV, p.views_w, LV, HV, H, rows, H, LV, p.views_b, 1, nullptr, 0, 0);
-      auto k3 = head_fwd_kernel<3>;
-      ANERF_TLAUNCH(k3, dim3((unsigned)((rows + 127) / 128)), dim3(128), st, (const float*)HV, (long long)H, H, p.rgb_w, p.rgb_b, rows, RAW, (long long)4);
-    }
-    // ---- compositing backward -> dL/d raw
-    {
-      CompositeBwdArgs a{};
-      a.raw = RAW; a.z = z; a.rays = c.in->rays; a.noise = noise;
-      a.g_rgb = g_rgb; a.g_disp = g_disp; a.g_acc = g_acc; a.g_alpha = g_alpha;
-      a.ray0 = ray0; a.n_rays_blk = nb; a.S = S; a.softplus = o.softplus; a.B = o.density_scale; a.shift = o.softplus_shift;
-      a.scratch = ws + w.cs; a.g_raw = GRAW;
-      auto k = composite_bwd_kernel;
-      ANERF_TLAUNCH(k, dim3((unsigned)((nb + 63) / 64)), dim3(64), st, a);
-    }
-    // ---- heads and the views layer
-    {
-      auto k3 = head_bwd_kernel<3>;
-      ANERF_TLAUNCH(k3, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)(H < 32 ? 32 : H)), st, (const float*)GRAW, (long long)4,
-                    (const float*)HV, (long long)H, H, p.rgb_w, rows, 64, 1, GHV, (long long)H, gr.rgb_w, gr.rgb_b);
-#if !defined(ANERF_SIMT_EMU)
-      if (c.tc) c.tc->produce_scan(st, GHV, H, H, rows);
-#endif
-    }
-    gemm_wgrad(c.tc, st, GHV, H, VIN, LV, gr.views_w, LV, rows, H, LV, gr.views_b);
-    const int Nv = (need_pose || need_fc) ? LV : W;         // the view-encoding columns only when something consumes them
-    gemm_rows<false>(c.tc, st, GHV, H, p.views_w, LV, GVIN, LV, rows, Nv, H, nullptr, 0, nullptr, 0, 0);
-    gemm_wgrad(c.tc, st, GVIN, LV, HL, HLld, gr.feature_w, W, rows, W, W, gr.feature_b);
-    {
-      auto k1 = head_bwd_kernel<1>;
-      ANERF_TLAUNCH(k1, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)W), st, (const float*)(GRAW + 3), (long long)4, HL, HLld, W,
-                    p.alpha_w, rows, 64, 0, GA, (long long)W, gr.alpha_w, gr.alpha_b);
-    }
-    // (GA now holds g_sigma (x) w_alpha; the GEMM below adds to it and registers the maximum of the sum)
-    // dL/dZ of the last trunk layer = (G_feature Wf + g_sigma (x) w_alpha) . (h > 0)
-    gemm_rows<false>(c.tc, st, GVIN, LV, p.feature_w, W, GA, W, rows, W, W, nullptr, 0, HL, HLld, 1);
-    // ---- trunk, last layer first
-    const float* cur = GA;
-    long long curld = W;
-    for (int l = D - 1; l >= 0; --l) {
-      gemm_wgrad(c.tc, st, cur, curld, in_ptr(l), in_ld(l), gr.pts_w[l], in_k(l), rows, W, in_k(l), gr.pts_b[l]);
-      if (l > 0) {
-        if ((l - 1) == d.skip) {        // input = cat[encoding, h]: h part masked, encoding part kept for the pose gradient
-          gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l] + P, in_k(l), GXS + P, LX, rows, W, W, nullptr, 0, XS + P, LX, 0);
-          if (need_pose) gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l], in_k(l), GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, 0);
-          cur = GXS + P; curld = LX;
-        } else {
-          float* nxt = (cur == GA) ? GB : GA;
-          gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l], in_k(l), nxt, W, rows, W, W, nullptr, 0, out_ptr(l - 1), out_ld(l - 1), 0);
-          cur = nxt; curld = W;
-        }
-      } else if (need_pose) {
-        gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[0], P, GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, d.skip >= 0 ? 1 : 0);
-      }
-    }
-    // ---- encodings backward
-    if (need_pose) {
-      EncodeBwdArgs e{};
-      e.rays = c.in->rays; e.skts = c.in->skts; e.z = z; e.pose_idx = c.in->pose_idx; e.n_poses = c.in->n_poses;
-      e.ray0 = ray0; e.n_rays_blk = nb; e.S = S; e.J = J; e.W = W; e.vq = view_per_joint(d);
-      e.tau_p = o.tau_pts; e.tau_v = o.tau_views;
-      for (int j = 0; j < kMaxJoints; ++j) { e.cut_p[j] = o.cutoff_pts[j]; e.cut_v[j] = o.cutoff_views[j]; }
-      e.gXS = GXS; e.ldxs = LX; e.gVIN = GVIN; e.ldv = LV; e.g_skts = c.g_skts;
-      auto k = encode_bwd_kernel;
-      ANERF_TLAUNCH(k, dim3((unsigned)((nb * J + 63) / 64)), dim3(64), st, e);
-    }
-    if (need_fc) {
-      auto k = framecode_bwd_kernel;
-      ANERF_TLAUNCH(k, dim3((unsigned)((nb * d.fc_ch + 127) / 128)), dim3(128), st, (const float*)GVIN, (long long)LV, W + in_views_ref(d),
-                    c.in->cams, ray0, nb, S, d.fc_ch, d.n_fc, gr.framecodes);
-    }
+    pass_forward(c, w, net, S, z, ray0, nb, st, false);
+    pass_backward(c, w, net, S, z, noise, g_rgb, g_disp, g_acc, g_alpha, ray0, nb, st);
   }
 }
 
@@ -490,6 +539,170 @@ inline int train_backward(const TrainCall& c, anerf_tstream st) {
   }
   return 0;
 }
+
+#if !defined(ANERF_SIMT_EMU)
+// ---------------------------------------------------------------------------------------------------------------
+// Training forward that KEEPS its activations (anerf_render_fwd_train / anerf_render_bwd_saved): the step's forward is
+// the layer-wise chain above instead of the fused render kernel, each pass in a workspace of its own inside one
+// "state" buffer, and the backward starts from those activations instead of recomputing them -- three GEMM passes per
+// step (forward, dgrad, wgrad) instead of four.  The per-ray stages between the network passes (a12 compositing, a13
+// importance sampling + sorted merge) are the fused kernel's own device functions, one warp per ray.
+// ---------------------------------------------------------------------------------------------------------------
+struct RayStageArgs {
+  const float* raw;      // [n_rays * S, 4] (r, g, b, sigma)
+  const float* z;        // [n_rays, S]
+  const float* rays;     // [n_rays, 8]
+  const float* noise;    // [n_rays, S] or NULL
+  int n_rays, S, softplus;
+  float B, shift;
+  float *alpha, *rgb, *disp, *acc;     // [n_rays,S] (or NULL), [n_rays,3], [n_rays], [n_rays]
+  int Si, blur;                        // Si > 0: importance sampling from this pass's weights + merge
+  const float* u_rand;                 // [n_rays, Si] or NULL (evenly spaced)
+  float* z_all;                        // [n_rays, S + Si]
+};
+
+inline __host__ __device__ int ray_stage_smem_floats(int S, int Si) { return 4 * S + 3 * S + (Si > 0 ? 2 * (S + Si) : 0); }
+constexpr int kRayStageWarps = 4;
+
+__global__ void __launch_bounds__(kRayStageWarps * 32) ray_stage_kernel(const RayStageArgs a) {
+  extern __shared__ __align__(16) float ray_stage_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * kRayStageWarps + warp;
+  if (ray >= a.n_rays) return;
+  const int S = a.S, Sf = S + a.Si;
+  float* base = ray_stage_smem + (size_t)warp * ray_stage_smem_floats(S, a.Si);
+  float4* raw_s = reinterpret_cast<float4*>(base);
+  float* z_s = base + 4 * S;
+  float* w_s = z_s + S;
+  float* cdf_s = w_s + S;
+  float* t_s = cdf_s + S;
+  float* za_s = t_s + Sf;
+  for (int i = lane; i < S; i += 32) {
+    raw_s[i] = __ldg(reinterpret_cast<const float4*>(a.raw) + (size_t)ray * S + i);
+    z_s[i] = __ldg(a.z + (size_t)ray * S + i);
+  }
+  const float* rp = a.rays + (size_t)ray * 8;
+  const float dnorm = sqrtf(rp[3] * rp[3] + rp[4] * rp[4] + rp[5] * rp[5]);
+  __syncwarp();
+  struct { float B; int softplus; float shift; } P{a.B, a.softplus, a.shift};
+  composite_ray(lane, S, z_s, raw_s, dnorm, a.noise ? a.noise + (size_t)ray * S : nullptr, P, w_s,
+                a.alpha ? a.alpha + (size_t)ray * S : nullptr, a.rgb + (size_t)ray * 3, a.disp + ray, a.acc + ray);
+  if (a.Si > 0) {
+    importance_cdf(lane, S, w_s, cdf_s, a.blur);
+    __syncwarp();
+    for (int e = lane; e < Sf; e += 32) {
+      float v;
+      if (e < S) v = z_s[e];
+      else {
+        const int m = e - S;
+        const float u = a.u_rand ? a.u_rand[(size_t)ray * a.Si + m] : linspace01(m, a.Si);
+        v = importance_sample(u, S, z_s, cdf_s);
+      }
+      t_s[e] = v;
+    }
+    __syncwarp();
+    for (int e = lane; e < Sf; e += 32) {          // stable rank sort == torch.sort on the values
+      const float x = t_s[e];
+      int rk = 0;
+      for (int k = 0; k < Sf; ++k) {
+        const float y = t_s[k];
+        rk += (y < x || (y == x && k < e)) ? 1 : 0;
+      }
+      za_s[rk] = x;
+    }
+    __syncwarp();
+    for (int e = lane; e < Sf; e += 32) a.z_all[(size_t)ray * Sf + e] = za_s[e];
+  }
+}
+
+inline int launch_ray_stage(const RayStageArgs& a, cudaStream_t st) {
+  const int smem = kRayStageWarps * ray_stage_smem_floats(a.S, a.Si) * (int)sizeof(float);
+  if (smem > 200 * 1024) return -1;
+  if (smem > 48 * 1024 && cudaFuncSetAttribute(ray_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return -1;
+  ray_stage_kernel<<<(unsigned)ceil_div(a.n_rays, kRayStageWarps), kRayStageWarps * 32, smem, st>>>(a);
+  return 0;
+}
+
+// Layout of the state buffer (floats): [workspace of the coarse pass][workspace of the fine pass][nearfar N*2][z_all N*Sf]
+struct TrainState {
+  Workspace w;
+  long long ws1, nearfar, z_all, total;
+  bool fits;             // every pass is a single block of rows (the activations of the whole batch stay resident)
+};
+inline TrainState make_train_state(const NetDims& d, int n_rays, int Sc, int Si) {
+  TrainState t{};
+  t.w = make_workspace(d, n_rays, Sc, Si, kStateRowsTarget);
+  t.fits = rays_per_block(n_rays, Sc, kStateRowsTarget) >= n_rays && (Si == 0 || rays_per_block(n_rays, Sc + Si, kStateRowsTarget) >= n_rays);
+  t.ws1 = t.w.total;
+  t.nearfar = t.ws1 + (Si > 0 ? t.w.total : 0);
+  t.z_all = t.nearfar + ((long long)n_rays * 2 + 3) / 4 * 4;
+  t.total = t.z_all + ((long long)n_rays * (Sc + Si) + 3) / 4 * 4;
+  return t;
+}
+
+struct TrainFwdOut {
+  float *rgb_map, *disp_map, *acc_map, *alpha, *rgb0, *disp0, *acc0, *alpha0;
+};
+
+// c.workspace = base of the state buffer, c.nearfar = state + nearfar (already filled), tc0 / tc1: engines bound to the
+// two workspaces (NULL: SIMT).  Returns 0, or a negative code.
+inline int train_forward(TrainCall c, const TrainState& t, TcEngine* tc0, TcEngine* tc1, const TrainFwdOut& out, cudaStream_t st) {
+  float* state = c.workspace;
+  const anerf_render_opts& o = *c.opts;
+  float* zc = state + t.w.z_coarse;
+  float* z_all = state + t.z_all;
+  {
+    const long long n = (long long)c.n_rays * c.Sc;
+    coarse_depths_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c.nearfar, c.in->t_rand, c.n_rays, c.Sc, o.lindisp, zc);
+  }
+  const bool fine = c.Si > 0;
+  for (int pass = 0; pass < (fine ? 2 : 1); ++pass) {
+    const int S = pass == 0 ? c.Sc : c.Sc + c.Si;
+    const float* z = pass == 0 ? zc : z_all;
+    c.workspace = state + (pass == 0 ? 0 : t.ws1);
+    c.tc = pass == 0 ? tc0 : tc1;
+    if (c.tc) { c.tc->new_pass(st); c.tc->new_block(st); }
+    pass_forward(c, t.w, pass, S, z, 0, c.n_rays, st, false);
+    RayStageArgs a{};
+    a.raw = c.workspace + t.w.raw; a.z = z; a.rays = c.in->rays; a.noise = pass == 0 ? c.in->noise0 : c.in->noise1;
+    a.n_rays = c.n_rays; a.S = S; a.softplus = o.softplus; a.B = o.density_scale; a.shift = o.softplus_shift;
+    const bool last = pass == (fine ? 1 : 0);
+    a.alpha = last ? out.alpha : out.alpha0; a.rgb = last ? out.rgb_map : out.rgb0;
+    a.disp = last ? out.disp_map : out.disp0; a.acc = last ? out.acc_map : out.acc0;
+    a.Si = (fine && pass == 0) ? c.Si : 0; a.blur = o.single_net; a.u_rand = c.in->u_rand; a.z_all = z_all;
+    if (launch_ray_stage(a, st) != 0) return -2;
+  }
+  return 0;
+}
+
+// Backward from the state train_forward left behind.  Same engine selection as the forward (the dry replay follows the
+// forward's bookkeeping step by step).
+inline int train_backward_saved(TrainCall c, const TrainState& t, TcEngine* tc0, TcEngine* tc1, cudaStream_t st) {
+  float* state = c.workspace;
+  const anerf_render_grads& g = *c.gout;
+  const int pm = c.pass_mask ? c.pass_mask : 3;
+  const bool fine = c.Si > 0;
+  for (int pass = 0; pass < (fine ? 2 : 1); ++pass) {
+    if (!(pm & (1 << pass))) continue;
+    const int S = pass == 0 ? c.Sc : c.Sc + c.Si;
+    const float* z = pass == 0 ? state + t.w.z_coarse : state + t.z_all;
+    c.workspace = state + (pass == 0 ? 0 : t.ws1);
+    c.tc = pass == 0 ? tc0 : tc1;
+    if (c.tc) {
+      c.tc->dry = true;
+      c.tc->new_pass(st); c.tc->new_block(st);
+      pass_forward(c, t.w, pass, S, z, 0, c.n_rays, st, true);
+      c.tc->dry = false;
+      c.tc->reset_unused_slots(st);
+    }
+    const bool last = pass == (fine ? 1 : 0);
+    pass_backward(c, t.w, pass, S, z, pass == 0 ? c.in->noise0 : c.in->noise1,
+                  last ? g.rgb_map : g.rgb0, last ? g.disp_map : g.disp0, last ? g.acc_map : g.acc0, last ? g.alpha : g.alpha0,
+                  0, c.n_rays, st);
+  }
+  return 0;
+}
+#endif  // !ANERF_SIMT_EMU
 
 }  // namespace train
 }  // namespace anerf

@@ -142,19 +142,33 @@ OUT_KEYS = ("rgb_map", "disp_map", "acc_map", "alpha", "rgb0", "disp0", "acc0", 
 
 
 class _RenderRaysFn(torch.autograd.Function):
-    """render_rays as a single autograd node (reference graph: core/raycasters.py:361-474).  forward = the fused
-    kernel (anerf_render_fwd), keeping only the repaired near/far and the sorted fine depths; backward =
-    anerf_render_bwd, which recomputes the activations layer by layer.  Differentiable inputs: `skts` (pose
+    """render_rays as a single autograd node (reference graph: core/raycasters.py:361-474).  When something needs a
+    gradient: forward = anerf_render_fwd_train (layer-wise chain, activations kept in the caster's state buffer), backward
+    = anerf_render_bwd_saved.  Otherwise, or when the batch is too large to keep (RayCaster.keep_activations = False turns
+    it off): forward = the fused kernel (anerf_render_fwd), keeping only the repaired near/far and the sorted fine depths;
+    backward = anerf_render_bwd, which recomputes the activations layer by layer.  Differentiable inputs: `skts` (pose
     refinement) and the parameters of both networks; sample positions carry no gradient (ray_utils.py:285)."""
 
     @staticmethod
     def forward(ctx, caster, opts, aux, skts, *params):
         plan = caster._get_plan()
-        p0 = caster._packed_image('network')
-        p1 = caster._packed_image('network_fine') if opts.n_importance > 0 else None
-        out = _lib.render_fwd(plan, p0, p1, opts, aux['rays'], skts, aux['cyls'], aux['cams'], aux['t_rand'], aux['u_rand'],
-                              aux['noise0'], aux['noise1'], keep_nearfar=True, want_z_all=True, pose_idx=aux.get('pose_idx'))
         ctx.caster, ctx.opts, ctx.aux = caster, opts, aux
+        ctx.state = None
+        # A step that will be differentiated runs the layer-wise chain and KEEPS its activations (anerf_render_fwd_train):
+        # the backward then has nothing to recompute.  Everything else is the fused kernel.
+        state = caster._train_state(opts, skts.device) if any(ctx.needs_input_grad[3:]) else None
+        if state is not None:
+            n0 = aux['n_params0']
+            det = [p.detach() for p in params]
+            out = _lib.render_fwd_train(plan, opts, det[:n0], det[n0:] if len(det) > n0 else None, aux['rays'], skts.detach(),
+                                        aux['cyls'], state, aux['cams'], aux['t_rand'], aux['u_rand'], aux['noise0'], aux['noise1'],
+                                        pose_idx=aux.get('pose_idx'))
+            ctx.state, ctx.state_epoch = state, caster._claim_train_state()
+        else:
+            p0 = caster._packed_image('network')
+            p1 = caster._packed_image('network_fine') if opts.n_importance > 0 else None
+            out = _lib.render_fwd(plan, p0, p1, opts, aux['rays'], skts, aux['cyls'], aux['cams'], aux['t_rand'], aux['u_rand'],
+                                  aux['noise0'], aux['noise1'], keep_nearfar=True, want_z_all=True, pose_idx=aux.get('pose_idx'))
         ctx.nearfar, ctx.z_all = out['nearfar'], out.get('z_all')
         ctx.save_for_backward(skts, *params)
         ctx.keys = [k for k in OUT_KEYS if k in out]
@@ -180,12 +194,14 @@ class _RenderRaysFn(torch.autograd.Function):
         usable = lambda p, w: direct and w and p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and p.grad.device == p.device
         into0 = [p.grad if usable(p, w) else None for p, w in zip(params0, want0)]
         into1 = None if params1 is None else [p.grad if usable(p, w) else None for p, w in zip(params1, want1)]
+        # the kept activations are this call's only while no later forward has re-used the state buffer
+        state = ctx.state if (ctx.state is not None and ctx.caster._train_state_epoch == ctx.state_epoch) else None
         with torch.cuda.device(skts.device):
             g0, g1, g_skts = _lib.render_bwd(ctx.caster._get_plan(), opts, [p.detach() for p in params0],
                                              None if params1 is None else [p.detach() for p in params1],
                                              aux['rays'], skts.detach(), aux['cams'], aux['t_rand'], aux['noise0'], aux['noise1'],
                                              ctx.nearfar, ctx.z_all, gout, want0, want1, want_skts, pose_idx=aux.get('pose_idx'),
-                                             into0=into0, into1=into1)
+                                             into0=into0, into1=into1, state=state)
         if not direct:
             return (None, None, None, g_skts, *g0, *(g1 or []))
         seen = {}
@@ -208,6 +224,7 @@ class _RenderRaysFn(torch.autograd.Function):
 # ------------------------------------------------------------------------------------------------
 class RayCaster(nn.Module):
     accumulate_param_grads_in_place = True       # see _RenderRaysFn.backward
+    keep_activations = os.environ.get("ANERF_KEEP_ACTIVATIONS", "1") != "0"     # see _RenderRaysFn.forward
 
     def __init__(self, network, embed_fn, embedbones_fn, embeddirs_fn, network_fine=None, joint_coords=None,
                  single_net=False, operand_format=None):
@@ -245,6 +262,30 @@ class RayCaster(nn.Module):
                                        net.n_framecodes if net.use_framecode else 0, self._operand_format,
                                        view_freqs=self.embeddirs_fn.num_freqs)
         return self._plan
+
+    def _train_state(self, opts, dev):
+        """The saved-activation state buffer for this batch shape (one per caster, re-used every step), or None when
+        the route is off or the batch is too large to keep resident."""
+        if not self.keep_activations:
+            return None
+        key = (opts.n_rays, opts.n_samples, opts.n_importance, dev)
+        cached = getattr(self, '_state_buf', None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        with torch.cuda.device(dev):
+            nb = _lib.train_state_bytes(self._get_plan(), opts)
+            self._state_buf = None                  # release the old one first
+            buf = torch.empty(nb, dtype=torch.uint8, device=dev) if nb > 0 else None
+        self._state_buf = (key, buf)
+        return buf
+
+    _train_state_epoch = 0
+
+    def _claim_train_state(self):
+        """Every forward that fills the state buffer takes a new epoch; a backward whose epoch is no longer current
+        (two forwards before one backward) falls back to recomputing."""
+        self._train_state_epoch += 1
+        return self._train_state_epoch
 
     def _packed_image(self, which):
         """Packed tensor-core image of a network, re-packed whenever a parameter changed in place

@@ -4,11 +4,12 @@
 `rgb + (1 - acc) * bg` against the targets, for the fine and the coarse pair) -> `loss.backward()` -> `optimizer.step()`.
 `FusedTrainStep` runs the same arithmetic as a fixed sequence of launches through the C ABI:
 
-    anerf_render_fwd            the fused forward kernel (keeps only near/far and the sorted fine depths)
+    anerf_render_fwd_train      forward as the layer-wise GEMM chain, activations of both passes kept in a state buffer
+                                (batches too large to keep: anerf_render_fwd, the fused kernel, and a recomputing backward)
     anerf_loss_seed  x2         loss values + d loss / d (rgb, acc) for the fine and the coarse outputs
-    anerf_render_bwd_pass(1)    backward of the coarse network's pass
+    anerf_render_bwd_saved(1)   backward of the coarse network's pass from the kept activations
       [NCCL all-reduce of the coarse network's gradients on a side stream, overlapping ...]
-    anerf_render_bwd_pass(2)    ... the backward of the fine network's pass
+    anerf_render_bwd_saved(2)   ... the backward of the fine network's pass
       [NCCL all-reduce of the fine network's gradients]
     anerf_adam_step             FusedAdam over all parameters (grad_scale = 1 / world: the all-reduces sum)
 
@@ -96,12 +97,19 @@ class FusedTrainStep:
         nets = [rc.network] + ([rc.network_fine] if Si > 0 else [])
         with torch.cuda.device(dev), torch.no_grad():
             plan = rc._get_plan()
-            p0 = rc._packed_image('network')
-            p1 = rc._packed_image('network_fine') if Si > 0 else None
             params = self._grad_views(nets, names)
             self._flat.zero_()
-            out = _lib.render_fwd(plan, p0, p1, opts, rays, skts_c.detach(), cyls_c, cams_c, t_rand, u_rand, noise0, noise1,
-                                  keep_nearfar=True, want_z_all=True, pose_idx=pidx)
+            det = [[p.detach() for p in ps] for ps in params]
+            state = rc._train_state(opts, dev)
+            if state is not None:       # the forward keeps its activations: nothing is recomputed in the backward
+                rc._claim_train_state()
+                out = _lib.render_fwd_train(plan, opts, det[0], det[1] if Si > 0 else None, rays, skts_c.detach(), cyls_c, state,
+                                            cams_c, t_rand, u_rand, noise0, noise1, pose_idx=pidx)
+            else:
+                p0 = rc._packed_image('network')
+                p1 = rc._packed_image('network_fine') if Si > 0 else None
+                out = _lib.render_fwd(plan, p0, p1, opts, rays, skts_c.detach(), cyls_c, cams_c, t_rand, u_rand, noise0, noise1,
+                                      keep_nearfar=True, want_z_all=True, pose_idx=pidx)
             # ---- loss + gradient seed
             sums = torch.zeros(4, dtype=torch.float32, device=dev)
             tgt = target.float().contiguous()
@@ -116,11 +124,11 @@ class FusedTrainStep:
             want = [[bool(p.requires_grad) for p in ps] for ps in params]
             want_skts = bool(skts_c.requires_grad)
             g_skts = torch.zeros_like(skts_c) if want_skts else None
-            if self._ws is None or self._ws.numel() < _lib.load().anerf_render_bwd_workspace_bytes(plan.handle, N, Sc, Si):
+            if state is None and (self._ws is None or self._ws.numel() < _lib.load().anerf_render_bwd_workspace_bytes(plan.handle, N, Sc, Si)):
                 self._ws = _lib.bwd_workspace(plan, opts, dev)
             into = [[p.grad if w else None for p, w in zip(ps, ws)] for ps, ws in zip(params, want)]
-            common = dict(pose_idx=pidx, into0=into[0], into1=into[1] if Si > 0 else None, g_skts=g_skts, workspace=self._ws)
-            args = (plan, opts, [p.detach() for p in params[0]], None if Si == 0 else [p.detach() for p in params[1]], rays, skts_c.detach(),
+            common = dict(pose_idx=pidx, into0=into[0], into1=into[1] if Si > 0 else None, g_skts=g_skts, workspace=self._ws, state=state)
+            args = (plan, opts, det[0], None if Si == 0 else det[1], rays, skts_c.detach(),
                     cams_c, t_rand, noise0, noise1, out['nearfar'].contiguous(), out.get('z_all'), gout, want[0], want[1] if Si > 0 else None, want_skts)
             handles = []
             if Si > 0:

@@ -239,6 +239,27 @@ int anerf_render_bwd_pass(const anerf_plan* plan, const anerf_net_params* coarse
                           const anerf_net_grads* g_fine, float* g_skts, void* workspace, size_t workspace_bytes,
                           int32_t pass_mask, void* stream);
 
+/* Training step without the recomputation: the forward of a training step run as the layer-wise GEMM chain of the
+ * backward pass (same fp32 parameters, same tensor-core engine), KEEPING the activations of both network passes in a
+ * caller-owned `state` buffer, and a backward that starts from that buffer -- three GEMM passes per step instead of the
+ * four of anerf_render_fwd + anerf_render_bwd (the reference: torch autograd keeps every activation as well,
+ * core/networks/nerf.py:94-148).  Outputs and their meaning are those of anerf_render_fwd (core/raycasters.py:711-724;
+ * `out->raw` is not provided); the per-ray stages (compositing, importance sampling, sorted merge) are the fused kernel's
+ * own code.
+ * anerf_train_state_bytes: size of `state` for a batch, or 0 when the batch is too large to keep resident (more than
+ * 524,288 samples in one network pass) -- use anerf_render_fwd + anerf_render_bwd then.
+ * anerf_render_fwd_train: `nearfar_out` [N,2] / out->z_all [N,Sc+Si] (optional) receive copies of what the state holds,
+ * so that a caller can still fall back to anerf_render_bwd.  The state stays valid for anerf_render_bwd_saved until the next
+ * anerf_render_fwd_train on the same buffer; both calls must see the same ANERF_TRAIN_GEMM setting. */
+size_t anerf_train_state_bytes(const anerf_plan* plan, int32_t n_rays, int32_t n_samples, int32_t n_importance);
+int anerf_render_fwd_train(const anerf_plan* plan, const anerf_net_params* coarse, const anerf_net_params* fine,
+                           const anerf_render_opts* opts, const anerf_render_inputs* in, const anerf_render_outputs* out,
+                           float* nearfar_out, void* state, size_t state_bytes, void* stream);
+int anerf_render_bwd_saved(const anerf_plan* plan, const anerf_net_params* coarse, const anerf_net_params* fine,
+                           const anerf_render_opts* opts, const anerf_render_inputs* in, const anerf_render_grads* grad_out,
+                           const anerf_net_grads* g_coarse, const anerf_net_grads* g_fine, float* g_skts, void* state,
+                           size_t state_bytes, int32_t pass_mask, void* stream);
+
 /* Raw (pre-activation) density of `n_points` world points under ONE pose: pts [P,3], skts [J,4,4],
  * sigma [P].  Uses tau_pts / cutoff_pts of `opts` (other fields ignored). */
 int anerf_density_points(const anerf_plan* plan, const void* packed, const anerf_render_opts* opts,
