@@ -1,7 +1,11 @@
-// Launch sequence of the training backward pass (host side): per network pass and per block of rays,
+// Launch sequences of the training path (host side).  Per network pass:
 //   encodings -> layer-wise forward (activations kept in the workspace) -> compositing backward ->
 //   layer-wise backward (weight / bias gradients accumulated atomically, input gradients masked by the
 //   ReLU derivative) -> encoding backward into the bone transforms / framecodes.
+// Two routes use it: anerf_render_bwd recomputes the forward half per block of rays right before the backward half
+// (train_backward); anerf_render_fwd_train runs the forward half of both passes as the step's forward, keeps the
+// activations in a state buffer, and anerf_render_bwd_saved runs only the backward half (train_forward /
+// train_backward_saved at the end of this file).
 // Reference autograd graph: core/raycasters.py:361-474 (render_rays), core/networks/nerf.py:94-205.
 //
 // The same code drives the CUDA kernels in the library (anerf_api.cu: anerf_render_bwd) and, in the host

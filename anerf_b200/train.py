@@ -8,9 +8,9 @@
                                 (batches too large to keep: anerf_render_fwd, the fused kernel, and a recomputing backward)
     anerf_loss_seed  x2         loss values + d loss / d (rgb, acc) for the fine and the coarse outputs
     anerf_render_bwd_saved(1)   backward of the coarse network's pass from the kept activations
-      [NCCL all-reduce of the coarse network's gradients on a side stream, overlapping ...]
+      [overlap_exchange=True: NCCL all-reduce of the coarse network's gradients on NCCL's stream, overlapping ...]
     anerf_render_bwd_saved(2)   ... the backward of the fine network's pass
-      [NCCL all-reduce of the fine network's gradients]
+      [NCCL all-reduce of the fine network's gradients -- by default of ALL gradients, one exchange per step]
     anerf_adam_step             FusedAdam over all parameters (grad_scale = 1 / world: the all-reduces sum)
 
 Gradients are accumulated into persistent `.grad` buffers (zeroed by one memset per step), the backward workspace is kept
@@ -18,7 +18,7 @@ across steps.  A `skts` tensor that requires grad (pose refinement: `PoseOptLaye
 `skts.backward(g_skts)`, which continues into the pose chain's own autograd node; everything else bypasses autograd.
 
 The result equals the autograd route (RayCaster in .train() mode + torch loss + backward + FusedAdam.step) -- checked
-in tests/test_gpu_trainstep.py -- at fewer launches and with the exchange overlapped.
+in tests/test_gpu_trainstep.py -- at fewer launches.
 """
 import math
 
@@ -30,7 +30,8 @@ from .optim import FusedAdam
 
 
 class FusedTrainStep:
-    def __init__(self, ray_caster, optimizer, loss_fn="L1", coarse_weight=1.0, use_background=True, base_bg=1.0, world=None):
+    def __init__(self, ray_caster, optimizer, loss_fn="L1", coarse_weight=1.0, use_background=True, base_bg=1.0, world=None,
+                 overlap_exchange=None):
         if not isinstance(optimizer, FusedAdam):
             raise TypeError("FusedTrainStep drives anerf_b200.optim.FusedAdam (what create_raycaster returns on a GPU)")
         if loss_fn not in ("L1", "MSE"):
@@ -38,6 +39,15 @@ class FusedTrainStep:
         self.rc, self.opt = ray_caster, optimizer
         self.mse, self.coarse_weight, self.use_bg, self.base_bg = loss_fn == "MSE", float(coarse_weight), bool(use_background), float(base_bg)
         self.world = world if world is not None else (dist.get_world_size() if dist.is_initialized() else 1)
+        # False (default): one all-reduce of all gradients after both passes.  True: the coarse network's gradients are
+        # exchanged while the fine pass's backward runs (two all-reduces).  Measured (profiles/r2_final.md, 3072 rays per
+        # rank): 2 GPUs 16.81 / 16.80 ms, 8 GPUs 16.76 / 16.91 ms against 16.62 / 16.68 on one -- at 8 ranks NCCL's CTAs
+        # displace CTAs of the persistent 148-CTA GEMM grids they overlap with, which costs more than the exposed
+        # 6.9 MB exchange.  ANERF_TRAIN_OVERLAP=0/1 sets the default.
+        if overlap_exchange is None:
+            import os
+            overlap_exchange = os.environ.get("ANERF_TRAIN_OVERLAP", "0") != "0"
+        self.overlap = bool(overlap_exchange)
         self._flat = None          # one buffer behind every parameter's .grad: coarse network first, then the fine one
         self._ws = None
         self._side = None
@@ -132,16 +142,17 @@ class FusedTrainStep:
                     cams_c, t_rand, noise0, noise1, out['nearfar'].contiguous(), out.get('z_all'), gout, want[0], want[1] if Si > 0 else None, want_skts)
             handles = []
             if Si > 0:
+                split = self.overlap and len(self._ranges) == 2
                 _lib.render_bwd(*args, pass_mask=1, **common)
-                if self.world > 1 and len(self._ranges) == 2:
+                if self.world > 1 and split:
                     handles.append(self._exchange(0))
                 _lib.render_bwd(*args, pass_mask=2, **common)
                 if self.world > 1:
-                    handles.append(self._exchange(1 if len(self._ranges) == 2 else 0))
+                    handles.append(self._exchange(1) if split else self._exchange(None))
             else:
                 _lib.render_bwd(*args, pass_mask=3, **common)
                 if self.world > 1:
-                    handles.append(self._exchange(0))
+                    handles.append(self._exchange(None))
             for h in handles:
                 h.wait()
             self.opt.step(grad_scale=1.0 / self.world)
@@ -155,7 +166,7 @@ class FusedTrainStep:
         return out, stats
 
     def _exchange(self, which):
-        a, b = self._ranges[which]
+        a, b = (0, self._flat.numel()) if which is None else self._ranges[which]
         return dist.all_reduce(self._flat[a:b], op=dist.ReduceOp.SUM, async_op=True)
 
     @staticmethod

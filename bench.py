@@ -291,8 +291,9 @@ def headline_parity(rc, kw, dev):
 
 def training_probe(dev, rank, world, n_rays=3072, n_importance=16, steps=5, n_poses=256):
     """Training step through the boundary, weak scaling (n_rays per rank), two routes:
-    `fused_step` (primary): anerf_b200.train.FusedTrainStep -- fused forward, loss seed, per-pass backward with the coarse
-        network's gradient all-reduce overlapping the fine pass, FusedAdam; pose refinement ON with the transforms coming
+    `fused_step` (primary): anerf_b200.train.FusedTrainStep -- forward that keeps its activations (anerf_render_fwd_train),
+        loss seed, per-pass backward from the kept activations (anerf_render_bwd_saved), one gradient all-reduce,
+        FusedAdam; pose refinement ON with the transforms coming
         from anerf_b200.pose_opt.PoseOptLayer once per POSE (n_poses poses, rays -> pose index; the reference's
         image_batching: N_sample_images 256, configs/mixamo/mixamo.txt) and d/d skts reduced per pose in the backward;
     `autograd_route`: create_raycaster's train kwargs in .train() mode with per-RAY transforms that require grad, torch loss,
@@ -369,7 +370,8 @@ def training_probe(dev, rank, world, n_rays=3072, n_importance=16, steps=5, n_po
     ms = timed(step_fused)
     rows = N * (N_SAMPLES + N_SAMPLES + n_importance)
     return {"metric": "training rays/sec (fwd + loss + bwd + grad all-reduce + Adam, pose refinement on)", "value": N * world / (ms * 1e-3),
-            "unit": "rays/s", "ms_per_step": ms, "route": "FusedTrainStep, per-pose transforms from PoseOptLayer (%d poses), d/dskts reduced per pose" % n_poses,
+            "unit": "rays/s", "ms_per_step": ms, "route": "FusedTrainStep (forward keeps its activations: 3 GEMM passes per step), per-pose transforms from PoseOptLayer (%d poses), d/dskts reduced per pose" % n_poses,
+            "activations_kept": getattr(rc, "_state_buf", None) is not None and rc._state_buf[1] is not None,
             "rays_per_rank": N, "samples": f"{N_SAMPLES}+{n_importance}", "pose_grad": True,
             "allreduce_bytes": int(sum(p.numel() for p in grad_vars) * 4) if world > 1 else 0,
             "algorithmic_tflops": 3 * rows * world * 1723648 / (ms * 1e-3) / 1e12,
