@@ -386,15 +386,17 @@ __device__ __forceinline__ void mma_layer(const Pipe& pp, uint32_t& a_seq, uint3
 
 // weight loader: one thread per CTA.  This CTA's half of every chunk of one layer.
 // packed chunk = [half 0: hi, lo][half 1: hi, lo], each half N*64 bytes.
-__device__ __forceinline__ void load_layer(const Pipe& pp, uint32_t& b_seq, const uint8_t* src, int N, int chunks) {
-  const uint32_t bytes = (uint32_t)N * 64u;
-  src += (size_t)pp.rank * bytes;
+__device__ __forceinline__ void load_layer(const Pipe& pp, uint32_t& b_seq, const uint8_t* src, int N, int chunks,
+                                           uint32_t debug_copy_bytes = 0) {
+  const uint32_t stride = (uint32_t)N * 64u;
+  const uint32_t bytes = debug_copy_bytes ? debug_copy_bytes : stride;      // (timing experiments copy less than a chunk)
+  src += (size_t)pp.rank * stride;
 #pragma unroll 1
   for (int c = 0; c < chunks; ++c) {
     uint32_t sb = b_seq % kBStages;
     mbar_wait(&pp.b_empty[sb], ((b_seq / kBStages) & 1) ^ 1, pp.st, 400 + sb);
     mbar_arrive_expect_tx(&pp.b_full[sb], bytes);
-    bulk_g2s(pp.b_ring + sb * kBStageBytes, src + (size_t)c * 2 * bytes, bytes, &pp.b_full[sb]);
+    bulk_g2s(pp.b_ring + sb * kBStageBytes, src + (size_t)c * 2 * stride, bytes, &pp.b_full[sb]);
     ++b_seq;
   }
 }

@@ -54,6 +54,7 @@ struct TcGemmArgs {
   const float* mask; long long mask_ms;   // mask(m, n) at mask[m*mask_ms + n]
   int relu, mode;           // mode 0: store, 1: C += r (then relu / mask), 2: atomicAdd
   DeviceStatus* status;
+  int debug;                // timing experiments only (ANERF_TC_DEBUG; results are WRONG): bit 0 skips the epilogue's global stores, bit 1 the producers' global loads, bit 2 copies 16 bytes per B chunk
   long long* trace;         // optional debug timeline of CTA 0 (anerf_debug_set_trace): stream 0 MMA warp, 1 worker warp 0, 2 worker warp 5
 };
 
@@ -66,12 +67,32 @@ inline __host__ __device__ size_t tc_packed_bytes(int N, int K) {
 
 #ifdef __CUDACC__
 
-constexpr int kTcProdWarps = 8;    // worker warps 0..7 produce the A operand (two groups of 4)
+inline __host__ __device__ int tc_gemm_smem_bytes() {
+  return kAStages * kAStageBytes + kBStages * kBStageBytes + 8 * (kNumBars + 2) + 16 + 64 + 8 * 32 * 36 * 4;
+}
+
+constexpr int kTcProdWarps = 8;    // worker warps 0..7 produce the A operand
 constexpr int kTcDrainWarps = 8;   // worker warps 8..15 drain the accumulators
 static_assert(kTcProdWarps + kTcDrainWarps == kWorkerWarps, "worker warp roles");
 
 // B(n, k) = src[n*s_n + k*s_k] (zero outside [0,N) x [0,K)) -> packed tiles.  One thread per (tile, chunk, 8-wide k
 // group, row of the tile); rows vary fastest so that both the strided reads (s_n == 1) and the 16-byte writes coalesce.
+// explicit shared-memory accesses for the epilogue's transposition buffer: its pointer is derived through an integer
+// alignment cast, which made the compiler emit GENERIC loads / stores (LD.E / ST.E, ~250 cycles each in a dependent chain:
+// the store loop of one 32 x 32 block took ~2000 cycles, tools/trace_gemm.py)
+__device__ __forceinline__ void sts_f4(uint32_t a, float x, float y, float z, float w) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float lds_f(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+  return v;
+}
 __device__ __forceinline__ float amax_value(const AmaxRef& r) {
   float a = r.p0 ? __ldg(r.p0) : 0.f;
   if (r.p1) a = fmaxf(a, __ldg(r.p1));
@@ -159,15 +180,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAStages * kAStageBytes + kBStages * kBStageBytes);
-  uint64_t* r_free = bars + kNumBars;            // [2]: the drain warps are done with accumulator region r
+  uint64_t* r_free = bars + kNumBars;            // [2] (leader's copy is used): the drain warps of the pair are done with accumulator region r
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_free + 2);
   float* stage_all = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);
   Pipe pp;
   pipe_init(pp, smem, smem + kAStages * kAStageBytes, bars, g.status);
   if (tid == 0) {
     pipe_init_barriers(pp);                      // an A chunk is produced by one group of 4 warps per CTA, as in the fused kernel
-    mbar_init(&r_free[0], kTcDrainWarps);
-    mbar_init(&r_free[1], kTcDrainWarps);
+    mbar_init(&r_free[0], 2 * kTcDrainWarps);      // the drain warps of BOTH CTAs arrive at the leader's barrier
+    mbar_init(&r_free[1], 2 * kTcDrainWarps);
     fence_mbar_init();
   }
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, kTmemCols);
@@ -195,8 +216,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     int it = 0;
     Trace trc; trc.init(lane == 0 ? g.trace : nullptr, 0);
     if (pp.rank == 0) {
-      for (int item = pair; item < items; item += n_pairs, ++it)
+      for (int item = pair; item < items; item += n_pairs, ++it) {
+        // the accumulator region this item's MMAs overwrite must have been drained (two items ago) in both CTAs.  The
+        // wait sits HERE, not in front of the producers: they run ahead into the A ring while the drain finishes
+        // (with the wait on their side they idled ~5 k of every ~31 k cycles, tools/trace_gemm.py)
+        if (it >= 2) {
+          mbar_wait_warp(&r_free[it & 1], ((it >> 1) - 1) & 1, pp.st, 700 + (it & 1));
+          tc_fence_after_sync();
+        }
         mma_layer<FMT>(pp, a_seq, b_seq, NT, slice_len(item / (m_tiles * g.n_tiles)), it & 1, trc.p ? &trc : nullptr);
+      }
     } else if (lane == 0) {
       for (int item = pair; item < items; item += n_pairs) relay_layer(pp, b_seq, slice_len(item / (m_tiles * g.n_tiles)));
     }
@@ -207,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
       for (int item = pair; item < items; item += n_pairs) {
         const int ks = item / (m_tiles * g.n_tiles), nt = item % g.n_tiles;
         const uint8_t* src = g.Bp + ((size_t)nt * g.chunks_total + (size_t)ks * g.slice_chunks) * NT * 128;
-        load_layer(pp, b_seq, src, NT, slice_len(ks));
+        load_layer(pp, b_seq, src, NT, slice_len(ks), (g.debug & 4) ? 16u : 0u);
       }
     }
     __syncwarp();
@@ -217,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     // are in production at any time.  The loads of a chunk go to registers BEFORE the wait for its ring stage and
     // are consumed before the arrive (whose release semantics would otherwise wait for loads still in flight);
     // everything further ahead is only pulled into L2 (prefetch.global.L2, no register or ordering cost).
-    //   row-major A (a_ks == 1): lane = (row % 8, 8-wide k group): a warp reads 8 rows x 128 contiguous bytes
+    //   row-major A (a_ks == 1): lane = (8-wide k group, row % 8): a warp reads 8 rows x 128 contiguous bytes
     //   otherwise              : lane = row, 4 k groups per lane (coalesced along the rows when a_ms == 1)
     // ------------------------------------------------------------------------------------------------------
     const int pg = warp >> 2;
@@ -226,11 +255,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     Trace trc; trc.init((lane == 0 && warp == 0) ? g.trace : nullptr, 1);
     Trace* tr = trc.p ? &trc : nullptr;
     // slot j (0..3) of this lane: row a_row(j), k group a_t(j)
-    auto a_row = [&](int j) { return vec_ok ? (32 * j + (lane_g >> 2)) : lane_g; };
-    auto a_t = [&](int j) { return vec_ok ? (lane_g & 3) : j; };
+    // (row-major: the 8 lanes of a quarter-warp take 8 DIFFERENT rows of one k group -- the packed stores of a phase then
+    // fall into 8 different 16-byte bank groups; with lane = (row, k group) in the other order every packed store was a
+    // 4-way bank conflict, 5.8 M conflict cycles per 196,608-row GEMM in ncu)
+    auto a_row = [&](int j) { return vec_ok ? (32 * j + 8 * (lane_g >> 5) + (lane_g & 7)) : lane_g; };
+    auto a_t = [&](int j) { return vec_ok ? ((lane_g >> 3) & 3) : j; };
     const long long a_cstep = (long long)kKC * g.a_ks;
     auto load8 = [&](const float* src, int k, float (&x)[8]) {
-      if (src == nullptr || k >= g.K) {
+      if (src == nullptr || k >= g.K || (g.debug & 2)) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) x[i] = 0.f;
       } else if (vec_ok && k + 8 <= g.K) {
@@ -243,6 +275,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     };
     uint32_t seq_base = 0;
     int it = 0;
+    // where slot j lands inside a packed A stage: slot 0's place + a per-slot constant
+    const int q0 = (a_t(0) >> 1) * 4096 + (a_t(0) & 1) * 2048 + (a_row(0) >> 3) * 128 + (a_row(0) & 7) * 16;
+    auto qoff = [&](int j) { return q0 + (vec_ok ? j * 512 : (j >> 1) * 4096 + (j & 1) * 2048); };
     for (int item = pair; item < items; item += n_pairs, ++it) {
       const int ks = item / (m_tiles * g.n_tiles);
       const int mt = (item % (m_tiles * g.n_tiles)) / g.n_tiles;
@@ -272,11 +307,38 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
       }
       if (tr) tr->mark(50);
-      // the accumulator region this item's MMAs will overwrite must have been drained (two items ago)
-      if (it >= 2) mbar_wait_warp(&r_free[it & 1], ((it >> 1) - 1) & 1, pp.st, 700 + (it & 1));
+      // interior item (every row of the tile and every k of the slice exists): no per-element predicates, one running
+      // pointer -- the loop head was ~1000 of a chunk's ~2800 cycles with the general address arithmetic
+      const bool interior = m0 + kTileM <= g.M && kbase + chunks * kKC <= g.K && !(g.debug & 2) && (vec_ok || g.a_ms == 1);
+      const float* rp = interior ? sp[0] + (long long)pg * a_cstep : nullptr;     // slot 0, this group's first chunk
+      const long long slot_step = vec_ok ? 32 * g.a_ms : 8 * g.a_ks;              // slot j is slot 0 + j * slot_step
 #pragma unroll 1
       for (int c = pg; c < chunks; c += 2) {
         float x[4][8];
+        if (interior) {
+          if (vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4* q4 = reinterpret_cast<const float4*>(rp + j * slot_step);
+              const float4 u = __ldg(q4), v = __ldg(q4 + 1);
+              x[j][0] = u.x; x[j][1] = u.y; x[j][2] = u.z; x[j][3] = u.w; x[j][4] = v.x; x[j][5] = v.y; x[j][6] = v.z; x[j][7] = v.w;
+            }
+            if (c + 4 < chunks) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + j * slot_step + 4 * kKC));
+            }
+          } else {                               // transposed operand: 32 consecutive k of this thread's row, a_ks apart
+            const float* t = rp;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { x[j][i] = __ldg(t); t += g.a_ks; }
+            }
+            // two rounds ahead: lane i asks for the 128-byte line that holds the warp's 32 rows at k + i
+            if (c + 4 < chunks) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + 4 * a_cstep + (long long)lane * (g.a_ks - 1)));
+          }
+          rp += 2 * a_cstep;
+        } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) load8(sp[j] ? sp[j] + (long long)c * a_cstep : nullptr, sk[j] + c * kKC, x[j]);
         // L2 prefetch, two of this group's rounds ahead (or the head of the next item)
@@ -290,9 +352,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
             if (q) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
           }
         }
+        }
         const uint32_t seq = seq_base + (uint32_t)c;
         const uint32_t stage = seq % kAStages;
+        if (tr) tr->mark(52);
         mbar_wait_warp(&pp.a_empty[stage], ((seq / kAStages) & 1) ^ 1, pp.st, 100 + stage);
+        if (tr) tr->mark(53);
         uint8_t* st0 = pp.a_ring + stage * kAStageBytes;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -305,15 +370,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
           Split<FMT>::pair(x[j][2], x[j][3], hi.y, lo.y);
           Split<FMT>::pair(x[j][4], x[j][5], hi.z, lo.z);
           Split<FMT>::pair(x[j][6], x[j][7], hi.w, lo.w);
-          const int rr = a_row(j), tt = a_t(j);
-          uint8_t* q = st0 + (tt >> 1) * 4096 + (tt & 1) * 2048 + (rr >> 3) * 128 + (rr & 7) * 16;
+          uint8_t* q = st0 + qoff(j);
           *reinterpret_cast<uint4*>(q) = hi;
           *reinterpret_cast<uint4*>(q + kAHalfBytes) = lo;
         }
+        if (tr) tr->mark(54);
         fence_proxy_async_smem();
         __syncwarp();
         if (elect_one()) a_chunk_ready(pp, stage);
         __syncwarp();
+        if (tr) tr->mark(55);
       }
       seq_base += (uint32_t)chunks;
       if (tr) tr->mark(51);
@@ -328,7 +394,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
     // ------------------------------------------------------------------------------------------------------
     const int dw = warp - kTcProdWarps;
     const int quarter = warp & 3, half = dw >> 2;
-    float* stg = stage_all + dw * (32 * 36);
+    const uint32_t stg = smem_u32(stage_all + dw * (32 * 36));        // byte address in shared memory
     Trace trc; trc.init((lane == 0 && dw == 0) ? g.trace : nullptr, 2);
     Trace* tr = trc.p ? &trc : nullptr;
     const bool transposed = g.c_ns == 1;
@@ -381,9 +447,44 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         uint32_t v[32];
         tmem_ld32(taddr + cb * 32, v);
         tmem_ld_wait();
+        if (tr) tr->mark(13);
+        const int nb = n0 + cb * 32;             // first column of the block
+        // ---- fast path: a full 32 x 32 block of a row-major output that is stored (forward and dgrad forms, the bulk of
+        // the training step): no per-row / per-column predicates, the operand scale folded into one FMA with the bias,
+        // one running output pointer.  (The general path below issued ~230 instructions per block at ~14 cycles each.)
+        if (vec_out && g.mode == 0 && m_warp + 32 <= g.M && nb + 32 <= g.N) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q)              // row stride 36 floats: 16-byte aligned, conflict-free in both phases
+            sts_f4(stg + (uint32_t)(lane * 36 + 4 * q) * 4u, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                   __uint_as_float(v[4 * q + 3]));
+          __syncwarp();
+          if (tr) tr->mark(14);
+          const int r4 = lane >> 3, n = nb + (lane & 7) * 4;
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (g.bias) b = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+          float* cp = g.C + (long long)(m_warp + r4) * g.c_ms + n;
+          const long long cstep = 4 * g.c_ms;
+          const float lo = g.relu ? 0.f : -3.0e38f;          // branch-free ReLU
+          const uint32_t sp = stg + (uint32_t)(r4 * 36 + (lane & 7) * 4) * 4u;
+          const bool has_mask = g.mask != nullptr;
+#pragma unroll
+          for (int i = 0; i < 8; ++i, cp += cstep) {
+            float4 w = lds_f4(sp + (uint32_t)(i * 4 * 36) * 4u);
+            w.x = fmaxf(fmaf(w.x, out_scale, b.x), lo); w.y = fmaxf(fmaf(w.y, out_scale, b.y), lo);
+            w.z = fmaxf(fmaf(w.z, out_scale, b.z), lo); w.w = fmaxf(fmaf(w.w, out_scale, b.w), lo);
+            if (has_mask) {
+              const float4 k = mk[i];
+              w.x = k.x > 0.f ? w.x : 0.f; w.y = k.y > 0.f ? w.y : 0.f; w.z = k.z > 0.f ? w.z : 0.f; w.w = k.w > 0.f ? w.w : 0.f;
+            }
+            if (!(g.debug & 1)) *reinterpret_cast<float4*>(cp) = w;
+            cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(w.x), fabsf(w.y))), fmaxf(fabsf(w.z), fabsf(w.w)));
+          }
+          __syncwarp();
+          if (tr) tr->mark(12);
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * out_scale);
-        const int nb = n0 + cb * 32;             // first column of the block
         if (!transposed) {
           if (m < g.M) {
             float* c = g.C + (long long)m * g.c_ms + (long long)nb * g.c_ns;
@@ -404,9 +505,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q)              // row stride 36 floats: 16-byte aligned, conflict-free in both phases
-          *reinterpret_cast<float4*>(stg + lane * 36 + 4 * q) =
-              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+          sts_f4(stg + (uint32_t)(lane * 36 + 4 * q) * 4u, __uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                 __uint_as_float(v[4 * q + 3]));
         __syncwarp();
+        if (tr) tr->mark(14);
         const int rmax = g.M - m_warp < 32 ? g.M - m_warp : 32;
         if (vec_out) {
           // a warp instruction covers 4 rows x 128 contiguous bytes: lane = (row % 4, 4-column group)
@@ -417,33 +519,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
           float* crow = g.C + (long long)(m_warp + r4) * g.c_ms + n;
           const long long cstep = 4 * g.c_ms;
           const float lo = g.relu ? 0.f : -3.0e38f;          // branch-free ReLU
-          const float* sp = stg + r4 * 36 + (lane & 7) * 4;
+          const uint32_t sp = stg + (uint32_t)(r4 * 36 + (lane & 7) * 4) * 4u;
           if (n_ok) {
-            if (!g.mask && g.mode == 0) {                     // forward form: bias, ReLU, store
+            // general path (edge tiles, C += forms); fully unrolled: mk[] must stay in registers
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (r4 + 4 * i < rmax) {
-                  float4 w = *reinterpret_cast<const float4*>(sp + i * 4 * 36);
-                  w.x = fmaxf(w.x + b.x, lo); w.y = fmaxf(w.y + b.y, lo); w.z = fmaxf(w.z + b.z, lo); w.w = fmaxf(w.w + b.w, lo);
-                  *reinterpret_cast<float4*>(crow + i * cstep) = w;
-                  cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(w.x), fabsf(w.y))), fmaxf(fabsf(w.z), fabsf(w.w)));
+            for (int i = 0; i < 8; ++i) {
+              if (r4 + 4 * i < rmax) {
+                float4 w = lds_f4(sp + (uint32_t)(i * 4 * 36) * 4u);
+                w.x += b.x; w.y += b.y; w.z += b.z; w.w += b.w;
+                if (g.mode == 1) { const float4 o = *reinterpret_cast<const float4*>(crow + i * cstep); w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
+                w.x = fmaxf(w.x, lo); w.y = fmaxf(w.y, lo); w.z = fmaxf(w.z, lo); w.w = fmaxf(w.w, lo);
+                if (g.mask) {
+                  const float4 k = mk[i];
+                  w.x = k.x > 0.f ? w.x : 0.f; w.y = k.y > 0.f ? w.y : 0.f; w.z = k.z > 0.f ? w.z : 0.f; w.w = k.w > 0.f ? w.w : 0.f;
                 }
-              }
-            } else {                                          // dgrad form: optional add to C, ReLU-derivative mask
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                if (r4 + 4 * i < rmax) {
-                  float4 w = *reinterpret_cast<const float4*>(sp + i * 4 * 36);
-                  w.x += b.x; w.y += b.y; w.z += b.z; w.w += b.w;
-                  if (g.mode == 1) { const float4 o = *reinterpret_cast<const float4*>(crow + i * cstep); w.x += o.x; w.y += o.y; w.z += o.z; w.w += o.w; }
-                  w.x = fmaxf(w.x, lo); w.y = fmaxf(w.y, lo); w.z = fmaxf(w.z, lo); w.w = fmaxf(w.w, lo);
-                  if (g.mask) {
-                    const float4 k = mk[i];
-                    w.x = k.x > 0.f ? w.x : 0.f; w.y = k.y > 0.f ? w.y : 0.f; w.z = k.z > 0.f ? w.z : 0.f; w.w = k.w > 0.f ? w.w : 0.f;
-                  }
-                  *reinterpret_cast<float4*>(crow + i * cstep) = w;
-                  cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(w.x), fabsf(w.y))), fmaxf(fabsf(w.z), fabsf(w.w)));
-                }
+                *reinterpret_cast<float4*>(crow + i * cstep) = w;
+                cmax = fmaxf(fmaxf(cmax, fmaxf(fabsf(w.x), fabsf(w.y))), fmaxf(fabsf(w.z), fabsf(w.w)));
               }
             }
           }
@@ -453,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
           const float b = (g.bias && n_ok) ? __ldg(g.bias + n) : 0.f;
 #pragma unroll 4
           for (int r = 0; r < rmax; ++r) {
-            float w = stg[r * 36 + lane];
+            float w = lds_f(stg + (uint32_t)(r * 36 + lane) * 4u);
             if (n_ok) {
               float* c = g.C + (long long)(m_warp + r) * g.c_ms + n;
               if (g.mode == 2) { atomicAdd(c, w); continue; }
@@ -472,7 +563,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_gemm_kernel(const __grid_const
       // hand the region back to the producers (its next MMAs overwrite it)
       tc_fence_before_sync();
       __syncwarp();
-      if (elect_one()) mbar_arrive(&r_free[region]);
+      if (elect_one()) { if (pp.rank == 0) mbar_arrive(&r_free[region]); else mbar_arrive_remote_cnt(&r_free[region], 0, 1); }
       __syncwarp();
       if (tr) tr->mark(61);
     }

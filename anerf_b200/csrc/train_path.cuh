@@ -173,11 +173,12 @@ struct TcEngine {
     g.C = C; g.c_ms = c_ms; g.c_ns = c_ns; g.bias = bias; g.mask = mask; g.mask_ms = mask_ms; g.relu = relu; g.mode = mode;
     g.status = status;
     g.trace = trace;
+    { static const int dbg = getenv("ANERF_TC_DEBUG") ? atoi(getenv("ANERF_TC_DEBUG")) : 0; g.debug = dbg; }
     const int items = g.k_slices * ceil_div(M, 2 * kTileM) * g.n_tiles;
     int pairs = n_sm / 2;
     if (pairs > items) pairs = items;
     if (pairs < 1) return;
-    const int smem = kAStages * kAStageBytes + kBStages * kBStageBytes + 8 * (kNumBars + 2) + 16 + 64 + kTcDrainWarps * 32 * 36 * 4;
+    const int smem = tc_gemm_smem_bytes();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * pairs);
     cfg.blockDim = dim3(kThreads);

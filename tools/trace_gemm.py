@@ -1,6 +1,8 @@
 """Timeline of CTA 0 for one training-path GEMM (debug aid): clock64 stamps of the MMA warp (stream 0) and two worker
-warps (streams 1, 2).  Tags: 1/2 first/later chunk ready, 3 item fully issued; 50/51 A production begin/end, 52 after the
-workers' barrier, 60/61 epilogue begin/end, 10/11 wait for / got the accumulators, 12 one 32-column block drained.
+warps (streams 1, 2).  Tags: 1/2 first/later chunk ready, 3 item fully issued; producers: 50/51 item begin/end, per chunk 52
+loads issued, 53 ring stage free, 54 converted + stored, 55 arrived; drain: 10/11 wait for / got the accumulators, per
+32-column block 13 TMEM load done, 14 staged, 12 stored; 61 item done.  ANERF_TC_DEBUG (bit 0: no C stores in the forward
+form, bit 1: no A loads, bit 2: 16-byte B copies) switches traffic off for timing experiments (profiles/r2_tc_gemm_analysis.md).
 
     python tools/trace_gemm.py [rows] [N] [K] [form: fwd|dgrad|wgrad]"""
 import os, sys
