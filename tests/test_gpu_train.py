@@ -132,6 +132,34 @@ def test_saved_activation_route(name, engine, monkeypatch):
     assert not bad, bad
 
 
+def test_saved_activation_route_at_the_sample_limit():
+    """384 + 128 samples per ray (the 512-sample limit of the entry points): the per-ray stage kernel then needs more than
+    48 KB of shared memory per CTA (opt-in attribute path).  Outputs against the fused kernel (coarse: 1e-4) and the oracle
+    at the route's own fine sample positions."""
+    scene = synthetic.make_scene(seed=5, n_rays=24, H=64, W=64, focal=60., n_joints=24)
+    sd0, sd1 = synthetic.make_net_weights(101), synthetic.make_net_weights(202)
+    from oracle import anerf_oracle as orc
+    cfg = orc.PathConfig(n_joints=24, N_samples=384, N_importance=128)
+    N = scene["rays_o"].shape[0]
+    cot = gt.cotangents(N, cfg.N_samples, cfg.N_importance)
+    g, out = gpu_grads(scene, sd0, sd1, cfg, None, cot, saved=True)
+    g_rec, out_fused = gpu_grads(scene, sd0, sd1, cfg, None, cot)
+    for k in ("rgb0", "disp0", "acc0", "alpha0", "nearfar"):
+        assert gt.rel_err(out[k], out_fused[k]) < 1e-4, k
+    out_orc, g_orc, _ = gt.oracle_grads(scene, sd0, sd1, cfg, None, cot, z_all_override=out["z_all"])
+    for k in out_orc:
+        assert gt.rel_err(out[k], out_orc[k]) < 1e-4, k
+    # the coarse pass of both routes is the same arithmetic on the same depths: equal up to the order of the atomic adds.
+    # (Against the oracle's fp32 autograd this 384-sample configuration is conditioned at ~1e-3 for the coarse network --
+    # sample spacings of 1e-3 of the ray -- so that comparison is only a sanity bound here.)
+    for k in g:
+        if k.startswith("net0."):
+            assert gt.rel_err(g[k], g_rec[k]) < 2e-5, k
+    errs = {k: gt.rel_err(g[k], g_orc[k]) for k in g}
+    assert max(errs.values()) < 5e-3, errs
+    assert max(v for k, v in errs.items() if k.startswith("net1.")) < 1e-3, errs          # 512 fine samples: measured 2.7e-4
+
+
 def test_frozen_parameters_and_no_pose_gradient():
     c, _ = load_golden("grad_j24_s24_i0")
     scene, sd0, sd1, cfg, draws = build_case(c)
