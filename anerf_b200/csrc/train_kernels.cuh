@@ -250,6 +250,65 @@ __global__ void colsum_kernel(const float* __restrict__ G, long long ld, int N, 
   atomicAdd(db + n, s);
 }
 
+// The feature layer has no activation, so it folds into the views layer (as in the fused render kernel):
+//   hv = relu([h | enc] [Wv_f Wf | Wv_e]^T + (Wv_f bf + bv)),   Wv = [Wv_f | Wv_e]  ([H, W + E]),  Wf [W, W]
+// -> one GEMM with K = W + E instead of two, and no feature-layer dgrad / wgrad in the backward pass.
+// wvf [H, LV] = [Wv_f Wf | Wv_e], bvf [H] = Wv_f bf + bv.  One thread per element of wvf, then of bvf.
+__global__ void fold_views_train_kernel(const float* __restrict__ wv, const float* __restrict__ bv, const float* __restrict__ wf,
+                                        const float* __restrict__ bf, int H, int W, int LV, float* __restrict__ wvf,
+                                        float* __restrict__ bvf) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < H * LV) {
+    const int h = idx / LV, c = idx % LV;
+    if (c >= W) { wvf[idx] = wv[idx]; return; }
+    float acc = 0.f;
+    for (int m = 0; m < W; ++m) acc = fmaf(wv[(long long)h * LV + m], wf[(long long)m * W + c], acc);
+    wvf[idx] = acc;
+  } else if (idx < H * LV + H) {
+    const int h = idx - H * LV;
+    float acc = bv[h];
+    for (int m = 0; m < W; ++m) acc = fmaf(wv[(long long)h * LV + m], bf[m], acc);
+    bvf[h] = acc;
+  }
+}
+// Backward of the fold: parameter gradients from d(wvf) [H, LV] and d(bvf) [H] (any output pointer may be NULL):
+//   g_wv[h, c >= W] += dwvf[h, c];   g_wv[h, m < W] += sum_c dwvf[h, c] wf[m, c] + dbvf[h] bf[m]
+//   g_wf[m, c] += sum_h wv[h, m] dwvf[h, c];   g_bf[m] += sum_h wv[h, m] dbvf[h];   g_bv[h] += dbvf[h]
+// One thread per output element: [H * LV | W * W | W | H].
+__global__ void unfold_views_grads_kernel(const float* __restrict__ dwvf, const float* __restrict__ dbvf, const float* __restrict__ wv,
+                                          const float* __restrict__ wf, const float* __restrict__ bf, int H, int W, int LV,
+                                          float* g_wv, float* g_bv, float* g_wf, float* g_bf) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < H * LV) {
+    if (!g_wv) return;
+    const int h = idx / LV, c = idx % LV;
+    if (c >= W) { g_wv[idx] += dwvf[idx]; return; }
+    float acc = dbvf[h] * bf[c];
+    for (int k = 0; k < W; ++k) acc = fmaf(dwvf[(long long)h * LV + k], wf[(long long)c * W + k], acc);
+    g_wv[idx] += acc;
+    return;
+  }
+  idx -= H * LV;
+  if (idx < W * W) {
+    if (!g_wf) return;
+    const int m = idx / W, c = idx % W;
+    float acc = 0.f;
+    for (int h = 0; h < H; ++h) acc = fmaf(wv[(long long)h * LV + m], dwvf[(long long)h * LV + c], acc);
+    g_wf[idx] += acc;
+    return;
+  }
+  idx -= W * W;
+  if (idx < W) {
+    if (!g_bf) return;
+    float acc = 0.f;
+    for (int h = 0; h < H; ++h) acc = fmaf(wv[(long long)h * LV + idx], dbvf[h], acc);
+    g_bf[idx] += acc;
+    return;
+  }
+  idx -= W;
+  if (idx < H && g_bv) g_bv[idx] += dbvf[idx];
+}
+
 // ------------------------------------------------------------------------------------------------
 // sampling positions
 // ------------------------------------------------------------------------------------------------

@@ -228,6 +228,7 @@ struct TrainCall {
 struct Workspace {
   long long rb;                  // rows per block
   long long z_coarse, xs, h[8], vin, hv, raw, graw, cs, ga, gb, gxs, gvin, ghv, tc_w, tc_g, tc_slots, total;   // offsets in floats
+  long long wvf, bvf, dwvf, dbvf;   // folded views weights [H, LV] / bias [H] of the pass and their gradients (train_kernels.cuh: fold_views_train_kernel)
   long long tc_w_floats, tc_g_floats;
   int P, LX, LV;                 // encoding width, leading dimension of XS (P + W), of VIN (W + 27J + fc)
 };
@@ -263,6 +264,10 @@ inline Workspace make_workspace(const NetDims& d, int n_rays, int Sc, int Si, lo
   w.gxs = take(rb * w.LX);
   w.gvin = take(rb * w.LV);
   w.ghv = take(rb * (d.W / 2));
+  w.wvf = take((long long)(d.W / 2) * w.LV);
+  w.bvf = take(d.W / 2);
+  w.dwvf = take((long long)(d.W / 2) * w.LV);
+  w.dbvf = take(d.W / 2);
   // tensor-core engine scratch: packed weight operands of one network pass (forward + transposed forms) and the
   // packed gradient operand of one wgrad (bf16 hi + lo = 4 bytes per element, rows padded to 128)
 #if !defined(ANERF_SIMT_EMU)
@@ -360,8 +365,10 @@ struct PassView {
   PassView(const NetDims& dims, const Workspace& wk, float* base)
       : d(dims), w(wk), ws(base), D(dims.D), W(dims.W), H(dims.W / 2), P(wk.P), LX(wk.LX), LV(wk.LV), J(dims.J),
         XS(base + wk.xs), VIN(base + wk.vin), HV(base + wk.hv), RAW(base + wk.raw) {}
-  float* out_ptr(int l) const { return l == d.skip ? XS + P : ws + w.h[l]; }
-  long long out_ld(int l) const { return l == d.skip ? LX : W; }
+  // the last trunk layer writes next to the view encoding (the views layer reads [h | enc] as one matrix: the feature
+  // layer is folded into it), the skip layer next to the point encoding
+  float* out_ptr(int l) const { return l == d.skip ? XS + P : (l == D - 1 ? VIN : ws + w.h[l]); }
+  long long out_ld(int l) const { return l == d.skip ? LX : (l == D - 1 ? LV : W); }
   const float* in_ptr(int l) const { return (l == 0 || (l - 1) == d.skip) ? XS : out_ptr(l - 1); }
   long long in_ld(int l) const { return (l == 0 || (l - 1) == d.skip) ? LX : out_ld(l - 1); }
   int in_k(int l) const { return l == 0 ? P : ((l - 1) == d.skip ? P + W : W); }
@@ -410,8 +417,11 @@ inline void pass_forward(const TrainCall& c, const Workspace& w, int net, int S,
   const long long HLld = v.out_ld(D - 1);
   auto k1 = head_fwd_kernel<1>;
   if (!dry) ANERF_TLAUNCH(k1, dim3((unsigned)((rows + 127) / 128)), dim3(128), st, HL, HLld, W, p.alpha_w, p.alpha_b, rows, RAW + 3, (long long)4);
-  gemm_rows<true>(c.tc, st, HL, HLld, p.feature_w, W, VIN, LV, rows, W, W, p.feature_b, 0, nullptr, 0, 0);
-  gemm_rows<true>(c.tc, st, VIN, LV, p.views_w, LV, HV, H, rows, H, LV, p.views_b, 1, nullptr, 0, 0);
+  // feature layer folded into the views layer: hv = relu([h | enc] WVF^T + BVF)
+  float* WVF = c.workspace + w.wvf; float* BVF = c.workspace + w.bvf;
+  auto kf = fold_views_train_kernel;
+  if (!dry) ANERF_TLAUNCH(kf, dim3((unsigned)((H * LV + H + 127) / 128)), dim3(128), st, p.views_w, p.views_b, p.feature_w, p.feature_b, H, W, LV, WVF, BVF);
+  gemm_rows<true>(c.tc, st, VIN, LV, WVF, LV, HV, H, rows, H, LV, BVF, 1, nullptr, 0, 0);
   auto k3 = head_fwd_kernel<3>;
   if (!dry) ANERF_TLAUNCH(k3, dim3((unsigned)((rows + 127) / 128)), dim3(128), st, (const float*)HV, (long long)H, H, p.rgb_w, p.rgb_b, rows, RAW, (long long)4);
 }
@@ -456,18 +466,26 @@ inline void pass_backward(const TrainCall& c, const Workspace& w, int net, int S
     if (c.tc) c.tc->produce_scan(st, GHV, H, H, rows);
 #endif
   }
-  gemm_wgrad(c.tc, st, GHV, H, VIN, LV, gr.views_w, LV, rows, H, LV, gr.views_b);
-  const int Nv = (need_pose || need_fc) ? LV : W;         // the view-encoding columns only when something consumes them
-  gemm_rows<false>(c.tc, st, GHV, H, p.views_w, LV, GVIN, LV, rows, Nv, H, nullptr, 0, nullptr, 0, 0);
-  gemm_wgrad(c.tc, st, GVIN, LV, HL, HLld, gr.feature_w, W, rows, W, W, gr.feature_b);
+  // folded views layer: gradients of [Wv_f Wf | Wv_e] and of the folded bias into scratch, then back to the four
+  // parameter tensors in weight space (no row-sized work for the feature layer at all)
+  float* WVF = ws + w.wvf; float* DWVF = ws + w.dwvf; float* DBVF = ws + w.dbvf;
+  if (gr.views_w || gr.views_b || gr.feature_w || gr.feature_b) {
+    ANERF_TZERO(DWVF, (size_t)((DBVF + H) - DWVF) * sizeof(float), st);              // dwvf and dbvf are adjacent in the workspace
+    gemm_wgrad(c.tc, st, GHV, H, VIN, LV, DWVF, LV, rows, H, LV, DBVF);
+    auto ku = unfold_views_grads_kernel;
+    ANERF_TLAUNCH(ku, dim3((unsigned)((H * LV + W * W + W + H + 127) / 128)), dim3(128), st, (const float*)DWVF, (const float*)DBVF, p.views_w,
+                  p.feature_w, p.feature_b, H, W, LV, gr.views_w, gr.views_b, gr.feature_w, gr.feature_b);
+  }
   {
     auto k1 = head_bwd_kernel<1>;
     ANERF_TLAUNCH(k1, dim3((unsigned)((rows + 63) / 64)), dim3((unsigned)W), st, (const float*)(GRAW + 3), (long long)4, HL, HLld, W,
                   p.alpha_w, rows, 64, 0, GA, (long long)W, gr.alpha_w, gr.alpha_b);
   }
   // (GA now holds g_sigma (x) w_alpha; the GEMM below adds to it and registers the maximum of the sum)
-  // dL/dZ of the last trunk layer = (G_feature Wf + g_sigma (x) w_alpha) . (h > 0)
-  gemm_rows<false>(c.tc, st, GVIN, LV, p.feature_w, W, GA, W, rows, W, W, nullptr, 0, HL, HLld, 1);
+  // dL/dZ of the last trunk layer = (G_hv [Wv_f Wf] + g_sigma (x) w_alpha) . (h > 0)
+  gemm_rows<false>(c.tc, st, GHV, H, WVF, LV, GA, W, rows, W, H, nullptr, 0, HL, HLld, 1);
+  // the view-encoding (+ framecode) columns only when something consumes them
+  if (need_pose || need_fc) gemm_rows<false>(c.tc, st, GHV, H, WVF + W, LV, GVIN + W, LV, rows, LV - W, H, nullptr, 0, nullptr, 0, 0);
   // ---- trunk, last layer first
   const float* cur = GA;
   long long curld = W;
