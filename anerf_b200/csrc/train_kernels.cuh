@@ -271,33 +271,19 @@ __global__ void fold_views_train_kernel(const float* __restrict__ wv, const floa
     bvf[h] = acc;
   }
 }
-// Backward of the fold: parameter gradients from d(wvf) [H, LV] and d(bvf) [H] (any output pointer may be NULL):
-//   g_wv[h, c >= W] += dwvf[h, c];   g_wv[h, m < W] += sum_c dwvf[h, c] wf[m, c] + dbvf[h] bf[m]
-//   g_wf[m, c] += sum_h wv[h, m] dwvf[h, c];   g_bf[m] += sum_h wv[h, m] dbvf[h];   g_bv[h] += dbvf[h]
-// One thread per output element: [H * LV | W * W | W | H].
+// Backward of the fold, the parts that are not matrix products (those run as two small GEMMs, train_path.cuh):
+//   g_wv[h, c >= W] += dwvf[h, c];   g_wv[h, m < W] += dbvf[h] bf[m];   g_bf[m] += sum_h wv[h, m] dbvf[h];   g_bv[h] += dbvf[h]
+// One thread per output element: [H * LV | W | H]; any output pointer may be NULL.
 __global__ void unfold_views_grads_kernel(const float* __restrict__ dwvf, const float* __restrict__ dbvf, const float* __restrict__ wv,
-                                          const float* __restrict__ wf, const float* __restrict__ bf, int H, int W, int LV,
-                                          float* g_wv, float* g_bv, float* g_wf, float* g_bf) {
+                                          const float* __restrict__ bf, int H, int W, int LV, float* g_wv, float* g_bv, float* g_bf) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx < H * LV) {
     if (!g_wv) return;
     const int h = idx / LV, c = idx % LV;
-    if (c >= W) { g_wv[idx] += dwvf[idx]; return; }
-    float acc = dbvf[h] * bf[c];
-    for (int k = 0; k < W; ++k) acc = fmaf(dwvf[(long long)h * LV + k], wf[(long long)c * W + k], acc);
-    g_wv[idx] += acc;
+    g_wv[idx] += c >= W ? dwvf[idx] : dbvf[h] * bf[c];
     return;
   }
   idx -= H * LV;
-  if (idx < W * W) {
-    if (!g_wf) return;
-    const int m = idx / W, c = idx % W;
-    float acc = 0.f;
-    for (int h = 0; h < H; ++h) acc = fmaf(wv[(long long)h * LV + m], dwvf[(long long)h * LV + c], acc);
-    g_wf[idx] += acc;
-    return;
-  }
-  idx -= W * W;
   if (idx < W) {
     if (!g_bf) return;
     float acc = 0.f;

@@ -472,9 +472,13 @@ inline void pass_backward(const TrainCall& c, const Workspace& w, int net, int S
   if (gr.views_w || gr.views_b || gr.feature_w || gr.feature_b) {
     ANERF_TZERO(DWVF, (size_t)((DBVF + H) - DWVF) * sizeof(float), st);              // dwvf and dbvf are adjacent in the workspace
     gemm_wgrad(c.tc, st, GHV, H, VIN, LV, DWVF, LV, rows, H, LV, DBVF);
+    // d views_w[:, :W] += dWVF[:, :W] Wf   and   d feature_w += Wv_f^T dWVF[:, :W]: two [128 x 256 x 256] products on the
+    // fp32 SIMT GEMM (weight-sized), the rest element-wise
+    if (gr.views_w) gemm_rows<true>(nullptr, st, DWVF, LV, p.feature_w, W, gr.views_w, LV, H, W, W, nullptr, 0, nullptr, 0, 1);
+    if (gr.feature_w) gemm_wgrad(nullptr, st, p.views_w, LV, DWVF, LV, gr.feature_w, W, H, W, W, nullptr);
     auto ku = unfold_views_grads_kernel;
-    ANERF_TLAUNCH(ku, dim3((unsigned)((H * LV + W * W + W + H + 127) / 128)), dim3(128), st, (const float*)DWVF, (const float*)DBVF, p.views_w,
-                  p.feature_w, p.feature_b, H, W, LV, gr.views_w, gr.views_b, gr.feature_w, gr.feature_b);
+    ANERF_TLAUNCH(ku, dim3((unsigned)((H * LV + W + H + 127) / 128)), dim3(128), st, (const float*)DWVF, (const float*)DBVF, p.views_w,
+                  p.feature_b, H, W, LV, gr.views_w, gr.views_b, gr.feature_b);
   }
   {
     auto k1 = head_bwd_kernel<1>;
