@@ -275,7 +275,10 @@ class RayCaster(nn.Module):
         with torch.cuda.device(dev):
             nb = _lib.train_state_bytes(self._get_plan(), opts)
             self._state_buf = None                  # release the old one first
-            buf = torch.empty(nb, dtype=torch.uint8, device=dev) if nb > 0 else None
+            try:
+                buf = torch.empty(nb, dtype=torch.uint8, device=dev) if nb > 0 else None
+            except torch.cuda.OutOfMemoryError:     # no room to keep the activations: the recomputing route needs ~half
+                buf = None
         self._state_buf = (key, buf)
         return buf
 
