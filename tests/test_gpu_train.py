@@ -132,8 +132,9 @@ def test_gradients_of_the_option_fixtures(name, saved, engine, monkeypatch):
     (22-bit operands): 24-ray batches put single samples in charge of whole columns, so a hidden unit whose pre-activation
     is within rounding of zero takes its ReLU derivative the other way than fp64 and moves the weight / bias gradients of
     its layer and the one below by up to a few percent (tools/probes/engine_option_probe.py: softplus fixture, fine
-    network, layers 0-1 at 6e-3 / 4e-2, every other tensor at 1e-5; the bf16 engine flips the same unit).  Bar: all
-    gradients together within 2e-3 (L2), at most 6 of the ~45 tensors above 2e-4, none above 1e-1."""
+    network, layers 0-1 at 6e-3 / 4e-2, every other tensor at 1e-5; the bf16 engine flips the same unit).  Bar per tensor:
+    2e-4, or 4x what the oracle's own fp32 autograd deviates from fp64 there (inverse-depth sampling: 1.6e-3); tensor-core
+    engine: all gradients together within 2e-3 (L2), at most 6 of the ~45 tensors above the bar, none above 1e-1."""
     monkeypatch.setenv("ANERF_TRAIN_GEMM", engine)
     case, _ = load_golden(name)
     scene, sd0, sd1, cfg, draws = build_case(case)
@@ -144,10 +145,12 @@ def test_gradients_of_the_option_fixtures(name, saved, engine, monkeypatch):
     cot = gt.cotangents(N, cfg.N_samples, cfg.N_importance)
     g, out = gpu_grads(scene, sd0, sd1, cfg, draws, cot, saved=saved)
     _, g64, _ = gt.oracle_grads(scene, sd0, sd1, cfg, draws, cot, dtype=torch.float64, z_all_override=out.get("z_all"))
+    _, g32, _ = gt.oracle_grads(scene, sd0, sd1, cfg, draws, cot, z_all_override=out.get("z_all"))
     assert set(g) == set(g64)
     errs = {k: gt.rel_err(g[k], g64[k]) for k in g}
-    print(name, engine, "saved" if saved else "recompute", "worst max-norm", max(errs, key=errs.get), max(errs.values()))
-    above = {k: e for k, e in errs.items() if not (e < 2e-4)}
+    yard = {k: gt.rel_err(g32[k], g64[k]) for k in g}      # what the oracle's own fp32 autograd deviates by (1.6e-3 with lindisp)
+    print(name, engine, "saved" if saved else "recompute", "worst max-norm", max(errs, key=errs.get), max(errs.values()), "oracle fp32:", max(yard.values()))
+    above = {k: e for k, e in errs.items() if not (e < max(2e-4, 4 * yard[k]))}
     if engine == "simt":
         assert not above, above
     else:
