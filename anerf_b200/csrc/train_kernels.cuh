@@ -250,6 +250,16 @@ __global__ void colsum_kernel(const float* __restrict__ G, long long ld, int N, 
   atomicAdd(db + n, s);
 }
 
+// Pose gradient: the two encoding-part dgrads (skip layer's [encoding | h] input and layer 0) as ONE product with the
+// contraction dimensions concatenated: wcat [2W, P] = [W_skip[:, :P] ; W_0]  (row k = output unit k of the layer).
+__global__ void stack_enc_weights_kernel(const float* __restrict__ w_skip, int ld_skip, const float* __restrict__ w0, int W, int P,
+                                         float* __restrict__ wcat) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * W * P) return;
+  const int k = idx / P, n = idx % P;
+  wcat[idx] = k < W ? w_skip[(long long)k * ld_skip + n] : w0[(long long)(k - W) * P + n];
+}
+
 // The feature layer has no activation, so it folds into the views layer (as in the fused render kernel):
 //   hv = relu([h | enc] [Wv_f Wf | Wv_e]^T + (Wv_f bf + bv)),   Wv = [Wv_f | Wv_e]  ([H, W + E]),  Wf [W, W]
 // -> one GEMM with K = W + E instead of two, and no feature-layer dgrad / wgrad in the backward pass.

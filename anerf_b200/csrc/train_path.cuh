@@ -228,6 +228,7 @@ struct TrainCall {
 struct Workspace {
   long long rb;                  // rows per block
   long long z_coarse, xs, h[8], vin, hv, raw, graw, cs, ga, gb, gxs, gvin, ghv, tc_w, tc_g, tc_slots, total;   // offsets in floats
+  long long gcat, wcat;             // [rows, 2W] gradients of the skip consumer | of layer 0, and the stacked [2W, P] encoding weights (pose gradient)
   long long wvf, bvf, dwvf, dbvf;   // folded views weights [H, LV] / bias [H] of the pass and their gradients (train_kernels.cuh: fold_views_train_kernel)
   long long tc_w_floats, tc_g_floats;
   int P, LX, LV;                 // encoding width, leading dimension of XS (P + W), of VIN (W + 27J + fc)
@@ -264,6 +265,8 @@ inline Workspace make_workspace(const NetDims& d, int n_rays, int Sc, int Si, lo
   w.gxs = take(rb * w.LX);
   w.gvin = take(rb * w.LV);
   w.ghv = take(rb * (d.W / 2));
+  w.gcat = take(rb * 2 * d.W);
+  w.wcat = take((long long)2 * d.W * w.P);
   w.wvf = take((long long)(d.W / 2) * w.LV);
   w.bvf = take(d.W / 2);
   w.dwvf = take((long long)(d.W / 2) * w.LV);
@@ -491,6 +494,11 @@ inline void pass_backward(const TrainCall& c, const Workspace& w, int net, int S
   // the view-encoding (+ framecode) columns only when something consumes them
   if (need_pose || need_fc) gemm_rows<false>(c.tc, st, GHV, H, WVF + W, LV, GVIN + W, LV, rows, LV - W, H, nullptr, 0, nullptr, 0, 0);
   // ---- trunk, last layer first
+  // Pose gradient: dL/d(encoding) = dZ_{skip+1} W_{skip+1}[:, :P] + dZ_0 W_0.  When both gradients come out of trunk dgrads
+  // they are written side by side (GCAT [rows, 2W]) and the two products run as one GEMM with K = 2W at the end, instead
+  // of a store and a read-add-store of the [rows, P] result.
+  const bool cat = need_pose && d.skip >= 1 && d.skip + 2 <= D - 1;
+  float* GCAT = ws + w.gcat;
   const float* cur = GA;
   long long curld = W;
   for (int l = D - 1; l >= 0; --l) {
@@ -498,15 +506,25 @@ inline void pass_backward(const TrainCall& c, const Workspace& w, int net, int S
     if (l > 0) {
       if ((l - 1) == d.skip) {        // input = cat[encoding, h]: h part masked, encoding part kept for the pose gradient
         gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l] + P, v.in_k(l), GXS + P, LX, rows, W, W, nullptr, 0, XS + P, LX, 0);
-        if (need_pose) gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l], v.in_k(l), GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, 0);
+        if (need_pose && !cat) gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l], v.in_k(l), GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, 0);
         cur = GXS + P; curld = LX;
       } else {
         float* nxt = (cur == GA) ? GB : GA;
-        gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l], v.in_k(l), nxt, W, rows, W, W, nullptr, 0, v.out_ptr(l - 1), v.out_ld(l - 1), 0);
-        cur = nxt; curld = W;
+        long long nld = W;
+        if (cat && l == d.skip + 2) { nxt = GCAT; nld = 2 * W; }              // dZ of the skip consumer
+        else if (cat && l == 1) { nxt = GCAT + W; nld = 2 * W; }              // dZ of layer 0
+        gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[l], v.in_k(l), nxt, nld, rows, W, W, nullptr, 0, v.out_ptr(l - 1), v.out_ld(l - 1), 0);
+        cur = nxt; curld = nld;
       }
     } else if (need_pose) {
-      gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[0], P, GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, d.skip >= 0 ? 1 : 0);
+      if (cat) {
+        float* WCAT = ws + w.wcat;
+        auto ks = stack_enc_weights_kernel;
+        ANERF_TLAUNCH(ks, dim3((unsigned)((2 * W * P + 255) / 256)), dim3(256), st, p.pts_w[d.skip + 1], P + W, p.pts_w[0], W, P, WCAT);
+        gemm_rows<false>(c.tc, st, GCAT, 2 * W, WCAT, P, GXS, LX, rows, P, 2 * W, nullptr, 0, nullptr, 0, 0);
+      } else {
+        gemm_rows<false>(c.tc, st, cur, curld, p.pts_w[0], P, GXS, LX, rows, P, W, nullptr, 0, nullptr, 0, d.skip >= 0 ? 1 : 0);
+      }
     }
   }
   // ---- encodings backward
